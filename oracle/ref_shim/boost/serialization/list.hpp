@@ -1,0 +1,3 @@
+// Shim (see nvp.hpp)
+#pragma once
+#include <boost/serialization/nvp.hpp>
