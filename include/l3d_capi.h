@@ -1,0 +1,114 @@
+/* include/l3d_capi.h — C ABI of libl3d_b200.so, the B200-native replacement of Line3D++'s accelerator boundary.
+ *
+ * What it replaces (reference paths relative to manhofer/Line3Dpp):
+ *   cudawrapper.h:54-80   match_lines_GPU / score_matches_GPU / replicator_dynamics_diffusion_GPU
+ *   called from           line3D.cc:1060 (matchingGPU), line3D.cc:1365 (scoringGPU), line3D.cc:2033 (performRDD)
+ * plus the host work the reference wraps around those calls and that this library moves onto the device:
+ *   cudawrapper.cu:592-650 (dense D2H + host kNN pass), line3D.cc:811-858 (orientation check),
+ *   line3D.cc:1311-1355 (sort + ranges + regularizers_tgt), line3D.cc:1672-1699 (inverse matches),
+ *   line3D.cc:1586-1669 (filter + best estimate), line3D.cc:1852-1979 (affinity matrix), sparsematrix.cc:8-135.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer, the library owns every device
+ * buffer; no ownership passes through the ABI (unlike SparseMatrix*& in cudawrapper.h:80).  Every entry returns
+ * 0 on success or a negative l3d_status; l3d_last_error() gives the message (the reference prints CUDA errors to
+ * cerr and carries on, dataArray.h:198-237).  A context is single-owner (not thread-safe), one per GPU, and runs
+ * on its own non-default stream.  There is NO CPU fallback: without a usable CUDA device l3d_ctx_create fails.
+ */
+#ifndef L3D_CAPI_H_
+#define L3D_CAPI_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct l3d_ctx l3d_ctx;
+
+typedef enum {
+    L3D_OK = 0,
+    L3D_ERR_INVALID = -1,      /* bad argument */
+    L3D_ERR_CUDA = -2,         /* CUDA runtime error; see l3d_last_error */
+    L3D_ERR_STATE = -3,        /* call order violated (e.g. match before set_views) */
+    L3D_ERR_UNSUPPORTED = -4,  /* valid in the reference but not implemented here (yet) */
+    L3D_ERR_NOMEM = -5
+} l3d_status;
+
+/* One view as the reference's View holds it after View::View (view.cc:6-42). */
+typedef struct {
+    uint32_t cam_id;        /* reference camID (line3D.h:104) */
+    int32_t width, height;  /* image size */
+    int32_t nseg;           /* number of 2D segments */
+    float RtKinv[9];        /* (float) R^T K^-1, row-major          view.cc:37-40 (RtKinv_DA_) */
+    float C[3];             /* (float) camera centre, UNtranslated  view.cc:35   (C_f3_)      */
+    double RtKinv_d[9];     /* double R^T K^-1                      view.cc:27                */
+    double C_d[3];          /* double camera centre in the (translated) working frame  view.cc:28, 510-514 */
+    float k;                /* spatial regulariser k_               view.cc:301-314           */
+    float median_depth;     /* median_depth_ (0 before matching)    view.h:108-121            */
+} l3d_view_desc;
+
+/* One emitted match of a source segment: the payload of L3DPP::Match (commons.h:186-203) minus the ids implied
+ * by its position.  24 bytes. */
+typedef struct {
+    uint32_t tgt_seg;
+    float overlap;
+    float d_p1, d_p2, d_q1, d_q2;
+} l3d_match_rec;
+
+/* Full L3DPP::Match mirror (40 bytes), used by the pipeline dumps. */
+typedef struct {
+    uint32_t src_cam, src_seg, tgt_cam, tgt_seg;
+    float overlap, score3D, d_p1, d_p2, d_q1, d_q2;
+} l3d_match;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int l3d_ctx_create(int device, l3d_ctx** out);
+void l3d_ctx_destroy(l3d_ctx* ctx);
+const char* l3d_last_error(const l3d_ctx* ctx);
+/* the CUDA stream the context launches on (cudaStream_t as void*), for event timing by the caller */
+void* l3d_stream(l3d_ctx* ctx);
+int l3d_sync(l3d_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long l3d_launch_count(const l3d_ctx* ctx);
+
+/* ---- views: replaces initSrcDataGPU / per-pair uploads (line3D.cc:1018-1026, 1049-1057) ---------------------- */
+/* segs_host[v] points to nseg*4 floats (x1,y1,x2,y2).  Data is device-resident after the call; a per-segment
+ * pre-pass caches rays and plane normals (the reference recomputes them per pair, cudawrapper.cu:148-154). */
+int l3d_set_views(l3d_ctx* ctx, int num_views, const l3d_view_desc* views, const float* const* segs_host);
+/* same, all segments in ONE flat array (view v starts at the prefix sum of nseg); on_device != 0: the array is already
+ * on this GPU (e.g. the output of the NCCL all-gather of per-view segment lists) and is used in place, not copied. */
+int l3d_set_views_flat(l3d_ctx* ctx, int num_views, const l3d_view_desc* views, const float* segs_flat, int on_device);
+/* update per-view k / median depth / double camera blocks without touching segments (after translate(), filter) */
+int l3d_update_view_params(l3d_ctx* ctx, int num_views, const l3d_view_desc* views);
+
+/* ---- matching: replaces match_lines_GPU (cudawrapper.h:54-64) for a whole batch of view pairs ----------------
+ * pairs[2*i], pairs[2*i+1] = (src view index, tgt view index) into the l3d_set_views array;
+ * F[9*i..] = float fundamental matrix of pair i, row-major, (float)F_double like eigen2dataArray line3D.cc:2775.
+ * For every src segment the kNN tgt segments with the highest epipolar overlap among those with
+ * overlap > epi_overlap and all four depths > 0 are kept (cudawrapper.cu:605-645); ties: smaller tgt_seg first.
+ * 1 <= knn <= 32.  Results stay on the device; fetch with the l3d_get_* calls. */
+int l3d_match_pairs(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn);
+/* sizes of the last l3d_match_pairs result */
+long long l3d_match_total_rows(const l3d_ctx* ctx);      /* sum of Ns over pairs */
+long long l3d_match_pair_evals(const l3d_ctx* ctx);      /* sum of Ns*Nt over pairs */
+/* counts_out[row_off(pair)+r] for all pairs (row_off = prefix sum of Ns in pair order); returns total matches */
+long long l3d_get_match_counts(l3d_ctx* ctx, int32_t* counts_out);
+/* one pair: counts_out[Ns], recs_out[Ns*knn] (slot r*knn+i valid for i < counts_out[r]) */
+int l3d_get_pair_matches(l3d_ctx* ctx, int pair, int32_t* counts_out, l3d_match_rec* recs_out);
+/* everything, compacted on the device to CSR before the D2H: row_ptr_out[total_rows+1], recs_out[capacity].
+ * Returns the number of records (even if > capacity; then nothing is copied). */
+long long l3d_get_matches_csr(l3d_ctx* ctx, int64_t* row_ptr_out, l3d_match_rec* recs_out, long long capacity);
+
+/* ---- dense device contract of K_match_lines (cudawrapper.cu:186-253): one launch fills
+ * depths[Ns*Nt] (float4: d_p1,d_p2,d_q1,d_q2 or -1) and overlaps[Ns*Nt], row-major by src.  Output pointers are
+ * DEVICE pointers if out_on_device != 0, else host buffers.  HBM-write-bound: 20 B per pair evaluation. */
+int l3d_match_dense(l3d_ctx* ctx, int src_view, int tgt_view, const float* F, float epi_overlap, float* depths,
+                    float* overlaps, int out_on_device);
+
+/* test hook: same contract with the conservative pre-filter disabled (every cell through the exact path) */
+int l3d_match_dense_nofilter(l3d_ctx* ctx, int src_view, int tgt_view, const float* F, float epi_overlap, float* depths,
+                             float* overlaps, int out_on_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L3D_CAPI_H_ */

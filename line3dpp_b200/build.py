@@ -1,0 +1,43 @@
+"""Build libl3d_b200.so (hand-written sm_100a kernels + the C ABI) in-tree with nvcc.
+
+    python -m line3dpp_b200.build [--force] [--verbose]
+
+-fmad=false is part of the arithmetic contract (csrc/l3d_device.cuh): plain `a*b+c` is two IEEE roundings, fused
+multiply-adds are spelled explicitly where they are wanted.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libl3d_b200.so")
+SOURCES = ["l3d_match.cu", "l3d_capi.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+         "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++"]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "l3d_capi.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(OUT)

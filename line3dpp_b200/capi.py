@@ -1,0 +1,177 @@
+"""ctypes binding of libl3d_b200.so (include/l3d_capi.h).  Thin: no arithmetic happens in Python.
+
+The library is REQUIRED: importing this module builds it if the .so is missing and raises if that fails; creating a
+context raises if there is no usable CUDA device.  There is no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class ViewDesc(C.Structure):
+    _fields_ = [("cam_id", C.c_uint32), ("width", C.c_int32), ("height", C.c_int32), ("nseg", C.c_int32),
+                ("RtKinv", C.c_float * 9), ("C", C.c_float * 3), ("RtKinv_d", C.c_double * 9), ("C_d", C.c_double * 3),
+                ("k", C.c_float), ("median_depth", C.c_float)]
+
+
+REC_DT = np.dtype([("tgt_seg", "<u4"), ("overlap", "<f4"), ("d_p1", "<f4"), ("d_p2", "<f4"), ("d_q1", "<f4"),
+                   ("d_q2", "<f4")])
+MATCH_DT = np.dtype([("src_cam", "<u4"), ("src_seg", "<u4"), ("tgt_cam", "<u4"), ("tgt_seg", "<u4"),
+                     ("overlap", "<f4"), ("score3D", "<f4"), ("d_p1", "<f4"), ("d_p2", "<f4"),
+                     ("d_q1", "<f4"), ("d_q2", "<f4")])
+
+_lib = None
+
+
+class L3DError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = C.CDLL(path)
+        L.l3d_last_error.restype = C.c_char_p
+        L.l3d_stream.restype = C.c_void_p
+        for n in ("l3d_launch_count", "l3d_match_total_rows", "l3d_match_pair_evals", "l3d_get_match_counts",
+                  "l3d_get_matches_csr"):
+            getattr(L, n).restype = C.c_longlong
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def make_view_descs(cam_ids, widths, heights, nsegs, RtKinv_d, C_untranslated_d, C_work_d, k, median_depth):
+    """Pack camera blocks (already computed by the host side, in double) into l3d_view_desc[]."""
+    V = len(cam_ids)
+    arr = (ViewDesc * V)()
+    for v in range(V):
+        d = arr[v]
+        d.cam_id, d.width, d.height, d.nseg = int(cam_ids[v]), int(widths[v]), int(heights[v]), int(nsegs[v])
+        R = np.asarray(RtKinv_d[v], np.float64).reshape(9)
+        d.RtKinv[:] = R.astype(np.float32).tolist()
+        d.RtKinv_d[:] = R.tolist()
+        d.C[:] = np.asarray(C_untranslated_d[v], np.float64).astype(np.float32).tolist()
+        d.C_d[:] = np.asarray(C_work_d[v], np.float64).tolist()
+        d.k = float(k[v])
+        d.median_depth = float(median_depth[v])
+    return arr
+
+
+class Context:
+    """One l3d_ctx (one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.l3d_ctx_create(int(device), C.byref(h))
+        if rc != 0 or not h:
+            raise L3DError(f"l3d_ctx_create(device={device}) failed with {rc}: no usable CUDA device "
+                           "(libl3d_b200 has no CPU fallback)")
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.l3d_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, rc, what):
+        if rc < 0:
+            raise L3DError(f"{what} failed ({rc}): {self.L.l3d_last_error(self.h).decode()}")
+        return rc
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.l3d_stream(self.h) or 0)
+
+    def sync(self):
+        self._chk(self.L.l3d_sync(self.h), "l3d_sync")
+
+    def launch_count(self) -> int:
+        return int(self.L.l3d_launch_count(self.h))
+
+    # ---- views
+    def set_views(self, descs, segs_list):
+        V = len(descs)
+        segs = [np.ascontiguousarray(s, np.float32) for s in segs_list]
+        ptrs = (C.c_void_p * V)(*[s.ctypes.data for s in segs])
+        self._keep = [descs, segs]
+        self._chk(self.L.l3d_set_views(self.h, V, descs, ptrs), "l3d_set_views")
+
+    def set_views_flat(self, descs, segs_flat_ptr: int, on_device: bool):
+        self._keep = [descs]
+        self._chk(self.L.l3d_set_views_flat(self.h, len(descs), descs, C.c_void_p(segs_flat_ptr), int(on_device)),
+                  "l3d_set_views_flat")
+
+    def update_view_params(self, descs):
+        self._chk(self.L.l3d_update_view_params(self.h, len(descs), descs), "l3d_update_view_params")
+
+    # ---- matching
+    def match_pairs(self, pairs, F, epi_overlap=0.25, knn=10):
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        F = np.ascontiguousarray(F, np.float32).reshape(-1, 9)
+        assert len(pairs) == len(F)
+        self._chk(self.L.l3d_match_pairs(self.h, len(pairs), _p(pairs), _p(F), C.c_float(epi_overlap), int(knn)),
+                  "l3d_match_pairs")
+        self._knn = int(knn)
+
+    def match_total_rows(self) -> int:
+        return int(self.L.l3d_match_total_rows(self.h))
+
+    def match_pair_evals(self) -> int:
+        return int(self.L.l3d_match_pair_evals(self.h))
+
+    def match_counts(self):
+        out = np.zeros(max(self.match_total_rows(), 0), np.int32)
+        total = self._chk(self.L.l3d_get_match_counts(self.h, _p(out)), "l3d_get_match_counts")
+        return out, int(total)
+
+    def pair_matches(self, pair: int, ns: int):
+        counts = np.zeros(ns, np.int32)
+        recs = np.zeros((ns, self._knn), REC_DT)
+        self._chk(self.L.l3d_get_pair_matches(self.h, int(pair), _p(counts), _p(recs)), "l3d_get_pair_matches")
+        return counts, recs
+
+    def matches_csr(self, row_ptr=None, recs=None):
+        rows = self.match_total_rows()
+        if row_ptr is None:
+            row_ptr = np.zeros(rows + 1, np.int64)
+        cap = 0 if recs is None else len(recs)
+        total = self._chk(self.L.l3d_get_matches_csr(self.h, _p(row_ptr), _p(recs), C.c_longlong(cap)),
+                          "l3d_get_matches_csr")
+        if recs is None or total > cap:
+            recs = np.zeros(total, REC_DT)
+            total = self._chk(self.L.l3d_get_matches_csr(self.h, _p(row_ptr), _p(recs), C.c_longlong(len(recs))),
+                              "l3d_get_matches_csr")
+        return row_ptr, recs[:total]
+
+    def matches_csr_raw(self, row_ptr_ptr: int, recs_ptr: int, capacity: int) -> int:
+        return int(self._chk(self.L.l3d_get_matches_csr(self.h, C.c_void_p(row_ptr_ptr), C.c_void_p(recs_ptr),
+                                                        C.c_longlong(capacity)), "l3d_get_matches_csr"))
+
+    def match_dense(self, src_view, tgt_view, F, epi_overlap, ns, nt, nofilter=False, dev_ptrs=None):
+        F = np.ascontiguousarray(F, np.float32).reshape(9)
+        fn = self.L.l3d_match_dense_nofilter if nofilter else self.L.l3d_match_dense
+        if dev_ptrs is not None:
+            self._chk(fn(self.h, int(src_view), int(tgt_view), _p(F), C.c_float(epi_overlap), C.c_void_p(dev_ptrs[0]),
+                         C.c_void_p(dev_ptrs[1]), 1), "l3d_match_dense")
+            return None
+        dep = np.empty((ns, nt, 4), np.float32)
+        ov = np.empty((ns, nt), np.float32)
+        self._chk(fn(self.h, int(src_view), int(tgt_view), _p(F), C.c_float(epi_overlap), _p(dep), _p(ov), 0),
+                  "l3d_match_dense")
+        return dep, ov

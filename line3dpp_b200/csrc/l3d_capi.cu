@@ -1,0 +1,325 @@
+// l3d_capi.cu — context, device memory and the C-ABI entry points declared in include/l3d_capi.h.
+// Host C++ only orchestrates: every byte of arithmetic on the hot path runs in the kernels of l3d_match.cu /
+// l3d_pipeline.cu.  There is no CPU fallback: every entry needs a live CUDA context and fails loudly otherwise.
+#include "l3d_ctx.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+int l3d_fail(l3d_ctx* c, int code, const char* what, cudaError_t e)
+{
+    if (c) {
+        char buf[512];
+        if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+        else snprintf(buf, sizeof(buf), "%s", what);
+        c->err = buf;
+    }
+    return code;
+}
+
+int l3d_reserve(l3d_ctx* c, DevBuf& b, size_t bytes, const char* what)
+{
+    if (bytes <= b.cap) return L3D_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&b.p, bytes); want = bytes; }
+    if (e != cudaSuccess) { b.p = nullptr; return l3d_fail(c, L3D_ERR_NOMEM, what, e); }
+    b.cap = want;
+    return L3D_OK;
+}
+
+struct CastI64 { __host__ __device__ long long operator()(int v) const { return (long long)v; } };
+
+extern "C" {
+
+int l3d_ctx_create(int device, l3d_ctx** out)
+{
+    if (!out) return L3D_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return L3D_ERR_CUDA;   // no GPU, no library: no CPU fallback
+    l3d_ctx* c = new l3d_ctx();
+    c->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return L3D_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    c->num_sms = prop.multiProcessorCount;
+    e = cudaFuncSetAttribute(k_match_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3d_match_smem_bytes());
+    if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return L3D_ERR_CUDA; }
+    *out = c;
+    return L3D_OK;
+}
+
+void l3d_ctx_destroy(l3d_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : c->all_bufs()) if (b->p) cudaFree(b->p);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* l3d_last_error(const l3d_ctx* c) { return c ? c->err.c_str() : "null context"; }
+void* l3d_stream(l3d_ctx* c) { return c ? (void*)c->stream : nullptr; }
+long long l3d_launch_count(const l3d_ctx* c) { return c ? c->launches : 0; }
+int l3d_sync(l3d_ctx* c)
+{
+    if (!c) return L3D_ERR_INVALID;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    return e == cudaSuccess ? L3D_OK : l3d_fail(c, L3D_ERR_CUDA, "l3d_sync", e);
+}
+
+// ------------------------------------------------------------------------------------------------ views
+static int set_views_common(l3d_ctx* c, int V, const l3d_view_desc* views)
+{
+    c->h_views.resize(V);
+    long long off = 0;
+    for (int v = 0; v < V; ++v) {
+        if (views[v].nseg < 0) return l3d_fail(c, L3D_ERR_INVALID, "l3d_set_views: negative nseg");
+        L3DViewDev& d = c->h_views[v];
+        d.seg_off = off; d.nseg = views[v].nseg; d.cam_id = views[v].cam_id; d.width = views[v].width; d.height = views[v].height;
+        memcpy(d.RtKinv, views[v].RtKinv, sizeof(d.RtKinv)); memcpy(d.C, views[v].C, sizeof(d.C));
+        memcpy(d.RtKinv_d, views[v].RtKinv_d, sizeof(d.RtKinv_d)); memcpy(d.C_d, views[v].C_d, sizeof(d.C_d));
+        d.k = views[v].k; d.median_depth = views[v].median_depth;
+        off += views[v].nseg;
+    }
+    c->num_views = V; c->total_segs = off;
+    return L3D_OK;
+}
+
+static int finish_views(l3d_ctx* c)
+{
+    int rc;
+    if ((rc = l3d_reserve(c, c->d_views, sizeof(L3DViewDev) * (size_t)c->num_views, "views"))) return rc;
+    if ((rc = l3d_reserve(c, c->d_cache, sizeof(float4) * 3 * (size_t)c->total_segs, "segment cache"))) return rc;
+    L3D_CUDA(c, cudaMemcpyAsync(c->d_views.p, c->h_views.data(), sizeof(L3DViewDev) * c->num_views, cudaMemcpyHostToDevice, c->stream), "upload views");
+    if (c->total_segs > 0) {
+        unsigned int blocks = (unsigned int)((c->total_segs + 255) / 256);
+        k_prep_segments<<<blocks, 256, 0, c->stream>>>(c->segs(), c->views(), c->num_views, c->total_segs, (float4*)c->d_cache.p);
+        ++c->launches;
+        L3D_CUDA(c, cudaGetLastError(), "k_prep_segments");
+    }
+    c->have_views = true; c->have_matches = false;
+    return L3D_OK;
+}
+
+int l3d_set_views(l3d_ctx* c, int V, const l3d_view_desc* views, const float* const* segs_host)
+{
+    if (!c || V <= 0 || !views || !segs_host) return l3d_fail(c, L3D_ERR_INVALID, "l3d_set_views: bad arguments");
+    cudaSetDevice(c->device);
+    int rc = set_views_common(c, V, views);
+    if (rc) return rc;
+    size_t bytes = sizeof(float4) * (size_t)c->total_segs;
+    if ((rc = l3d_reserve(c, c->d_segs, bytes, "segments"))) return rc;
+    if (bytes > c->h_stage_cap) {           // pinned staging so the H2D is one full-speed async copy
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr; c->h_stage_cap = 0;
+        L3D_CUDA(c, cudaMallocHost(&c->h_stage, bytes), "pinned staging");
+        c->h_stage_cap = bytes;
+    }
+    L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync before staging");
+    for (int v = 0; v < V; ++v)
+        if (views[v].nseg) memcpy((char*)c->h_stage + sizeof(float4) * c->h_views[v].seg_off, segs_host[v], sizeof(float4) * (size_t)views[v].nseg);
+    if (bytes) L3D_CUDA(c, cudaMemcpyAsync(c->d_segs.p, c->h_stage, bytes, cudaMemcpyHostToDevice, c->stream), "upload segments");
+    c->segs_ext = nullptr;
+    return finish_views(c);
+}
+
+int l3d_set_views_flat(l3d_ctx* c, int V, const l3d_view_desc* views, const float* segs_flat, int on_device)
+{
+    if (!c || V <= 0 || !views || !segs_flat) return l3d_fail(c, L3D_ERR_INVALID, "l3d_set_views_flat: bad arguments");
+    cudaSetDevice(c->device);
+    int rc = set_views_common(c, V, views);
+    if (rc) return rc;
+    size_t bytes = sizeof(float4) * (size_t)c->total_segs;
+    if (on_device) {
+        if (((uintptr_t)segs_flat & 15) != 0) return l3d_fail(c, L3D_ERR_INVALID, "l3d_set_views_flat: device array must be 16-byte aligned");
+        c->segs_ext = (const float4*)segs_flat;
+    } else {
+        if ((rc = l3d_reserve(c, c->d_segs, bytes, "segments"))) return rc;
+        if (bytes) L3D_CUDA(c, cudaMemcpyAsync(c->d_segs.p, segs_flat, bytes, cudaMemcpyHostToDevice, c->stream), "upload segments");
+        c->segs_ext = nullptr;
+    }
+    return finish_views(c);
+}
+
+int l3d_update_view_params(l3d_ctx* c, int V, const l3d_view_desc* views)
+{
+    if (!c || !views || V != c->num_views || !c->have_views) return l3d_fail(c, L3D_ERR_STATE, "l3d_update_view_params: views not set / count mismatch");
+    cudaSetDevice(c->device);
+    for (int v = 0; v < V; ++v) {
+        L3DViewDev& d = c->h_views[v];
+        memcpy(d.RtKinv_d, views[v].RtKinv_d, sizeof(d.RtKinv_d)); memcpy(d.C_d, views[v].C_d, sizeof(d.C_d));
+        d.k = views[v].k; d.median_depth = views[v].median_depth;
+    }
+    L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync before view update");
+    L3D_CUDA(c, cudaMemcpyAsync(c->d_views.p, c->h_views.data(), sizeof(L3DViewDev) * V, cudaMemcpyHostToDevice, c->stream), "upload views");
+    return L3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ matching
+int l3d_match_pairs(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn)
+{
+    if (!c) return L3D_ERR_INVALID;
+    if (!c->have_views) return l3d_fail(c, L3D_ERR_STATE, "l3d_match_pairs: call l3d_set_views first");
+    if (num_pairs < 0 || (num_pairs && (!pairs || !F))) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs: bad arguments");
+    if (knn <= 0) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: kNN <= 0 (keep all matches) is not implemented; use l3d_match_dense");
+    if (knn > 32) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: kNN > 32 not implemented");
+    cudaSetDevice(c->device);
+    L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync before pair staging");   // h_pairs/h_tiles may still be in flight
+    c->h_pairs.resize(num_pairs);
+    c->h_tiles.clear();
+    long long rows = 0, evals = 0;
+    for (int i = 0; i < num_pairs; ++i) {
+        int s = pairs[2 * i], t = pairs[2 * i + 1];
+        if (s < 0 || t < 0 || s >= c->num_views || t >= c->num_views) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs: view index out of range");
+        L3DPairDev& p = c->h_pairs[i];
+        p.src = s; p.tgt = t; memcpy(p.F, F + 9 * (size_t)i, sizeof(p.F)); p.row_off = rows;
+        int Ns = c->h_views[s].nseg, Nt = c->h_views[t].nseg;
+        if (Nt >= (1 << 24)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: more than 2^24 segments in one view");
+        if (Nt > 0)
+            for (int r0 = 0; r0 < Ns; r0 += MK_ROWS) c->h_tiles.push_back(make_int2(i, r0));
+        rows += Ns; evals += (long long)Ns * Nt;
+    }
+    c->num_pairs = num_pairs; c->knn = knn; c->epi = epi_overlap; c->total_rows = rows; c->pair_evals = evals;
+    int rc;
+    if ((rc = l3d_reserve(c, c->d_pairs, sizeof(L3DPairDev) * (size_t)std::max(num_pairs, 1), "pairs"))) return rc;
+    if ((rc = l3d_reserve(c, c->d_tiles, sizeof(int2) * std::max<size_t>(c->h_tiles.size(), 1), "tiles"))) return rc;
+    if ((rc = l3d_reserve(c, c->d_counts, sizeof(int) * (size_t)std::max<long long>(rows, 1), "match counts"))) return rc;
+    if ((rc = l3d_reserve(c, c->d_recs, sizeof(l3d_match_rec) * (size_t)std::max<long long>(rows, 1) * knn, "match records"))) return rc;
+    if (num_pairs) L3D_CUDA(c, cudaMemcpyAsync(c->d_pairs.p, c->h_pairs.data(), sizeof(L3DPairDev) * num_pairs, cudaMemcpyHostToDevice, c->stream), "upload pairs");
+    if (!c->h_tiles.empty()) L3D_CUDA(c, cudaMemcpyAsync(c->d_tiles.p, c->h_tiles.data(), sizeof(int2) * c->h_tiles.size(), cudaMemcpyHostToDevice, c->stream), "upload tiles");
+    if (rows) L3D_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(int) * rows, c->stream), "clear counts");   // rows of pairs with Nt == 0
+    if (!c->h_tiles.empty()) {
+        k_match_topk<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
+            c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, knn,
+            epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p);
+        ++c->launches;
+        L3D_CUDA(c, cudaGetLastError(), "k_match_topk");
+    }
+    c->have_matches = true;
+    return L3D_OK;
+}
+
+long long l3d_match_total_rows(const l3d_ctx* c) { return c && c->have_matches ? c->total_rows : -1; }
+long long l3d_match_pair_evals(const l3d_ctx* c) { return c && c->have_matches ? c->pair_evals : -1; }
+
+long long l3d_get_match_counts(l3d_ctx* c, int32_t* counts_out)
+{
+    if (!c || !counts_out) return L3D_ERR_INVALID;
+    if (!c->have_matches) return l3d_fail(c, L3D_ERR_STATE, "l3d_get_match_counts: no match result");
+    cudaSetDevice(c->device);
+    if (c->total_rows) {
+        cudaError_t e = cudaMemcpyAsync(counts_out, c->d_counts.p, sizeof(int) * c->total_rows, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return l3d_fail(c, L3D_ERR_CUDA, "download counts", e);
+    }
+    long long total = 0;
+    for (long long i = 0; i < c->total_rows; ++i) total += counts_out[i];
+    return total;
+}
+
+int l3d_get_pair_matches(l3d_ctx* c, int pair, int32_t* counts_out, l3d_match_rec* recs_out)
+{
+    if (!c || !counts_out || !recs_out) return L3D_ERR_INVALID;
+    if (!c->have_matches) return l3d_fail(c, L3D_ERR_STATE, "l3d_get_pair_matches: no match result");
+    if (pair < 0 || pair >= c->num_pairs) return l3d_fail(c, L3D_ERR_INVALID, "l3d_get_pair_matches: pair out of range");
+    cudaSetDevice(c->device);
+    const L3DPairDev& p = c->h_pairs[pair];
+    int Ns = c->h_views[p.src].nseg;
+    if (Ns == 0) return L3D_OK;
+    L3D_CUDA(c, cudaMemcpyAsync(counts_out, (const int*)c->d_counts.p + p.row_off, sizeof(int) * Ns, cudaMemcpyDeviceToHost, c->stream), "download pair counts");
+    L3D_CUDA(c, cudaMemcpyAsync(recs_out, (const l3d_match_rec*)c->d_recs.p + p.row_off * c->knn, sizeof(l3d_match_rec) * (size_t)Ns * c->knn, cudaMemcpyDeviceToHost, c->stream), "download pair records");
+    L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync");
+    return L3D_OK;
+}
+
+long long l3d_get_matches_csr(l3d_ctx* c, int64_t* row_ptr_out, l3d_match_rec* recs_out, long long capacity)
+{
+    if (!c || !row_ptr_out) return L3D_ERR_INVALID;
+    if (!c->have_matches) return l3d_fail(c, L3D_ERR_STATE, "l3d_get_matches_csr: no match result");
+    cudaSetDevice(c->device);
+    const long long rows = c->total_rows;
+    if (rows == 0) { row_ptr_out[0] = 0; return 0; }
+    int rc;
+    if ((rc = l3d_reserve(c, c->d_rowptr, sizeof(long long) * (size_t)(rows + 1), "row_ptr"))) return rc;
+    cub::TransformInputIterator<long long, CastI64, const int*> in((const int*)c->d_counts.p, CastI64());
+    size_t tmp_bytes = 0;
+    // rows+1 items: the element past the end is never read by an exclusive scan's last output
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, (long long*)c->d_rowptr.p, rows, c->stream);
+    if ((rc = l3d_reserve(c, c->d_scan_tmp, tmp_bytes, "scan temp"))) return rc;
+    L3D_CUDA(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp_bytes, in, (long long*)c->d_rowptr.p, rows, c->stream), "row_ptr scan");
+    c->launches += 2;   // cub: decoupled look-back init + scan kernels
+    long long last_ptr = 0; int last_cnt = 0;
+    L3D_CUDA(c, cudaMemcpyAsync(&last_ptr, (const long long*)c->d_rowptr.p + rows - 1, sizeof(long long), cudaMemcpyDeviceToHost, c->stream), "read total");
+    L3D_CUDA(c, cudaMemcpyAsync(&last_cnt, (const int*)c->d_counts.p + rows - 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream), "read total");
+    L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync");
+    const long long total = last_ptr + last_cnt;
+    L3D_CUDA(c, cudaMemcpyAsync((long long*)c->d_rowptr.p + rows, &total, sizeof(long long), cudaMemcpyHostToDevice, c->stream), "write total");
+    if ((rc = l3d_reserve(c, c->d_csr, sizeof(l3d_match_rec) * (size_t)std::max<long long>(total, 1), "csr records"))) return rc;
+    long long cells = rows * c->knn;
+    k_compact_matches<<<(unsigned int)((cells + 255) / 256), 256, 0, c->stream>>>((const int*)c->d_counts.p, (const long long*)c->d_rowptr.p,
+                                                                                   (const l3d_match_rec*)c->d_recs.p, c->knn, rows, (l3d_match_rec*)c->d_csr.p);
+    ++c->launches;
+    L3D_CUDA(c, cudaGetLastError(), "k_compact_matches");
+    L3D_CUDA(c, cudaMemcpyAsync(row_ptr_out, c->d_rowptr.p, sizeof(long long) * (rows + 1), cudaMemcpyDeviceToHost, c->stream), "download row_ptr");
+    if (recs_out && total <= capacity && total > 0)
+        L3D_CUDA(c, cudaMemcpyAsync(recs_out, c->d_csr.p, sizeof(l3d_match_rec) * (size_t)total, cudaMemcpyDeviceToHost, c->stream), "download records");
+    L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync");
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------------ dense contract
+static int match_dense_impl(l3d_ctx* c, int sv, int tv, const float* F, float epi, float* depths, float* overlaps, int on_dev, bool filter)
+{
+    if (!c) return L3D_ERR_INVALID;
+    if (!c->have_views) return l3d_fail(c, L3D_ERR_STATE, "l3d_match_dense: call l3d_set_views first");
+    if (!F || !depths || !overlaps || sv < 0 || tv < 0 || sv >= c->num_views || tv >= c->num_views) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_dense: bad arguments");
+    cudaSetDevice(c->device);
+    const L3DViewDev& vs = c->h_views[sv]; const L3DViewDev& vt = c->h_views[tv];
+    const int Ns = vs.nseg, Nt = vt.nseg;
+    if (Ns == 0 || Nt == 0) return L3D_OK;
+    const size_t cells = (size_t)Ns * Nt;
+    float4* d_dep = (float4*)depths; float* d_ov = overlaps;
+    if (!on_dev) {
+        int rc;
+        if ((rc = l3d_reserve(c, c->d_dense_dep, sizeof(float4) * cells, "dense depths"))) return rc;
+        if ((rc = l3d_reserve(c, c->d_dense_ov, sizeof(float) * cells, "dense overlaps"))) return rc;
+        d_dep = (float4*)c->d_dense_dep.p; d_ov = (float*)c->d_dense_ov.p;
+    }
+    L3DMat3 Fm; memcpy(Fm.m, F, sizeof(Fm.m));
+    dim3 grid((Nt + DK_THREADS - 1) / DK_THREADS, (Ns + DK_ROWS - 1) / DK_ROWS);
+    const float4* cache = (const float4*)c->d_cache.p;
+    if (filter)
+        k_match_dense<<<grid, DK_THREADS, 0, c->stream>>>(c->segs() + vs.seg_off, Ns, c->segs() + vt.seg_off, Nt, cache + 3 * vs.seg_off, cache + 3 * vt.seg_off, Fm,
+                                                          make_float3(vs.C[0], vs.C[1], vs.C[2]), make_float3(vt.C[0], vt.C[1], vt.C[2]), epi, d_dep, d_ov);
+    else
+        k_match_dense_nofilter<<<grid, DK_THREADS, 0, c->stream>>>(c->segs() + vs.seg_off, Ns, c->segs() + vt.seg_off, Nt, cache + 3 * vs.seg_off, cache + 3 * vt.seg_off, Fm,
+                                                                   make_float3(vs.C[0], vs.C[1], vs.C[2]), make_float3(vt.C[0], vt.C[1], vt.C[2]), epi, d_dep, d_ov);
+    ++c->launches;
+    L3D_CUDA(c, cudaGetLastError(), "k_match_dense");
+    if (!on_dev) {
+        L3D_CUDA(c, cudaMemcpyAsync(depths, d_dep, sizeof(float4) * cells, cudaMemcpyDeviceToHost, c->stream), "download dense depths");
+        L3D_CUDA(c, cudaMemcpyAsync(overlaps, d_ov, sizeof(float) * cells, cudaMemcpyDeviceToHost, c->stream), "download dense overlaps");
+        L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync");
+    }
+    return L3D_OK;
+}
+
+int l3d_match_dense(l3d_ctx* c, int sv, int tv, const float* F, float epi, float* depths, float* overlaps, int on_dev)
+{ return match_dense_impl(c, sv, tv, F, epi, depths, overlaps, on_dev, true); }
+int l3d_match_dense_nofilter(l3d_ctx* c, int sv, int tv, const float* F, float epi, float* depths, float* overlaps, int on_dev)
+{ return match_dense_impl(c, sv, tv, F, epi, depths, overlaps, on_dev, false); }
+
+} // extern "C"

@@ -1,0 +1,36 @@
+// l3d_match.cuh — launch geometry + kernel declarations shared by l3d_match.cu and l3d_capi.cu
+#pragma once
+#include "l3d_device.cuh"
+#include "../../include/l3d_capi.h"
+
+#define MK_THREADS 256
+#define MK_WARPS 8
+#define MK_RPW 8                        /* source rows per warp */
+#define MK_ROWS (MK_WARPS * MK_RPW)     /* source rows per CTA  */
+#define MK_TT 2048                      /* target segments per TMA stage (32 KB) */
+#define MK_T 4                          /* target segments per lane per step */
+#define MK_CAP 64                       /* survivor keys kept per row before pruning to k */
+
+#define DK_THREADS 256
+#define DK_ROWS 32
+
+struct L3DMat3 { float m[9]; };
+
+size_t l3d_match_smem_bytes();
+
+__global__ void k_prep_segments(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int num_views,
+                                long long total, float4* __restrict__ cache);
+__global__ void k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache,
+                             const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
+                             const int2* __restrict__ tiles, int knn, float epi, int* __restrict__ counts_out,
+                             l3d_match_rec* __restrict__ recs_out);
+__global__ void k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
+                              const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F, float3 Cs,
+                              float3 Ct, float epi, float4* __restrict__ depths, float* __restrict__ overlaps);
+__global__ void k_match_dense_nofilter(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
+                                       const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F,
+                                       float3 Cs, float3 Ct, float epi, float4* __restrict__ depths,
+                                       float* __restrict__ overlaps);
+__global__ void k_compact_matches(const int* __restrict__ counts, const long long* __restrict__ row_ptr,
+                                  const l3d_match_rec* __restrict__ recs, int knn, long long rows,
+                                  l3d_match_rec* __restrict__ out);
