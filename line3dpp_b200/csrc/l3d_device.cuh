@@ -141,21 +141,23 @@ __device__ __forceinline__ void exact_depths(const SegRays& s, const SegRays& t,
 // exceed `thr`.  NaN/Inf (a-b == 0, i.e. epipolar line parallel to the segment) never reject.
 #define L3D_FILTER_M0 2e-3f
 #define L3D_FILTER_C1 4e-3f
-__device__ __forceinline__ bool filter_may_survive(float4 q, float4 rA, float4 rB, float thr_scaled, float cm)
+__device__ __forceinline__ float rcp_approx(float x)
+{ float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // MUFU.RCP, 1 ulp; the filter has 1e-3 margins
+// rA = (e1.x, e1.y, e1.z, e2.x)  rB = (e2.y, e2.z, g, thr_scaled)   thr_scaled = 0.95 * (score a pair must exceed)
+__device__ __forceinline__ bool filter_may_survive(float4 q, float4 rA, float4 rB)
 {
-    // rA = (e1.x, e1.y, e1.z, e2.x)  rB = (e2.y, e2.z, g, -)
     float a1 = __fmaf_rn(rA.x, q.x, __fmaf_rn(rA.y, q.y, rA.z));
     float b1 = __fmaf_rn(rA.x, q.z, __fmaf_rn(rA.y, q.w, rA.z));
     float a2 = __fmaf_rn(rA.w, q.x, __fmaf_rn(rB.x, q.y, rB.y));
     float b2 = __fmaf_rn(rA.w, q.z, __fmaf_rn(rB.x, q.w, rB.y));
-    float r1 = __frcp_rn(a1 - b1), r2 = __frcp_rn(a2 - b2);
+    float r1 = rcp_approx(a1 - b1), r2 = rcp_approx(a2 - b2);
     float t1 = a1 * r1, t2 = a2 * r2;
     float tmin = fminf(t1, t2), tmax = fmaxf(t1, t2);
     float inner = fminf(tmax, 1.0f) - fmaxf(tmin, 0.0f);
     float outer = fmaxf(tmax, 1.0f) - fminf(tmin, 0.0f);
     float m = __fmaf_rn(rB.z, fmaxf(fabsf(r1), fabsf(r2)), L3D_FILTER_M0);
-    // survive  <=>  inner + 2m > thr_scaled * (outer - 2m)   <=>  inner - thr_scaled*outer + cm*m > 0,  cm = 2 + 2*thr_scaled
-    float v = __fmaf_rn(cm, m, __fmaf_rn(-thr_scaled, outer, inner));
+    // survive  <=>  inner + 2m > thr_scaled * (outer - 2m)   <=>  inner - thr_scaled*outer + (2 + 2*thr_scaled)*m > 0
+    float v = __fmaf_rn(__fmaf_rn(2.0f, rB.w, 2.0f), m, __fmaf_rn(-rB.w, outer, inner));
     // The reference's case analysis (which endpoint lies inside which interval, cudawrapper.cu:99-131) is decided by
     // the signs of t and t-1.  If an intersection sits within m of a segment end, its float evaluation may take a
     // different branch than the geometry suggests (and then return a ratio unrelated to inner/outer), so such pairs

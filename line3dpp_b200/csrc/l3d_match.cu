@@ -4,7 +4,7 @@
 //                     segment (the reference recomputes 4 mat-vecs + 5 normalisations per surviving PAIR,
 //                     cudawrapper.cu:148-154).
 //   k_match_topk    : production kernel.  One CTA = 64 source segments of one view pair; the target view's raw
-//                     float4 segment array is streamed through shared memory in 2048-segment stages by 1-D TMA
+//                     float4 segment array is streamed through shared memory in 1024-segment stages by 1-D TMA
 //                     (cp.async.bulk + mbarrier, double buffered); lanes own target segments, rows are broadcast;
 //                     a conservative FMA pre-filter (27 flop + 2 rcp) discards ~98 % of the pairs, survivors are
 //                     compacted with ballots into a per-warp queue and evaluated 32 at a time by the exact,
@@ -41,38 +41,40 @@ struct MatchSmem {
     float4 stage[2][MK_TT];                          // TMA-staged target segments (x1,y1,x2,y2)
     unsigned long long lists[MK_ROWS][MK_CAP];       // per-row survivor keys
     float4 rowA[MK_ROWS];                            // (e1.x, e1.y, e1.z, e2.x)
-    float4 rowB[MK_ROWS];                            // (e2.y, e2.z, g, 0)
+    float4 rowB[MK_ROWS];                            // (e2.y, e2.z, g, 0.95 * score-to-beat)
+    float row_thr[MK_ROWS];                          // overlap of the current k-th best survivor (0 until k are known)
     int list_cnt[MK_ROWS];
     unsigned int queue[MK_WARPS][64];                // candidate queue per warp: (row_local << 24) | tgt
     unsigned long long bars[2];
 };
 size_t l3d_match_smem_bytes() { return sizeof(MatchSmem); }
 
-// rank every entry of a row's key list among the others; lane handles entries lane and lane+32
-__device__ __forceinline__ void rank_row(const unsigned long long* list, int n, int lane, unsigned long long& k0,
-                                         unsigned long long& k1, int& r0, int& r1)
+// rank of lane's key among the n <= 32 keys of a row list (number of larger keys; keys are unique)
+__device__ __forceinline__ int rank_in_row(const unsigned long long* list, int n, unsigned long long k)
 {
-    k0 = lane < n ? list[lane] : 0ull;
-    k1 = lane + 32 < n ? list[lane + 32] : 0ull;
-    r0 = 0; r1 = 0;
-    for (int j = 0; j < n; ++j) {
-        unsigned long long kj = list[j];
-        r0 += kj > k0;
-        r1 += kj > k1;
-    }
+    int r = 0;
+    for (int j = 0; j < n; ++j) r += list[j] > k;
+    return r;
 }
 
-__device__ __forceinline__ void prune_row(MatchSmem& S, int row, int knn, int lane)
+// keep the k best keys of a full row list (sorted, best first) and raise the row's score-to-beat
+__device__ __forceinline__ void prune_row(MatchSmem& S, int row, int knn, float epi, int lane)
 {
     __syncwarp();
-    int n = min(S.list_cnt[row], MK_CAP);
-    unsigned long long k0, k1; int r0, r1;
-    rank_row(S.lists[row], n, lane, k0, k1, r0, r1);
+    const int n = min(S.list_cnt[row], MK_CAP);
+    const unsigned long long k = lane < n ? S.lists[row][lane] : 0ull;
+    const int r = rank_in_row(S.lists[row], n, k);
     __syncwarp();
-    if (lane < n && r0 < knn) S.lists[row][r0] = k0;
-    if (lane + 32 < n && r1 < knn) S.lists[row][r1] = k1;
+    if (lane < n && r < knn) S.lists[row][r] = k;
     __syncwarp();
-    if (lane == 0) S.list_cnt[row] = min(n, knn);
+    if (lane == 0) {
+        S.list_cnt[row] = min(n, knn);
+        if (n >= knn) {
+            const float kth = key_overlap(S.lists[row][knn - 1]);
+            S.row_thr[row] = kth;
+            S.rowB[row].w = 0.95f * fmaxf(kth, epi);
+        }
+    }
     __syncwarp();
 }
 
@@ -91,7 +93,7 @@ __device__ __forceinline__ void exact_batch(MatchSmem& S, unsigned int entry, bo
         float4 rA = S.rowA[rl], rB = S.rowB[rl];
         bool inv;
         float ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
-        if (ov > epi) {
+        if (ov > epi && ov >= S.row_thr[rl]) {      // below the current k-th best it can never be selected
             SegRays s = load_rays(cache, src_base + rl), t = load_rays(cache, toff + j);
             float d[4];
             exact_depths(s, t, Cs, Ct, d);
@@ -105,18 +107,29 @@ __device__ __forceinline__ void exact_batch(MatchSmem& S, unsigned int entry, bo
         }
         unsigned int pm = __ballot_sync(0xffffffffu, pending);
         if (!pm) break;
-        unsigned int todo = pm;                       // a row list overflowed: keep its k best and retry
+        unsigned int todo = pm;                       // a row list is full: keep its k best and retry
         while (todo) {
             int leader = __ffs(todo) - 1;
             int row = __shfl_sync(0xffffffffu, rl, leader);
-            prune_row(S, row, knn, lane);
-            todo &= ~__ballot_sync(0xffffffffu, pending && rl == row);
+            prune_row(S, row, knn, epi, lane);
+            unsigned int mine = __ballot_sync(0xffffffffu, pending && rl == row);
+            todo &= ~mine;
+            if (knn >= MK_CAP) {                      // list stays full (k == capacity): fold the pending keys in one by one
+                while (mine) {
+                    int l = __ffs(mine) - 1;
+                    mine &= mine - 1;
+                    unsigned long long k = __shfl_sync(0xffffffffu, key, l);
+                    if (lane == 0 && k > S.lists[row][MK_CAP - 1]) S.lists[row][MK_CAP - 1] = k;
+                    if (lane == l) pending = false;
+                    prune_row(S, row, knn, epi, lane);   // re-sort; also refreshes the score-to-beat
+                }
+            }
         }
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(MK_THREADS, 2)
+__global__ void __launch_bounds__(MK_THREADS, MK_MINB)
 k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
              const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
              int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out)
@@ -133,29 +146,29 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
     const int Ns = vs->nseg, Nt = vt->nseg;
     const int nrows = min(MK_ROWS, Ns - row0);
     const float4* tsegs = segs + toff;
-    const float3 Cs = make_float3(vs->C[0], vs->C[1], vs->C[2]);
-    const float3 Ct = make_float3(vt->C[0], vt->C[1], vt->C[2]);
+    const int nchunks = (Nt + MK_TT - 1) / MK_TT;
 
-    if (tid == 0) { mbar_init(&S.bars[0], 1); mbar_init(&S.bars[1], 1); mbar_fence_init(); }
+    if (tid == 0) {
+        mbar_init(&S.bars[0], 1); mbar_init(&S.bars[1], 1); mbar_fence_init();
+        unsigned int bytes = (unsigned int)min(MK_TT, Nt) * 16u;       // first stage in flight while the rows are set up
+        mbar_expect_tx(&S.bars[0], bytes);
+        tma_load_1d(S.stage[0], tsegs, bytes, &S.bars[0]);
+    }
     if (tid < MK_ROWS) {
         S.list_cnt[tid] = 0;
+        S.row_thr[tid] = 0.0f;
         if (tid < nrows) {
             float4 s = __ldg(segs + soff + row0 + tid);
             float3 e1 = mulmat_h(P->F, s.x, s.y), e2 = mulmat_h(P->F, s.z, s.w);     // epipolar lines F*p (cudawrapper.cu:216-217)
             float g = L3D_FILTER_C1 * fmaxf(sqrtf(e1.x * e1.x + e1.y * e1.y), sqrtf(e2.x * e2.x + e2.y * e2.y));
             S.rowA[tid] = make_float4(e1.x, e1.y, e1.z, e2.x);
-            S.rowB[tid] = make_float4(e2.y, e2.z, g, 0.f);
+            S.rowB[tid] = make_float4(e2.y, e2.z, g, 0.95f * epi);
         }
     }
+    const float3 Cs = make_float3(vs->C[0], vs->C[1], vs->C[2]);
+    const float3 Ct = make_float3(vt->C[0], vt->C[1], vt->C[2]);
     __syncthreads();
 
-    const int nchunks = (Nt + MK_TT - 1) / MK_TT;
-    if (tid == 0 && nchunks > 0) {
-        unsigned int bytes = (unsigned int)min(MK_TT, Nt) * 16u;
-        mbar_expect_tx(&S.bars[0], bytes);
-        tma_load_1d(S.stage[0], tsegs, bytes, &S.bars[0]);
-    }
-    const float thr_scaled = 0.95f * epi, cm = 2.0f + 2.0f * thr_scaled;
     const unsigned int lt_mask = (1u << lane) - 1u;
     int qn = 0;   // warp-uniform number of queued candidates
 
@@ -184,24 +197,30 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
                     const int rl = warp * MK_RPW + r;
                     if (rl >= nrows) break;
                     const float4 rA = S.rowA[rl], rB = S.rowB[rl];
+                    bool pass[MK_T];
 #pragma unroll
-                    for (int t = 0; t < MK_T; ++t) {
-                        bool pass = ok[t] && filter_may_survive(q[t], rA, rB, thr_scaled, cm);
-                        unsigned int b = __ballot_sync(0xffffffffu, pass);
-                        if (b) {
-                            if (pass) S.queue[warp][qn + __popc(b & lt_mask)] = ((unsigned int)rl << 24) | (unsigned int)(base + j0 + t * 32 + lane);
-                            qn += __popc(b);
-                            __syncwarp();
-                            if (qn >= 32) {
-                                qn -= 32;
-                                exact_batch(S, S.queue[warp][qn + lane], true, tsegs, cache, soff + row0, toff, Cs, Ct, epi, knn, lane);
+                    for (int t = 0; t < MK_T; ++t) pass[t] = ok[t] && filter_may_survive(q[t], rA, rB);   // MK_T independent chains
+                    unsigned int b[MK_T], any = 0u;
+#pragma unroll
+                    for (int t = 0; t < MK_T; ++t) { b[t] = __ballot_sync(0xffffffffu, pass[t]); any |= b[t]; }
+                    if (any) {
+#pragma unroll
+                        for (int t = 0; t < MK_T; ++t) {
+                            if (b[t]) {
+                                if (pass[t]) S.queue[warp][qn + __popc(b[t] & lt_mask)] = ((unsigned int)rl << 24) | (unsigned int)(base + j0 + t * 32 + lane);
+                                qn += __popc(b[t]);
+                                __syncwarp();
+                                if (qn >= 32) {
+                                    qn -= 32;
+                                    exact_batch(S, S.queue[warp][qn + lane], true, tsegs, cache, soff + row0, toff, Cs, Ct, epi, knn, lane);
+                                }
                             }
                         }
                     }
                 }
             }
         }
-        __syncthreads();
+        if (c + 2 < nchunks) __syncthreads();       // only needed when this stage buffer will be refilled
     }
     if (qn > 0) {
         bool has = lane < qn;
@@ -217,23 +236,17 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
         const long long R = P->row_off + row0 + rl;
         if (lane == 0) counts_out[R] = min(n, knn);
         if (n == 0) continue;
-        unsigned long long k0, k1; int r0, r1;
-        rank_row(S.lists[rl], n, lane, k0, k1, r0, r1);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const unsigned long long key = h ? k1 : k0;
-            const int rank = h ? r1 : r0;
-            const bool valid = (lane + 32 * h) < n && rank < knn;
-            if (valid) {
-                unsigned int j = key_tgt(key);
-                SegRays s = load_rays(cache, soff + row0 + rl), t = load_rays(cache, toff + j);
-                float d[4];
-                exact_depths(s, t, Cs, Ct, d);
-                l3d_match_rec rec;
-                rec.tgt_seg = j; rec.overlap = key_overlap(key);
-                rec.d_p1 = d[0]; rec.d_p2 = d[1]; rec.d_q1 = d[2]; rec.d_q2 = d[3];
-                recs_out[R * knn + rank] = rec;
-            }
+        const unsigned long long key = lane < n ? S.lists[rl][lane] : 0ull;
+        const int rank = rank_in_row(S.lists[rl], n, key);
+        if (lane < n && rank < knn) {
+            unsigned int j = key_tgt(key);
+            SegRays s = load_rays(cache, soff + row0 + rl), t = load_rays(cache, toff + j);
+            float d[4];
+            exact_depths(s, t, Cs, Ct, d);
+            l3d_match_rec rec;
+            rec.tgt_seg = j; rec.overlap = key_overlap(key);
+            rec.d_p1 = d[0]; rec.d_p2 = d[1]; rec.d_q1 = d[2]; rec.d_q2 = d[3];
+            recs_out[R * knn + rank] = rec;
         }
     }
 }
@@ -263,7 +276,7 @@ k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict
         const float4 rA = rowA[r], rB = rowB[r];
         float4 res = make_float4(-1.f, -1.f, -1.f, -1.f);
         float ov = 0.0f;
-        if (filter_may_survive(q, rA, rB, 0.0f, 2.0f)) {
+        if (filter_may_survive(q, rA, rB)) {
             bool inv;
             ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
             if (ov > epi) {

@@ -7,9 +7,12 @@
 #define MK_WARPS 8
 #define MK_RPW 8                        /* source rows per warp */
 #define MK_ROWS (MK_WARPS * MK_RPW)     /* source rows per CTA  */
-#define MK_TT 2048                      /* target segments per TMA stage (32 KB) */
+#define MK_TT 1024                      /* target segments per TMA stage (16 KB) */
 #define MK_T 4                          /* target segments per lane per step */
-#define MK_CAP 64                       /* survivor keys kept per row before pruning to k */
+#define MK_CAP 32                       /* survivor keys kept per row before pruning to k */
+#ifndef MK_MINB
+#define MK_MINB 3                       /* resident CTAs per SM the register budget is tuned for */
+#endif
 
 #define DK_THREADS 256
 #define DK_ROWS 32
