@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Line3D++ matching hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric: matched line-pairs/sec = (source segment, target segment) pair evaluations per second of the epipolar matching
++ fused kNN selection (unit of work of SURVEY.md §8(d)); every unordered view pair is evaluated once.
+Workload (BASELINE.json configs[3]): synthetic 1000 views x 3000 segments/view per GPU, ring +-5 visual neighbours
+(5000 view pairs, 4.5e10 pair evaluations per GPU).  Weak scaling: N GPUs match a ring of N*1000 views; every rank
+owns 1000 views, one NCCL all-gather of the per-view segment lists makes all views resident, then each rank matches
+the view pairs whose source view it owns (no other collective on the data path).
+
+One step = all-gather (N>1) + per-segment pre-pass + one fused match/top-k launch over this rank's pairs.
+  value : device-timed, inputs already in HBM.
+  e2e   : same step through the C ABI with HOST buffers: H2D of this rank's segments from pinned memory, match,
+          device-side CSR compaction, D2H of every emitted match record into pinned memory.
+`--impl reference` times the reference's CPU/OpenMP matching path (oracle port of matchingCPU, line3D.cc:900-1015;
+line3D.cc itself cannot be compiled in this image) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VIEWS_PER_GPU, SEGS_PER_VIEW, RING, KNN, EPI = 1000, 3000, 5, 10, 0.25
+FLOP_PER_PAIR_EVAL = 100.0     # algorithmic FP32 flop per pair evaluation (DESIGN.md "Roofline")
+DENSE_BYTES_PER_CELL = 20.0    # float4 depths + float overlap per cell (cudawrapper.cu:226-251)
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- workload
+def build_rank_workload(rank: int, world: int):
+    """This rank's views (global ids rank*1000 ..), the camera blocks of ALL views and this rank's view-pair list."""
+    from line3dpp_b200 import synth
+    V = VIEWS_PER_GPU * world
+    # one global scene definition; each rank only materialises the segments of its own views
+    t0 = time.time()
+    scene = synth.make_scene(V, SEGS_PER_VIEW, 1004, f"ring{RING}") if world == 1 else None
+    if scene is None:
+        scene = synth.make_scene_views(V, SEGS_PER_VIEW, 1004, f"ring{RING}", range(rank * VIEWS_PER_GPU, (rank + 1) * VIEWS_PER_GPU))
+    pairs = synth.view_pairs(scene.neighbors)
+    lo, hi = rank * VIEWS_PER_GPU, (rank + 1) * VIEWS_PER_GPU
+    mine = pairs[(pairs[:, 0] >= lo) & (pairs[:, 0] < hi)]
+    F = np.zeros((len(mine), 9), np.float32)
+    for i, (s, t) in enumerate(mine):
+        F[i] = synth.fundamental(scene.K[s], scene.R[s], scene.t[s], scene.K[t], scene.R[t], scene.t[t]).astype(np.float32).reshape(9)
+    return scene, mine, F, time.time() - t0
+
+
+def make_descs(scene, nsegs):
+    from line3dpp_b200 import capi, synth
+    RtKinv, C = synth.camera_blocks(scene)
+    V = scene.num_views
+    return capi.make_view_descs(scene.cam_ids, [scene.width] * V, [scene.height] * V, nsegs, RtKinv, C, C,
+                                np.zeros(V, np.float32), np.zeros(V, np.float32))
+
+
+# ---------------------------------------------------------------------------------------------- reference arm / cpu baseline
+def cpu_matching_sample(seconds_target: float = 12.0, threads: int | None = None):
+    """Times the oracle port of the reference CPU/OpenMP matching path (matchingCPU, double) on view pairs of the bench
+    workload until ~seconds_target of wall time is used.  Returns (pair_evals_per_s, cores, sample description)."""
+    from line3dpp_b200 import synth
+    from oracle import pyoracle as po
+    po.build(ref=False)
+    cores = threads or os.cpu_count() or 1
+    po.set_threads(cores)
+    sc = synth.make_scene(12, SEGS_PER_VIEW, 1004, f"ring{RING}")
+    RtKinv, C = synth.camera_blocks(sc)
+    pairs = synth.view_pairs(sc.neighbors)
+    done, t_used, n = 0, 0.0, 0
+    fn = po.lib().orc_match_lines_f64
+    for (s, t) in pairs:
+        F = synth.fundamental(sc.K[s], sc.R[s], sc.t[s], sc.K[t], sc.R[t], sc.t[t])
+        t0 = time.perf_counter()
+        po.match_lines(fn, sc.segs[s], sc.segs[t], F, RtKinv[s], RtKinv[t], C[s], C[t], int(s), int(t), EPI, KNN, f64=True)
+        t_used += time.perf_counter() - t0
+        done += len(sc.segs[s]) * len(sc.segs[t]); n += 1
+        if t_used >= seconds_target:
+            break
+    return done / t_used, cores, f"{n} view pairs of {SEGS_PER_VIEW}x{SEGS_PER_VIEW} segments ({done:.3g} pair evaluations, {t_used:.1f} s), matchingCPU double path, OpenMP over source segments"
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    per_step = []
+    sample = ""
+    cores = os.cpu_count() or 1
+    for i in range(args.warmup + args.steps):
+        budget = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
+        v, cores, sample = cpu_matching_sample(budget)
+        if i >= args.warmup:
+            per_step.append(v)
+    value = float(np.mean(per_step))
+    pe_step = 4.5e10 * max(world, 1)
+    line = {"impl": "reference", "metric": "matched_line_pairs_per_sec", "value": value, "unit": "pair-evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": pe_step / value * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference CPU/OpenMP matching path (oracle port of line3D.cc:900-1015; line3D.cc needs Eigen/OpenCV/Boost, absent here); "
+                    "ms_per_step is the time the full step's pair evaluations would take at this rate"}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n):
+    return {"workload": f"BASELINE.json configs[3]: synthetic {VIEWS_PER_GPU} views x {SEGS_PER_VIEW} segments per GPU, ring +-{RING} neighbours, "
+                        f"kNN={KNN}, epi_overlap={EPI}; {n} GPU(s) -> ring of {n * VIEWS_PER_GPU} views, {n * 5000} view pairs",
+            "views": n * VIEWS_PER_GPU, "segments_per_view": SEGS_PER_VIEW, "view_pairs": n * 5000, "knn": KNN,
+            "epi_overlap": EPI, "sharding": f"views sharded over {n} GPU(s), one NCCL all-gather of segment lists" if n > 1 else "single GPU",
+            "l2": "flushed between timed steps (256 MiB write); outputs (3.6 GB/step) exceed L2"}
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from line3dpp_b200 import capi
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"}))
+            return 2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = capi.Context(local_rank)
+    st = torch.cuda.ExternalStream(ctx.stream)
+
+    scene, pairs, F, gen_s = build_rank_workload(rank, world)
+    V = scene.num_views
+    lo, hi = rank * VIEWS_PER_GPU, (rank + 1) * VIEWS_PER_GPU
+    nsegs = [SEGS_PER_VIEW] * V
+    my = np.concatenate([scene.segs[v] for v in range(lo, hi)]).astype(np.float32)
+    assert my.shape == (VIEWS_PER_GPU * SEGS_PER_VIEW, 4), my.shape   # equal-sized shards: all_gather_into_tensor
+    descs = make_descs(scene, nsegs)
+    host_my = torch.from_numpy(my).pin_memory()
+    with torch.cuda.stream(st):
+        dev_my = host_my.to("cuda", non_blocking=True)
+        dev_all = torch.empty((V * SEGS_PER_VIEW, 4), dtype=torch.float32, device="cuda") if world > 1 else dev_my
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ctx.sync()
+
+    def step_device():
+        """inputs resident in HBM -> matches resident in HBM"""
+        with torch.cuda.stream(st):
+            if world > 1:
+                dist.all_gather_into_tensor(dev_all, dev_my)
+            ctx.set_views_flat(descs, dev_all.data_ptr(), True)
+            ctx.match_pairs(pairs, F, EPI, KNN)
+
+    state = {"cap": 0, "recs": None, "rowptr": None, "total": 0}
+
+    def step_e2e():
+        """host buffers in -> host buffers out, through the C ABI"""
+        with torch.cuda.stream(st):
+            if world > 1:
+                dev_my.copy_(host_my, non_blocking=True)
+                dist.all_gather_into_tensor(dev_all, dev_my)
+                ctx.set_views_flat(descs, dev_all.data_ptr(), True)
+            else:
+                ctx.set_views_flat(descs, host_my.data_ptr(), False)
+            ctx.match_pairs(pairs, F, EPI, KNN)
+            rows = ctx.match_total_rows()
+            if state["rowptr"] is None:
+                state["rowptr"] = torch.empty(rows + 1, dtype=torch.int64).pin_memory()
+            total = ctx.matches_csr_raw(state["rowptr"].data_ptr(), state["recs"].data_ptr() if state["recs"] is not None else 0, state["cap"])
+            if total > state["cap"]:
+                state["cap"] = int(total * 1.05) + 1024
+                state["recs"] = torch.empty(state["cap"] * 24, dtype=torch.uint8).pin_memory()
+                total = ctx.matches_csr_raw(state["rowptr"].data_ptr(), state["recs"].data_ptr(), state["cap"])
+            state["total"] = total
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ms = []
+        for _ in range(steps):
+            with torch.cuda.stream(st):
+                flush.fill_(1)                     # evict L2 between timed steps (not timed)
+            ctx.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(st)
+            fn()
+            e1.record(st)
+            ctx.sync()
+            wall = (time.perf_counter() - t0) * 1e3
+            ms.append((e0.elapsed_time(e1), wall))
+        barrier()
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count()
+    if rank == 0:
+        sampler.start()
+    dev_ms = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (ctx.launch_count() - launches0) / (args.steps + args.warmup)
+    pe_local = ctx.match_pair_evals()
+    e2e_ms = timed(step_e2e, args.steps, max(args.warmup, 1) + 1)   # +1: first call sizes the pinned output buffers
+
+    # ---- roofline legs measured live (rank 0): FP32 peak probe + HBM-bound dense kernel
+    extra = {}
+    if rank == 0:
+        extra = roofline_legs(ctx, st, scene, torch)
+
+    dev_total = sum(m[0] for m in dev_ms)
+    e2e_total = sum(max(m) for m in e2e_ms)          # e2e includes host-side waits: take max(device, wall) per step
+    t = torch.tensor([dev_total, e2e_total, float(pe_local), float(state["total"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_total, e2e_total, pe_all, matches_all = tmax[0].item(), tmax[1].item(), tsum[2].item(), tsum[3].item()
+    else:
+        pe_all, matches_all = float(pe_local), float(state["total"])
+    if rank == 0:
+        ms_step = dev_total / args.steps
+        value = pe_all / (ms_step * 1e-3)
+        e2e_step = e2e_total / args.steps
+        h2d = int(my.nbytes + len(pairs) * (8 + 36) + V * 232)
+        d2h = int(state["total"] * 24 + (ctx.match_total_rows() + 1) * 8)
+        fp32_peak = extra.get("fp32_peak_tflops")
+        achieved_tf = pe_all / world * FLOP_PER_PAIR_EVAL / (ms_step * 1e-3) / 1e12
+        peaks = load_peaks()
+        line = {
+            "metric": "matched_line_pairs_per_sec", "value": value, "unit": "pair-evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "emitted_matches_per_sec": matches_all / (ms_step * 1e-3),
+            "e2e": {"value": pe_all / (e2e_step * 1e-3), "unit": "pair-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_step},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "k_match_topk", "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": (achieved_tf / fp32_peak) if fp32_peak else None,
+                         "peak_source": "FFMA probe kernel run live in this process (MEASURED_PEAKS.json has no FP32 non-tensor figure)",
+                         "algorithmic_flop_per_pair_eval": FLOP_PER_PAIR_EVAL,
+                         "hbm_frac": (pe_all / world * 0.1 / (ms_step * 1e-3) / 1e9) / peaks["hbm_gbs"],
+                         "traffic": extra.get("topk_traffic")},
+            "roofline_hbm": extra.get("roofline_hbm"),
+            "peaks": peaks,
+        }
+        cpu_v, cores, sample = cpu_matching_sample(12.0)
+        line["cpu_baseline"] = {"value": cpu_v, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def roofline_legs(ctx, st, scene, torch):
+    """HBM-bound leg: the dense-contract kernel (20 B written per pair evaluation), timed with CUDA events on the
+    launching stream over outputs larger than L2; plus the FP32 FFMA peak probe."""
+    out = {}
+    try:
+        out["fp32_peak_tflops"] = ctx.fp32_peak_tflops()
+    except Exception as e:   # noqa
+        out["fp32_peak_tflops"] = None
+    Ns = Nt = SEGS_PER_VIEW
+    nbuf = 8                                            # 8 x 180 MB of output, round-robin: never L2 resident
+    dep = [torch.empty(Ns * Nt * 4, dtype=torch.float32, device="cuda") for _ in range(nbuf)]
+    ov = [torch.empty(Ns * Nt, dtype=torch.float32, device="cuda") for _ in range(nbuf)]
+    from line3dpp_b200 import synth
+    F = [synth.fundamental(scene.K[0], scene.R[0], scene.t[0], scene.K[t], scene.R[t], scene.t[t]).astype(np.float32) for t in range(1, 1 + nbuf)]
+    for rep in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for i in range(nbuf):
+            ctx.match_dense(0, 1 + i, F[i], EPI, Ns, Nt, dev_ptrs=(dep[i].data_ptr(), ov[i].data_ptr()))
+        e1.record(st)
+        ctx.sync()
+        ms = e0.elapsed_time(e1) / nbuf
+    peaks = load_peaks()
+    gbs = Ns * Nt * DENSE_BYTES_PER_CELL / (ms * 1e-3) / 1e9
+    out["roofline_hbm"] = [{"kernel": "k_match_dense", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
+                            "algorithmic_bytes_per_pair_eval": DENSE_BYTES_PER_CELL, "cells_per_launch": Ns * Nt,
+                            "pair_evals_per_sec": Ns * Nt / (ms * 1e-3)}]
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

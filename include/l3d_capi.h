@@ -108,6 +108,10 @@ int l3d_match_dense(l3d_ctx* ctx, int src_view, int tgt_view, const float* F, fl
 int l3d_match_dense_nofilter(l3d_ctx* ctx, int src_view, int tgt_view, const float* F, float epi_overlap, float* depths,
                              float* overlaps, int out_on_device);
 
+/* measurement aid: achieved non-tensor FP32 FFMA throughput of this GPU right now (TFLOP/s), the denominator of the
+ * fused kernel's compute roofline */
+int l3d_fp32_peak_probe(l3d_ctx* ctx, double* tflops_out);
+
 #ifdef __cplusplus
 }
 #endif

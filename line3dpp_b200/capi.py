@@ -163,6 +163,11 @@ class Context:
         return int(self._chk(self.L.l3d_get_matches_csr(self.h, C.c_void_p(row_ptr_ptr), C.c_void_p(recs_ptr),
                                                         C.c_longlong(capacity)), "l3d_get_matches_csr"))
 
+    def fp32_peak_tflops(self) -> float:
+        v = C.c_double(0)
+        self._chk(self.L.l3d_fp32_peak_probe(self.h, C.byref(v)), "l3d_fp32_peak_probe")
+        return v.value
+
     def match_dense(self, src_view, tgt_view, F, epi_overlap, ns, nt, nofilter=False, dev_ptrs=None):
         F = np.ascontiguousarray(F, np.float32).reshape(9)
         fn = self.L.l3d_match_dense_nofilter if nofilter else self.L.l3d_match_dense

@@ -317,6 +317,31 @@ static int match_dense_impl(l3d_ctx* c, int sv, int tv, const float* F, float ep
     return L3D_OK;
 }
 
+int l3d_fp32_peak_probe(l3d_ctx* c, double* tflops_out)
+{
+    if (!c || !tflops_out) return L3D_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc;
+    if ((rc = l3d_reserve(c, c->d_scan_tmp, 256, "probe"))) return rc;
+    const int iters = 4096, blocks = c->num_sms * 8;
+    cudaEvent_t e0, e1;
+    L3D_CUDA(c, cudaEventCreate(&e0), "event"); L3D_CUDA(c, cudaEventCreate(&e1), "event");
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, c->stream);
+        k_fp32_peak<<<blocks, 256, 0, c->stream>>>((float*)c->d_scan_tmp.p, iters, 1.0000001f, 1e-9f);
+        cudaEventRecord(e1, c->stream);
+        ++c->launches;
+        L3D_CUDA(c, cudaStreamSynchronize(c->stream), "k_fp32_peak");
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 16.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops_out = best;
+    return L3D_OK;
+}
+
 int l3d_match_dense(l3d_ctx* c, int sv, int tv, const float* F, float epi, float* depths, float* overlaps, int on_dev)
 { return match_dense_impl(c, sv, tv, F, epi, depths, overlaps, on_dev, true); }
 int l3d_match_dense_nofilter(l3d_ctx* c, int sv, int tv, const float* F, float epi, float* depths, float* overlaps, int on_dev)

@@ -37,3 +37,4 @@ __global__ void k_match_dense_nofilter(const float4* __restrict__ ssegs, int Ns,
 __global__ void k_compact_matches(const int* __restrict__ counts, const long long* __restrict__ row_ptr,
                                   const l3d_match_rec* __restrict__ recs, int knn, long long rows,
                                   l3d_match_rec* __restrict__ out);
+__global__ void k_fp32_peak(float* __restrict__ out, int iters, float a, float b);

@@ -62,8 +62,14 @@ def dense_neighbors(V: int) -> list:
     return [np.array([j for j in range(V) if j != i], dtype=np.uint32) for i in range(V)]
 
 
+def make_scene_views(num_views, segs_per_view, seed, neighbors, views, noise_px: float = 0.5) -> Scene:
+    """Same scene as make_scene but only the 2D segments of `views` are materialised (the others are empty arrays):
+    every rank of a multi-GPU run builds the identical global scene definition and only its own shard of segments."""
+    return make_scene(num_views, segs_per_view, seed, neighbors, noise_px, only_views=set(int(v) for v in views))
+
+
 def make_scene(num_views: int, segs_per_view: int, seed: int, neighbors: str | int = "ring5",
-               noise_px: float = 0.5) -> Scene:
+               noise_px: float = 0.5, only_views=None) -> Scene:
     rng = np.random.default_rng(seed)
     V, N = num_views, segs_per_view
     L = 2 * N
@@ -86,6 +92,9 @@ def make_scene(num_views: int, segs_per_view: int, seed: int, neighbors: str | i
         C = np.array([4.0 * np.cos(th), heights[i], 4.0 * np.sin(th)])
         R, t = look_at_camera(C)
         Rs[i], ts[i] = R, t
+        if only_views is not None and i not in only_views:
+            segs.append(np.zeros((0, 4), np.float32)); line_ids.append(np.zeros(0, np.int64))
+            continue
         vrng = np.random.default_rng([seed, i])
         perm = vrng.permutation(L)
         X1 = (R @ P1[perm].T).T + t
