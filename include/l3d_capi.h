@@ -108,6 +108,23 @@ int l3d_match_dense(l3d_ctx* ctx, int src_view, int tgt_view, const float* F, fl
 int l3d_match_dense_nofilter(l3d_ctx* ctx, int src_view, int tgt_view, const float* F, float epi_overlap, float* depths,
                              float* overlaps, int out_on_device);
 
+/* ---- scoring sweep: replaces, for ALL views in one call, the per-view sequence of Line3D::computeMatches after
+ * matching (line3D.cc:745-773): checkMatchOrientation (811-858), scoringGPU incl. its host staging (1297-1414) and
+ * score_matches_GPU (cudawrapper.h:67-74), storeInverseMatches (1672-1699), filterMatches (1586-1669).
+ * Views are processed in ascending cam_id (the reference's std::map order); REF_GPU semantics (cudawrapper.cu:256-367).
+ * Uses views[].k and views[].C_d / RtKinv_d of the last l3d_set_views / l3d_update_view_params call.
+ *   two_sigA_sqr      2*sigma_a^2                          (line3D.cc:397)
+ *   min_similarity    L3D_DEF_MIN_SIMILARITY_3D   0.50     (commons.h:58)
+ *   min_best_score    L3D_DEF_MIN_BEST_SCORE_3D   0.75     (commons.h:59)
+ *   min_best_perc     L3D_DEF_MIN_BEST_SCORE_PERC 0.10     (commons.h:60) */
+int l3d_score_sweep(l3d_ctx* ctx, float two_sigA_sqr, float min_similarity, float min_best_score, float min_best_perc);
+/* matches of one view after scoring in the reference's list order (segment; tgt cam; tgt seg).  kept_only != 0: only
+ * those that survived filterMatches.  Returns the count (even if > cap). */
+long long l3d_get_view_matches(l3d_ctx* ctx, int view, int kept_only, l3d_match* out, long long cap);
+/* estimated_position3D_ (line3D.cc:1635-1647) in (view, segment) order: best match + unprojected P1,P2 (6 doubles, in
+ * the working frame of C_d).  Returns the count. */
+long long l3d_get_estimates(l3d_ctx* ctx, l3d_match* best_out, double* p1p2_out, long long cap);
+
 /* measurement aid: achieved non-tensor FP32 FFMA throughput of this GPU right now (TFLOP/s), the denominator of the
  * fused kernel's compute roofline */
 int l3d_fp32_peak_probe(l3d_ctx* ctx, double* tflops_out);

@@ -110,7 +110,7 @@ static int finish_views(l3d_ctx* c)
         ++c->launches;
         L3D_CUDA(c, cudaGetLastError(), "k_prep_segments");
     }
-    c->have_views = true; c->have_matches = false;
+    c->have_views = true; c->have_matches = false; c->sweep.valid = false;
     return L3D_OK;
 }
 
@@ -208,7 +208,7 @@ int l3d_match_pairs(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float
         ++c->launches;
         L3D_CUDA(c, cudaGetLastError(), "k_match_topk");
     }
-    c->have_matches = true;
+    c->have_matches = true; c->sweep.valid = false;
     return L3D_OK;
 }
 

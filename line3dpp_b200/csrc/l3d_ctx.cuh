@@ -7,6 +7,20 @@
 
 struct DevBuf { void* p = nullptr; size_t cap = 0; };   // grow-only device allocation
 
+// state of the per-view scoring sweep (l3d_pipeline.cu)
+struct SweepState {
+    bool valid = false;
+    std::vector<int> order;                 // view indices in processing order (ascending camID)
+    std::vector<int> U, h_M;                // per view: candidate upper bound / number of scored matches (by processing rank for h_M)
+    std::vector<long long> region_off;      // per processing rank: first match slot of the view's region
+    long long total = 0;
+    DevBuf d_slot_score, d_keys, d_keys2, d_vals, d_vals2, d_reg, d_dir, d_meta, d_dep, d_os, d_kept, d_ranges, d_est_best, d_est_P,
+        d_M, d_vmax, d_work, d_camrank, d_viewofrank, d_sort_tmp;
+    std::vector<DevBuf*> bufs()
+    { return {&d_slot_score, &d_keys, &d_keys2, &d_vals, &d_vals2, &d_reg, &d_dir, &d_meta, &d_dep, &d_os, &d_kept, &d_ranges, &d_est_best,
+              &d_est_P, &d_M, &d_vmax, &d_work, &d_camrank, &d_viewofrank, &d_sort_tmp}; }
+};
+
 struct l3d_ctx {
     int device = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
@@ -31,10 +45,16 @@ struct l3d_ctx {
     std::vector<int2> h_tiles;
     DevBuf d_pairs, d_tiles, d_counts, d_recs, d_rowptr, d_csr, d_scan_tmp, d_dense_dep, d_dense_ov;
 
+    SweepState sweep;
+
     const float4* segs() const { return segs_ext ? segs_ext : (const float4*)d_segs.p; }
     const L3DViewDev* views() const { return (const L3DViewDev*)d_views.p; }
     std::vector<DevBuf*> all_bufs()
-    { return {&d_segs, &d_cache, &d_views, &d_pairs, &d_tiles, &d_counts, &d_recs, &d_rowptr, &d_csr, &d_scan_tmp, &d_dense_dep, &d_dense_ov}; }
+    {
+        std::vector<DevBuf*> b = {&d_segs, &d_cache, &d_views, &d_pairs, &d_tiles, &d_counts, &d_recs, &d_rowptr, &d_csr, &d_scan_tmp, &d_dense_dep, &d_dense_ov};
+        for (DevBuf* x : sweep.bufs()) b.push_back(x);
+        return b;
+    }
 };
 
 int l3d_fail(l3d_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess);
