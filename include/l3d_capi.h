@@ -125,6 +125,21 @@ long long l3d_get_view_matches(l3d_ctx* ctx, int view, int kept_only, l3d_match*
  * the working frame of C_d).  Returns the count. */
 long long l3d_get_estimates(l3d_ctx* ctx, l3d_match* best_out, double* p1p2_out, long long cap);
 
+/* ---- affinity: Line3D::similarity (line3D.cc:1467-1553) for every kept match whose two segments have a 3D estimate,
+ * i.e. the arithmetic of computingAffinityMatrix (line3D.cc:1852-1979).  Emits, in the reference's emission order,
+ * the candidates with similarity > min_affinity (L3D_DEF_MIN_AFFINITY 0.5) as (global seg i, global seg j, w); the
+ * "unused" de-duplication and local-id assignment stay on the host (line3D.cc:1881-1900, 1982-2023).  Needs
+ * views[].median_depth to be current (l3d_update_view_params).  Returns the number of edges (even if > cap). */
+long long l3d_affinity_edges(l3d_ctx* ctx, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity,
+                             long long* out_gi, long long* out_gj, float* out_w, long long cap);
+
+/* ---- diffusion: replaces replicator_dynamics_diffusion_GPU (cudawrapper.h:80, cudawrapper.cu:708-766) incl. the
+ * SparseMatrix construction it needs (sparsematrix.cc:8-135).  Input: the CLEdge list A_ (clustering.h:47-51) as three
+ * arrays and the number of rows n; iters = L3D_DEF_RDD_MAX_ITER (10).  Output: the diffused matrix as row-sorted COO
+ * with nnz entries (what the reference downloads from W, line3D.cc:2036-2044).  No ownership transfer. */
+int l3d_rdd(l3d_ctx* ctx, int n, long long nnz, const int* ei, const int* ej, const float* ew, int iters, int* out_i,
+            int* out_j, float* out_w, float* kernel_ms);
+
 /* measurement aid: achieved non-tensor FP32 FFMA throughput of this GPU right now (TFLOP/s), the denominator of the
  * fused kernel's compute roofline */
 int l3d_fp32_peak_probe(l3d_ctx* ctx, double* tflops_out);

@@ -1,0 +1,310 @@
+// l3d_affinity.cu — pairwise affinities between 3D hypotheses and the replicator-dynamics diffusion.
+//
+//   k_affinity        : Line3D::similarity (line3D.cc:1467-1553) for every kept match whose two segments both have a
+//                       3D estimate; the reference does this on the host under three mutexes (computingAffinityMatrix,
+//                       line3D.cc:1852-1979).  One thread per match slot, deterministic output order.
+//   l3d_rdd           : replicator_dynamics_diffusion_GPU (cudawrapper.cu:708-766) on CSR/CSC SoA arrays instead of two
+//                       AoS float4 COO copies: 20 B/nnz/iteration of compulsory traffic instead of >= 64.  The arithmetic
+//                       (positional lock-step product, per-row sequential sums, clamps) is kept operation for operation,
+//                       so the result is bit-identical to the reference kernels; the linear search for the transposed
+//                       slot (cudawrapper.cu:524-542) is replaced by a precomputed permutation.
+#include "l3d_ctx.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#define L3D_EPS_D 1e-12
+#define L3D_PI_D 3.14159265358979323846
+
+struct A3 { double x, y, z; };
+__device__ __forceinline__ A3 a3(double x, double y, double z) { A3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ A3 asub(A3 a, A3 b) { return a3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ double adot(A3 a, A3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double anorm(A3 a) { return sqrt(adot(a, a)); }
+struct ASeg { A3 P1, P2, dir; float length; };
+// Segment3D(P1,P2) (segment3D.h:48-66)
+__device__ __forceinline__ ASeg make_seg(const double* p)
+{
+    ASeg s;
+    A3 P1 = a3(p[0], p[1], p[2]), P2 = a3(p[3], p[4], p[5]);
+    s.length = (float)anorm(asub(P1, P2));
+    if (s.length > L3D_EPS_D) {
+        s.P1 = P1; s.P2 = P2;
+        A3 d = asub(P2, P1);
+        double n2 = adot(d, d);
+        if (n2 > 0) { double n = sqrt(n2); d = a3(d.x / n, d.y / n, d.z / n); }
+        s.dir = d;
+    } else { s.P1 = s.P2 = s.dir = a3(0, 0, 0); s.length = 0.0f; }
+    return s;
+}
+// Segment3D::distance_Point2Line (segment3D.h:69-73): P1 + (dir * (P-P1)^T) * dir, evaluated as (outer product) * dir
+__device__ __forceinline__ float dist_p2l(const ASeg& s, A3 P)
+{
+    A3 w = asub(P, s.P1);
+    double d[3] = {s.dir.x, s.dir.y, s.dir.z}, ww[3] = {w.x, w.y, w.z}, h[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) h[i] = (d[i] * ww[0]) * d[0] + (d[i] * ww[1]) * d[1] + (d[i] * ww[2]) * d[2];
+    A3 hp = a3(s.P1.x + h[0], s.P1.y + h[1], s.P1.z + h[2]);
+    return (float)anorm(asub(hp, P));
+}
+
+__global__ void __launch_bounds__(256)
+k_affinity(const L3DViewDev* __restrict__ views, const long long* __restrict__ region_off, const int* __restrict__ order,
+           const int* __restrict__ rank_of_view, int V, long long total, const unsigned char* __restrict__ kept,
+           const int4* __restrict__ m_meta, const float4* __restrict__ m_dep, const int* __restrict__ est_best,
+           const double* __restrict__ est_P, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity,
+           float* __restrict__ sim_out, int* __restrict__ flag_out, long long* __restrict__ gi_out, long long* __restrict__ gj_out)
+{
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= total) return;
+    int flag = 0; float sim = 0.0f; long long gi = -1, gj = -1;
+    if (kept[x]) {
+        int lo = 0, hi = V - 1;                  // processing rank whose region contains x
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (region_off[mid] <= x) lo = mid; else hi = mid - 1; }
+        const int v1i = order[lo];
+        const int4 me = m_meta[x];
+        const L3DViewDev* v1 = views + v1i;
+        const L3DViewDev* v2 = views + me.y;
+        gi = v1->seg_off + me.x; gj = v2->seg_off + me.z;
+        const int b1 = est_best[gi], b2 = est_best[gj];
+        if (b1 >= 0 && b2 >= 0) {
+            const ASeg s1 = make_seg(est_P + 6 * gi), s2 = make_seg(est_P + 6 * gj);
+            if (!(s1.length < L3D_EPS_D || s2.length < L3D_EPS_D)) {
+                const float4 m1 = m_dep[region_off[lo] + b1], m2 = m_dep[region_off[rank_of_view[me.y]] + b2];
+                float dot_p = (float)adot(s1.dir, s2.dir);                               // angleBetweenSeg3D (line3D.cc:1571-1583)
+                float angle = (float)((double)acosf(fmaxf(fminf(dot_p, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
+                if (angle > 90.0f) angle = 180.0f - angle;
+                float sim_a = expf(-angle * angle / two_sigA_sqr);
+                float cutoff1 = v1->median_depth, cutoff2 = v2->median_depth;
+                if (med_scene_depth_lines > L3D_EPS_D) { cutoff1 = fminf(cutoff1, med_scene_depth_lines); cutoff2 = fminf(cutoff2, med_scene_depth_lines); }
+                float d11 = dist_p2l(s2, s1.P1), d12 = dist_p2l(s2, s1.P2), d21 = dist_p2l(s1, s2.P1), d22 = dist_p2l(s1, s2.P2);
+                float sig11 = m1.x > cutoff1 ? cutoff1 * v1->k : m1.x * v1->k;
+                float sig12 = m1.y > cutoff1 ? cutoff1 * v1->k : m1.y * v1->k;
+                float reg11 = 2.0f * sig11 * sig11, reg12 = 2.0f * sig12 * sig12;
+                float sig21 = m2.x > cutoff2 ? cutoff2 * v2->k : m2.x * v2->k;
+                float sig22 = m2.y > cutoff2 ? cutoff2 * v2->k : m2.y * v2->k;
+                float reg21 = 2.0f * sig21 * sig21, reg22 = 2.0f * sig22 * sig22;
+                float sim_p1 = fminf(expf(-d11 * d11 / reg11), expf(-d12 * d12 / reg12));
+                float sim_p2 = fminf(expf(-d21 * d21 / reg21), expf(-d22 * d22 / reg22));
+                sim = fminf(sim_a, fminf(sim_p1, sim_p2));
+                flag = sim > min_affinity ? 1 : 0;
+            }
+        }
+    }
+    sim_out[x] = sim; flag_out[x] = flag; gi_out[x] = gi; gj_out[x] = gj;
+}
+
+__global__ void __launch_bounds__(256)
+k_affinity_compact(long long total, const int* __restrict__ flag, const long long* __restrict__ pos, const float* __restrict__ sim,
+                   const long long* __restrict__ gi, const long long* __restrict__ gj, long long* __restrict__ out_i,
+                   long long* __restrict__ out_j, float* __restrict__ out_w)
+{
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= total || !flag[x]) return;
+    const long long p = pos[x];
+    out_i[p] = gi[x]; out_j[p] = gj[x]; out_w[p] = sim[x];
+}
+
+// ================================================================================================ diffusion
+__global__ void __launch_bounds__(256)
+k_rdd_keys(long long nnz, const int* __restrict__ ei, const int* __restrict__ ej, unsigned long long* __restrict__ krow,
+           unsigned long long* __restrict__ kcol, unsigned int* __restrict__ idx)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    krow[e] = ((unsigned long long)(unsigned int)ei[e] << 32) | (unsigned int)ej[e];
+    kcol[e] = ((unsigned long long)(unsigned int)ej[e] << 32) | (unsigned int)ei[e];
+    idx[e] = (unsigned int)e;
+}
+// gather sorted values + row/col of each entry, mark row (or col) starts
+__global__ void __launch_bounds__(256)
+k_rdd_gather(long long nnz, const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ idx,
+             const float* __restrict__ w, float* __restrict__ val, int* __restrict__ major, int* __restrict__ minor)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const unsigned long long k = keys[e];
+    const int ma = (int)(k >> 32), mi = (int)(k & 0xFFFFFFFFull);
+    val[e] = w[idx[e]]; major[e] = ma; minor[e] = mi;
+}
+// CSR/CSC pointers: ptr[r] = first sorted position whose major index is >= r (r = 0..n), by binary search
+__global__ void __launch_bounds__(256) k_rdd_ptr(int n, int nnz, const int* __restrict__ major, int* __restrict__ ptr)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    int lo = 0, hi = nnz;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (major[mid] < r) lo = mid + 1; else hi = mid; }
+    ptr[r] = lo;
+}
+// transposed slot of every row-sorted entry (a,b): first position of (b,a) in row b, -1 if absent
+__global__ void __launch_bounds__(256)
+k_rdd_tslot(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr, int* __restrict__ tslot)
+{
+    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= nnz) return;
+    const int a = prow[y], b = pcol[y];
+    int lo = rowptr[b], hi = rowptr[b + 1];
+    const int end = hi;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (pcol[mid] < a) lo = mid + 1; else hi = mid; }
+    tslot[y] = (lo < end && pcol[lo] == a) ? lo : -1;
+}
+// K_sparseMat_row_normalization (cudawrapper.cu:432-477): sequential sum in slot order, clamp, divide
+__global__ void __launch_bounds__(128)
+k_rdd_normalize(int n, const int* __restrict__ rowptr, float* __restrict__ val)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int s = rowptr[r], e = rowptr[r + 1];
+    if (s == e) return;
+    float sum = 0.0f;
+    for (int i = s; i < e; ++i) sum += val[i];
+    if (sum < L3D_EPS_F) sum = L3D_EPS_F;
+    for (int i = s; i < e; ++i) val[i] /= sum;
+}
+// K_sparseMat_diffusion_step (cudawrapper.cu:480-544): entry y = (a,b) of P produces P'(b,a) = max(eps, P(a,b) * sum_k P.row(b)[k] * W.col(a)[k])
+__global__ void __launch_bounds__(256)
+k_rdd_step(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr,
+           const int* __restrict__ colptr, const float* __restrict__ P, const float* __restrict__ W,
+           const int* __restrict__ tslot, float* __restrict__ Pn)
+{
+    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= nnz) return;
+    const int c = prow[y], r = pcol[y];                 // "transpose" (cudawrapper.cu:493-495)
+    int sp = rowptr[r], sw = colptr[c];
+    const int ep = rowptr[r + 1], ew = colptr[c + 1];
+    float mul = 0.0f;
+    while (sp < ep && sw < ew) { mul += P[sp] * W[sw]; ++sp; ++sw; }
+    mul *= P[y];
+    if (mul < L3D_EPS_F) mul = L3D_EPS_F;
+    const int t = tslot[y];
+    if (t >= 0) Pn[t] = mul;
+}
+
+extern "C" {
+
+// Affinity edges between segments with 3D estimates, in the reference's emission order (estimate order, then match
+// list order), BEFORE the "unused" de-duplication and local-id assignment (host side, line3D.cc:1881-1900).
+// out_gi/out_gj are GLOBAL segment indices (view seg offset + seg id in l3d_set_views order).  Returns the count.
+long long l3d_affinity_edges(l3d_ctx* c, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity,
+                             long long* out_gi, long long* out_gj, float* out_w, long long cap)
+{
+    if (!c) return L3D_ERR_INVALID;
+    if (!c->sweep.valid) return l3d_fail(c, L3D_ERR_STATE, "l3d_affinity_edges: call l3d_score_sweep first");
+    cudaSetDevice(c->device);
+    SweepState& S = c->sweep;
+    const long long total = S.total;
+    if (total == 0) return 0;
+    const int V = c->num_views;
+    int rc;
+    DevBuf &d_sim = S.d_aff_sim, &d_flag = S.d_aff_flag, &d_gi = S.d_aff_gi, &d_gj = S.d_aff_gj, &d_pos = S.d_aff_pos;
+    if ((rc = l3d_reserve(c, d_sim, 4 * (size_t)total, "affinity sims"))) return rc;
+    if ((rc = l3d_reserve(c, d_flag, 4 * (size_t)total, "affinity flags"))) return rc;
+    if ((rc = l3d_reserve(c, d_gi, 8 * (size_t)total, "affinity gi"))) return rc;
+    if ((rc = l3d_reserve(c, d_gj, 8 * (size_t)total, "affinity gj"))) return rc;
+    if ((rc = l3d_reserve(c, d_pos, 8 * (size_t)(total + 1), "affinity pos"))) return rc;
+    std::vector<int> rank_of_view(V);
+    for (int i = 0; i < V; ++i) rank_of_view[S.order[i]] = i;
+    if ((rc = l3d_reserve(c, S.d_order, 4 * (size_t)V, "order"))) return rc;
+    if ((rc = l3d_reserve(c, S.d_rankofview, 4 * (size_t)V, "rank of view"))) return rc;
+    if ((rc = l3d_reserve(c, S.d_region_off, 8 * (size_t)(V + 1), "region offsets"))) return rc;
+    cudaStream_t st = c->stream;
+    L3D_CUDA(c, cudaMemcpyAsync(S.d_order.p, S.order.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "order");
+    L3D_CUDA(c, cudaMemcpyAsync(S.d_rankofview.p, rank_of_view.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "rank of view");
+    L3D_CUDA(c, cudaMemcpyAsync(S.d_region_off.p, S.region_off.data(), 8 * (size_t)(V + 1), cudaMemcpyHostToDevice, st), "region offsets");
+    const unsigned int nb = (unsigned int)((total + 255) / 256);
+    k_affinity<<<nb, 256, 0, st>>>(c->views(), (const long long*)S.d_region_off.p, (const int*)S.d_order.p, (const int*)S.d_rankofview.p, V, total,
+                                   (const unsigned char*)S.d_kept.p, (const int4*)S.d_meta.p, (const float4*)S.d_dep.p, (const int*)S.d_est_best.p,
+                                   (const double*)S.d_est_P.p, two_sigA_sqr, med_scene_depth_lines, min_affinity, (float*)d_sim.p, (int*)d_flag.p,
+                                   (long long*)d_gi.p, (long long*)d_gj.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)d_flag.p, (long long*)d_pos.p, total, st);
+    if ((rc = l3d_reserve(c, S.d_sort_tmp, tb, "scan temp"))) return rc;
+    tb = S.d_sort_tmp.cap;   // scan over `total` items; the edge count is pos[total-1] + flag[total-1]
+    L3D_CUDA(c, cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tb, (const int*)d_flag.p, (long long*)d_pos.p, total, st), "affinity scan");
+    long long last_pos = 0; int last_flag = 0;
+    L3D_CUDA(c, cudaMemcpyAsync(&last_pos, (long long*)d_pos.p + total - 1, 8, cudaMemcpyDeviceToHost, st), "count");
+    L3D_CUDA(c, cudaMemcpyAsync(&last_flag, (int*)d_flag.p + total - 1, 4, cudaMemcpyDeviceToHost, st), "count");
+    L3D_CUDA(c, cudaStreamSynchronize(st), "affinity");
+    const long long ne = last_pos + last_flag;
+    c->launches += 3;
+    if (ne == 0 || !out_gi || ne > cap) return ne;
+    DevBuf &o_i = S.d_aff_oi, &o_j = S.d_aff_oj, &o_w = S.d_aff_ow;
+    if ((rc = l3d_reserve(c, o_i, 8 * (size_t)ne, "edges i"))) return rc;
+    if ((rc = l3d_reserve(c, o_j, 8 * (size_t)ne, "edges j"))) return rc;
+    if ((rc = l3d_reserve(c, o_w, 4 * (size_t)ne, "edges w"))) return rc;
+    k_affinity_compact<<<nb, 256, 0, st>>>(total, (const int*)d_flag.p, (const long long*)d_pos.p, (const float*)d_sim.p, (const long long*)d_gi.p,
+                                           (const long long*)d_gj.p, (long long*)o_i.p, (long long*)o_j.p, (float*)o_w.p);
+    ++c->launches;
+    L3D_CUDA(c, cudaMemcpyAsync(out_gi, o_i.p, 8 * (size_t)ne, cudaMemcpyDeviceToHost, st), "download edges");
+    L3D_CUDA(c, cudaMemcpyAsync(out_gj, o_j.p, 8 * (size_t)ne, cudaMemcpyDeviceToHost, st), "download edges");
+    L3D_CUDA(c, cudaMemcpyAsync(out_w, o_w.p, 4 * (size_t)ne, cudaMemcpyDeviceToHost, st), "download edges");
+    L3D_CUDA(c, cudaStreamSynchronize(st), "affinity download");
+    return ne;
+}
+
+// replicator_dynamics_diffusion_GPU (cudawrapper.h:80) on a COO edge list (the CLEdge list A_ of line3D.cc:2030).
+// out_*: row-sorted COO of the diffused matrix, nnz entries (same order as the reference's downloaded W).
+// kernel_ms (optional): device time of the `iters` diffusion iterations only (CUDA events on the context's stream).
+int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, const float* ew, int iters, int* out_i, int* out_j,
+            float* out_w, float* kernel_ms)
+{
+    if (!c || n <= 0 || nnz < 0 || (nnz && (!ei || !ej || !ew || !out_i || !out_j || !out_w))) return l3d_fail(c, L3D_ERR_INVALID, "l3d_rdd: bad arguments");
+    if (nnz == 0) return L3D_OK;
+    if (nnz >= (1ll << 31) - 2) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_rdd: more than 2^31 entries");
+    cudaSetDevice(c->device);
+    RddState& R = c->rdd;
+    int rc;
+#define RES(buf, bytes, what) if ((rc = l3d_reserve(c, buf, (size_t)(bytes), what))) return rc
+    RES(R.d_ei, 4 * nnz, "rdd i"); RES(R.d_ej, 4 * nnz, "rdd j"); RES(R.d_ew, 4 * nnz, "rdd w");
+    RES(R.d_krow, 8 * nnz, "rdd keys"); RES(R.d_kcol, 8 * nnz, "rdd keys"); RES(R.d_k2, 8 * nnz, "rdd keys"); RES(R.d_idx, 4 * nnz, "rdd idx"); RES(R.d_idx2, 4 * nnz, "rdd idx");
+    RES(R.d_P, 4 * nnz, "rdd P"); RES(R.d_Pn, 4 * nnz, "rdd P'"); RES(R.d_W, 4 * nnz, "rdd W");
+    RES(R.d_prow, 4 * nnz, "rdd rows"); RES(R.d_pcol, 4 * nnz, "rdd cols"); RES(R.d_wmaj, 4 * nnz, "rdd cols"); RES(R.d_wmin, 4 * nnz, "rdd rows");
+    RES(R.d_rowptr, 4 * ((size_t)n + 1), "rdd rowptr"); RES(R.d_colptr, 4 * ((size_t)n + 1), "rdd colptr"); RES(R.d_tslot, 4 * nnz, "rdd tslot");
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)nnz, 0, 64, c->stream);
+    RES(R.d_tmp, sb, "rdd sort temp");
+#undef RES
+    cudaStream_t st = c->stream;
+    L3D_CUDA(c, cudaMemcpyAsync(R.d_ei.p, ei, 4 * nnz, cudaMemcpyHostToDevice, st), "rdd upload");
+    L3D_CUDA(c, cudaMemcpyAsync(R.d_ej.p, ej, 4 * nnz, cudaMemcpyHostToDevice, st), "rdd upload");
+    L3D_CUDA(c, cudaMemcpyAsync(R.d_ew.p, ew, 4 * nnz, cudaMemcpyHostToDevice, st), "rdd upload");
+    const unsigned int nb = (unsigned int)((nnz + 255) / 256);
+    k_rdd_keys<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_ei.p, (const int*)R.d_ej.p, (unsigned long long*)R.d_krow.p, (unsigned long long*)R.d_kcol.p, (unsigned int*)R.d_idx.p);
+    size_t tb = R.d_tmp.cap;
+    // P: row-sorted (stable, like std::list::sort with sortCLEdgesByRow, sparsematrix.cc:22-25 / 104-107)
+    cub::DeviceRadixSort::SortPairs(R.d_tmp.p, tb, (const unsigned long long*)R.d_krow.p, (unsigned long long*)R.d_k2.p, (const unsigned int*)R.d_idx.p, (unsigned int*)R.d_idx2.p, (int)nnz, 0, 64, st);
+    k_rdd_gather<<<nb, 256, 0, st>>>(nnz, (const unsigned long long*)R.d_k2.p, (const unsigned int*)R.d_idx2.p, (const float*)R.d_ew.p, (float*)R.d_P.p, (int*)R.d_prow.p, (int*)R.d_pcol.p);
+    // W: col-sorted
+    tb = R.d_tmp.cap;
+    cub::DeviceRadixSort::SortPairs(R.d_tmp.p, tb, (const unsigned long long*)R.d_kcol.p, (unsigned long long*)R.d_k2.p, (const unsigned int*)R.d_idx.p, (unsigned int*)R.d_idx2.p, (int)nnz, 0, 64, st);
+    k_rdd_gather<<<nb, 256, 0, st>>>(nnz, (const unsigned long long*)R.d_k2.p, (const unsigned int*)R.d_idx2.p, (const float*)R.d_ew.p, (float*)R.d_W.p, (int*)R.d_wmaj.p, (int*)R.d_wmin.p);
+    k_rdd_ptr<<<(n + 256) / 256, 256, 0, st>>>(n, (int)nnz, (const int*)R.d_prow.p, (int*)R.d_rowptr.p);
+    k_rdd_ptr<<<(n + 256) / 256, 256, 0, st>>>(n, (int)nnz, (const int*)R.d_wmaj.p, (int*)R.d_colptr.p);
+    k_rdd_tslot<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (int*)R.d_tslot.p);
+    // P' starts as a copy of the un-normalised P (cudawrapper.cu:724), then P is row-normalised (727)
+    L3D_CUDA(c, cudaMemcpyAsync(R.d_Pn.p, R.d_P.p, 4 * nnz, cudaMemcpyDeviceToDevice, st), "rdd copy");
+    const unsigned int nbr = (unsigned int)((n + 127) / 128);
+    k_rdd_normalize<<<nbr, 128, 0, st>>>(n, (const int*)R.d_rowptr.p, (float*)R.d_P.p);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    float* P = (float*)R.d_P.p; float* Pn = (float*)R.d_Pn.p;
+    for (int it = 0; it < iters; ++it) {
+        k_rdd_step<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_colptr.p, P, (const float*)R.d_W.p, (const int*)R.d_tslot.p, Pn);
+        std::swap(P, Pn);
+        if (it < iters - 1) k_rdd_normalize<<<nbr, 128, 0, st>>>(n, (const int*)R.d_rowptr.p, P);
+    }
+    if (kernel_ms) cudaEventRecord(e1, st);
+    c->launches += 9 + 16 + 2 * iters;
+    L3D_CUDA(c, cudaGetLastError(), "rdd kernels");
+    L3D_CUDA(c, cudaMemcpyAsync(out_w, P, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
+    L3D_CUDA(c, cudaMemcpyAsync(out_i, R.d_prow.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
+    L3D_CUDA(c, cudaMemcpyAsync(out_j, R.d_pcol.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
+    L3D_CUDA(c, cudaStreamSynchronize(st), "rdd");
+    if (kernel_ms) { cudaEventElapsedTime(kernel_ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    return L3D_OK;
+}
+
+} // extern "C"

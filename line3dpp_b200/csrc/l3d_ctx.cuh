@@ -15,10 +15,20 @@ struct SweepState {
     std::vector<long long> region_off;      // per processing rank: first match slot of the view's region
     long long total = 0;
     DevBuf d_slot_score, d_keys, d_keys2, d_vals, d_vals2, d_reg, d_dir, d_meta, d_dep, d_os, d_kept, d_ranges, d_est_best, d_est_P,
-        d_M, d_vmax, d_work, d_camrank, d_viewofrank, d_sort_tmp;
+        d_M, d_vmax, d_work, d_camrank, d_viewofrank, d_sort_tmp, d_aff_sim, d_aff_flag, d_aff_gi, d_aff_gj, d_aff_pos, d_aff_oi, d_aff_oj,
+        d_aff_ow, d_order, d_rankofview, d_region_off;
     std::vector<DevBuf*> bufs()
     { return {&d_slot_score, &d_keys, &d_keys2, &d_vals, &d_vals2, &d_reg, &d_dir, &d_meta, &d_dep, &d_os, &d_kept, &d_ranges, &d_est_best,
-              &d_est_P, &d_M, &d_vmax, &d_work, &d_camrank, &d_viewofrank, &d_sort_tmp}; }
+              &d_est_P, &d_M, &d_vmax, &d_work, &d_camrank, &d_viewofrank, &d_sort_tmp, &d_aff_sim, &d_aff_flag, &d_aff_gi, &d_aff_gj,
+              &d_aff_pos, &d_aff_oi, &d_aff_oj, &d_aff_ow, &d_order, &d_rankofview, &d_region_off}; }
+};
+
+// device buffers of the diffusion (l3d_affinity.cu)
+struct RddState {
+    DevBuf d_ei, d_ej, d_ew, d_krow, d_kcol, d_k2, d_idx, d_idx2, d_P, d_Pn, d_W, d_prow, d_pcol, d_wmaj, d_wmin, d_rowptr, d_colptr, d_tslot, d_tmp;
+    std::vector<DevBuf*> bufs()
+    { return {&d_ei, &d_ej, &d_ew, &d_krow, &d_kcol, &d_k2, &d_idx, &d_idx2, &d_P, &d_Pn, &d_W, &d_prow, &d_pcol, &d_wmaj, &d_wmin, &d_rowptr,
+              &d_colptr, &d_tslot, &d_tmp}; }
 };
 
 struct l3d_ctx {
@@ -46,6 +56,7 @@ struct l3d_ctx {
     DevBuf d_pairs, d_tiles, d_counts, d_recs, d_rowptr, d_csr, d_scan_tmp, d_dense_dep, d_dense_ov;
 
     SweepState sweep;
+    RddState rdd;
 
     const float4* segs() const { return segs_ext ? segs_ext : (const float4*)d_segs.p; }
     const L3DViewDev* views() const { return (const L3DViewDev*)d_views.p; }
@@ -53,6 +64,7 @@ struct l3d_ctx {
     {
         std::vector<DevBuf*> b = {&d_segs, &d_cache, &d_views, &d_pairs, &d_tiles, &d_counts, &d_recs, &d_rowptr, &d_csr, &d_scan_tmp, &d_dense_dep, &d_dense_ov};
         for (DevBuf* x : sweep.bufs()) b.push_back(x);
+        for (DevBuf* x : rdd.bufs()) b.push_back(x);
         return b;
     }
 };
