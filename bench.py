@@ -308,7 +308,13 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    # tensors allocated under the context's stream must die before the stream does
+    del dev_my, dev_all, flush, host_my
+    state.clear()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     ctx.close()
+    sys.stdout.flush()
     return 0
 
 

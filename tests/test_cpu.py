@@ -1,0 +1,200 @@
+"""CPU-only tests (`pytest -m "not gpu"`): the oracle against the golden vectors produced by the UNMODIFIED reference
+kernels on a B200 (tests/golden/), against the reference's clustering.cc compiled in place (runs on the CPU), the
+oracle pipeline on synthetic scenes with known 3D lines, host-side sharding logic, and the C-ABI surface of the product
+library (load + exported symbols; no compute without a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from line3dpp_b200 import synth
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "ref_kernels_v1.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    if not os.path.exists(GOLD):
+        pytest.skip("golden vectors not generated yet (tests/golden/make_golden.py on a GPU box)")
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def gscene(gold):
+    v, n, seed = [int(x) for x in gold["scene_args"]]
+    sc = synth.make_scene(v, n, seed, "dense")
+    assert np.array_equal(np.stack(sc.segs), gold["segs"]), "synthetic scene generator changed: regenerate the golden file"
+    return sc
+
+
+# ---------------------------------------------------------------------------------------------- oracle vs golden
+@pytest.mark.parametrize("tag,s,t", [("p01", 0, 1), ("p24", 2, 4)])
+def test_oracle_match_dense_vs_reference_golden(oracle, gold, gscene, tag, s, t):
+    g = lambda k: gold[f"{tag}_{k}"]
+    dep, ov, _ = oracle.match_dense(oracle.lib().orc_match_dense_f32, gscene.segs[s], gscene.segs[t], g("F"), g("Rs"), g("Rt"), g("Cs"), g("Ct"), 0.25)
+    assert np.array_equal(util.bits(ov), util.bits(g("dense_ov")))            # overlap: bit-exact on the CPU
+    sel = g("dense_ov") > 0.25
+    assert sel.sum() > 200
+    rel = np.abs(dep[sel] - g("dense_dep")[sel]) / np.maximum(np.abs(g("dense_dep")[sel]), 1e-3)
+    assert np.median(rel) < 1e-6 and np.quantile(rel, 0.999) < 1e-2          # depths: host rsqrt vs MUFU.RSQ
+    assert np.array_equal(dep[~sel], g("dense_dep")[~sel])                   # -1 everywhere else
+
+
+@pytest.mark.parametrize("tag,s,t", [("p01", 0, 1), ("p24", 2, 4)])
+def test_oracle_knn_lists_vs_reference_golden(oracle, gold, gscene, tag, s, t):
+    g = lambda k: gold[f"{tag}_{k}"]
+    counts, out, total, _ = oracle.match_lines(oracle.lib().orc_match_lines_f32, gscene.segs[s], gscene.segs[t], g("F"), g("Rs"), g("Rt"), g("Cs"), g("Ct"), s, t, 0.25, 10)
+    assert np.array_equal(counts, g("knn_counts")) and total == g("knn_counts").sum()
+    ref = g("knn")
+    for r in range(len(counts)):
+        a, b = out[r, :counts[r]], ref[r, :counts[r]]
+        assert np.array_equal(a["tgt_seg"], b["tgt_seg"]) and np.array_equal(util.bits(a["overlap"]), util.bits(b["overlap"]))
+
+
+def test_oracle_scores_vs_reference_golden(oracle, gold, gscene):
+    p = gold["score_params"]
+    scores, _ = oracle.score_matches(oracle.lib().orc_score_matches_f32, gscene.segs[0], gold["score_m4"], gold["score_ranges"], gold["score_reg"],
+                                     gold["score_R"], gold["score_C"], float(p[0]), float(p[1]), float(p[2]))
+    ref = gold["score_out"]
+    assert len(ref) > 1000 and (ref > 0).sum() > 100
+    off = ~np.isclose(scores, ref, rtol=1e-4, atol=1e-5)
+    assert off.mean() < 5e-3       # a similarity at the 0.5 truncation may flip with a 1-ulp expf/acosf difference
+    assert np.median(np.abs(scores - ref)) < 1e-6
+
+
+def test_oracle_rdd_vs_reference_golden(oracle, gold):
+    n = int(gold["rdd_n"][0])
+    oi, oj, ow, _ = oracle.rdd(oracle.lib().orc_rdd_f32, gold["rdd_ei"], gold["rdd_ej"], gold["rdd_ew"], n)
+    assert np.array_equal(oi, gold["rdd_oi"]) and np.array_equal(oj, gold["rdd_oj"])
+    assert np.array_equal(util.bits(ow), util.bits(gold["rdd_ow"]))           # + - * / only: bit-exact
+
+
+def test_oracle_cluster_vs_reference_golden(oracle, gold):
+    n = int(gold["rdd_n"][0])
+    lab = oracle.cluster(oracle.lib().orc_cluster, gold["rdd_ei"], gold["rdd_ej"], gold["rdd_ew"], n)
+    assert np.array_equal(lab, gold["cluster_labels"])
+    lab2 = oracle.cluster(oracle.lib().orc_cluster, gold["rdd_oi"], gold["rdd_oj"], gold["rdd_ow"], n)
+    assert np.array_equal(lab2, gold["cluster_labels_rdd"])
+
+
+def test_oracle_cluster_vs_reference_clustering_cc_live(oracle, ref_nofma):
+    """the reference's clustering.cc (compiled in place into oracle/_ref) runs on the CPU: compare live on random graphs"""
+    rng = np.random.default_rng(1)
+    for n, m in [(10, 30), (500, 4000), (2000, 3000)]:
+        ei, ej = rng.integers(0, n, m).astype(np.int32), rng.integers(0, n, m).astype(np.int32)
+        ew = rng.choice(np.linspace(0.5, 1.0, 23), m).astype(np.float32)     # many ties: stable-sort order matters
+        a = oracle.cluster(oracle.lib().orc_cluster, ei, ej, ew, n)
+        b = oracle.cluster(ref_nofma.ref_cluster, ei, ej, ew, n)
+        assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------- oracle pipeline sanity
+def _dist_to_gt(pts, gt):
+    a = gt[:, :3]
+    d = gt[:, 3:] - a
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    w = pts[:, None, :] - a[None]
+    return np.linalg.norm(w - (w * d[None]).sum(-1, keepdims=True) * d[None], axis=-1).min(1)
+
+
+@pytest.mark.parametrize("use_gpu,diffusion", [(1, False), (1, True), (0, False)])
+def test_oracle_pipeline_recovers_ground_truth_lines(oracle, use_gpu, diffusion):
+    sc = synth.make_scene(10, 250, 9, "ring3")
+    P = oracle.OraclePipeline(False, use_gpu)
+    P.add_scene(sc)
+    assert P.match_images() == 0
+    assert P.pair_evals() == sum(len(sc.segs[s]) * len(sc.segs[t]) for s, t in synth.view_pairs(sc.neighbors))
+    assert np.array_equal(P.pairs(), synth.view_pairs(sc.neighbors))
+    assert P.reconstruct(3, diffusion) == 0
+    s = P.segments3d()
+    assert P.num_lines() > 150
+    assert np.median(_dist_to_gt(s["p1"], sc.lines3d)) < 5e-3 and np.median(_dist_to_gt(s["p2"], sc.lines3d)) < 5e-3
+
+
+def test_oracle_gpu_and_cpu_semantics_agree_statistically(oracle):
+    sc = synth.make_scene(10, 250, 9, "ring3")
+    n = []
+    for use_gpu in (1, 0):
+        P = oracle.OraclePipeline(False, use_gpu)
+        P.add_scene(sc)
+        P.match_images()
+        P.reconstruct(3, False)
+        n.append(P.num_lines())
+    assert abs(n[0] - n[1]) <= 0.05 * n[0]
+
+
+def test_oracle_edge_cases(oracle):
+    L = oracle.lib()
+    P = oracle.OraclePipeline(False, 1)
+    K = np.array([[1000., 0, 500], [0, 1000., 400], [0, 0, 1]])
+    seg = np.array([[10, 10, 100, 100]], np.float32)
+    assert P.add_view(0, 600, 400, K, np.eye(3), np.zeros(3), 1.0, [1], seg) == -1     # image too small (line3D.cc:119)
+    assert P.add_view(0, 1000, 800, K, np.eye(3), np.zeros(3), 1.0, [], seg) == -3      # no neighbours (line3D.cc:154)
+    assert P.add_view(0, 1000, 800, K, np.eye(3), np.zeros(3), 1.0, [1], seg) == 0
+    assert P.add_view(0, 1000, 800, K, np.eye(3), np.zeros(3), 1.0, [1], seg) == -2     # duplicate id (line3D.cc:130)
+    assert P.match_images() == 0                                                        # neighbour 1 does not exist: nothing to match
+    assert P.reconstruct(3, False) == -1                                                # no estimates (line3D.cc:1712)
+    # degenerate geometry: identical cameras -> F = 0 -> every intersection invalid -> no matches, no crash
+    z = np.zeros(9, np.float32)
+    c, o, tot, _ = oracle.match_lines(L.orc_match_lines_f32, seg, seg, z, np.eye(3, dtype=np.float32).ravel(), np.eye(3, dtype=np.float32).ravel(),
+                                      np.zeros(3, np.float32), np.zeros(3, np.float32), 0, 1, 0.25, 10)
+    assert tot == 0
+
+
+# ---------------------------------------------------------------------------------------------- host logic
+def test_view_pairs_follow_reference_order():
+    nb = [np.array([1, 2], np.uint32), np.array([0], np.uint32), np.array([3], np.uint32), np.array([0, 2], np.uint32)]
+    assert synth.view_pairs(nb).tolist() == [[0, 1], [0, 2], [2, 3], [3, 0]]
+    assert len(synth.view_pairs(synth.ring_neighbors(1000, 5))) == 5000
+    assert len(synth.view_pairs(synth.dense_neighbors(200))) == 19900
+
+
+def test_scene_shards_are_consistent():
+    full = synth.make_scene(12, 100, 4, "ring2")
+    part = synth.make_scene_views(12, 100, 4, "ring2", [3, 4, 5])
+    for v in (3, 4, 5):
+        assert np.array_equal(full.segs[v], part.segs[v])
+    assert len(part.segs[0]) == 0 and np.array_equal(full.K, part.K) and np.array_equal(full.R, part.R)
+
+
+# ---------------------------------------------------------------------------------------------- product library surface
+def test_capi_library_loads_and_exports_every_declared_symbol():
+    from line3dpp_b200 import build
+    so = build.build()
+    lib = ctypes.CDLL(so)
+    hdr = open(os.path.join(ROOT, "include", "l3d_capi.h")).read()
+    names = sorted(set(re.findall(r"\b(l3d_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/l3d_capi.h but not exported"
+    for n in ("l3dpp_create", "l3dpp_add_image", "l3dpp_match_images", "l3dpp_reconstruct", "l3dpp_save_txt"):
+        assert hasattr(lib, n)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """without a CUDA device the product must fail loudly, not compute on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from line3dpp_b200 import capi, line3d
+    h = ctypes.c_void_p()
+    assert capi.lib().l3d_ctx_create(0, ctypes.byref(h)) < 0 and not h
+    with pytest.raises(capi.L3DError):
+        capi.Context(0)
+    with pytest.raises(capi.L3DError):
+        line3d.Line3D(False, True)
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "line3dpp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                for line in open(os.path.join(root, f)):
+                    if re.match(r"\s*(#\s*include|import|from)\b", line) or "CDLL" in line or "dlopen" in line:
+                        assert "oracle" not in line, (f, line)
