@@ -299,10 +299,11 @@ static int match_dense_impl(l3d_ctx* c, int sv, int tv, const float* F, float ep
         d_dep = (float4*)c->d_dense_dep.p; d_ov = (float*)c->d_dense_ov.p;
     }
     L3DMat3 Fm; memcpy(Fm.m, F, sizeof(Fm.m));
-    dim3 grid((Nt + DK_THREADS - 1) / DK_THREADS, (Ns + DK_ROWS - 1) / DK_ROWS);
+    dim3 grid((Nt + DK_THREADS - 1) / DK_THREADS, (Ns + DKN_ROWS - 1) / DKN_ROWS);
+    dim3 gridf((Nt + DK_WARPS * DK_T * 32 - 1) / (DK_WARPS * DK_T * 32), (Ns + DK_ROWS - 1) / DK_ROWS);
     const float4* cache = (const float4*)c->d_cache.p;
     if (filter)
-        k_match_dense<<<grid, DK_THREADS, 0, c->stream>>>(c->segs() + vs.seg_off, Ns, c->segs() + vt.seg_off, Nt, cache + 3 * vs.seg_off, cache + 3 * vt.seg_off, Fm,
+        k_match_dense<<<gridf, DK_THREADS, 0, c->stream>>>(c->segs() + vs.seg_off, Ns, c->segs() + vt.seg_off, Nt, cache + 3 * vs.seg_off, cache + 3 * vt.seg_off, Fm,
                                                           make_float3(vs.C[0], vs.C[1], vs.C[2]), make_float3(vt.C[0], vt.C[1], vt.C[2]), epi, d_dep, d_ov);
     else
         k_match_dense_nofilter<<<grid, DK_THREADS, 0, c->stream>>>(c->segs() + vs.seg_off, Ns, c->segs() + vt.seg_off, Nt, cache + 3 * vs.seg_off, cache + 3 * vt.seg_off, Fm,

@@ -268,44 +268,89 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
 }
 
 // ------------------------------------------------------------------------------------------------ dense contract
+// K_match_lines' device contract: depths[Ns][Nt] (float4) + overlaps[Ns][Nt] (float) for EVERY cell, 20 B written per
+// pair evaluation -> HBM-write bound.  A warp owns DK_T*32 consecutive target columns and walks DK_ROWS source rows:
+// cells the filter proves empty are stored at once, coalesced ((-1,-1,-1,-1), 0); the others are ballot-compacted into
+// a per-warp queue and evaluated 32 at a time by the exact path, which stores its 20 bytes itself.
+struct DenseSmem {
+    float4 rowA[DK_ROWS], rowB[DK_ROWS];
+    unsigned int queue[DK_WARPS][64];
+    const float4* tsegs; const float4* scache; const float4* tcache;
+    float4* depths; float* overlaps;
+    float3 Cs, Ct;
+    float epi; int Nt, row0;
+};
+
+__device__ __noinline__ void dense_exact_batch(DenseSmem& S, unsigned int entry, bool has)
+{
+    if (!has) return;
+    const int r = (int)(entry >> 24), x = (int)(entry & 0xFFFFFFu);
+    const float4 q = __ldg(S.tsegs + x);
+    const float4 rA = S.rowA[r], rB = S.rowB[r];
+    float4 res = make_float4(-1.f, -1.f, -1.f, -1.f);
+    bool inv;
+    const float ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
+    if (ov > S.epi) {
+        SegRays s = load_rays(S.scache, S.row0 + r), t = load_rays(S.tcache, x);
+        float d[4];
+        exact_depths(s, t, S.Cs, S.Ct, d);
+        res = make_float4(d[0], d[1], d[2], d[3]);
+    }
+    const size_t o = (size_t)(S.row0 + r) * S.Nt + x;
+    __stcs(S.depths + o, res);
+    __stcs(S.overlaps + o, ov);
+}
+
 __global__ void __launch_bounds__(DK_THREADS)
 k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
               const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F, float3 Cs, float3 Ct,
               float epi, float4* __restrict__ depths, float* __restrict__ overlaps)
 {
-    __shared__ float4 rowA[DK_ROWS], rowB[DK_ROWS];
-    const int tid = threadIdx.x;
+    __shared__ DenseSmem S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = blockIdx.y * DK_ROWS;
     const int nrows = min(DK_ROWS, Ns - row0);
+    if (tid == 0) {
+        S.tsegs = tsegs; S.scache = scache; S.tcache = tcache; S.depths = depths; S.overlaps = overlaps;
+        S.Cs = Cs; S.Ct = Ct; S.epi = epi; S.Nt = Nt; S.row0 = row0;
+    }
     if (tid < nrows) {
         float4 s = __ldg(ssegs + row0 + tid);
         float3 e1 = mulmat_h(F.m, s.x, s.y), e2 = mulmat_h(F.m, s.z, s.w);
         float g = L3D_FILTER_C1 * fmaxf(sqrtf(e1.x * e1.x + e1.y * e1.y), sqrtf(e2.x * e2.x + e2.y * e2.y));
-        rowA[tid] = make_float4(e1.x, e1.y, e1.z, e2.x);
-        rowB[tid] = make_float4(e2.y, e2.z, g, 0.f);
+        S.rowA[tid] = make_float4(e1.x, e1.y, e1.z, e2.x);
+        S.rowB[tid] = make_float4(e2.y, e2.z, g, 0.f);      // threshold 0: reject only provably empty cells
     }
     __syncthreads();
-    const int x = blockIdx.x * DK_THREADS + tid;
-    if (x >= Nt) return;
-    const float4 q = __ldg(tsegs + x);
+    const int x0 = (blockIdx.x * DK_WARPS + warp) * (32 * DK_T);
+    if (x0 >= Nt) return;
+    float4 q[DK_T];
+    bool ok[DK_T];
+#pragma unroll
+    for (int t = 0; t < DK_T; ++t) { const int x = x0 + t * 32 + lane; ok[t] = x < Nt; q[t] = __ldg(tsegs + (ok[t] ? x : 0)); }
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const float4 none = make_float4(-1.f, -1.f, -1.f, -1.f);
+    int qn = 0;
     for (int r = 0; r < nrows; ++r) {
-        const float4 rA = rowA[r], rB = rowB[r];
-        float4 res = make_float4(-1.f, -1.f, -1.f, -1.f);
-        float ov = 0.0f;
-        if (filter_may_survive(q, rA, rB)) {
-            bool inv;
-            ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
-            if (ov > epi) {
-                SegRays s = load_rays(scache, row0 + r), t = load_rays(tcache, x);
-                float d[4];
-                exact_depths(s, t, Cs, Ct, d);
-                res = make_float4(d[0], d[1], d[2], d[3]);
+        const float4 rA = S.rowA[r], rB = S.rowB[r];
+        const size_t orow = (size_t)(row0 + r) * Nt;
+        bool pass[DK_T];
+#pragma unroll
+        for (int t = 0; t < DK_T; ++t) pass[t] = ok[t] && filter_may_survive(q[t], rA, rB);
+#pragma unroll
+        for (int t = 0; t < DK_T; ++t) {
+            const int x = x0 + t * 32 + lane;
+            if (ok[t] && !pass[t]) { __stcs(depths + orow + x, none); __stcs(overlaps + orow + x, 0.0f); }
+            const unsigned int b = __ballot_sync(0xffffffffu, pass[t]);
+            if (b) {
+                if (pass[t]) S.queue[warp][qn + __popc(b & lt_mask)] = ((unsigned int)r << 24) | (unsigned int)x;
+                qn += __popc(b);
+                __syncwarp();
+                if (qn >= 32) { qn -= 32; dense_exact_batch(S, S.queue[warp][qn + lane], true); }
             }
         }
-        const size_t o = (size_t)(row0 + r) * Nt + x;
-        __stcs(depths + o, res);
-        __stcs(overlaps + o, ov);
     }
+    if (qn > 0) dense_exact_batch(S, lane < qn ? S.queue[warp][lane] : 0u, lane < qn);
 }
 
 // same contract, NO pre-filter: every cell goes through the exact path.  Test-only cross-check of the filter.
@@ -315,8 +360,8 @@ k_match_dense_nofilter(const float4* __restrict__ ssegs, int Ns, const float4* _
                        float3 Ct, float epi, float4* __restrict__ depths, float* __restrict__ overlaps)
 {
     const int x = blockIdx.x * DK_THREADS + threadIdx.x;
-    const int row0 = blockIdx.y * DK_ROWS;
-    const int nrows = min(DK_ROWS, Ns - row0);
+    const int row0 = blockIdx.y * DKN_ROWS;
+    const int nrows = min(DKN_ROWS, Ns - row0);
     if (x >= Nt) return;
     const float4 q = __ldg(tsegs + x);
     for (int r = 0; r < nrows; ++r) {

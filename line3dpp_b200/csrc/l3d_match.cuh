@@ -15,7 +15,10 @@
 #endif
 
 #define DK_THREADS 256
-#define DK_ROWS 32
+#define DK_WARPS 8
+#define DK_ROWS 16                      /* source rows per CTA of the dense kernel */
+#define DK_T 4                          /* target columns per lane: a CTA covers DK_ROWS x (8*4*32 = 1024) cells */
+#define DKN_ROWS 32                     /* rows per CTA of the unfiltered test kernel */
 
 struct L3DMat3 { float m[9]; };
 
