@@ -198,3 +198,31 @@ def test_product_never_imports_the_oracle():
                 for line in open(os.path.join(root, f)):
                     if re.match(r"\s*(#\s*include|import|from)\b", line) or "CDLL" in line or "dlopen" in line:
                         assert "oracle" not in line, (f, line)
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE configs[0]: vsfm_result.nvm on the CPU path
+def test_nvm_cpu_reference_run_matches_fixture_statistically(oracle):
+    """testdata/vsfm_result.nvm, 26 views, default parameters (README.md:214-221), segments from cv2's LSD (committed
+    inputs, tests/golden/make_nvm_inputs.py).  The oracle's restatement of the reference pipeline must reproduce the
+    reference's own result testdata/Line3D++_ref statistically: line count within 3 %, symmetric chamfer distance of
+    points sampled on the 3D segments below 0.5 % of the scene depth (median) - the same order as the distance between
+    the oracle's REF_GPU and REF_CPU semantics.  Index parity is impossible here (different LSD build)."""
+    from tests import nvm_util as nu
+    oracle.set_threads(os.cpu_count() or 1)
+    inp = nu.load_inputs()
+    fx, fl, fr = nu.load_fixture()
+    P = oracle.OraclePipeline(True, 1)
+    nu.add_all(P.add_view, inp)
+    assert P.match_images() == 0 and P.reconstruct(3, False) == 0
+    oracle.set_threads(1)
+    n_ref = len(set(fl.tolist()))
+    assert abs(P.num_lines() - n_ref) <= 0.03 * n_ref, (P.num_lines(), n_ref)
+    assert abs(len(P.residuals()) - len(fr)) <= 0.05 * len(fr)
+    s = P.segments3d()
+    mine = np.concatenate([s["p1"], s["p2"]], 1)
+    a, b = nu.sample_points(mine), nu.sample_points(fx)
+    depth = float(np.median(inp["median_depth"]))
+    m1, p1 = nu.chamfer(a, b)
+    m2, p2 = nu.chamfer(b, a)
+    assert m1 < 0.005 * depth and m2 < 0.005 * depth, (m1, m2)
+    assert p1 < 0.02 * depth and p2 < 0.02 * depth, (p1, p2)

@@ -170,3 +170,42 @@ def test_rdd_bit_exact_vs_reference(gpu_ctx, oracle, ref_nofma):
     assert np.array_equal(util.bits(ow), util.bits(rw))
     ci, cj, cw, _ = oracle.rdd(oracle.lib().orc_rdd_f32, ei, ej, ew, n)
     assert np.array_equal(ci, ri) and np.array_equal(util.bits(cw), util.bits(rw))     # pins the CPU restatement too
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE configs[1]: vsfm_result.nvm on 1 x B200
+def test_nvm_b200_vs_reference_kernels_and_fixture(oracle, ref_nofma):
+    """testdata/vsfm_result.nvm through L3DPP::Line3D on the B200 (neighbours from world points, default parameters):
+    index-exact against the oracle host logic driving the UNMODIFIED reference kernels, 3D endpoints within 1e-6 scene
+    units, and statistically equal to the reference's own result fixture testdata/Line3D++_ref."""
+    from tests import nvm_util as nu
+    inp = nu.load_inputs()
+    fx, fl, fr = nu.load_fixture()
+    L = line3d.Line3D(neighbors_by_worldpoints=True, use_gpu=True)
+    nu.add_all(L.add_image, inp)
+    L.match_images()
+    L.reconstruct_3d_lines(3, False)
+    P = oracle.OraclePipeline(True, 1, backend=ref_nofma)
+    nu.add_all(P.add_view, inp)
+    assert P.match_images() == 0 and P.reconstruct(3, False) == 0
+    assert np.array_equal(L.pairs(), P.pairs())
+    for cam in range(inp["V"]):
+        _same_matches(L.view_matches(cam, kept_only=True), P.matches(cam), exact_scores=True)
+    assert np.array_equal(L.local2global(), P.local2global())
+    st = L.stats()
+    assert st["lines3D"] == P.num_lines()
+    mr, orr = L.residuals(), P.residuals()
+    assert np.array_equal(mr["cam"], orr["cam"]) and np.array_equal(mr["seg"], orr["seg"])
+    ms, os_ = L.segments3d(), P.segments3d()
+    a = np.sort(np.stack([ms["p1"], ms["p2"]], 1), axis=1)
+    b = np.sort(np.stack([os_["p1"], os_["p2"]], 1), axis=1)
+    np.testing.assert_allclose(a, b, atol=1e-6)
+    # statistical comparison with the reference's own output
+    n_ref = len(set(fl.tolist()))
+    assert abs(st["lines3D"] - n_ref) <= 0.03 * n_ref, (st["lines3D"], n_ref)
+    mine = np.concatenate([ms["p1"], ms["p2"]], 1)
+    depth = float(np.median(inp["median_depth"]))
+    m1, _ = nu.chamfer(nu.sample_points(mine), nu.sample_points(fx))
+    m2, _ = nu.chamfer(nu.sample_points(fx), nu.sample_points(mine))
+    assert m1 < 0.005 * depth and m2 < 0.005 * depth, (m1, m2)
+    print("nvm on B200:", st)
+    L.close()
