@@ -88,8 +88,8 @@ def build_rank_workload(rank: int, world: int):
     if scene is None:
         scene = synth.make_scene_views(V, SEGS_PER_VIEW, 1004, f"ring{RING}", range(rank * VIEWS_PER_GPU, (rank + 1) * VIEWS_PER_GPU))
     pairs = synth.view_pairs(scene.neighbors)
-    lo, hi = rank * VIEWS_PER_GPU, (rank + 1) * VIEWS_PER_GPU
-    mine = pairs[(pairs[:, 0] >= lo) & (pairs[:, 0] < hi)]
+    from line3dpp_b200 import shard
+    mine = shard.rank_pairs(pairs, rank, world, V)        # pairs whose SOURCE view this rank owns
     F = np.zeros((len(mine), 9), np.float32)
     for i, (s, t) in enumerate(mine):
         F[i] = synth.fundamental(scene.K[s], scene.R[s], scene.t[s], scene.K[t], scene.R[t], scene.t[t]).astype(np.float32).reshape(9)
