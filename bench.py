@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 VIEWS_PER_GPU, SEGS_PER_VIEW, RING, KNN, EPI = 1000, 3000, 5, 10, 0.25
 FLOP_PER_PAIR_EVAL = 100.0     # algorithmic FP32 flop per pair evaluation (DESIGN.md "Roofline")
 DENSE_BYTES_PER_CELL = 20.0    # float4 depths + float overlap per cell (cudawrapper.cu:226-251)
+RDD_BYTES_PER_NNZ = 20.0       # P val + col idx + W val + transpose slot + P' store
 
 
 def dist_env():
@@ -175,6 +176,7 @@ def run_ours(args):
             print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"}))
             return 2
     torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = capi.Context(local_rank)
@@ -354,6 +356,27 @@ def roofline_legs(ctx, st, scene, torch):
                             "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
                             "algorithmic_bytes_per_pair_eval": DENSE_BYTES_PER_CELL, "cells_per_launch": Ns * Nt,
                             "pair_evals_per_sec": Ns * Nt / (ms * 1e-3)}]
+    # diffusion (SpMV-like, HBM-bound): random symmetric affinity graph, 2M rows, ~32M entries, 10 iterations
+    try:
+        rng = np.random.default_rng(7)
+        n, deg = 2_000_000, 8
+        a = np.repeat(np.arange(n, dtype=np.int64), deg)
+        b = rng.integers(0, n, n * deg)
+        keep = a != b
+        key = np.unique(np.minimum(a[keep], b[keep]) * n + np.maximum(a[keep], b[keep]))
+        a, b = (key // n).astype(np.int32), (key % n).astype(np.int32)
+        w = rng.uniform(0.5, 1.0, len(a)).astype(np.float32)
+        ei, ej, ew = np.concatenate([a, b]), np.concatenate([b, a]), np.concatenate([w, w])
+        iters = 10
+        _, _, _, ms = ctx.rdd(n, ei, ej, ew, iters)
+        _, _, _, ms = ctx.rdd(n, ei, ej, ew, iters)
+        nnz = len(ei)
+        gbs = iters * (RDD_BYTES_PER_NNZ * nnz + 8.0 * n) / (ms * 1e-3) / 1e9
+        out["roofline_hbm"].append({"kernel": "k_rdd_step+k_rdd_normalize", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_iteration": ms / iters, "rows": n, "nnz": nnz,
+                                    "algorithmic_bytes_per_nnz_per_iteration": RDD_BYTES_PER_NNZ})
+    except Exception as e:   # noqa
+        out["roofline_hbm"].append({"kernel": "k_rdd_step", "error": str(e)[:200]})
     return out
 
 

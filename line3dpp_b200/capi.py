@@ -163,6 +163,15 @@ class Context:
         return int(self._chk(self.L.l3d_get_matches_csr(self.h, C.c_void_p(row_ptr_ptr), C.c_void_p(recs_ptr),
                                                         C.c_longlong(capacity)), "l3d_get_matches_csr"))
 
+    def rdd(self, n, ei, ej, ew, iters=10):
+        """l3d_rdd: returns (out_i, out_j, out_w, device ms of the diffusion iterations)"""
+        ei = np.ascontiguousarray(ei, np.int32); ej = np.ascontiguousarray(ej, np.int32); ew = np.ascontiguousarray(ew, np.float32)
+        oi, oj, ow = np.empty_like(ei), np.empty_like(ej), np.empty_like(ew)
+        ms = C.c_float(0)
+        self._chk(self.L.l3d_rdd(self.h, int(n), C.c_longlong(len(ei)), _p(ei), _p(ej), _p(ew), int(iters), _p(oi), _p(oj), _p(ow),
+                                 C.byref(ms)), "l3d_rdd")
+        return oi, oj, ow, ms.value
+
     def fp32_peak_tflops(self) -> float:
         v = C.c_double(0)
         self._chk(self.L.l3d_fp32_peak_probe(self.h, C.byref(v)), "l3d_fp32_peak_probe")

@@ -44,13 +44,13 @@ struct MatchSmem {
     float4 rowB[MK_ROWS];                            // (e2.y, e2.z, g, 0.95 * score-to-beat)
     float row_thr[MK_ROWS];                          // overlap of the current k-th best survivor (0 until k are known)
     int list_cnt[MK_ROWS];
-    unsigned int queue[MK_WARPS][64];                // candidate queue per warp: (row_local << 24) | tgt
+    unsigned int queue[MK_WARPS][32 * MK_T + 32];    // candidate queue per warp: (row_local << 24) | tgt
     unsigned long long bars[2];
     // per-CTA constants of the (rarely executed, deliberately out-of-line) exact path
     const float4* tsegs; const float4* cache;
     long long src_base, toff;
     float3 Cs, Ct;
-    float epi; int knn;
+    float epi; int knn, Nt;
 };
 size_t l3d_match_smem_bytes() { return sizeof(MatchSmem); }
 
@@ -98,11 +98,12 @@ __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool 
     if (has) {
         rl = (int)(entry >> 24);
         unsigned int j = entry & 0xFFFFFFu;
+        if (j >= (unsigned int)S.Nt) j = 0u, has = false;         // padding segment of a partial stage
         float4 q = __ldg(tsegs + j);
         float4 rA = S.rowA[rl], rB = S.rowB[rl];
         bool inv;
         float ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
-        if (ov > epi && ov >= S.row_thr[rl]) {      // below the current k-th best it can never be selected
+        if (has && ov > epi && ov >= S.row_thr[rl]) {      // below the current k-th best it can never be selected
             SegRays s = load_rays(cache, src_base + rl), t = load_rays(cache, toff + j);
             float d[4];
             exact_depths(s, t, Cs, Ct, d);
@@ -185,7 +186,7 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
     const int nchunks = (Nt + MK_TT - 1) / MK_TT;
 
     if (tid == 0) {
-        S.tsegs = tsegs; S.cache = cache; S.src_base = soff + row0; S.toff = toff; S.epi = epi; S.knn = knn;
+        S.tsegs = tsegs; S.cache = cache; S.src_base = soff + row0; S.toff = toff; S.epi = epi; S.knn = knn; S.Nt = Nt;
         S.Cs = make_float3(vs->C[0], vs->C[1], vs->C[2]); S.Ct = make_float3(vt->C[0], vt->C[1], vt->C[2]);
         mbar_init(&S.bars[0], 1); mbar_init(&S.bars[1], 1); mbar_fence_init();
         unsigned int bytes = (unsigned int)min(MK_TT, Nt) * 16u;       // first stage in flight while the rows are set up
@@ -218,39 +219,43 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
         mbar_wait(&S.bars[c & 1], (unsigned int)((c >> 1) & 1));
         const int base = c * MK_TT;
         const int n = min(MK_TT, Nt - base);
+        if (n & (32 * MK_T - 1)) {
+            // last, partial stage: pad it to a multiple of the warp step with a segment 3e7 px away that the filter
+            // rejects (should an epipolar line ever pass through it, exact_batch drops indices >= Nt), so the hot loop
+            // needs no per-lane bounds predicate
+            const int pad = ((n + 32 * MK_T - 1) & ~(32 * MK_T - 1)) - n;
+            if (tid < pad) S.stage[c & 1][n + tid] = make_float4(3.0e7f, 3.0e7f, 3.0e7f + 100.0f, 3.0e7f);
+            __syncthreads();
+        }
         const float4* st = S.stage[c & 1];
-        if (warp * MK_RPW < nrows) {
+        const int my_rows = min(MK_RPW, nrows - warp * MK_RPW);
+        if (my_rows > 0) {
             for (int j0 = 0; j0 < n; j0 += 32 * MK_T) {
                 float4 q[MK_T];
-                bool ok[MK_T];
 #pragma unroll
-                for (int t = 0; t < MK_T; ++t) {
-                    int idx = j0 + t * 32 + lane;
-                    ok[t] = idx < n;
-                    q[t] = st[ok[t] ? idx : 0];
-                }
-                for (int r = 0; r < MK_RPW; ++r) {
+                for (int t = 0; t < MK_T; ++t) q[t] = st[j0 + t * 32 + lane];
+                for (int r = 0; r < my_rows; ++r) {
                     const int rl = warp * MK_RPW + r;
-                    if (rl >= nrows) break;
                     const float4 rA = S.rowA[rl], rB = S.rowB[rl];
                     bool pass[MK_T];
 #pragma unroll
-                    for (int t = 0; t < MK_T; ++t) pass[t] = ok[t] && filter_may_survive(q[t], rA, rB);   // MK_T independent chains
+                    for (int t = 0; t < MK_T; ++t) pass[t] = filter_may_survive(q[t], rA, rB);   // MK_T independent chains
                     unsigned int b[MK_T], any = 0u;
 #pragma unroll
                     for (int t = 0; t < MK_T; ++t) { b[t] = __ballot_sync(0xffffffffu, pass[t]); any |= b[t]; }
                     if (any) {
+                        const unsigned int e0 = ((unsigned int)rl << 24) | (unsigned int)(base + j0 + lane);
+                        int off = qn;
 #pragma unroll
                         for (int t = 0; t < MK_T; ++t) {
-                            if (b[t]) {
-                                if (pass[t]) S.queue[warp][qn + __popc(b[t] & lt_mask)] = ((unsigned int)rl << 24) | (unsigned int)(base + j0 + t * 32 + lane);
-                                qn += __popc(b[t]);
-                                __syncwarp();
-                                if (qn >= 32) {
-                                    qn -= 32;
-                                    exact_batch(S, S.queue[warp][qn + lane], true, lane);
-                                }
-                            }
+                            if (pass[t]) S.queue[warp][off + __popc(b[t] & lt_mask)] = e0 + 32u * t;
+                            off += __popc(b[t]);
+                        }
+                        qn = off;
+                        __syncwarp();
+                        while (qn >= 32) {
+                            qn -= 32;
+                            exact_batch(S, S.queue[warp][qn + lane], true, lane);
                         }
                     }
                 }
