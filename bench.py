@@ -356,12 +356,13 @@ def roofline_legs(ctx, st, scene, torch):
                             "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
                             "algorithmic_bytes_per_pair_eval": DENSE_BYTES_PER_CELL, "cells_per_launch": Ns * Nt,
                             "pair_evals_per_sec": Ns * Nt / (ms * 1e-3)}]
-    # diffusion (SpMV-like, HBM-bound): random symmetric affinity graph, 2M rows, ~32M entries, 10 iterations
+    # diffusion (SpMV-like, HBM-bound): banded random symmetric affinity graph, 2M rows, ~32M entries, 10 iterations
     try:
         rng = np.random.default_rng(7)
         n, deg = 2_000_000, 8
         a = np.repeat(np.arange(n, dtype=np.int64), deg)
-        b = rng.integers(0, n, n * deg)
+        # banded like the real affinity matrix: local ids follow (view, segment) order and matches join nearby views
+        b = np.clip(a + rng.integers(-3000, 3001, n * deg), 0, n - 1)
         keep = a != b
         key = np.unique(np.minimum(a[keep], b[keep]) * n + np.maximum(a[keep], b[keep]))
         a, b = (key // n).astype(np.int32), (key % n).astype(np.int32)

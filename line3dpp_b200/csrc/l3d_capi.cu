@@ -54,6 +54,7 @@ int l3d_ctx_create(int device, l3d_ctx** out)
     cudaGetDeviceProperties(&prop, device);
     c->num_sms = prop.multiProcessorCount;
     e = cudaFuncSetAttribute(k_match_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3d_match_smem_bytes());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3d_dense_smem_bytes());
     if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return L3D_ERR_CUDA; }
     *out = c;
     return L3D_OK;
@@ -303,7 +304,7 @@ static int match_dense_impl(l3d_ctx* c, int sv, int tv, const float* F, float ep
     dim3 gridf((Nt + DK_WARPS * DK_T * 32 - 1) / (DK_WARPS * DK_T * 32), (Ns + DK_ROWS - 1) / DK_ROWS);
     const float4* cache = (const float4*)c->d_cache.p;
     if (filter)
-        k_match_dense<<<gridf, DK_THREADS, 0, c->stream>>>(c->segs() + vs.seg_off, Ns, c->segs() + vt.seg_off, Nt, cache + 3 * vs.seg_off, cache + 3 * vt.seg_off, Fm,
+        k_match_dense<<<gridf, DK_THREADS, l3d_dense_smem_bytes(), c->stream>>>(c->segs() + vs.seg_off, Ns, c->segs() + vt.seg_off, Nt, cache + 3 * vs.seg_off, cache + 3 * vt.seg_off, Fm,
                                                           make_float3(vs.C[0], vs.C[1], vs.C[2]), make_float3(vt.C[0], vt.C[1], vt.C[2]), epi, d_dep, d_ov);
     else
         k_match_dense_nofilter<<<grid, DK_THREADS, 0, c->stream>>>(c->segs() + vs.seg_off, Ns, c->segs() + vt.seg_off, Nt, cache + 3 * vs.seg_off, cache + 3 * vt.seg_off, Fm,

@@ -279,24 +279,35 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
 // a per-warp queue and evaluated 32 at a time by the exact path, which stores its 20 bytes itself.
 struct DenseSmem {
     float4 rowA[DK_ROWS], rowB[DK_ROWS];
+    float4 sray[DK_ROWS][3];                       // cached rays / plane normal of the CTA's source rows
+    float4 tq[DK_WARPS][32 * DK_T];                // target segments of each warp's columns
+    float4 tray[DK_WARPS][32 * DK_T][3];           // their cached rays / plane normals
     unsigned int queue[DK_WARPS][64];
-    const float4* tsegs; const float4* scache; const float4* tcache;
     float4* depths; float* overlaps;
     float3 Cs, Ct;
     float epi; int Nt, row0;
 };
+size_t l3d_dense_smem_bytes() { return sizeof(DenseSmem); }
 
-__device__ __noinline__ void dense_exact_batch(DenseSmem& S, unsigned int entry, bool has)
+__device__ __forceinline__ SegRays rays_from_smem(const float4* p)
+{
+    const float4 a = p[0], b = p[1], c = p[2];
+    SegRays s;
+    s.r1 = make_float3(a.x, a.y, a.z); s.r2 = make_float3(a.w, b.x, b.y); s.n = make_float3(b.z, b.w, c.x);
+    return s;
+}
+
+__device__ __noinline__ void dense_exact_batch(DenseSmem& S, unsigned int entry, bool has, int warp, int x0)
 {
     if (!has) return;
-    const int r = (int)(entry >> 24), x = (int)(entry & 0xFFFFFFu);
-    const float4 q = __ldg(S.tsegs + x);
+    const int r = (int)(entry >> 24), x = (int)(entry & 0xFFFFFFu), col = x - x0;
+    const float4 q = S.tq[warp][col];
     const float4 rA = S.rowA[r], rB = S.rowB[r];
     float4 res = make_float4(-1.f, -1.f, -1.f, -1.f);
     bool inv;
     const float ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
     if (ov > S.epi) {
-        SegRays s = load_rays(S.scache, S.row0 + r), t = load_rays(S.tcache, x);
+        const SegRays s = rays_from_smem(S.sray[r]), t = rays_from_smem(S.tray[warp][col]);
         float d[4];
         exact_depths(s, t, S.Cs, S.Ct, d);
         res = make_float4(d[0], d[1], d[2], d[3]);
@@ -306,19 +317,17 @@ __device__ __noinline__ void dense_exact_batch(DenseSmem& S, unsigned int entry,
     __stcs(S.overlaps + o, ov);
 }
 
-__global__ void __launch_bounds__(DK_THREADS)
+__global__ void __launch_bounds__(DK_THREADS, 3)
 k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
               const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F, float3 Cs, float3 Ct,
               float epi, float4* __restrict__ depths, float* __restrict__ overlaps)
 {
-    __shared__ DenseSmem S;
+    extern __shared__ __align__(128) unsigned char dense_smem_raw[];
+    DenseSmem& S = *reinterpret_cast<DenseSmem*>(dense_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = blockIdx.y * DK_ROWS;
     const int nrows = min(DK_ROWS, Ns - row0);
-    if (tid == 0) {
-        S.tsegs = tsegs; S.scache = scache; S.tcache = tcache; S.depths = depths; S.overlaps = overlaps;
-        S.Cs = Cs; S.Ct = Ct; S.epi = epi; S.Nt = Nt; S.row0 = row0;
-    }
+    if (tid == 0) { S.depths = depths; S.overlaps = overlaps; S.Cs = Cs; S.Ct = Ct; S.epi = epi; S.Nt = Nt; S.row0 = row0; }
     if (tid < nrows) {
         float4 s = __ldg(ssegs + row0 + tid);
         float3 e1 = mulmat_h(F.m, s.x, s.y), e2 = mulmat_h(F.m, s.z, s.w);
@@ -326,13 +335,23 @@ k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict
         S.rowA[tid] = make_float4(e1.x, e1.y, e1.z, e2.x);
         S.rowB[tid] = make_float4(e2.y, e2.z, g, 0.f);      // threshold 0: reject only provably empty cells
     }
-    __syncthreads();
+    if (tid < 3 * nrows) S.sray[tid / 3][tid % 3] = __ldg(scache + 3 * (size_t)row0 + tid);
     const int x0 = (blockIdx.x * DK_WARPS + warp) * (32 * DK_T);
-    if (x0 >= Nt) return;
     float4 q[DK_T];
     bool ok[DK_T];
 #pragma unroll
-    for (int t = 0; t < DK_T; ++t) { const int x = x0 + t * 32 + lane; ok[t] = x < Nt; q[t] = __ldg(tsegs + (ok[t] ? x : 0)); }
+    for (int t = 0; t < DK_T; ++t) {
+        const int x = x0 + t * 32 + lane;
+        ok[t] = x < Nt;
+        q[t] = __ldg(tsegs + (ok[t] ? x : 0));
+        S.tq[warp][t * 32 + lane] = q[t];
+    }
+    {   // this warp's 32*DK_T columns x 3 float4 of cached rays, coalesced
+        const int ncol = max(0, min(32 * DK_T, Nt - x0));
+        for (int i = lane; i < 3 * ncol; i += 32) (&S.tray[warp][0][0])[i] = __ldg(tcache + 3 * (size_t)x0 + i);
+    }
+    __syncthreads();
+    if (x0 >= Nt) return;
     const unsigned int lt_mask = (1u << lane) - 1u;
     const float4 none = make_float4(-1.f, -1.f, -1.f, -1.f);
     int qn = 0;
@@ -351,11 +370,11 @@ k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict
                 if (pass[t]) S.queue[warp][qn + __popc(b & lt_mask)] = ((unsigned int)r << 24) | (unsigned int)x;
                 qn += __popc(b);
                 __syncwarp();
-                if (qn >= 32) { qn -= 32; dense_exact_batch(S, S.queue[warp][qn + lane], true); }
+                if (qn >= 32) { qn -= 32; dense_exact_batch(S, S.queue[warp][qn + lane], true, warp, x0); }
             }
         }
     }
-    if (qn > 0) dense_exact_batch(S, lane < qn ? S.queue[warp][lane] : 0u, lane < qn);
+    if (qn > 0) dense_exact_batch(S, lane < qn ? S.queue[warp][lane] : 0u, lane < qn, warp, x0);
 }
 
 // same contract, NO pre-filter: every cell goes through the exact path.  Test-only cross-check of the filter.

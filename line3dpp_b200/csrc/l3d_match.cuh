@@ -23,6 +23,7 @@
 struct L3DMat3 { float m[9]; };
 
 size_t l3d_match_smem_bytes();
+size_t l3d_dense_smem_bytes();
 
 __global__ void k_prep_segments(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int num_views,
                                 long long total, float4* __restrict__ cache);

@@ -15,6 +15,8 @@
 #include "l3d_ctx.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -247,6 +249,30 @@ k_filter(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, 
     }
 }
 
+// compact list of the segments that have a 3D estimate: their best match (L3DPP::Match layout) and P1,P2
+struct HasEstimate { __host__ __device__ long long operator()(int best) const { return best >= 0 ? 1ll : 0ll; } };
+__global__ void __launch_bounds__(256)
+k_collect_estimates(const L3DViewDev* __restrict__ views, int V, long long N, const long long* __restrict__ reg_of_view,
+                    const int* __restrict__ est_best, const long long* __restrict__ pos, const int4* __restrict__ m_meta,
+                    const float4* __restrict__ m_dep, const float2* __restrict__ m_os, const double* __restrict__ est_P,
+                    l3d_match* __restrict__ out_best, double* __restrict__ out_P)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const int b = est_best[g];
+    if (b < 0) return;
+    int lo = 0, hi = V - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (views[mid].seg_off <= g) lo = mid; else hi = mid - 1; }
+    const long long x = reg_of_view[lo] + b;
+    const int4 me = m_meta[x]; const float4 dep = m_dep[x]; const float2 os = m_os[x];
+    l3d_match m;
+    m.src_cam = views[lo].cam_id; m.src_seg = (unsigned int)(g - views[lo].seg_off); m.tgt_cam = views[me.y].cam_id; m.tgt_seg = (unsigned int)me.z;
+    m.overlap = os.x; m.score3D = os.y; m.d_p1 = dep.x; m.d_p2 = dep.y; m.d_q1 = dep.z; m.d_q2 = dep.w;
+    const long long p = pos[g];
+    out_best[p] = m;
+    for (int i = 0; i < 6; ++i) out_P[6 * p + i] = est_P[6 * g + i];
+}
+
 // ---------------------------------------------------------------------------------------------- host driver
 extern "C" {
 
@@ -358,7 +384,37 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     }
     S.h_M.resize(V);
     L3D_CUDA(c, cudaMemcpyAsync(S.h_M.data(), S.d_M.p, 4 * (size_t)V, cudaMemcpyDeviceToHost, st), "download counts");
-    L3D_CUDA(c, cudaStreamSynchronize(st), "score sweep");
+    // compact the estimates on the device: flags -> exclusive scan -> gather (best match record + P1,P2)
+    {
+        const long long N = c->total_segs;
+        std::vector<long long> reg_of_view(V);
+        for (int i = 0; i < V; ++i) reg_of_view[S.order[i]] = S.region_off[i];
+        if ((rc = l3d_reserve(c, S.d_reg_of_view, 8 * (size_t)V, "region of view"))) return rc;
+        if ((rc = l3d_reserve(c, S.d_est_pos, 8 * (size_t)(N + 1), "estimate positions"))) return rc;
+        L3D_CUDA(c, cudaMemcpyAsync(S.d_reg_of_view.p, reg_of_view.data(), 8 * (size_t)V, cudaMemcpyHostToDevice, st), "region of view");
+        cub::TransformInputIterator<long long, HasEstimate, const int*> flags((const int*)S.d_est_best.p, HasEstimate());
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, (long long*)S.d_est_pos.p, N, st);
+        if ((rc = l3d_reserve(c, S.d_sort_tmp, tb, "scan temp"))) return rc;
+        tb = S.d_sort_tmp.cap;
+        L3D_CUDA(c, cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tb, flags, (long long*)S.d_est_pos.p, N, st), "estimate scan");
+        long long last_pos = 0; int last_best = -1;
+        L3D_CUDA(c, cudaMemcpyAsync(&last_pos, (long long*)S.d_est_pos.p + N - 1, 8, cudaMemcpyDeviceToHost, st), "estimate count");
+        L3D_CUDA(c, cudaMemcpyAsync(&last_best, (int*)S.d_est_best.p + N - 1, 4, cudaMemcpyDeviceToHost, st), "estimate count");
+        L3D_CUDA(c, cudaStreamSynchronize(st), "score sweep");
+        S.n_est = last_pos + (last_best >= 0 ? 1 : 0);
+        if ((rc = l3d_reserve(c, S.d_est_out_best, sizeof(l3d_match) * (size_t)std::max<long long>(S.n_est, 1), "estimate records"))) return rc;
+        if ((rc = l3d_reserve(c, S.d_est_out_P, 48 * (size_t)std::max<long long>(S.n_est, 1), "estimate points"))) return rc;
+        if (S.n_est > 0) {
+            k_collect_estimates<<<(unsigned int)((N + 255) / 256), 256, 0, st>>>(views, V, N, (const long long*)S.d_reg_of_view.p, (const int*)S.d_est_best.p,
+                                                                               (const long long*)S.d_est_pos.p, (const int4*)S.d_meta.p, (const float4*)S.d_dep.p,
+                                                                               (const float2*)S.d_os.p, (const double*)S.d_est_P.p,
+                                                                               (l3d_match*)S.d_est_out_best.p, (double*)S.d_est_out_P.p);
+            c->launches += 3;
+            L3D_CUDA(c, cudaGetLastError(), "k_collect_estimates");
+        }
+        L3D_CUDA(c, cudaStreamSynchronize(st), "score sweep");
+    }
     S.valid = true;
     return L3D_OK;
 }
@@ -397,44 +453,19 @@ long long l3d_get_view_matches(l3d_ctx* c, int view, int kept_only, l3d_match* o
     return n;
 }
 
-// best-match 3D estimates (estimated_position3D_, line3D.cc:1635-1647) in processing order (view, segment).
+// best-match 3D estimates (estimated_position3D_, line3D.cc:1635-1647), compacted on the device by k_collect_estimates
+// at the end of the sweep, in global segment order (view index, segment).
 long long l3d_get_estimates(l3d_ctx* c, l3d_match* best_out, double* p1p2_out, long long cap)
 {
     if (!c) return L3D_ERR_INVALID;
     if (!c->sweep.valid) return l3d_fail(c, L3D_ERR_STATE, "l3d_get_estimates: call l3d_score_sweep first");
     cudaSetDevice(c->device);
     SweepState& S = c->sweep;
-    const long long N = c->total_segs;
-    std::vector<int> best(N); std::vector<double> P(6 * (size_t)N);
-    L3D_CUDA(c, cudaMemcpyAsync(best.data(), S.d_est_best.p, 4 * (size_t)N, cudaMemcpyDeviceToHost, c->stream), "download");
-    L3D_CUDA(c, cudaMemcpyAsync(P.data(), S.d_est_P.p, 48 * (size_t)N, cudaMemcpyDeviceToHost, c->stream), "download");
+    const long long n = S.n_est;
+    if (n == 0 || n > cap) return n;
+    if (best_out) L3D_CUDA(c, cudaMemcpyAsync(best_out, S.d_est_out_best.p, sizeof(l3d_match) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "download estimates");
+    if (p1p2_out) L3D_CUDA(c, cudaMemcpyAsync(p1p2_out, S.d_est_out_P.p, 48 * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "download estimates");
     L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync");
-    long long n = 0;
-    for (int i = 0; i < c->num_views; ++i) {
-        const int v = S.order[i];
-        const L3DViewDev& V = c->h_views[v];
-        std::vector<int4> meta; std::vector<float4> dep; std::vector<float2> os;
-        bool loaded = false;
-        for (int s = 0; s < V.nseg; ++s) {
-            const int b = best[V.seg_off + s];
-            if (b < 0) continue;
-            if (best_out && n < cap) {
-                if (!loaded) {
-                    const int M = S.h_M[i]; const long long ro = S.region_off[i];
-                    meta.resize(M); dep.resize(M); os.resize(M);
-                    cudaMemcpy(meta.data(), (int4*)S.d_meta.p + ro, 16 * (size_t)M, cudaMemcpyDeviceToHost);
-                    cudaMemcpy(dep.data(), (float4*)S.d_dep.p + ro, 16 * (size_t)M, cudaMemcpyDeviceToHost);
-                    cudaMemcpy(os.data(), (float2*)S.d_os.p + ro, 8 * (size_t)M, cudaMemcpyDeviceToHost);
-                    loaded = true;
-                }
-                l3d_match& m = best_out[n];
-                m.src_cam = V.cam_id; m.src_seg = (uint32_t)s; m.tgt_cam = c->h_views[meta[b].y].cam_id; m.tgt_seg = (uint32_t)meta[b].z;
-                m.overlap = os[b].x; m.score3D = os[b].y; m.d_p1 = dep[b].x; m.d_p2 = dep[b].y; m.d_q1 = dep[b].z; m.d_q2 = dep[b].w;
-            }
-            if (p1p2_out && n < cap) memcpy(p1p2_out + 6 * n, &P[6 * (size_t)(V.seg_off + s)], 48);
-            ++n;
-        }
-    }
     return n;
 }
 
