@@ -153,7 +153,7 @@ k_build(const float4* __restrict__ segs, const float4* __restrict__ cache, const
 __global__ void __launch_bounds__(128)
 k_score(const L3DViewDev* __restrict__ views, int v, const int* __restrict__ Mcount, const int4* __restrict__ m_meta,
         const float4* __restrict__ m_dep, const float2* __restrict__ m_reg, const float4* __restrict__ m_dir,
-        const int2* __restrict__ ranges, float angle_reg, float sim_t, float2* __restrict__ m_os)
+        const int2* __restrict__ ranges, float angle_reg, float sim_t, float q_thr, float cos_thr, float2* __restrict__ m_os)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= *Mcount) return;
@@ -178,15 +178,24 @@ k_score(const L3DViewDev* __restrict__ views, int v, const int* __restrict__ Mco
         if (tgt_cam_src != tgt_cam_tgt) {
             const float4 d2 = m_dep[i];
             const float4 dt = m_dir[i];
-            // D_undirected_angle_3D_DEG (cudawrapper.cu:46-53): float acos, DOUBLE divide by pi, times 180, back to float
-            float dp = dir_src.x * dt.x + dir_src.y * dt.y + dir_src.z * dt.z;
-            float angle = (float)((double)acosf(fmaxf(fminf(dp, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
-            if (angle > 90.0f) angle = 180.0f - angle;
-            float sim_a = expf(-angle * angle / angle_reg);
-            float e1 = d1_src - d2.x, e2 = d2_src - d2.y;
-            float sim_p1 = expf(-e1 * e1 / pos_reg1), sim_p2 = expf(-e2 * e2 / pos_reg2);
-            float sim = fminf(sim_a, fminf(sim_p1, sim_p2));
-            if (sim < sim_t) sim = 0.0f;
+            const float dp = dir_src.x * dt.x + dir_src.y * dt.y + dir_src.z * dt.z;
+            const float e1 = d1_src - d2.x, e2 = d2_src - d2.y;
+            float sim;
+            // Exact shortcut: sim = min(three terms), then truncated to 0 below sim_t.  If ONE term is certainly below
+            // sim_t the result is 0 whatever the others are (fminf ignores NaN).  exp(-q) < sim_t is certain when
+            // q > q_thr = 1.01 * -ln(sim_t) (1 % margin >> the rounding of the division and of expf), and the angular
+            // term is certainly below sim_t when |cos| < cos_thr (same margin on the angle).  Everything inside the
+            // margins takes the full, reference-order path.
+            if (e1 * e1 > q_thr * pos_reg1 || e2 * e2 > q_thr * pos_reg2 || fabsf(dp) < cos_thr) sim = 0.0f;
+            else {
+                // D_undirected_angle_3D_DEG (cudawrapper.cu:46-53): float acos, DOUBLE divide by pi, times 180, back to float
+                float angle = (float)((double)acosf(fmaxf(fminf(dp, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
+                if (angle > 90.0f) angle = 180.0f - angle;
+                float sim_a = expf(-angle * angle / angle_reg);
+                float sim_p1 = expf(-e1 * e1 / pos_reg1), sim_p2 = expf(-e2 * e2 / pos_reg2);
+                sim = fminf(sim_a, fminf(sim_p1, sim_p2));
+                if (sim < sim_t) sim = 0.0f;
+            }
             current_max_sim = fmaxf(current_max_sim, sim);
             if (current_cam != tgt_cam_tgt) { score3D += current_max_sim; current_max_sim = 0.0f; current_cam = tgt_cam_tgt; }
         }
@@ -337,6 +346,13 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     L3D_CUDA(c, cudaMemcpyAsync(S.d_viewofrank.p, view_of_rank.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "view of rank");
     L3D_CUDA(c, cudaStreamSynchronize(st), "sync");   // rank/view_of_rank are stack-scoped
 
+    // shortcut thresholds of k_score (see there); disabled (never true) when sim_t <= 0 or the margins do not apply
+    float q_thr = INFINITY, cos_thr = -1.0f;
+    if (min_similarity > 0.0f && min_similarity < 1.0f) {
+        q_thr = 1.01f * -std::log(min_similarity);
+        const double ang = std::sqrt((double)q_thr * (double)two_sigA_sqr);           // degrees
+        cos_thr = ang < 89.0 ? (float)(std::cos(ang * L3D_PI_D / 180.0) * (1.0 - 1e-4)) : -1.0f;
+    }
     const float4* segs = c->segs(); const float4* cache = (const float4*)c->d_cache.p;
     const L3DViewDev* views = c->views(); const L3DPairDev* pairs = (const L3DPairDev*)c->d_pairs.p;
     const int* counts = (const int*)c->d_counts.p; const l3d_match_rec* recs = (const l3d_match_rec*)c->d_recs.p;
@@ -369,7 +385,7 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
                                     (const unsigned int*)S.d_vals2.p, Mc, (const int*)S.d_viewofrank.p, m_meta, m_dep, m_os,
                                     (float2*)S.d_reg.p, (float4*)S.d_dir.p, ranges);
         k_score<<<(U + 127) / 128, 128, 0, st>>>(views, v, Mc, m_meta, m_dep, (const float2*)S.d_reg.p, (const float4*)S.d_dir.p, ranges,
-                                                two_sigA_sqr, min_similarity, m_os);
+                                                two_sigA_sqr, min_similarity, q_thr, cos_thr, m_os);
         k_post_score<<<nb, 256, 0, st>>>(Mc, m_meta, m_os, (float*)S.d_slot_score.p, vmax);
         k_filter<<<(nseg + 255) / 256, 256, 0, st>>>(segs, views, v, ranges, m_meta, m_dep, m_os, vmax, min_best_score, min_best_perc, kept,
                                                     (int*)S.d_est_best.p, (double*)S.d_est_P.p);
