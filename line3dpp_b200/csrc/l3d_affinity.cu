@@ -183,6 +183,76 @@ k_rdd_step(long long nnz, const int* __restrict__ prow, const int* __restrict__ 
     if (t >= 0) Pn[t] = mul;
 }
 
+// One diffusion iteration, fused with the row normalisation that follows it (cudawrapper.cu:739-756), HBM/L2-friendly:
+// a half-warp owns one row r of P'.  Lane k keeps P.row(r)[k]; for every entry t=(r,c) of the row the half-warp reads
+// the run W.col(c)[0..m) with ONE coalesced load, multiplies lane-wise, and parks the products in a padded shared tile;
+// lane t then adds its entry's products strictly in k order (the reference's sequential float sum), multiplies by the
+// transposed entry P(c,r), clamps, and the row sum / division again run in slot order.  Rows longer than 16 entries take
+// the scalar path with the same operation order.
+#define RDD_G 16
+__global__ void __launch_bounds__(256)
+k_rdd_iter(int n, const int* __restrict__ rowptr, const int* __restrict__ pcol, const int* __restrict__ colptr,
+           const int* __restrict__ tslot, const float* __restrict__ P, const float* __restrict__ W, float* __restrict__ Pn,
+           int normalize)
+{
+    __shared__ float tile[256 / RDD_G][RDD_G][RDD_G + 1];
+    const int hw = threadIdx.x / RDD_G, hl = threadIdx.x % RDD_G;
+    const int r = blockIdx.x * (256 / RDD_G) + hw;
+    const unsigned int hmask = 0xFFFFu << (16 * ((threadIdx.x >> 4) & 1));     // the 16 lanes of this half-warp
+    const int base = (threadIdx.x & 16);                                          // first lane of the half-warp inside the warp
+    if (r >= n) return;                                                           // whole half-warps leave together
+    const int s = rowptr[r], deg = rowptr[r + 1] - s;
+    if (deg == 0) return;
+    if (deg <= RDD_G) {
+        const bool mine = hl < deg;
+        const float p = mine ? P[s + hl] : 0.0f;
+        const int c_mine = mine ? pcol[s + hl] : 0;
+        const int cs_mine = mine ? colptr[c_mine] : 0;
+        const int m_mine = mine ? min(deg, colptr[c_mine + 1] - cs_mine) : 0;
+        const int ts = mine ? tslot[s + hl] : -1;
+        for (int t = 0; t < deg; ++t) {
+            const int cs = __shfl_sync(hmask, cs_mine, base + t), m = __shfl_sync(hmask, m_mine, base + t);
+            if (hl < m) tile[hw][t][hl] = p * W[cs + hl];
+        }
+        __syncwarp(hmask);
+        float v = 0.0f;
+        if (mine) {
+            float mul = 0.0f;
+            for (int k = 0; k < m_mine; ++k) mul += tile[hw][hl][k];
+            if (ts >= 0) {
+                mul *= P[ts];
+                if (mul < L3D_EPS_F) mul = L3D_EPS_F;
+                v = mul;
+            } else v = Pn[s + hl];                    // no transposed entry: the reference leaves this slot untouched
+        }
+        if (normalize) {
+            float sum = 0.0f;
+            for (int t = 0; t < deg; ++t) sum += __shfl_sync(hmask, v, base + t);
+            if (sum < L3D_EPS_F) sum = L3D_EPS_F;
+            v /= sum;
+        }
+        if (mine) Pn[s + hl] = v;
+    } else {
+        // long row: lane handles entries hl, hl+16, ... with the scalar lock-step walk
+        for (int t = hl; t < deg; t += RDD_G) {
+            const int c = pcol[s + t];
+            int sp = s, sw = colptr[c];
+            const int ew = colptr[c + 1];
+            float mul = 0.0f;
+            while (sp < s + deg && sw < ew) { mul += P[sp] * W[sw]; ++sp; ++sw; }
+            const int ts = tslot[s + t];
+            if (ts >= 0) { mul *= P[ts]; if (mul < L3D_EPS_F) mul = L3D_EPS_F; Pn[s + t] = mul; }
+        }
+        __syncwarp(hmask);
+        if (normalize) {
+            float sum = 0.0f;
+            if (hl == 0) { for (int t = 0; t < deg; ++t) sum += Pn[s + t]; if (sum < L3D_EPS_F) sum = L3D_EPS_F; }
+            sum = __shfl_sync(hmask, sum, base);
+            for (int t = hl; t < deg; t += RDD_G) Pn[s + t] /= sum;
+        }
+    }
+}
+
 extern "C" {
 
 // Affinity edges between segments with 3D estimates, in the reference's emission order (estimate order, then match
@@ -292,12 +362,12 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     float* P = (float*)R.d_P.p; float* Pn = (float*)R.d_Pn.p;
     for (int it = 0; it < iters; ++it) {
-        k_rdd_step<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_colptr.p, P, (const float*)R.d_W.p, (const int*)R.d_tslot.p, Pn);
+        k_rdd_iter<<<(unsigned int)((n + 256 / RDD_G - 1) / (256 / RDD_G)), 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_pcol.p, (const int*)R.d_colptr.p,
+                                                                                           (const int*)R.d_tslot.p, P, (const float*)R.d_W.p, Pn, it < iters - 1 ? 1 : 0);
         std::swap(P, Pn);
-        if (it < iters - 1) k_rdd_normalize<<<nbr, 128, 0, st>>>(n, (const int*)R.d_rowptr.p, P);
     }
     if (kernel_ms) cudaEventRecord(e1, st);
-    c->launches += 9 + 16 + 2 * iters;
+    c->launches += 9 + 16 + iters;
     L3D_CUDA(c, cudaGetLastError(), "rdd kernels");
     L3D_CUDA(c, cudaMemcpyAsync(out_w, P, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
     L3D_CUDA(c, cudaMemcpyAsync(out_i, R.d_prow.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");

@@ -392,7 +392,10 @@ long long orc_match_lines_f32(const float* lines_src, int Ns, const float* lines
 #pragma omp parallel for num_threads(g_threads) schedule(dynamic, 16) reduction(+ : total)
     for (int r = 0; r < Ns; ++r) {
         f4 ls = {lines_src[4 * r], lines_src[4 * r + 1], lines_src[4 * r + 2], lines_src[4 * r + 3]};
-        knn_queue q;
+        // storage reserved up front: letting the vector grow inside the parallel loop (as the reference's per-row
+        // pairwise_matches does) serialises the threads on malloc and would understate the CPU baseline
+        std::vector<orc_match_t> q_store; q_store.reserve(1024);
+        knn_queue q(MatchKNN(), std::move(q_store));
         int n_new = 0;
         for (int c = 0; c < Nt; ++c) {
             f4 lt = {lines_tgt[4 * c], lines_tgt[4 * c + 1], lines_tgt[4 * c + 2], lines_tgt[4 * c + 3]};
@@ -440,7 +443,10 @@ long long orc_match_lines_f64(const float* lines_src, int Ns, const float* lines
         int n_new = 0;
         V3 p1 = V(lines_src[4 * r], lines_src[4 * r + 1], 1.0), p2 = V(lines_src[4 * r + 2], lines_src[4 * r + 3], 1.0);
         V3 epi_p1 = mul(F, p1), epi_p2 = mul(F, p2);
-        knn_queue q;
+        // storage reserved up front: letting the vector grow inside the parallel loop (as the reference's per-row
+        // pairwise_matches does) serialises the threads on malloc and would understate the CPU baseline
+        std::vector<orc_match_t> q_store; q_store.reserve(1024);
+        knn_queue q(MatchKNN(), std::move(q_store));
         for (int c = 0; c < Nt; ++c) {
             V3 q1 = V(lines_tgt[4 * c], lines_tgt[4 * c + 1], 1.0), q2 = V(lines_tgt[4 * c + 2], lines_tgt[4 * c + 3], 1.0);
             V3 l2 = crossd(q1, q2);
