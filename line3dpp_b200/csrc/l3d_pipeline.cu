@@ -60,6 +60,11 @@ __device__ __forceinline__ DSeg dunproject(const L3DViewDev* v, float4 s, float 
     return o;
 }
 
+// sort key of a candidate match: (segment | rank of the target camera | target segment), packed as tightly as the
+// problem allows so that the radix sort touches few bits; bit `end_bit-1` is reserved for "invalid" (all ones)
+struct KeyBits { int seg_shift, cam_shift, end_bit; unsigned long long cam_mask, tgt_mask; };
+static int bits_for(long long n) { int b = 1; while ((1ll << b) < n) ++b; return b; }
+
 // ---------------------------------------------------------------------------------------------- kernels
 // G1: enumerate the candidate matches of view v (direct records of pairs with src == v, inverse records of pairs with
 //     tgt == v whose src was processed earlier and scored them > 0), apply the orientation check, emit sort keys.
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(256)
 k_gather(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
          const int* __restrict__ counts, const l3d_match_rec* __restrict__ recs, const float* __restrict__ slot_score,
          const int4* __restrict__ work, int nwork, int v, int knn, const int* __restrict__ cam_rank,
-         unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals, int U, int* __restrict__ Mcount)
+         unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals, int U, int* __restrict__ Mcount, KeyBits kb)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
@@ -97,7 +102,7 @@ k_gather(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, 
                 double ang = acos(fmin(fmax(ddot(r1, S3.dir), -1.0), 1.0));
                 if (ang > (double)L3D_PI_1_32_F && ang < (double)L3D_PI_31_32_F) {
                     valid = true;
-                    key = ((unsigned long long)seg << 40) | ((unsigned long long)cam_rank[tgt_view] << 24) | (unsigned long long)tgt_seg;
+                    key = ((unsigned long long)seg << kb.seg_shift) | ((unsigned long long)cam_rank[tgt_view] << kb.cam_shift) | (unsigned long long)tgt_seg;
                     val = (unsigned int)g | (wk.y ? 0x80000000u : 0u);
                 }
             }
@@ -115,13 +120,13 @@ k_build(const float4* __restrict__ segs, const float4* __restrict__ cache, const
         int v, int knn, const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals,
         const int* __restrict__ Mcount, const int* __restrict__ view_of_camrank,
         int4* __restrict__ m_meta, float4* __restrict__ m_dep, float2* __restrict__ m_os, float2* __restrict__ m_reg,
-        float4* __restrict__ m_dir, int2* __restrict__ ranges)
+        float4* __restrict__ m_dir, int2* __restrict__ ranges, KeyBits kb)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int M = *Mcount;
     if (x >= M) return;
     const unsigned long long key = keys[x];
-    const int seg = (int)(key >> 40), tgt_view = view_of_camrank[(int)((key >> 24) & 0xFFFFull)], tgt_seg = (int)(key & 0xFFFFFFull);
+    const int seg = (int)(key >> kb.seg_shift), tgt_view = view_of_camrank[(int)((key >> kb.cam_shift) & kb.cam_mask)], tgt_seg = (int)(key & kb.tgt_mask);
     const unsigned int val = vals[x];
     const bool inv = (val & 0x80000000u) != 0u;
     const l3d_match_rec rec = recs[val & 0x7FFFFFFFu];
@@ -145,8 +150,8 @@ k_build(const float4* __restrict__ segs, const float4* __restrict__ cache, const
         float3 dir = normalize3(make_float3(P2.x - P1.x, P2.y - P1.y, P2.z - P1.z));
         m_dir[x] = make_float4(dir.x, dir.y, dir.z, 0.f);
     }
-    if (x == 0 || (int)(keys[x - 1] >> 40) != seg) ranges[seg].x = x;
-    if (x == M - 1 || (int)(keys[x + 1] >> 40) != seg) ranges[seg].y = x;
+    if (x == 0 || (int)(keys[x - 1] >> kb.seg_shift) != seg) ranges[seg].x = x;
+    if (x == M - 1 || (int)(keys[x + 1] >> kb.seg_shift) != seg) ranges[seg].y = x;
 }
 
 // G3: K_score_matches (cudawrapper.cu:256-367), one thread per match, same operation order.
@@ -321,6 +326,13 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
         nseg_max = std::max(nseg_max, c->h_views[v].nseg);
     }
     S.region_off[V] = total; S.total = total;
+    KeyBits kb;
+    {
+        const int bt = bits_for(nseg_max), bc = bits_for(V);
+        kb.cam_shift = bt; kb.seg_shift = bt + bc; kb.end_bit = bt + bc + bt + 1;
+        kb.cam_mask = (1ull << bc) - 1ull; kb.tgt_mask = (1ull << bt) - 1ull;
+        if (kb.end_bit > 64) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: views x segments too large for a 64-bit sort key");
+    }
     if (Umax >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: view with more than 2^31 candidates");
 
     int rc;
@@ -334,7 +346,7 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     RES(S.d_M, 4 * (size_t)V, "match counts"); RES(S.d_vmax, 4 * (size_t)V, "view max"); RES(S.d_work, 16 * (size_t)wmax, "work items");
     RES(S.d_camrank, 4 * (size_t)V, "cam rank"); RES(S.d_viewofrank, 4 * (size_t)V, "view of rank");
     size_t sort_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)Umax, 0, 64, c->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)Umax, 0, kb.end_bit, c->stream);
     RES(S.d_sort_tmp, sort_bytes, "sort temp");
 #undef RES
     cudaStream_t st = c->stream;
@@ -377,13 +389,13 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
         const int nb = (U + 255) / 256;
         k_gather<<<nb, 256, 0, st>>>(segs, views, pairs, counts, recs, (const float*)S.d_slot_score.p, (const int4*)S.d_work.p + work_off[i],
                                      work_off[i + 1] - work_off[i], v, knn, (const int*)S.d_camrank.p, (unsigned long long*)S.d_keys.p,
-                                     (unsigned int*)S.d_vals.p, U, Mc);
+                                     (unsigned int*)S.d_vals.p, U, Mc, kb);
         size_t tb = S.d_sort_tmp.cap;
         cub::DeviceRadixSort::SortPairs(S.d_sort_tmp.p, tb, (const unsigned long long*)S.d_keys.p, (unsigned long long*)S.d_keys2.p,
-                                        (const unsigned int*)S.d_vals.p, (unsigned int*)S.d_vals2.p, U, 0, 64, st);
+                                        (const unsigned int*)S.d_vals.p, (unsigned int*)S.d_vals2.p, U, 0, kb.end_bit, st);
         k_build<<<nb, 256, 0, st>>>(segs, cache, views, pairs, recs, v, knn, (const unsigned long long*)S.d_keys2.p,
                                     (const unsigned int*)S.d_vals2.p, Mc, (const int*)S.d_viewofrank.p, m_meta, m_dep, m_os,
-                                    (float2*)S.d_reg.p, (float4*)S.d_dir.p, ranges);
+                                    (float2*)S.d_reg.p, (float4*)S.d_dir.p, ranges, kb);
         k_score<<<(U + 127) / 128, 128, 0, st>>>(views, v, Mc, m_meta, m_dep, (const float2*)S.d_reg.p, (const float4*)S.d_dir.p, ranges,
                                                 two_sigA_sqr, min_similarity, q_thr, cos_thr, m_os);
         k_post_score<<<nb, 256, 0, st>>>(Mc, m_meta, m_os, (float*)S.d_slot_score.p, vmax);

@@ -143,3 +143,36 @@ def test_filter_never_drops_at_scale(gpu_ctx, oracle):
         d2, o2 = gpu_ctx.match_dense(s, t, F, 0.25, 2000, 2000, nofilter=True)
         assert np.array_equal(util.bits(o1), util.bits(o2))
         assert np.array_equal(util.bits(d1), util.bits(d2))
+
+
+def test_sharded_matching_equals_unsharded(gpu_ctx):
+    """pair sharding (what N ranks do) does not change a single bit: match the full pair list at once, then the two
+    rank shards separately, and compare every record."""
+    from line3dpp_b200 import shard
+    sc = synth.make_scene(12, 300, 13, "ring3")
+    gpu_ctx.set_views(util.scene_descs(sc), sc.segs)
+    pairs = synth.view_pairs(sc.neighbors)
+    F = util.pair_F(sc, pairs)
+    gpu_ctx.match_pairs(pairs, F, 0.25, 10)
+    row_ptr, recs = gpu_ctx.matches_csr()
+    full = {}
+    off = 0
+    for p, (s, t) in enumerate(pairs):
+        n = len(sc.segs[s])
+        full[(int(s), int(t))] = (np.diff(row_ptr[off:off + n + 1]).copy(), recs[row_ptr[off]:row_ptr[off + n]].copy())
+        off += n
+    seen = 0
+    for rank in range(2):
+        mine = shard.rank_pairs(pairs, rank, 2, sc.num_views)
+        sel = np.array([i for i, pr in enumerate(pairs.tolist()) if pr in mine.tolist()])
+        gpu_ctx.match_pairs(mine, F[sel], 0.25, 10)
+        rp, rc = gpu_ctx.matches_csr()
+        off = 0
+        for (s, t) in mine:
+            n = len(sc.segs[s])
+            cnt, rr = full[(int(s), int(t))]
+            assert np.array_equal(np.diff(rp[off:off + n + 1]), cnt)
+            assert np.array_equal(rc[rp[off]:rp[off + n]], rr)
+            off += n
+            seen += 1
+    assert seen == len(pairs)
