@@ -133,6 +133,16 @@ long long l3d_get_estimates(l3d_ctx* ctx, l3d_match* best_out, double* p1p2_out,
 long long l3d_affinity_edges(l3d_ctx* ctx, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity,
                              long long* out_gi, long long* out_gj, float* out_w, long long cap);
 
+/* The complete affinity matrix on the device: the candidates of l3d_affinity_edges, then the reference's "unused" pair
+ * filter (line3D.cc:1982-2002: only the first candidate of an unordered segment pair, in emission order) and first-come
+ * local ids (line3D.cc:2005-2023), reproduced with stable sorts and atomic minima instead of mutex-protected maps.
+ * out_i/out_j/out_w: the CLEdge list A_ in the reference's order ((id1,id2,w),(id2,id1,w) per accepted edge);
+ * out_local2global[id] = global segment index.  Returns the number of list entries (even if the capacities are too
+ * small; then nothing is copied) and sets *num_ids. */
+long long l3d_affinity_matrix(l3d_ctx* ctx, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity, int* out_i,
+                              int* out_j, float* out_w, long long cap_edges, long long* out_local2global, long long cap_ids,
+                              long long* num_ids);
+
 /* ---- diffusion: replaces replicator_dynamics_diffusion_GPU (cudawrapper.h:80, cudawrapper.cu:708-766) incl. the
  * SparseMatrix construction it needs (sparsematrix.cc:8-135).  Input: the CLEdge list A_ (clustering.h:47-51) as three
  * arrays and the number of rows n; iters = L3D_DEF_RDD_MAX_ITER (10).  Output: the diffused matrix as row-sorted COO

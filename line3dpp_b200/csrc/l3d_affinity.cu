@@ -189,21 +189,21 @@ k_rdd_step(long long nnz, const int* __restrict__ prow, const int* __restrict__ 
 // lane t then adds its entry's products strictly in k order (the reference's sequential float sum), multiplies by the
 // transposed entry P(c,r), clamps, and the row sum / division again run in slot order.  Rows longer than 16 entries take
 // the scalar path with the same operation order.
-#define RDD_G 16
+template <int G>
 __global__ void __launch_bounds__(256)
 k_rdd_iter(int n, const int* __restrict__ rowptr, const int* __restrict__ pcol, const int* __restrict__ colptr,
            const int* __restrict__ tslot, const float* __restrict__ P, const float* __restrict__ W, float* __restrict__ Pn,
            int normalize)
 {
-    __shared__ float tile[256 / RDD_G][RDD_G][RDD_G + 1];
-    const int hw = threadIdx.x / RDD_G, hl = threadIdx.x % RDD_G;
-    const int r = blockIdx.x * (256 / RDD_G) + hw;
-    const unsigned int hmask = 0xFFFFu << (16 * ((threadIdx.x >> 4) & 1));     // the 16 lanes of this half-warp
-    const int base = (threadIdx.x & 16);                                          // first lane of the half-warp inside the warp
-    if (r >= n) return;                                                           // whole half-warps leave together
+    __shared__ float tile[256 / G][G][G + 1];
+    const int hw = threadIdx.x / G, hl = threadIdx.x % G;
+    const int r = blockIdx.x * (256 / G) + hw;
+    const int base = (threadIdx.x & 31) - hl;                                     // first lane of this group inside the warp
+    const unsigned int hmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << base);
+    if (r >= n) return;                                                           // whole groups leave together
     const int s = rowptr[r], deg = rowptr[r + 1] - s;
     if (deg == 0) return;
-    if (deg <= RDD_G) {
+    if (deg <= G) {
         const bool mine = hl < deg;
         const float p = mine ? P[s + hl] : 0.0f;
         const int c_mine = mine ? pcol[s + hl] : 0;
@@ -233,8 +233,8 @@ k_rdd_iter(int n, const int* __restrict__ rowptr, const int* __restrict__ pcol, 
         }
         if (mine) Pn[s + hl] = v;
     } else {
-        // long row: lane handles entries hl, hl+16, ... with the scalar lock-step walk
-        for (int t = hl; t < deg; t += RDD_G) {
+        // long row: lane handles entries hl, hl+G, ... with the scalar lock-step walk
+        for (int t = hl; t < deg; t += G) {
             const int c = pcol[s + t];
             int sp = s, sw = colptr[c];
             const int ew = colptr[c + 1];
@@ -248,22 +248,71 @@ k_rdd_iter(int n, const int* __restrict__ rowptr, const int* __restrict__ pcol, 
             float sum = 0.0f;
             if (hl == 0) { for (int t = 0; t < deg; ++t) sum += Pn[s + t]; if (sum < L3D_EPS_F) sum = L3D_EPS_F; }
             sum = __shfl_sync(hmask, sum, base);
-            for (int t = hl; t < deg; t += RDD_G) Pn[s + t] /= sum;
+            for (int t = hl; t < deg; t += G) Pn[s + t] /= sum;
         }
     }
 }
 
+// ---- affinity matrix bookkeeping on the device (see l3d_affinity_matrix) ----------------------------------------
+static int bits_i64(long long n) { int b = 1; while ((1ll << b) < n) ++b; return b; }
+__global__ void __launch_bounds__(256) k_aff_keys(long long ne, const long long* __restrict__ gi, const long long* __restrict__ gj,
+                                                  unsigned long long* __restrict__ key, unsigned int* __restrict__ val)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const unsigned long long a = (unsigned long long)min(gi[e], gj[e]), b = (unsigned long long)max(gi[e], gj[e]);
+    key[e] = (a << 32) | b; val[e] = (unsigned int)e;
+}
+__global__ void __launch_bounds__(256) k_aff_first(long long ne, const unsigned long long* __restrict__ key, const unsigned int* __restrict__ val, int* __restrict__ keep)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    if (e == 0 || key[e - 1] != key[e]) keep[val[e]] = 1;      // stable sort: the head of a run is the first in emission order
+}
+__global__ void __launch_bounds__(256) k_aff_time(long long ne, const int* __restrict__ keep, const long long* __restrict__ q, const long long* __restrict__ gi,
+                                                  const long long* __restrict__ gj, unsigned long long* __restrict__ time)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne || !keep[e]) return;
+    atomicMin(time + gi[e], 2ull * (unsigned long long)q[e]);          // id1 is looked up before id2 (line3D.cc:1884-1887)
+    atomicMin(time + gj[e], 2ull * (unsigned long long)q[e] + 1ull);
+}
+__global__ void __launch_bounds__(256) k_aff_nodeflags(long long N, const unsigned long long* __restrict__ time, int* __restrict__ flag)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < N) flag[g] = time[g] != ~0ull;
+}
+__global__ void __launch_bounds__(256) k_aff_nodes(long long N, const int* __restrict__ flag, const long long* __restrict__ pos, const unsigned long long* __restrict__ time,
+                                                   unsigned long long* __restrict__ key, unsigned int* __restrict__ val)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N || !flag[g]) return;
+    key[pos[g]] = time[g]; val[pos[g]] = (unsigned int)g;
+}
+__global__ void __launch_bounds__(256) k_aff_ids(long long n, const unsigned int* __restrict__ seg_sorted, int* __restrict__ id_of, long long* __restrict__ l2g)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    id_of[seg_sorted[i]] = (int)i; l2g[i] = (long long)seg_sorted[i];
+}
+__global__ void __launch_bounds__(256) k_aff_emit(long long ne, const int* __restrict__ keep, const long long* __restrict__ q, const long long* __restrict__ gi,
+                                                  const long long* __restrict__ gj, const float* __restrict__ w, const int* __restrict__ id_of,
+                                                  int* __restrict__ ei, int* __restrict__ ej, float* __restrict__ ew)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne || !keep[e]) return;
+    const long long o = 2 * q[e];
+    const int a = id_of[gi[e]], b = id_of[gj[e]];
+    ei[o] = a; ej[o] = b; ew[o] = w[e];
+    ei[o + 1] = b; ej[o + 1] = a; ew[o + 1] = w[e];
+}
+
 extern "C" {
 
-// Affinity edges between segments with 3D estimates, in the reference's emission order (estimate order, then match
-// list order), BEFORE the "unused" de-duplication and local-id assignment (host side, line3D.cc:1881-1900).
-// out_gi/out_gj are GLOBAL segment indices (view seg offset + seg id in l3d_set_views order).  Returns the count.
-long long l3d_affinity_edges(l3d_ctx* c, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity,
-                             long long* out_gi, long long* out_gj, float* out_w, long long cap)
+// device part shared by l3d_affinity_edges / l3d_affinity_matrix: similarities of all kept matches, then the candidates with
+// sim > min_affinity compacted IN EMISSION ORDER into S.d_aff_oi / oj / ow.  Returns their number (or < 0).
+static long long affinity_candidates(l3d_ctx* c, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity)
 {
-    if (!c) return L3D_ERR_INVALID;
-    if (!c->sweep.valid) return l3d_fail(c, L3D_ERR_STATE, "l3d_affinity_edges: call l3d_score_sweep first");
-    cudaSetDevice(c->device);
     SweepState& S = c->sweep;
     const long long total = S.total;
     if (total == 0) return 0;
@@ -300,7 +349,7 @@ long long l3d_affinity_edges(l3d_ctx* c, float two_sigA_sqr, float med_scene_dep
     L3D_CUDA(c, cudaStreamSynchronize(st), "affinity");
     const long long ne = last_pos + last_flag;
     c->launches += 3;
-    if (ne == 0 || !out_gi || ne > cap) return ne;
+    if (ne == 0) return 0;
     DevBuf &o_i = S.d_aff_oi, &o_j = S.d_aff_oj, &o_w = S.d_aff_ow;
     if ((rc = l3d_reserve(c, o_i, 8 * (size_t)ne, "edges i"))) return rc;
     if ((rc = l3d_reserve(c, o_j, 8 * (size_t)ne, "edges j"))) return rc;
@@ -308,11 +357,109 @@ long long l3d_affinity_edges(l3d_ctx* c, float two_sigA_sqr, float med_scene_dep
     k_affinity_compact<<<nb, 256, 0, st>>>(total, (const int*)d_flag.p, (const long long*)d_pos.p, (const float*)d_sim.p, (const long long*)d_gi.p,
                                            (const long long*)d_gj.p, (long long*)o_i.p, (long long*)o_j.p, (float*)o_w.p);
     ++c->launches;
-    L3D_CUDA(c, cudaMemcpyAsync(out_gi, o_i.p, 8 * (size_t)ne, cudaMemcpyDeviceToHost, st), "download edges");
-    L3D_CUDA(c, cudaMemcpyAsync(out_gj, o_j.p, 8 * (size_t)ne, cudaMemcpyDeviceToHost, st), "download edges");
-    L3D_CUDA(c, cudaMemcpyAsync(out_w, o_w.p, 4 * (size_t)ne, cudaMemcpyDeviceToHost, st), "download edges");
+    L3D_CUDA(c, cudaGetLastError(), "k_affinity_compact");
+    return ne;
+}
+
+// Affinity edges between segments with 3D estimates, in the reference's emission order (estimate order, then match
+// list order), BEFORE the "unused" de-duplication and local-id assignment (line3D.cc:1881-1900).
+// out_gi/out_gj are GLOBAL segment indices (view seg offset + seg id in l3d_set_views order).  Returns the count.
+long long l3d_affinity_edges(l3d_ctx* c, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity,
+                             long long* out_gi, long long* out_gj, float* out_w, long long cap)
+{
+    if (!c) return L3D_ERR_INVALID;
+    if (!c->sweep.valid) return l3d_fail(c, L3D_ERR_STATE, "l3d_affinity_edges: call l3d_score_sweep first");
+    cudaSetDevice(c->device);
+    SweepState& S = c->sweep;
+    const long long ne = affinity_candidates(c, two_sigA_sqr, med_scene_depth_lines, min_affinity);
+    if (ne <= 0 || !out_gi || ne > cap) return ne;
+    cudaStream_t st = c->stream;
+    L3D_CUDA(c, cudaMemcpyAsync(out_gi, S.d_aff_oi.p, 8 * (size_t)ne, cudaMemcpyDeviceToHost, st), "download edges");
+    L3D_CUDA(c, cudaMemcpyAsync(out_gj, S.d_aff_oj.p, 8 * (size_t)ne, cudaMemcpyDeviceToHost, st), "download edges");
+    L3D_CUDA(c, cudaMemcpyAsync(out_w, S.d_aff_ow.p, 4 * (size_t)ne, cudaMemcpyDeviceToHost, st), "download edges");
     L3D_CUDA(c, cudaStreamSynchronize(st), "affinity download");
     return ne;
+}
+
+// The complete affinity matrix A_ of computingAffinityMatrix (line3D.cc:1852-1979) built on the device: candidates as
+// above, then the reference's bookkeeping reproduced with sorts instead of mutex-protected maps:
+//   unused(i,j)   (line3D.cc:1982-2002): of all candidates of an unordered segment pair only the FIRST in emission order
+//                 survives                      -> stable radix sort by pair key, keep the head of every run;
+//   getLocalID    (line3D.cc:2005-2023): ids in order of first appearance (source of an accepted edge before its target)
+//                                               -> atomicMin of the appearance time per segment, sort segments by it.
+// Output: the CLEdge list in the reference's order, (id1,id2,w),(id2,id1,w) per accepted edge, and local2global as
+// global segment indices.  Returns the number of list entries (2 per edge), even if > cap_edges (then nothing is copied).
+long long l3d_affinity_matrix(l3d_ctx* c, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity, int* out_i, int* out_j,
+                              float* out_w, long long cap_edges, long long* out_local2global, long long cap_ids, long long* num_ids)
+{
+    if (!c || !num_ids) return L3D_ERR_INVALID;
+    if (!c->sweep.valid) return l3d_fail(c, L3D_ERR_STATE, "l3d_affinity_matrix: call l3d_score_sweep first");
+    cudaSetDevice(c->device);
+    SweepState& S = c->sweep;
+    AffinityState& A = c->aff;
+    cudaStream_t st = c->stream;
+    int rc;
+    if (!A.valid || A.two_sigA_sqr != two_sigA_sqr || A.med != med_scene_depth_lines || A.min_aff != min_affinity) {
+        A.valid = false;
+        const long long ne = affinity_candidates(c, two_sigA_sqr, med_scene_depth_lines, min_affinity);
+        if (ne < 0) return ne;
+        A.K = 0; A.n_ids = 0;
+        if (ne > 0) {
+            if (ne >= (1ll << 32) || c->total_segs >= (1ll << 32)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_affinity_matrix: more than 2^32 candidates / segments");
+            const long long N = c->total_segs;
+#define RES(buf, bytes, what) if ((rc = l3d_reserve(c, buf, (size_t)std::max<long long>((long long)(bytes), 16), what))) return rc
+            RES(A.d_key, 8 * ne, "pair keys"); RES(A.d_key2, 8 * ne, "pair keys"); RES(A.d_val, 4 * ne, "pair vals"); RES(A.d_val2, 4 * ne, "pair vals");
+            RES(A.d_keep, 4 * ne, "keep flags"); RES(A.d_q, 8 * (ne + 1), "edge positions"); RES(A.d_time, 8 * N, "appearance times");
+            RES(A.d_nflag, 4 * N, "node flags"); RES(A.d_npos, 8 * (N + 1), "node positions"); RES(A.d_idof, 4 * N, "id of segment");
+            const int bseg = bits_i64(N);
+            size_t tb1 = 0, tb2 = 0, tb3 = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb1, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)ne, 0, 32 + bseg, st);
+            cub::DeviceScan::ExclusiveSum(nullptr, tb2, (const int*)nullptr, (long long*)nullptr, std::max(ne, N), st);
+            cub::DeviceRadixSort::SortPairs(nullptr, tb3, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)std::min<long long>(N, 2 * ne), 0, 64, st);
+            RES(S.d_sort_tmp, std::max(tb1, std::max(tb2, tb3)), "sort temp");
+            const unsigned int nbe = (unsigned int)((ne + 255) / 256), nbn = (unsigned int)((N + 255) / 256);
+            k_aff_keys<<<nbe, 256, 0, st>>>(ne, (const long long*)S.d_aff_oi.p, (const long long*)S.d_aff_oj.p, (unsigned long long*)A.d_key.p, (unsigned int*)A.d_val.p);
+            size_t tb = S.d_sort_tmp.cap;
+            cub::DeviceRadixSort::SortPairs(S.d_sort_tmp.p, tb, (const unsigned long long*)A.d_key.p, (unsigned long long*)A.d_key2.p, (const unsigned int*)A.d_val.p, (unsigned int*)A.d_val2.p, (int)ne, 0, 32 + bseg, st);
+            L3D_CUDA(c, cudaMemsetAsync(A.d_keep.p, 0, 4 * ne, st), "clear keep");
+            k_aff_first<<<nbe, 256, 0, st>>>(ne, (const unsigned long long*)A.d_key2.p, (const unsigned int*)A.d_val2.p, (int*)A.d_keep.p);
+            tb = S.d_sort_tmp.cap;
+            cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tb, (const int*)A.d_keep.p, (long long*)A.d_q.p, ne, st);
+            L3D_CUDA(c, cudaMemsetAsync(A.d_time.p, 0xFF, 8 * N, st), "init times");
+            k_aff_time<<<nbe, 256, 0, st>>>(ne, (const int*)A.d_keep.p, (const long long*)A.d_q.p, (const long long*)S.d_aff_oi.p, (const long long*)S.d_aff_oj.p, (unsigned long long*)A.d_time.p);
+            k_aff_nodeflags<<<nbn, 256, 0, st>>>(N, (const unsigned long long*)A.d_time.p, (int*)A.d_nflag.p);
+            tb = S.d_sort_tmp.cap;
+            cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tb, (const int*)A.d_nflag.p, (long long*)A.d_npos.p, N, st);
+            long long lq = 0, lp = 0; int lk = 0, lf = 0;
+            L3D_CUDA(c, cudaMemcpyAsync(&lq, (long long*)A.d_q.p + ne - 1, 8, cudaMemcpyDeviceToHost, st), "count");
+            L3D_CUDA(c, cudaMemcpyAsync(&lk, (int*)A.d_keep.p + ne - 1, 4, cudaMemcpyDeviceToHost, st), "count");
+            L3D_CUDA(c, cudaMemcpyAsync(&lp, (long long*)A.d_npos.p + N - 1, 8, cudaMemcpyDeviceToHost, st), "count");
+            L3D_CUDA(c, cudaMemcpyAsync(&lf, (int*)A.d_nflag.p + N - 1, 4, cudaMemcpyDeviceToHost, st), "count");
+            L3D_CUDA(c, cudaStreamSynchronize(st), "affinity matrix");
+            A.K = lq + lk; A.n_ids = lp + lf;
+            RES(A.d_nkey, 8 * A.n_ids, "node keys"); RES(A.d_nkey2, 8 * A.n_ids, "node keys"); RES(A.d_nval, 4 * A.n_ids, "node vals"); RES(A.d_nval2, 4 * A.n_ids, "node vals");
+            RES(A.d_l2g, 8 * A.n_ids, "local2global"); RES(A.d_ei, 4 * 2 * A.K, "A i"); RES(A.d_ej, 4 * 2 * A.K, "A j"); RES(A.d_ew, 4 * 2 * A.K, "A w");
+#undef RES
+            k_aff_nodes<<<nbn, 256, 0, st>>>(N, (const int*)A.d_nflag.p, (const long long*)A.d_npos.p, (const unsigned long long*)A.d_time.p, (unsigned long long*)A.d_nkey.p, (unsigned int*)A.d_nval.p);
+            tb = S.d_sort_tmp.cap;
+            cub::DeviceRadixSort::SortPairs(S.d_sort_tmp.p, tb, (const unsigned long long*)A.d_nkey.p, (unsigned long long*)A.d_nkey2.p, (const unsigned int*)A.d_nval.p, (unsigned int*)A.d_nval2.p, (int)A.n_ids, 0, 64, st);
+            k_aff_ids<<<(unsigned int)((A.n_ids + 255) / 256), 256, 0, st>>>(A.n_ids, (const unsigned int*)A.d_nval2.p, (int*)A.d_idof.p, (long long*)A.d_l2g.p);
+            k_aff_emit<<<nbe, 256, 0, st>>>(ne, (const int*)A.d_keep.p, (const long long*)A.d_q.p, (const long long*)S.d_aff_oi.p, (const long long*)S.d_aff_oj.p,
+                                            (const float*)S.d_aff_ow.p, (const int*)A.d_idof.p, (int*)A.d_ei.p, (int*)A.d_ej.p, (float*)A.d_ew.p);
+            c->launches += 8 + 30;
+            L3D_CUDA(c, cudaGetLastError(), "affinity matrix kernels");
+        }
+        A.valid = true; A.two_sigA_sqr = two_sigA_sqr; A.med = med_scene_depth_lines; A.min_aff = min_affinity;
+    }
+    *num_ids = A.n_ids;
+    const long long nE = 2 * A.K;
+    if (nE == 0 || !out_i || nE > cap_edges || A.n_ids > cap_ids) return nE;
+    L3D_CUDA(c, cudaMemcpyAsync(out_i, A.d_ei.p, 4 * (size_t)nE, cudaMemcpyDeviceToHost, st), "download A");
+    L3D_CUDA(c, cudaMemcpyAsync(out_j, A.d_ej.p, 4 * (size_t)nE, cudaMemcpyDeviceToHost, st), "download A");
+    L3D_CUDA(c, cudaMemcpyAsync(out_w, A.d_ew.p, 4 * (size_t)nE, cudaMemcpyDeviceToHost, st), "download A");
+    if (out_local2global) L3D_CUDA(c, cudaMemcpyAsync(out_local2global, A.d_l2g.p, 8 * (size_t)A.n_ids, cudaMemcpyDeviceToHost, st), "download ids");
+    L3D_CUDA(c, cudaStreamSynchronize(st), "affinity matrix download");
+    return nE;
 }
 
 // replicator_dynamics_diffusion_GPU (cudawrapper.h:80) on a COO edge list (the CLEdge list A_ of line3D.cc:2030).
@@ -362,8 +509,13 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     float* P = (float*)R.d_P.p; float* Pn = (float*)R.d_Pn.p;
     for (int it = 0; it < iters; ++it) {
-        k_rdd_iter<<<(unsigned int)((n + 256 / RDD_G - 1) / (256 / RDD_G)), 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_pcol.p, (const int*)R.d_colptr.p,
-                                                                                           (const int*)R.d_tslot.p, P, (const float*)R.d_W.p, Pn, it < iters - 1 ? 1 : 0);
+        // group size: 16 lanes per row for sparse matrices, a whole warp when rows are longer on average
+        if (nnz <= 12ll * n)
+            k_rdd_iter<16><<<(unsigned int)((n + 15) / 16), 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_pcol.p, (const int*)R.d_colptr.p,
+                                                                        (const int*)R.d_tslot.p, P, (const float*)R.d_W.p, Pn, it < iters - 1 ? 1 : 0);
+        else
+            k_rdd_iter<32><<<(unsigned int)((n + 7) / 8), 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_pcol.p, (const int*)R.d_colptr.p,
+                                                                      (const int*)R.d_tslot.p, P, (const float*)R.d_W.p, Pn, it < iters - 1 ? 1 : 0);
         std::swap(P, Pn);
     }
     if (kernel_ms) cudaEventRecord(e1, st);

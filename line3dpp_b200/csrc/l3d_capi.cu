@@ -164,6 +164,7 @@ int l3d_update_view_params(l3d_ctx* c, int V, const l3d_view_desc* views)
         memcpy(d.RtKinv_d, views[v].RtKinv_d, sizeof(d.RtKinv_d)); memcpy(d.C_d, views[v].C_d, sizeof(d.C_d));
         d.k = views[v].k; d.median_depth = views[v].median_depth;
     }
+    c->aff.valid = false;
     L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync before view update");
     L3D_CUDA(c, cudaMemcpyAsync(c->d_views.p, c->h_views.data(), sizeof(L3DViewDev) * V, cudaMemcpyHostToDevice, c->stream), "upload views");
     return L3D_OK;

@@ -25,6 +25,15 @@ struct SweepState {
               &d_est_out_best, &d_est_out_P}; }
 };
 
+// device state of the affinity-matrix bookkeeping (l3d_affinity.cu)
+struct AffinityState {
+    bool valid = false; float two_sigA_sqr = 0.f, med = 0.f, min_aff = 0.f; long long K = 0, n_ids = 0;
+    DevBuf d_key, d_key2, d_val, d_val2, d_keep, d_q, d_time, d_nflag, d_npos, d_idof, d_nkey, d_nkey2, d_nval, d_nval2, d_l2g, d_ei, d_ej, d_ew;
+    std::vector<DevBuf*> bufs()
+    { return {&d_key, &d_key2, &d_val, &d_val2, &d_keep, &d_q, &d_time, &d_nflag, &d_npos, &d_idof, &d_nkey, &d_nkey2, &d_nval, &d_nval2, &d_l2g,
+              &d_ei, &d_ej, &d_ew}; }
+};
+
 // device buffers of the diffusion (l3d_affinity.cu)
 struct RddState {
     DevBuf d_ei, d_ej, d_ew, d_krow, d_kcol, d_k2, d_idx, d_idx2, d_P, d_Pn, d_W, d_prow, d_pcol, d_wmaj, d_wmin, d_rowptr, d_colptr, d_tslot, d_tmp;
@@ -59,6 +68,7 @@ struct l3d_ctx {
 
     SweepState sweep;
     RddState rdd;
+    AffinityState aff;
 
     const float4* segs() const { return segs_ext ? segs_ext : (const float4*)d_segs.p; }
     const L3DViewDev* views() const { return (const L3DViewDev*)d_views.p; }
@@ -67,6 +77,7 @@ struct l3d_ctx {
         std::vector<DevBuf*> b = {&d_segs, &d_cache, &d_views, &d_pairs, &d_tiles, &d_counts, &d_recs, &d_rowptr, &d_csr, &d_scan_tmp, &d_dense_dep, &d_dense_ov};
         for (DevBuf* x : sweep.bufs()) b.push_back(x);
         for (DevBuf* x : rdd.bufs()) b.push_back(x);
+        for (DevBuf* x : aff.bufs()) b.push_back(x);
         return b;
     }
 };

@@ -299,6 +299,7 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     if (V >= 65536) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: more than 65535 views");
     if (c->total_rows * (long long)knn >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: more than 2^31 match slots");
     SweepState& S = c->sweep;
+    S.valid = false; c->aff.valid = false;
     // processing order = ascending camID (std::map iteration, line3D.cc:704)
     S.order.resize(V);
     std::iota(S.order.begin(), S.order.end(), 0);

@@ -532,26 +532,20 @@ void Line3D::reconstruct3Dlines(const unsigned int visibility_t, const bool perf
     std::vector<l3d_view_desc> d = P.descs();
     auto t0 = std::chrono::steady_clock::now();
     bool ok = P.chk(l3d_update_view_params(P.ctx, (int)d.size(), d.data()), "l3d_update_view_params");
-    long long ne = ok ? l3d_affinity_edges(P.ctx, P.two_sigA_sqr, P.med_scene_depth_lines, MIN_AFFINITY, nullptr, nullptr, nullptr, 0) : -1;
-    ok = ok && P.chk(ne, "l3d_affinity_edges");
-    std::vector<long long> gi((size_t)std::max<long long>(ne, 1)), gj(gi.size()); std::vector<float> gw(gi.size());
-    if (ok && ne > 0) ok = P.chk(l3d_affinity_edges(P.ctx, P.two_sigA_sqr, P.med_scene_depth_lines, MIN_AFFINITY, gi.data(), gj.data(), gw.data(), ne), "l3d_affinity_edges");
-    if (!ok) { P.untranslate(); return; }
-    // "unused" pairs + first-come local ids (line3D.cc:1881-1900, 1982-2023), in emission order
+    // affinity matrix incl. the "unused" pair filter and first-come local ids (line3D.cc:1881-1900, 1982-2023), on the device
+    long long nids = 0;
+    long long nA = ok ? l3d_affinity_matrix(P.ctx, P.two_sigA_sqr, P.med_scene_depth_lines, MIN_AFFINITY, nullptr, nullptr, nullptr, 0, nullptr, 0, &nids) : -1;
+    ok = ok && P.chk(nA, "l3d_affinity_matrix");
     P.A.clear(); P.local2global.clear();
-    {
-        std::unordered_map<long long, int> g2l;
-        std::unordered_set<unsigned long long> used;
-        const unsigned long long NS = (unsigned long long)std::max<long long>(P.vlist.back()->seg_off + (long long)P.vlist.back()->lines.size(), 1);
-        auto lid = [&](long long gs) { auto it = g2l.find(gs); if (it != g2l.end()) return it->second; const int id = (int)P.local2global.size(); g2l[gs] = id; P.local2global.push_back(gs); return id; };
-        for (long long e = 0; e < ne; ++e) {
-            const unsigned long long a = (unsigned long long)std::min(gi[e], gj[e]), b = (unsigned long long)std::max(gi[e], gj[e]);
-            if (!used.insert(a * NS + b).second) continue;
-            const int id1 = lid(gi[e]), id2 = lid(gj[e]);
-            Edge e1 = {id1, id2, gw[e]}, e2 = {id2, id1, gw[e]};
-            P.A.push_back(e1); P.A.push_back(e2);
-        }
+    if (ok && nA > 0) {
+        std::vector<int> ai((size_t)nA), aj((size_t)nA); std::vector<float> aw((size_t)nA);
+        P.local2global.resize((size_t)nids);
+        ok = P.chk(l3d_affinity_matrix(P.ctx, P.two_sigA_sqr, P.med_scene_depth_lines, MIN_AFFINITY, ai.data(), aj.data(), aw.data(), nA,
+                                       P.local2global.data(), nids, &nids), "l3d_affinity_matrix");
+        P.A.resize((size_t)nA);
+        for (long long e = 0; e < nA; ++e) { P.A[e].i = ai[e]; P.A[e].j = aj[e]; P.A[e].w = aw[e]; }
     }
+    if (!ok) { P.untranslate(); return; }
     P.A_raw = P.A;
     auto t1 = std::chrono::steady_clock::now();
     const int n = (int)P.local2global.size();
