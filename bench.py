@@ -145,6 +145,35 @@ def cpu_matching_sample(seconds_target: float = 12.0, threads: int | None = None
     return done / t_used, cores, f"{n} view pairs of {SEGS_PER_VIEW}x{SEGS_PER_VIEW} segments ({done:.3g} pair evaluations, {t_used:.1f} s), matchingCPU double path, OpenMP over source segments"
 
 
+def ref_cuda_sample(scene, npairs: int = 6):
+    """B-CUDA of BASELINE.md: the reference's OWN CUDA matching path on this B200 — the unmodified match_lines_GPU
+    (kernel + dense D2H of 20 B per pair evaluation + host priority-queue pass, cudawrapper.cu:549-658) from the stock
+    nvcc build oracle/_ref/libl3dref_default.so, staged like matchingGPU (line3D.cc:1040-1074), on view pairs of the
+    bench workload.  Part of the baseline leg (checker code, never on the product path); None if oracle/_ref is absent."""
+    try:
+        from line3dpp_b200 import synth
+        from oracle import pyoracle as po
+        ref = po.ref_lib("default")
+        if ref is None or ref.ref_device_count() <= 0:
+            return None
+        RtKinv, C = synth.camera_blocks(scene)
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        done, ms_total = 0, 0.0
+        for i in range(npairs + 1):
+            s, t = 0 + i, 1 + i
+            F = synth.fundamental(scene.K[s], scene.R[s], scene.t[s], scene.K[t], scene.R[t], scene.t[t])
+            _, _, _, ms = po.match_lines(ref.ref_match_lines, scene.segs[s], scene.segs[t], f32(F), f32(RtKinv[s]), f32(RtKinv[t]), f32(C[s]), f32(C[t]),
+                                         int(s), int(t), EPI, KNN)
+            if i == 0:
+                continue                      # warm-up (CUDA context, first cudaMallocPitch)
+            ms_total += ms
+            done += len(scene.segs[s]) * len(scene.segs[t])
+        return {"value": done / (ms_total * 1e-3), "unit": "pair-evals/s", "kind": "reference (unmodified cudawrapper.cu, stock nvcc flags, sm_100a)",
+                "sample": f"{npairs} view pairs of {SEGS_PER_VIEW}x{SEGS_PER_VIEW} segments, per-pair wall time of match_lines_GPU incl. its uploads/downloads and host kNN pass"}
+    except Exception as e:   # noqa
+        return {"error": str(e)[:200]}
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -321,6 +350,7 @@ def run_ours(args):
         }
         cpu_v, cores, sample = cpu_matching_sample(12.0)
         line["cpu_baseline"] = {"value": cpu_v, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample}
+        line["ref_cuda_baseline"] = ref_cuda_sample(scene)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
