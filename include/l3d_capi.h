@@ -150,6 +150,10 @@ long long l3d_affinity_matrix(l3d_ctx* ctx, float two_sigA_sqr, float med_scene_
 int l3d_rdd(l3d_ctx* ctx, int n, long long nnz, const int* ei, const int* ej, const float* ew, int iters, int* out_i,
             int* out_j, float* out_w, float* kernel_ms);
 
+/* stable ascending argsort of float keys on the device: the weight sort of performClustering (clustering.cc:13-14) for
+ * large edge lists.  perm_out[i] = index of the i-th smallest key, ties in input order. */
+int l3d_argsort_f32(l3d_ctx* ctx, long long n, const float* keys, unsigned int* perm_out);
+
 /* measurement aid: achieved non-tensor FP32 FFMA throughput of this GPU right now (TFLOP/s), the denominator of the
  * fused kernel's compute roofline */
 int l3d_fp32_peak_probe(l3d_ctx* ctx, double* tflops_out);

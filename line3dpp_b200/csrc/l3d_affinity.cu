@@ -183,74 +183,87 @@ k_rdd_step(long long nnz, const int* __restrict__ prow, const int* __restrict__ 
     if (t >= 0) Pn[t] = mul;
 }
 
-// One diffusion iteration, fused with the row normalisation that follows it (cudawrapper.cu:739-756), HBM/L2-friendly:
-// a half-warp owns one row r of P'.  Lane k keeps P.row(r)[k]; for every entry t=(r,c) of the row the half-warp reads
-// the run W.col(c)[0..m) with ONE coalesced load, multiplies lane-wise, and parks the products in a padded shared tile;
-// lane t then adds its entry's products strictly in k order (the reference's sequential float sum), multiplies by the
-// transposed entry P(c,r), clamps, and the row sum / division again run in slot order.  Rows longer than 16 entries take
-// the scalar path with the same operation order.
-template <int G>
-__global__ void __launch_bounds__(256)
-k_rdd_iter(int n, const int* __restrict__ rowptr, const int* __restrict__ pcol, const int* __restrict__ colptr,
-           const int* __restrict__ tslot, const float* __restrict__ P, const float* __restrict__ W, float* __restrict__ Pn,
-           int normalize)
+// ---- 16-byte-aligned rows --------------------------------------------------------------------------------------------
+// The lock-step walk reads a run of P.row(r) and a run of W.col(c) per entry.  With 4-byte loads every thread of a warp
+// touches a different 128-byte line on every step (one L1 wavefront per thread and step: the first version was bound by
+// exactly that).  Values are therefore kept in PADDED arrays whose rows/columns start on float4 boundaries (rp4/cp4 =
+// start in float4 units, rows padded with zeros to a multiple of 4); the walk loads float4 and still adds the products
+// strictly in k order, so the sums round exactly like the reference's.
+__global__ void __launch_bounds__(256) k_rdd_len4(int n, const int* __restrict__ ptr, int* __restrict__ len4)
 {
-    __shared__ float tile[256 / G][G][G + 1];
-    const int hw = threadIdx.x / G, hl = threadIdx.x % G;
-    const int r = blockIdx.x * (256 / G) + hw;
-    const int base = (threadIdx.x & 31) - hl;                                     // first lane of this group inside the warp
-    const unsigned int hmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << base);
-    if (r >= n) return;                                                           // whole groups leave together
-    const int s = rowptr[r], deg = rowptr[r + 1] - s;
-    if (deg == 0) return;
-    if (deg <= G) {
-        const bool mine = hl < deg;
-        const float p = mine ? P[s + hl] : 0.0f;
-        const int c_mine = mine ? pcol[s + hl] : 0;
-        const int cs_mine = mine ? colptr[c_mine] : 0;
-        const int m_mine = mine ? min(deg, colptr[c_mine + 1] - cs_mine) : 0;
-        const int ts = mine ? tslot[s + hl] : -1;
-        for (int t = 0; t < deg; ++t) {
-            const int cs = __shfl_sync(hmask, cs_mine, base + t), m = __shfl_sync(hmask, m_mine, base + t);
-            if (hl < m) tile[hw][t][hl] = p * W[cs + hl];
-        }
-        __syncwarp(hmask);
-        float v = 0.0f;
-        if (mine) {
-            float mul = 0.0f;
-            for (int k = 0; k < m_mine; ++k) mul += tile[hw][hl][k];
-            if (ts >= 0) {
-                mul *= P[ts];
-                if (mul < L3D_EPS_F) mul = L3D_EPS_F;
-                v = mul;
-            } else v = Pn[s + hl];                    // no transposed entry: the reference leaves this slot untouched
-        }
-        if (normalize) {
-            float sum = 0.0f;
-            for (int t = 0; t < deg; ++t) sum += __shfl_sync(hmask, v, base + t);
-            if (sum < L3D_EPS_F) sum = L3D_EPS_F;
-            v /= sum;
-        }
-        if (mine) Pn[s + hl] = v;
-    } else {
-        // long row: lane handles entries hl, hl+G, ... with the scalar lock-step walk
-        for (int t = hl; t < deg; t += G) {
-            const int c = pcol[s + t];
-            int sp = s, sw = colptr[c];
-            const int ew = colptr[c + 1];
-            float mul = 0.0f;
-            while (sp < s + deg && sw < ew) { mul += P[sp] * W[sw]; ++sp; ++sw; }
-            const int ts = tslot[s + t];
-            if (ts >= 0) { mul *= P[ts]; if (mul < L3D_EPS_F) mul = L3D_EPS_F; Pn[s + t] = mul; }
-        }
-        __syncwarp(hmask);
-        if (normalize) {
-            float sum = 0.0f;
-            if (hl == 0) { for (int t = 0; t < deg; ++t) sum += Pn[s + t]; if (sum < L3D_EPS_F) sum = L3D_EPS_F; }
-            sum = __shfl_sync(hmask, sum, base);
-            for (int t = hl; t < deg; t += G) Pn[s + t] /= sum;
-        }
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) len4[r] = (ptr[r + 1] - ptr[r] + 3) >> 2;
+}
+__global__ void __launch_bounds__(256) k_rdd_pad(long long nnz, const int* __restrict__ major, const int* __restrict__ ptr, const int* __restrict__ p4,
+                                                 const float* __restrict__ val, float* __restrict__ padded)
+{
+    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= nnz) return;
+    const int r = major[y];
+    padded[4ll * p4[r] + (y - ptr[r])] = val[y];
+}
+__global__ void __launch_bounds__(256) k_rdd_unpad(long long nnz, const int* __restrict__ major, const int* __restrict__ ptr, const int* __restrict__ p4,
+                                                   const float* __restrict__ padded, float* __restrict__ val)
+{
+    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= nnz) return;
+    const int r = major[y];
+    val[y] = padded[4ll * p4[r] + (y - ptr[r])];
+}
+// K_sparseMat_row_normalization on the padded array
+__global__ void __launch_bounds__(128) k_rdd_normalize4(int n, const int* __restrict__ rowptr, const int* __restrict__ rp4, float* __restrict__ Pp)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int len = rowptr[r + 1] - rowptr[r];
+    if (len == 0) return;
+    float4* row = reinterpret_cast<float4*>(Pp) + rp4[r];
+    const int n4 = (len + 3) >> 2;
+    float sum = 0.0f;
+    for (int k4 = 0; k4 < n4; ++k4) {
+        const float4 v = row[k4];
+        const int rem = len - 4 * k4;
+        sum += v.x; if (rem > 1) sum += v.y; if (rem > 2) sum += v.z; if (rem > 3) sum += v.w;
     }
+    if (sum < L3D_EPS_F) sum = L3D_EPS_F;
+    for (int k4 = 0; k4 < n4; ++k4) {
+        float4 v = row[k4];
+        const int rem = len - 4 * k4;
+        v.x /= sum; if (rem > 1) v.y /= sum; if (rem > 2) v.z /= sum; if (rem > 3) v.w /= sum;
+        row[k4] = v;
+    }
+}
+// K_sparseMat_diffusion_step on the padded arrays: entry y = (a,b) of P produces P'(b,a)
+__global__ void __launch_bounds__(256)
+k_rdd_step4(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr, const int* __restrict__ colptr,
+            const int* __restrict__ rp4, const int* __restrict__ cp4, const float* __restrict__ Pp, const float* __restrict__ Wp,
+            const int* __restrict__ tslot, float* __restrict__ Pnp)
+{
+    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= nnz) return;
+    const int c = prow[y], r = pcol[y];                 // "transpose" (cudawrapper.cu:493-495)
+    const int rs = rowptr[r], m = min(rowptr[r + 1] - rs, colptr[c + 1] - colptr[c]);
+    const float4* __restrict__ pr = reinterpret_cast<const float4*>(Pp) + rp4[r];
+    const float4* __restrict__ wc = reinterpret_cast<const float4*>(Wp) + cp4[c];
+    float mul = 0.0f;
+    for (int k4 = 0; 4 * k4 < m; ++k4) {
+        const float4 pv = pr[k4], wv = wc[k4];
+        const int rem = m - 4 * k4;
+        mul += pv.x * wv.x;
+        if (rem > 1) mul += pv.y * wv.y;
+        if (rem > 2) mul += pv.z * wv.z;
+        if (rem > 3) mul += pv.w * wv.w;
+    }
+    mul *= Pp[4ll * rp4[c] + (y - rowptr[c])];          // P(a,b) itself
+    if (mul < L3D_EPS_F) mul = L3D_EPS_F;
+    const int t = tslot[y];
+    if (t >= 0) Pnp[4ll * rp4[r] + (t - rs)] = mul;
+}
+
+__global__ void __launch_bounds__(256) k_iota(long long n, unsigned int* __restrict__ idx)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = (unsigned int)i;
 }
 
 // ---- affinity matrix bookkeeping on the device (see l3d_affinity_matrix) ----------------------------------------
@@ -501,31 +514,81 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     k_rdd_ptr<<<(n + 256) / 256, 256, 0, st>>>(n, (int)nnz, (const int*)R.d_prow.p, (int*)R.d_rowptr.p);
     k_rdd_ptr<<<(n + 256) / 256, 256, 0, st>>>(n, (int)nnz, (const int*)R.d_wmaj.p, (int*)R.d_colptr.p);
     k_rdd_tslot<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (int*)R.d_tslot.p);
+    // padded value arrays (rows / columns on float4 boundaries)
+    if ((rc = l3d_reserve(c, R.d_len4, 4 * ((size_t)n + 1), "rdd len4"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_rp4, 4 * ((size_t)n + 1), "rdd rp4"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_cp4, 4 * ((size_t)n + 1), "rdd cp4"))) return rc;
+    int tot4[2] = {0, 0};
+    for (int pass = 0; pass < 2; ++pass) {
+        const int* ptr = (const int*)(pass ? R.d_colptr.p : R.d_rowptr.p);
+        int* p4 = (int*)(pass ? R.d_cp4.p : R.d_rp4.p);
+        L3D_CUDA(c, cudaMemsetAsync(R.d_len4.p, 0, 4 * ((size_t)n + 1), st), "rdd len4");
+        k_rdd_len4<<<(n + 255) / 256, 256, 0, st>>>(n, ptr, (int*)R.d_len4.p);
+        tb = R.d_tmp.cap;
+        size_t need = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need, (const int*)R.d_len4.p, p4, n + 1, st);
+        if (need > tb) { if ((rc = l3d_reserve(c, R.d_tmp, need, "rdd scan temp"))) return rc; tb = R.d_tmp.cap; }
+        L3D_CUDA(c, cub::DeviceScan::ExclusiveSum(R.d_tmp.p, tb, (const int*)R.d_len4.p, p4, n + 1, st), "rdd scan");
+        L3D_CUDA(c, cudaMemcpyAsync(&tot4[pass], p4 + n, 4, cudaMemcpyDeviceToHost, st), "rdd padded size");
+    }
+    L3D_CUDA(c, cudaStreamSynchronize(st), "rdd padded size");
+    const size_t pbytes = 16 * (size_t)std::max(tot4[0], 1), wbytes = 16 * (size_t)std::max(tot4[1], 1);
+    if ((rc = l3d_reserve(c, R.d_Pp, pbytes, "rdd P padded"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_Pnp, pbytes, "rdd P' padded"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_Wp, wbytes, "rdd W padded"))) return rc;
+    L3D_CUDA(c, cudaMemsetAsync(R.d_Pp.p, 0, pbytes, st), "rdd pad"); L3D_CUDA(c, cudaMemsetAsync(R.d_Wp.p, 0, wbytes, st), "rdd pad");
+    k_rdd_pad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, (const float*)R.d_P.p, (float*)R.d_Pp.p);
+    k_rdd_pad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_wmaj.p, (const int*)R.d_colptr.p, (const int*)R.d_cp4.p, (const float*)R.d_W.p, (float*)R.d_Wp.p);
     // P' starts as a copy of the un-normalised P (cudawrapper.cu:724), then P is row-normalised (727)
-    L3D_CUDA(c, cudaMemcpyAsync(R.d_Pn.p, R.d_P.p, 4 * nnz, cudaMemcpyDeviceToDevice, st), "rdd copy");
+    L3D_CUDA(c, cudaMemcpyAsync(R.d_Pnp.p, R.d_Pp.p, pbytes, cudaMemcpyDeviceToDevice, st), "rdd copy");
     const unsigned int nbr = (unsigned int)((n + 127) / 128);
-    k_rdd_normalize<<<nbr, 128, 0, st>>>(n, (const int*)R.d_rowptr.p, (float*)R.d_P.p);
+    k_rdd_normalize4<<<nbr, 128, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, (float*)R.d_Pp.p);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
-    float* P = (float*)R.d_P.p; float* Pn = (float*)R.d_Pn.p;
+    float* P = (float*)R.d_Pp.p; float* Pn = (float*)R.d_Pnp.p;
     for (int it = 0; it < iters; ++it) {
-        // group size: 16 lanes per row for sparse matrices, a whole warp when rows are longer on average
-        if (nnz <= 12ll * n)
-            k_rdd_iter<16><<<(unsigned int)((n + 15) / 16), 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_pcol.p, (const int*)R.d_colptr.p,
-                                                                        (const int*)R.d_tslot.p, P, (const float*)R.d_W.p, Pn, it < iters - 1 ? 1 : 0);
-        else
-            k_rdd_iter<32><<<(unsigned int)((n + 7) / 8), 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_pcol.p, (const int*)R.d_colptr.p,
-                                                                      (const int*)R.d_tslot.p, P, (const float*)R.d_W.p, Pn, it < iters - 1 ? 1 : 0);
+        k_rdd_step4<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_colptr.p,
+                                        (const int*)R.d_rp4.p, (const int*)R.d_cp4.p, P, (const float*)R.d_Wp.p, (const int*)R.d_tslot.p, Pn);
         std::swap(P, Pn);
+        if (it < iters - 1) k_rdd_normalize4<<<nbr, 128, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, P);
     }
     if (kernel_ms) cudaEventRecord(e1, st);
-    c->launches += 9 + 16 + iters;
+    k_rdd_unpad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, P, (float*)R.d_P.p);
+    c->launches += 9 + 16 + 10 + 2 * iters;
     L3D_CUDA(c, cudaGetLastError(), "rdd kernels");
-    L3D_CUDA(c, cudaMemcpyAsync(out_w, P, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
+    L3D_CUDA(c, cudaMemcpyAsync(out_w, R.d_P.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
     L3D_CUDA(c, cudaMemcpyAsync(out_i, R.d_prow.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
     L3D_CUDA(c, cudaMemcpyAsync(out_j, R.d_pcol.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
     L3D_CUDA(c, cudaStreamSynchronize(st), "rdd");
     if (kernel_ms) { cudaEventElapsedTime(kernel_ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    return L3D_OK;
+}
+
+// Stable ascending argsort of float keys on the device (the edge-weight sort of performClustering, clustering.cc:13-14:
+// std::list::sort by weight is stable).  perm_out[i] = index of the i-th smallest key; equal keys keep their input order.
+int l3d_argsort_f32(l3d_ctx* c, long long n, const float* keys, unsigned int* perm_out)
+{
+    if (!c || n < 0 || (n && (!keys || !perm_out))) return l3d_fail(c, L3D_ERR_INVALID, "l3d_argsort_f32: bad arguments");
+    if (n == 0) return L3D_OK;
+    if (n >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_argsort_f32: more than 2^31 keys");
+    cudaSetDevice(c->device);
+    RddState& R = c->rdd;
+    int rc;
+    if ((rc = l3d_reserve(c, R.d_ew, 4 * (size_t)n, "sort keys"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_ei, 4 * (size_t)n, "sort keys"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_idx, 4 * (size_t)n, "sort idx"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_idx2, 4 * (size_t)n, "sort idx"))) return rc;
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, (float*)nullptr, (float*)nullptr, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)n, 0, 32, c->stream);
+    if ((rc = l3d_reserve(c, R.d_tmp, sb, "sort temp"))) return rc;
+    cudaStream_t st = c->stream;
+    L3D_CUDA(c, cudaMemcpyAsync(R.d_ew.p, keys, 4 * (size_t)n, cudaMemcpyHostToDevice, st), "sort upload");
+    k_iota<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(n, (unsigned int*)R.d_idx.p);
+    size_t tb = R.d_tmp.cap;
+    L3D_CUDA(c, cub::DeviceRadixSort::SortPairs(R.d_tmp.p, tb, (const float*)R.d_ew.p, (float*)R.d_ei.p, (const unsigned int*)R.d_idx.p, (unsigned int*)R.d_idx2.p, (int)n, 0, 32, st), "argsort");
+    c->launches += 6;
+    L3D_CUDA(c, cudaMemcpyAsync(perm_out, R.d_idx2.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st), "sort download");
+    L3D_CUDA(c, cudaStreamSynchronize(st), "argsort");
     return L3D_OK;
 }
 

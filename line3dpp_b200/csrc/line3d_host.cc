@@ -96,12 +96,20 @@ private:
     std::vector<int> parent_, rank_, size_;
 };
 
-std::vector<int> segment_graph(std::vector<Edge> edges, int n, float c)
+// `order` (optional): indices of `edges` by ascending weight, ties in list order (from l3d_argsort_f32 for big lists)
+std::vector<int> segment_graph(const std::vector<Edge>& edges, int n, float c, const std::vector<unsigned int>* order)
 {
-    std::stable_sort(edges.begin(), edges.end(), [](const Edge& a, const Edge& b) { return a.w < b.w; });
+    std::vector<unsigned int> local;
+    if (!order) {
+        local.resize(edges.size());
+        for (size_t i = 0; i < local.size(); ++i) local[i] = (unsigned int)i;
+        std::stable_sort(local.begin(), local.end(), [&](unsigned int a, unsigned int b) { return edges[a].w < edges[b].w; });
+        order = &local;
+    }
     DisjointSets u(n);
     std::vector<float> thr(n, c);
-    for (const Edge& e : edges) {
+    for (unsigned int idx : *order) {
+        const Edge& e = edges[idx];
         int a = u.find(e.i), b = u.find(e.j);
         if (a == b || !(e.w <= thr[a] && e.w <= thr[b])) continue;
         u.unite(a, b);
@@ -573,7 +581,14 @@ void Line3D::reconstruct3Dlines(const unsigned int visibility_t, const bool perf
     std::vector<LineCluster3D> clusters;
     P.st.clusters_total = 0;
     if (!P.A.empty()) {
-        const std::vector<int> label = segment_graph(P.A, n, 3.0f);
+        std::vector<unsigned int> worder;
+        if (P.A.size() > (1u << 20)) {          // big list: sort the weights on the device (stable, like std::list::sort)
+            std::vector<float> w(P.A.size());
+            for (size_t e = 0; e < w.size(); ++e) w[e] = P.A[e].w;
+            worder.resize(w.size());
+            if (!P.chk(l3d_argsort_f32(P.ctx, (long long)w.size(), w.data(), worder.data()), "l3d_argsort_f32")) { P.untranslate(); return; }
+        }
+        const std::vector<int> label = segment_graph(P.A, n, 3.0f, worder.empty() ? nullptr : &worder);
         std::map<int, std::list<Segment2D> > members; std::map<int, std::set<unsigned int> > cams; std::vector<int> order;
         for (int id = 0; id < n; ++id) {
             const int cl = label[id];
