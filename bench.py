@@ -344,7 +344,9 @@ def run_ours(args):
                          "peak_source": "FFMA probe kernel run live in this process (MEASURED_PEAKS.json has no FP32 non-tensor figure)",
                          "algorithmic_flop_per_pair_eval": FLOP_PER_PAIR_EVAL,
                          "hbm_frac": (pe_all / world * 0.1 / (ms_step * 1e-3) / 1e9) / peaks["hbm_gbs"],
-                         "traffic": extra.get("topk_traffic")},
+                         "traffic": committed_traffic("k_match_topk"),
+                         "traffic_note": "DRAM read+write bytes per launch from the committed ncu --set full capture of this command (profiles/traffic.json); "
+                                         "algorithmic output is 24 B per emitted match + 4 B per (pair,row) count"},
             "roofline_hbm": extra.get("roofline_hbm"),
             "peaks": peaks,
         }
@@ -363,6 +365,14 @@ def run_ours(args):
     ctx.close()
     sys.stdout.flush()
     return 0
+
+
+def committed_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["bytes_per_launch"]
+    except Exception:   # noqa
+        return None
 
 
 def load_peaks():

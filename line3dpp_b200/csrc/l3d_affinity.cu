@@ -233,18 +233,33 @@ __global__ void __launch_bounds__(128) k_rdd_normalize4(int n, const int* __rest
         row[k4] = v;
     }
 }
-// K_sparseMat_diffusion_step on the padded arrays: entry y = (a,b) of P produces P'(b,a)
+// per-entry walk descriptors, built once (the structure is constant over the iterations): everything the step needs is
+// then read with coalesced 16-byte loads instead of eight dependent scattered pointer look-ups per entry
+//   x = first float4 of P.row(r)   y = first float4 of W.col(c)   z = walk length min(len_r, len_c)   w = own padded slot
+// and dst = padded slot of the transposed entry P'(r,c) (or -1)
 __global__ void __launch_bounds__(256)
-k_rdd_step4(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr, const int* __restrict__ colptr,
-            const int* __restrict__ rp4, const int* __restrict__ cp4, const float* __restrict__ Pp, const float* __restrict__ Wp,
-            const int* __restrict__ tslot, float* __restrict__ Pnp)
+k_rdd_plan(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr, const int* __restrict__ colptr,
+           const int* __restrict__ rp4, const int* __restrict__ cp4, const int* __restrict__ tslot, int4* __restrict__ plan, int* __restrict__ dst)
 {
     const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= nnz) return;
     const int c = prow[y], r = pcol[y];                 // "transpose" (cudawrapper.cu:493-495)
     const int rs = rowptr[r], m = min(rowptr[r + 1] - rs, colptr[c + 1] - colptr[c]);
-    const float4* __restrict__ pr = reinterpret_cast<const float4*>(Pp) + rp4[r];
-    const float4* __restrict__ wc = reinterpret_cast<const float4*>(Wp) + cp4[c];
+    plan[y] = make_int4(rp4[r], cp4[c], m, 4 * rp4[c] + (int)(y - rowptr[c]));
+    const int t = tslot[y];
+    dst[y] = t >= 0 ? 4 * rp4[r] + (t - rs) : -1;
+}
+// K_sparseMat_diffusion_step on the padded arrays: entry y = (a,b) of P produces P'(b,a)
+__global__ void __launch_bounds__(256)
+k_rdd_step4(long long nnz, const int4* __restrict__ plan, const int* __restrict__ dst, const float* __restrict__ Pp, const float* __restrict__ Wp,
+            float* __restrict__ Pnp)
+{
+    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= nnz) return;
+    const int4 pl = plan[y];
+    const float4* __restrict__ pr = reinterpret_cast<const float4*>(Pp) + pl.x;
+    const float4* __restrict__ wc = reinterpret_cast<const float4*>(Wp) + pl.y;
+    const int m = pl.z;
     float mul = 0.0f;
     for (int k4 = 0; 4 * k4 < m; ++k4) {
         const float4 pv = pr[k4], wv = wc[k4];
@@ -254,10 +269,10 @@ k_rdd_step4(long long nnz, const int* __restrict__ prow, const int* __restrict__
         if (rem > 2) mul += pv.z * wv.z;
         if (rem > 3) mul += pv.w * wv.w;
     }
-    mul *= Pp[4ll * rp4[c] + (y - rowptr[c])];          // P(a,b) itself
+    mul *= Pp[pl.w];                                    // P(a,b) itself
     if (mul < L3D_EPS_F) mul = L3D_EPS_F;
-    const int t = tslot[y];
-    if (t >= 0) Pnp[4ll * rp4[r] + (t - rs)] = mul;
+    const int t = dst[y];
+    if (t >= 0) Pnp[t] = mul;
 }
 
 __global__ void __launch_bounds__(256) k_iota(long long n, unsigned int* __restrict__ idx)
@@ -539,6 +554,11 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     L3D_CUDA(c, cudaMemsetAsync(R.d_Pp.p, 0, pbytes, st), "rdd pad"); L3D_CUDA(c, cudaMemsetAsync(R.d_Wp.p, 0, wbytes, st), "rdd pad");
     k_rdd_pad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, (const float*)R.d_P.p, (float*)R.d_Pp.p);
     k_rdd_pad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_wmaj.p, (const int*)R.d_colptr.p, (const int*)R.d_cp4.p, (const float*)R.d_W.p, (float*)R.d_Wp.p);
+    if (4ll * std::max(tot4[0], tot4[1]) >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_rdd: padded matrix too large for 32-bit slots");
+    if ((rc = l3d_reserve(c, R.d_plan, 16 * (size_t)nnz, "rdd plan"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_dst, 4 * (size_t)nnz, "rdd dst"))) return rc;
+    k_rdd_plan<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_colptr.p,
+                                   (const int*)R.d_rp4.p, (const int*)R.d_cp4.p, (const int*)R.d_tslot.p, (int4*)R.d_plan.p, (int*)R.d_dst.p);
     // P' starts as a copy of the un-normalised P (cudawrapper.cu:724), then P is row-normalised (727)
     L3D_CUDA(c, cudaMemcpyAsync(R.d_Pnp.p, R.d_Pp.p, pbytes, cudaMemcpyDeviceToDevice, st), "rdd copy");
     const unsigned int nbr = (unsigned int)((n + 127) / 128);
@@ -547,8 +567,7 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     float* P = (float*)R.d_Pp.p; float* Pn = (float*)R.d_Pnp.p;
     for (int it = 0; it < iters; ++it) {
-        k_rdd_step4<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_colptr.p,
-                                        (const int*)R.d_rp4.p, (const int*)R.d_cp4.p, P, (const float*)R.d_Wp.p, (const int*)R.d_tslot.p, Pn);
+        k_rdd_step4<<<nb, 256, 0, st>>>(nnz, (const int4*)R.d_plan.p, (const int*)R.d_dst.p, P, (const float*)R.d_Wp.p, Pn);
         std::swap(P, Pn);
         if (it < iters - 1) k_rdd_normalize4<<<nbr, 128, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, P);
     }

@@ -38,14 +38,14 @@ __global__ void __launch_bounds__(256) k_prep_segments(const float4* __restrict_
 
 // ------------------------------------------------------------------------------------------------ fused match + top-k
 struct MatchSmem {
-    float4 stage[2][MK_TT];                          // TMA-staged target segments (x1,y1,x2,y2)
+    float4 stage[MK_STAGES][MK_TT];                  // TMA-staged target segments (x1,y1,x2,y2)
     unsigned long long lists[MK_ROWS][MK_CAP];       // per-row survivor keys
     float4 rowA[MK_ROWS];                            // (e1.x, e1.y, e1.z, e2.x)
     float4 rowB[MK_ROWS];                            // (e2.y, e2.z, g, 0.95 * score-to-beat)
     float row_thr[MK_ROWS];                          // overlap of the current k-th best survivor (0 until k are known)
     int list_cnt[MK_ROWS];
     unsigned int queue[MK_WARPS][32 * MK_T + 32];    // candidate queue per warp: (row_local << 24) | tgt
-    unsigned long long bars[2];
+    unsigned long long bars[MK_STAGES];
     // per-CTA constants of the (rarely executed, deliberately out-of-line) exact path
     const float4* tsegs; const float4* cache;
     long long src_base, toff;
@@ -188,11 +188,22 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
     if (tid == 0) {
         S.tsegs = tsegs; S.cache = cache; S.src_base = soff + row0; S.toff = toff; S.epi = epi; S.knn = knn; S.Nt = Nt;
         S.Cs = make_float3(vs->C[0], vs->C[1], vs->C[2]); S.Ct = make_float3(vt->C[0], vt->C[1], vt->C[2]);
-        mbar_init(&S.bars[0], 1); mbar_init(&S.bars[1], 1); mbar_fence_init();
-        unsigned int bytes = (unsigned int)min(MK_TT, Nt) * 16u;       // first stage in flight while the rows are set up
-        mbar_expect_tx(&S.bars[0], bytes);
-        tma_load_1d(S.stage[0], tsegs, bytes, &S.bars[0]);
+        for (int i = 0; i < MK_STAGES; ++i) mbar_init(&S.bars[i], 1);
+        mbar_fence_init();
+        for (int i = 0; i < MK_STAGES && i < nchunks; ++i) {           // whole ring in flight while the rows are set up
+            const unsigned int bytes = (unsigned int)min(MK_TT, Nt - i * MK_TT) * 16u;
+            mbar_expect_tx(&S.bars[i], bytes);
+            tma_load_1d(S.stage[i], tsegs + (size_t)i * MK_TT, bytes, &S.bars[i]);
+        }
     }
+    // The last stage is usually partial: pad it to a multiple of the warp step with a segment 3e7 px away that the filter
+    // rejects (should an epipolar line ever pass through it, exact_batch drops indices >= Nt), so the hot loop needs no
+    // per-lane bounds predicate.  When the ring is not reused (Nt <= MK_STAGES*MK_TT, the common case) the padding is
+    // written now - TMA only fills the first n entries of that stage - and the chunk loop runs without any CTA barrier.
+    const int n_last = Nt - (nchunks - 1) * MK_TT;
+    const int pad_last = ((n_last + 32 * MK_T - 1) & ~(32 * MK_T - 1)) - n_last;
+    const bool ring_reused = nchunks > MK_STAGES;
+    if (!ring_reused && nchunks > 0 && tid < pad_last) S.stage[(nchunks - 1) % MK_STAGES][n_last + tid] = make_float4(3.0e7f, 3.0e7f, 3.0e7f + 100.0f, 3.0e7f);
     if (tid < MK_ROWS) {
         S.list_cnt[tid] = 0;
         S.row_thr[tid] = 0.0f;
@@ -210,24 +221,15 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
     int qn = 0;   // warp-uniform number of queued candidates
 
     for (int c = 0; c < nchunks; ++c) {
-        if (tid == 0 && c + 1 < nchunks) {          // stage (c+1)&1 was released by the __syncthreads closing chunk c-1
-            int base1 = (c + 1) * MK_TT;
-            unsigned int bytes = (unsigned int)min(MK_TT, Nt - base1) * 16u;
-            mbar_expect_tx(&S.bars[(c + 1) & 1], bytes);
-            tma_load_1d(S.stage[(c + 1) & 1], tsegs + base1, bytes, &S.bars[(c + 1) & 1]);
-        }
-        mbar_wait(&S.bars[c & 1], (unsigned int)((c >> 1) & 1));
+        const int sg = c % MK_STAGES;
+        mbar_wait(&S.bars[sg], (unsigned int)((c / MK_STAGES) & 1));
         const int base = c * MK_TT;
         const int n = min(MK_TT, Nt - base);
-        if (n & (32 * MK_T - 1)) {
-            // last, partial stage: pad it to a multiple of the warp step with a segment 3e7 px away that the filter
-            // rejects (should an epipolar line ever pass through it, exact_batch drops indices >= Nt), so the hot loop
-            // needs no per-lane bounds predicate
-            const int pad = ((n + 32 * MK_T - 1) & ~(32 * MK_T - 1)) - n;
-            if (tid < pad) S.stage[c & 1][n + tid] = make_float4(3.0e7f, 3.0e7f, 3.0e7f + 100.0f, 3.0e7f);
+        if (ring_reused && c == nchunks - 1 && pad_last) {
+            if (tid < pad_last) S.stage[sg][n + tid] = make_float4(3.0e7f, 3.0e7f, 3.0e7f + 100.0f, 3.0e7f);
             __syncthreads();
         }
-        const float4* st = S.stage[c & 1];
+        const float4* st = S.stage[sg];
         const int my_rows = min(MK_RPW, nrows - warp * MK_RPW);
         if (my_rows > 0) {
             for (int j0 = 0; j0 < n; j0 += 32 * MK_T) {
@@ -261,7 +263,15 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
                 }
             }
         }
-        if (c + 2 < nchunks) __syncthreads();       // only needed when this stage buffer will be refilled
+        if (c + MK_STAGES < nchunks) {              // this stage buffer will be refilled: everybody must be done with it
+            __syncthreads();
+            if (tid == 0) {
+                const int base1 = (c + MK_STAGES) * MK_TT;
+                const unsigned int bytes = (unsigned int)min(MK_TT, Nt - base1) * 16u;
+                mbar_expect_tx(&S.bars[sg], bytes);
+                tma_load_1d(S.stage[sg], tsegs + base1, bytes, &S.bars[sg]);
+            }
+        }
     }
     if (qn > 0) {
         bool has = lane < qn;

@@ -8,6 +8,7 @@
 #define MK_RPW 8                        /* source rows per warp */
 #define MK_ROWS (MK_WARPS * MK_RPW)     /* source rows per CTA  */
 #define MK_TT 1024                      /* target segments per TMA stage (16 KB) */
+#define MK_STAGES 3                     /* TMA ring depth: 3072 target segments resident without reuse */
 #define MK_T 4                          /* target segments per lane per step */
 #define MK_CAP 32                       /* survivor keys kept per row before pruning to k */
 #ifndef MK_MINB

@@ -176,3 +176,46 @@ def test_sharded_matching_equals_unsharded(gpu_ctx):
             off += n
             seen += 1
     assert seen == len(pairs)
+
+
+def test_large_target_views_reuse_the_tma_ring(gpu_ctx, oracle):
+    """target views larger than the resident TMA ring (3 x 1024 segments): stages are refilled, last stage partial"""
+    sc = synth.make_scene(3, 3600, 17, "dense")
+    sc.segs[0] = sc.segs[0][:150].copy()
+    sc.segs[2] = np.concatenate([sc.segs[2], sc.segs[1][:3409]]).copy()      # 7009 segments: 7 stages, 865 in the last
+    gpu_ctx.set_views(util.scene_descs(sc), sc.segs)
+    pairs = np.array([(0, 1), (0, 2)], np.int32)
+    gpu_ctx.match_pairs(pairs, util.pair_F(sc, pairs), 0.25, 10)
+    for p, (s, t) in enumerate(pairs):
+        pi = util.pair_inputs(sc, s, t)
+        oc, oo, _, _ = oracle.match_lines(oracle.lib().orc_match_lines_f32, pi["ls"], pi["lt"], pi["F"], pi["Rs"], pi["Rt"], pi["Cs"], pi["Ct"], s, t, 0.25, 10)
+        counts, recs = gpu_ctx.pair_matches(p, len(pi["ls"]))
+        assert np.array_equal(counts, oc)
+        f = ("tgt_seg", "overlap")
+        assert util.rows_as_sets(counts, recs, f) == util.rows_as_sets(oc, oo, f)
+
+
+def test_capi_error_behaviour(gpu_ctx):
+    """every entry returns a negative l3d_status + message instead of printing and carrying on (dataArray.h:198-237)"""
+    import ctypes as C
+    from line3dpp_b200 import capi
+    L = gpu_ctx.L
+    fresh = capi.Context(0)
+    assert L.l3d_match_pairs(fresh.h, 0, None, None, C.c_float(0.25), 10) == -3            # L3D_ERR_STATE: no views yet
+    assert b"l3d_set_views" in L.l3d_last_error(fresh.h)
+    assert L.l3d_score_sweep(fresh.h, C.c_float(200), C.c_float(.5), C.c_float(.75), C.c_float(.1)) == -3
+    sc = synth.make_scene(3, 50, 2, "dense")
+    fresh.set_views(util.scene_descs(sc), sc.segs)
+    pairs = np.array([[0, 7]], np.int32)
+    F = np.zeros((1, 9), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 10) == -1         # view index out of range
+    pairs[0, 1] = 1
+    assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 0) == -4          # kNN <= 0: unsupported
+    assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 33) == -4
+    assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 5) == 0           # F = 0: valid call, no matches
+    counts, total = fresh.match_counts()
+    assert total == 0
+    assert L.l3d_get_pair_matches(fresh.h, 3, p(counts), p(counts)) == -1
+    assert L.l3d_rdd(fresh.h, 0, C.c_longlong(0), None, None, None, 10, None, None, None, None) == -1
+    fresh.close()
