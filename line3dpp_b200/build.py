@@ -17,7 +17,7 @@ OUT = os.path.join(HERE, "libl3d_b200.so")
 SOURCES = ["l3d_match.cu", "l3d_capi.cu", "l3d_pipeline.cu", "l3d_affinity.cu", "line3d_host.cc"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
-         "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++"]
+         "-Xcompiler", "-fPIC,-Wno-deprecated-declarations", "-shared", "-ccbin", "/usr/bin/g++"]
 
 
 def needs_build() -> bool:
@@ -28,10 +28,15 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """defines / out: build a variant (e.g. defines=("MK_T=2",), out="libl3d_b200_T2.so") for the tile sweep"""
+    if out is None and not force and not needs_build():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    target = OUT if out is None else os.path.join(HERE, out)
+    cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
+    if out is not None:
+        subprocess.check_call(cmd)
+        return target
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -36,7 +36,7 @@ class L3DError(RuntimeError):
 def lib():
     global _lib
     if _lib is None:
-        path = _build.build()
+        path = os.environ.get("L3D_LIB") or _build.build()     # L3D_LIB: load a tile-sweep variant instead
         L = C.CDLL(path)
         L.l3d_last_error.restype = C.c_char_p
         L.l3d_stream.restype = C.c_void_p

@@ -249,30 +249,56 @@ k_rdd_plan(long long nnz, const int* __restrict__ prow, const int* __restrict__ 
     const int t = tslot[y];
     dst[y] = t >= 0 ? 4 * rp4[r] + (t - rs) : -1;
 }
-// K_sparseMat_diffusion_step on the padded arrays: entry y = (a,b) of P produces P'(b,a)
+// K_sparseMat_diffusion_step on the padded arrays: entry y = (a,b) of P produces P'(b,a).
+// A thread owns RDD_ITEMS entries (strided by the block size, so the descriptor loads stay coalesced) and walks them
+// k-step by k-step together: the float4 gathers of the different entries are independent, which is the memory-level
+// parallelism this latency-bound gather needs; every entry still accumulates its own products strictly in k order.
+#define RDD_ITEMS 4
 __global__ void __launch_bounds__(256)
 k_rdd_step4(long long nnz, const int4* __restrict__ plan, const int* __restrict__ dst, const float* __restrict__ Pp, const float* __restrict__ Wp,
             float* __restrict__ Pnp)
 {
-    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= nnz) return;
-    const int4 pl = plan[y];
-    const float4* __restrict__ pr = reinterpret_cast<const float4*>(Pp) + pl.x;
-    const float4* __restrict__ wc = reinterpret_cast<const float4*>(Wp) + pl.y;
-    const int m = pl.z;
-    float mul = 0.0f;
-    for (int k4 = 0; 4 * k4 < m; ++k4) {
-        const float4 pv = pr[k4], wv = wc[k4];
-        const int rem = m - 4 * k4;
-        mul += pv.x * wv.x;
-        if (rem > 1) mul += pv.y * wv.y;
-        if (rem > 2) mul += pv.z * wv.z;
-        if (rem > 3) mul += pv.w * wv.w;
+    const long long y0 = (long long)blockIdx.x * (256 * RDD_ITEMS) + threadIdx.x;
+    int4 pl[RDD_ITEMS];
+    int d[RDD_ITEMS];
+    float own[RDD_ITEMS], mul[RDD_ITEMS];
+    int mmax = 0;
+#pragma unroll
+    for (int i = 0; i < RDD_ITEMS; ++i) {
+        const long long y = y0 + 256ll * i;
+        const bool ok = y < nnz;
+        pl[i] = ok ? plan[y] : make_int4(0, 0, 0, 0);
+        d[i] = ok ? dst[y] : -1;
+        mmax = max(mmax, pl[i].z);
+        mul[i] = 0.0f;
     }
-    mul *= Pp[pl.w];                                    // P(a,b) itself
-    if (mul < L3D_EPS_F) mul = L3D_EPS_F;
-    const int t = dst[y];
-    if (t >= 0) Pnp[t] = mul;
+#pragma unroll
+    for (int i = 0; i < RDD_ITEMS; ++i) own[i] = pl[i].z > 0 || d[i] >= 0 ? Pp[pl[i].w] : 0.0f;
+    for (int k4 = 0; 4 * k4 < mmax; ++k4) {
+        float4 pv[RDD_ITEMS], wv[RDD_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RDD_ITEMS; ++i)
+            if (4 * k4 < pl[i].z) {
+                pv[i] = (reinterpret_cast<const float4*>(Pp) + pl[i].x)[k4];
+                wv[i] = (reinterpret_cast<const float4*>(Wp) + pl[i].y)[k4];
+            }
+#pragma unroll
+        for (int i = 0; i < RDD_ITEMS; ++i) {
+            const int rem = pl[i].z - 4 * k4;
+            if (rem > 0) {
+                mul[i] += pv[i].x * wv[i].x;
+                if (rem > 1) mul[i] += pv[i].y * wv[i].y;
+                if (rem > 2) mul[i] += pv[i].z * wv[i].z;
+                if (rem > 3) mul[i] += pv[i].w * wv[i].w;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RDD_ITEMS; ++i) {
+        float m = mul[i] * own[i];                      // times P(a,b) itself
+        if (m < L3D_EPS_F) m = L3D_EPS_F;
+        if (d[i] >= 0) Pnp[d[i]] = m;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_iota(long long n, unsigned int* __restrict__ idx)
@@ -567,7 +593,7 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     float* P = (float*)R.d_Pp.p; float* Pn = (float*)R.d_Pnp.p;
     for (int it = 0; it < iters; ++it) {
-        k_rdd_step4<<<nb, 256, 0, st>>>(nnz, (const int4*)R.d_plan.p, (const int*)R.d_dst.p, P, (const float*)R.d_Wp.p, Pn);
+        k_rdd_step4<<<(unsigned int)((nnz + 256 * RDD_ITEMS - 1) / (256 * RDD_ITEMS)), 256, 0, st>>>(nnz, (const int4*)R.d_plan.p, (const int*)R.d_dst.p, P, (const float*)R.d_Wp.p, Pn);
         std::swap(P, Pn);
         if (it < iters - 1) k_rdd_normalize4<<<nbr, 128, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, P);
     }

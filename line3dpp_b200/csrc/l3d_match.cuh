@@ -3,14 +3,27 @@
 #include "l3d_device.cuh"
 #include "../../include/l3d_capi.h"
 
-#define MK_THREADS 256
+/* geometry of k_match_topk; every knob can be overridden with -D for the tile sweep (tools/sweep_tiles.py) */
+#ifndef MK_WARPS
 #define MK_WARPS 8
+#endif
+#define MK_THREADS (32 * MK_WARPS)
+#ifndef MK_RPW
 #define MK_RPW 8                        /* source rows per warp */
+#endif
 #define MK_ROWS (MK_WARPS * MK_RPW)     /* source rows per CTA  */
+#ifndef MK_TT
 #define MK_TT 1024                      /* target segments per TMA stage (16 KB) */
+#endif
+#ifndef MK_STAGES
 #define MK_STAGES 3                     /* TMA ring depth: 3072 target segments resident without reuse */
+#endif
+#ifndef MK_T
 #define MK_T 4                          /* target segments per lane per step */
-#define MK_CAP 32                       /* survivor keys kept per row before pruning to k */
+#endif
+#ifndef MK_CAP
+#define MK_CAP 32                       /* survivor keys kept per row before pruning to k (<= 32: one key per lane) */
+#endif
 #ifndef MK_MINB
 #define MK_MINB 3                       /* resident CTAs per SM the register budget is tuned for */
 #endif

@@ -23,6 +23,8 @@ for it in range(4):
     print(f"match_pairs: {ms:.2f} ms  pairs={len(pairs)} pair_evals={pe:.3e}  -> {pe/ms*1e3:.3e} pair-evals/s", flush=True)
 counts, total = ctx.match_counts()
 print("matches", total, "per row", total / max(len(counts), 1), "frac of evals", total / pe)
+if len(sys.argv) > 4 and sys.argv[4] == "nodense":
+    sys.exit(0)
 # dense kernel
 Ns, Nt = len(sc.segs[0]), len(sc.segs[1])
 dep = torch.empty(Ns * Nt * 4, device="cuda"); ov = torch.empty(Ns * Nt, device="cuda")
