@@ -87,6 +87,30 @@ int l3d_update_view_params(l3d_ctx* ctx, int num_views, const l3d_view_desc* vie
  * overlap > epi_overlap and all four depths > 0 are kept (cudawrapper.cu:605-645); ties: smaller tgt_seg first.
  * 1 <= knn <= 32.  Results stay on the device; fetch with the l3d_get_* calls. */
 int l3d_match_pairs(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn);
+/* sharded form (view pairs are independent given all segment lists): the whole pair list is staged, so
+ * row offsets and buffer sizes are those of the full job, but only pairs [first_pair, last_pair) are evaluated here;
+ * the rows of the other pairs are filled in by the caller (l3d_match_device_buffers + a broadcast from their owner)
+ * before l3d_score_sweep. l3d_match_pairs == the range [0, num_pairs). */
+int l3d_match_pairs_range(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn,
+                          int first_pair, int last_pair);
+/* REF_CPU semantics (the reference built without CUDA or constructed with use_GPU=false, line3D.cc:49-53): matchingCPU's
+ * double-precision twin of the path (line3D.cc:900-1015: mutualOverlap 1086-1165, triangulationDepths 1168-1193, depths
+ * must exceed 1e-12) on the GPU.  Fd[9*i..] = the DOUBLE fundamental matrix of pair i.  Same outputs and accessors as
+ * l3d_match_pairs_range; the scoring sweep that follows uses scoringCPU's rules (true per-camera maximum, line3D.cc:1208-1294)
+ * and keeps the match lists in the reference's unsorted list order.  There is still no CPU fallback. */
+int l3d_match_pairs_f64(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const double* Fd, float epi_overlap, int knn,
+                        int first_pair, int last_pair);
+#define L3D_SEM_REF_GPU 0
+#define L3D_SEM_REF_CPU 1
+/* semantics of the last match result (L3D_SEM_*), or < 0 */
+int l3d_match_semantics(const l3d_ctx* ctx);
+/* device addresses of the last match result: counts int32[total_rows], recs l3d_match_rec[total_rows*knn] (fixed slots) */
+int l3d_match_device_buffers(l3d_ctx* ctx, void** counts_dev, void** recs_dev);
+/* row_off_out[num_pairs+1]: first row of every pair in those buffers (prefix sum of Ns), last = total_rows */
+int l3d_pair_row_offsets(l3d_ctx* ctx, long long* row_off_out);
+/* pure host helper: contiguous split of n items with the given costs into `parts` ranges of near-equal cost;
+ * bounds_out[parts+1], bounds_out[0] = 0, bounds_out[parts] = n. The same split on every rank. */
+int l3d_balanced_split(const long long* cost, int n, int parts, int32_t* bounds_out);
 /* sizes of the last l3d_match_pairs result */
 long long l3d_match_total_rows(const l3d_ctx* ctx);      /* sum of Ns over pairs */
 long long l3d_match_pair_evals(const l3d_ctx* ctx);      /* sum of Ns*Nt over pairs */

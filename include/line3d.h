@@ -141,6 +141,14 @@ public:
     const Line3DStats& stats() const;
     const char* lastError() const;     /* empty string if the last call succeeded */
     void setVerbose(bool v);
+    /* Multi-GPU matching. One Line3D per GPU / process, every one fed the same images. With world > 1
+     * matchImages evaluates only this rank's contiguous, cost-balanced share of the view pairs and then calls
+     * `exchange(user, counts_dev, recs_dev, row_bounds, world, knn)`: rank r owns rows [row_bounds[r], row_bounds[r+1]) of
+     * counts (int32 per row) and recs (knn * 24 B per row), both DEVICE pointers; on return every rank must hold all rows
+     * (an NCCL broadcast per owner; line3dpp_b200/dist.py does it with torch.distributed). Scoring, affinity, diffusion and
+     * clustering then run replicated, so every rank ends with the single-GPU result bit for bit. Return 0 on success. */
+    typedef int (*MatchExchangeFn)(void* user, void* counts_dev, void* recs_dev, const long long* row_bounds, int world, int knn);
+    void setShard(int rank, int world, MatchExchangeFn exchange, void* user);
     struct Impl;
     Impl* impl() { return p_; }        /* for the C wrapper used by the tests */
 private:

@@ -129,6 +129,26 @@ class Context:
                   "l3d_match_pairs")
         self._knn = int(knn)
 
+    def match_pairs_range(self, pairs, F, first, last, epi_overlap=0.25, knn=10):
+        """sharded form: stage all pairs, evaluate only [first, last) here (include/l3d_capi.h)"""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        F = np.ascontiguousarray(F, np.float32).reshape(-1, 9)
+        assert len(pairs) == len(F)
+        self._chk(self.L.l3d_match_pairs_range(self.h, len(pairs), _p(pairs), _p(F), C.c_float(epi_overlap), int(knn), int(first), int(last)),
+                  "l3d_match_pairs_range")
+        self._knn = int(knn)
+
+    def match_device_buffers(self):
+        """(counts_ptr, recs_ptr) device addresses of the last match result"""
+        a, b = C.c_void_p(), C.c_void_p()
+        self._chk(self.L.l3d_match_device_buffers(self.h, C.byref(a), C.byref(b)), "l3d_match_device_buffers")
+        return a.value or 0, b.value or 0
+
+    def pair_row_offsets(self, num_pairs):
+        out = np.zeros(num_pairs + 1, np.int64)
+        self._chk(self.L.l3d_pair_row_offsets(self.h, _p(out)), "l3d_pair_row_offsets")
+        return out
+
     def match_total_rows(self) -> int:
         return int(self.L.l3d_match_total_rows(self.h))
 

@@ -172,10 +172,26 @@ int l3d_update_view_params(l3d_ctx* c, int V, const l3d_view_desc* views)
 
 // ------------------------------------------------------------------------------------------------ matching
 int l3d_match_pairs(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn)
+{ return l3d_match_pairs_range(c, num_pairs, pairs, F, epi_overlap, knn, 0, num_pairs); }
+
+static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, const double* Fd, float epi_overlap, int knn, int first_pair, int last_pair);
+
+int l3d_match_pairs_range(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn, int first_pair, int last_pair)
+{ return match_impl(c, num_pairs, pairs, F, nullptr, epi_overlap, knn, first_pair, last_pair); }
+
+int l3d_match_pairs_f64(l3d_ctx* c, int num_pairs, const int32_t* pairs, const double* Fd, float epi_overlap, int knn, int first_pair, int last_pair)
+{
+    if (!c) return L3D_ERR_INVALID;
+    if (num_pairs > 0 && !Fd) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs_f64: bad arguments");
+    return match_impl(c, num_pairs, pairs, nullptr, Fd, epi_overlap, knn, first_pair, last_pair);
+}
+
+static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, const double* Fd, float epi_overlap, int knn, int first_pair, int last_pair)
 {
     if (!c) return L3D_ERR_INVALID;
     if (!c->have_views) return l3d_fail(c, L3D_ERR_STATE, "l3d_match_pairs: call l3d_set_views first");
-    if (num_pairs < 0 || (num_pairs && (!pairs || !F))) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs: bad arguments");
+    if (num_pairs < 0 || (num_pairs && (!pairs || (!F && !Fd)))) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs: bad arguments");
+    if (first_pair < 0 || last_pair < first_pair || last_pair > num_pairs) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs_range: bad pair range");
     if (knn <= 0) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: kNN <= 0 (keep all matches) is not implemented; use l3d_match_dense");
     if (knn > 32) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: kNN > 32 not implemented");
     cudaSetDevice(c->device);
@@ -187,12 +203,17 @@ int l3d_match_pairs(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float
         int s = pairs[2 * i], t = pairs[2 * i + 1];
         if (s < 0 || t < 0 || s >= c->num_views || t >= c->num_views) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs: view index out of range");
         L3DPairDev& p = c->h_pairs[i];
-        p.src = s; p.tgt = t; memcpy(p.F, F + 9 * (size_t)i, sizeof(p.F)); p.row_off = rows;
+        p.src = s; p.tgt = t; p.row_off = rows;
+        if (Fd) {     // REF_CPU: the double matrix decides; the float copy (eigen2dataArray-style cast) only feeds the conservative filter
+            memcpy(p.Fd, Fd + 9 * (size_t)i, sizeof(p.Fd));
+            for (int k = 0; k < 9; ++k) p.F[k] = (float)p.Fd[k];
+        } else { memcpy(p.F, F + 9 * (size_t)i, sizeof(p.F)); memset(p.Fd, 0, sizeof(p.Fd)); }
         int Ns = c->h_views[s].nseg, Nt = c->h_views[t].nseg;
         if (Nt >= (1 << 24)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: more than 2^24 segments in one view");
-        if (Nt > 0)
+        if (Nt > 0 && i >= first_pair && i < last_pair)
             for (int r0 = 0; r0 < Ns; r0 += MK_ROWS) c->h_tiles.push_back(make_int2(i, r0));
-        rows += Ns; evals += (long long)Ns * Nt;
+        rows += Ns;
+        if (i >= first_pair && i < last_pair) evals += (long long)Ns * Nt;     // evaluated HERE
     }
     c->num_pairs = num_pairs; c->knn = knn; c->epi = epi_overlap; c->total_rows = rows; c->pair_evals = evals;
     int rc;
@@ -203,10 +224,19 @@ int l3d_match_pairs(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float
     if (num_pairs) L3D_CUDA(c, cudaMemcpyAsync(c->d_pairs.p, c->h_pairs.data(), sizeof(L3DPairDev) * num_pairs, cudaMemcpyHostToDevice, c->stream), "upload pairs");
     if (!c->h_tiles.empty()) L3D_CUDA(c, cudaMemcpyAsync(c->d_tiles.p, c->h_tiles.data(), sizeof(int2) * c->h_tiles.size(), cudaMemcpyHostToDevice, c->stream), "upload tiles");
     if (rows) L3D_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(int) * rows, c->stream), "clear counts");   // rows of pairs with Nt == 0
+    const double* cache_d = nullptr;
+    if (Fd && c->total_segs > 0) {      // matchingCPU's rays / plane normals in double; camera blocks may have been updated since set_views
+        if ((rc = l3d_reserve(c, c->d_cache_d, sizeof(double) * 9 * (size_t)c->total_segs, "double segment cache"))) return rc;
+        k_prep_segments_f64<<<(unsigned int)((c->total_segs + 255) / 256), 256, 0, c->stream>>>(c->segs(), c->views(), c->num_views, c->total_segs, (double*)c->d_cache_d.p);
+        ++c->launches;
+        L3D_CUDA(c, cudaGetLastError(), "k_prep_segments_f64");
+        cache_d = (const double*)c->d_cache_d.p;
+    }
+    c->semantics = Fd ? L3D_SEM_REF_CPU : L3D_SEM_REF_GPU;
     if (!c->h_tiles.empty()) {
         k_match_topk<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
             c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, knn,
-            epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p);
+            epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, cache_d);
         ++c->launches;
         L3D_CUDA(c, cudaGetLastError(), "k_match_topk");
     }
@@ -214,6 +244,44 @@ int l3d_match_pairs(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float
     return L3D_OK;
 }
 
+int l3d_match_device_buffers(l3d_ctx* c, void** counts_dev, void** recs_dev)
+{
+    if (!c || !counts_dev || !recs_dev) return L3D_ERR_INVALID;
+    if (!c->have_matches) return l3d_fail(c, L3D_ERR_STATE, "l3d_match_device_buffers: no match result");
+    *counts_dev = c->d_counts.p; *recs_dev = c->d_recs.p;
+    c->sweep.valid = false;                 // the caller may overwrite rows
+    return L3D_OK;
+}
+
+int l3d_pair_row_offsets(l3d_ctx* c, long long* out)
+{
+    if (!c || !out) return L3D_ERR_INVALID;
+    if (!c->have_matches) return l3d_fail(c, L3D_ERR_STATE, "l3d_pair_row_offsets: no match result");
+    for (int i = 0; i < c->num_pairs; ++i) out[i] = c->h_pairs[i].row_off;
+    out[c->num_pairs] = c->total_rows;
+    return L3D_OK;
+}
+
+int l3d_balanced_split(const long long* cost, int n, int parts, int32_t* bounds)
+{
+    if (n < 0 || parts < 1 || !bounds || (n && !cost)) return L3D_ERR_INVALID;
+    long long total = 0;
+    for (int i = 0; i < n; ++i) { if (cost[i] < 0) return L3D_ERR_INVALID; total += cost[i]; }
+    // item i goes to the part whose cost window contains the midpoint of i's cost interval: monotone, so ranges are contiguous
+    bounds[0] = 0;
+    int part = 0; long long before = 0;
+    for (int i = 0; i < n; ++i) {
+        const long double mid = (long double)before + 0.5L * (long double)cost[i];
+        int want = total > 0 ? (int)(mid * parts / (long double)total) : (int)((long long)i * parts / n);
+        if (want >= parts) want = parts - 1;
+        while (part < want) bounds[++part] = i;
+        before += cost[i];
+    }
+    while (part < parts) bounds[++part] = n;
+    return L3D_OK;
+}
+
+int l3d_match_semantics(const l3d_ctx* c) { return c && c->have_matches ? c->semantics : L3D_ERR_STATE; }
 long long l3d_match_total_rows(const l3d_ctx* c) { return c && c->have_matches ? c->total_rows : -1; }
 long long l3d_match_pair_evals(const l3d_ctx* c) { return c && c->have_matches ? c->pair_evals : -1; }
 

@@ -54,7 +54,7 @@ struct l3d_ctx {
     int num_views = 0;
     long long total_segs = 0;
     std::vector<L3DViewDev> h_views;
-    DevBuf d_segs, d_cache, d_views;
+    DevBuf d_segs, d_cache, d_cache_d, d_views;
     const float4* segs_ext = nullptr;       // caller-owned device segment array (l3d_set_views_flat on_device)
     void* h_stage = nullptr; size_t h_stage_cap = 0;
 
@@ -62,6 +62,7 @@ struct l3d_ctx {
     bool have_matches = false;
     int num_pairs = 0, knn = 0;
     float epi = 0.f;
+    int semantics = 0;                      // L3D_SEM_* of the last match result; the scoring sweep follows it
     long long total_rows = 0, pair_evals = 0;
     std::vector<L3DPairDev> h_pairs;
     std::vector<int2> h_tiles;
@@ -75,7 +76,7 @@ struct l3d_ctx {
     const L3DViewDev* views() const { return (const L3DViewDev*)d_views.p; }
     std::vector<DevBuf*> all_bufs()
     {
-        std::vector<DevBuf*> b = {&d_segs, &d_cache, &d_views, &d_pairs, &d_tiles, &d_counts, &d_recs, &d_rowptr, &d_csr, &d_scan_tmp, &d_dense_dep, &d_dense_ov};
+        std::vector<DevBuf*> b = {&d_segs, &d_cache, &d_cache_d, &d_views, &d_pairs, &d_tiles, &d_counts, &d_recs, &d_rowptr, &d_csr, &d_scan_tmp, &d_dense_dep, &d_dense_ov};
         for (DevBuf* x : sweep.bufs()) b.push_back(x);
         for (DevBuf* x : rdd.bufs()) b.push_back(x);
         for (DevBuf* x : aff.bufs()) b.push_back(x);

@@ -30,6 +30,7 @@ struct L3DPairDev {
     int src, tgt;           // view indices
     float F[9];             // row-major float fundamental matrix
     long long row_off;      // first output row of this pair (prefix sum of Ns)
+    double Fd[9];           // the double matrix (REF_CPU semantics, l3d_match_pairs_f64); unused otherwise
 };
 
 // per-segment cache written by k_prep_segments: 3 float4 per segment

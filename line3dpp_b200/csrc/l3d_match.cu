@@ -14,6 +14,7 @@
 //   k_match_dense   : the reference's device contract (float4 depths + float overlap for EVERY cell,
 //                     cudawrapper.cu:186-253), same filter + exact path, coalesced 20 B/cell writes: HBM-write bound.
 #include "l3d_match.cuh"
+#include "l3d_device_f64.cuh"
 
 // ------------------------------------------------------------------------------------------------ pre-pass
 __global__ void __launch_bounds__(256) k_prep_segments(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views,
@@ -36,6 +37,25 @@ __global__ void __launch_bounds__(256) k_prep_segments(const float4* __restrict_
     cache[3 * idx + 2] = make_float4(n.z, 0.f, 0.f, 0.f);
 }
 
+// same for the double path (REF_CPU semantics): rays and plane normal exactly as triangulationDepths forms them
+__global__ void __launch_bounds__(256) k_prep_segments_f64(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views,
+                                                           int num_views, long long total, double* __restrict__ cache)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int lo = 0, hi = num_views - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (views[mid].seg_off <= idx) lo = mid; else hi = mid - 1;
+    }
+    const L3DViewDev* v = views + lo;
+    float4 s = segs[idx];
+    D3 r1 = dray(v->RtKinv_d, (double)s.x, (double)s.y), r2 = dray(v->RtKinv_d, (double)s.z, (double)s.w);
+    D3 n = dnormalized(dcross(r1, r2));
+    double* o = cache + 9 * idx;
+    o[0] = r1.x; o[1] = r1.y; o[2] = r1.z; o[3] = r2.x; o[4] = r2.y; o[5] = r2.z; o[6] = n.x; o[7] = n.y; o[8] = n.z;
+}
+
 // ------------------------------------------------------------------------------------------------ fused match + top-k
 struct MatchSmem {
     float4 stage[MK_STAGES][MK_TT];                  // TMA-staged target segments (x1,y1,x2,y2)
@@ -51,6 +71,10 @@ struct MatchSmem {
     long long src_base, toff;
     float3 Cs, Ct;
     float epi; int knn, Nt;
+    // REF_CPU semantics (mode 1): the exact path is matchingCPU's double arithmetic; the float filter stays the same
+    int mode;
+    const double* cache_d; const float4* ssegs;
+    double Fd[9]; D3 Csd, Ctd;
 };
 size_t l3d_match_smem_bytes() { return sizeof(MatchSmem); }
 
@@ -84,6 +108,22 @@ __device__ __noinline__ void prune_row(MatchSmem& S, int row, int lane)
     __syncwarp();
 }
 
+// matchingCPU's evaluation of one candidate (line3D.cc:925-1003): double overlap, double depths > 1e-12
+__device__ __noinline__ bool eval_candidate_f64(const MatchSmem& S, int rl, unsigned int j, unsigned long long* key)
+{
+    const float4 sp = __ldg(S.ssegs + rl);
+    const D3 e1 = dmulmat(S.Fd, d3((double)sp.x, (double)sp.y, 1.0)), e2 = dmulmat(S.Fd, d3((double)sp.z, (double)sp.w, 1.0));
+    bool valid;
+    const float ov = exact_overlap_f64(__ldg(S.tsegs + j), e1, e2, &valid);
+    if (!(valid && ov > S.epi && ov >= S.row_thr[rl])) return false;
+    const SegRaysD s = load_rays_d(S.cache_d, S.src_base + rl), t = load_rays_d(S.cache_d, S.toff + j);
+    double d[4];
+    exact_depths_f64(s, t, S.Csd, S.Ctd, d);
+    if (!(d[0] > L3D_EPS_D && d[1] > L3D_EPS_D && d[2] > L3D_EPS_D && d[3] > L3D_EPS_D)) return false;
+    *key = make_key(ov, j);
+    return true;
+}
+
 // exact evaluation of up to 32 queued candidates (one per lane).  Out of line on purpose: the hot filter loop must
 // stay inside the instruction cache (the first version inlined this 5x -> 64 KB of SASS, 55 % "no instruction" stalls).
 __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool has, int lane)
@@ -99,15 +139,18 @@ __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool 
         rl = (int)(entry >> 24);
         unsigned int j = entry & 0xFFFFFFu;
         if (j >= (unsigned int)S.Nt) j = 0u, has = false;         // padding segment of a partial stage
-        float4 q = __ldg(tsegs + j);
-        float4 rA = S.rowA[rl], rB = S.rowB[rl];
-        bool inv;
-        float ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
-        if (has && ov > epi && ov >= S.row_thr[rl]) {      // below the current k-th best it can never be selected
-            SegRays s = load_rays(cache, src_base + rl), t = load_rays(cache, toff + j);
-            float d[4];
-            exact_depths(s, t, Cs, Ct, d);
-            if (d[0] > 0.0f && d[1] > 0.0f && d[2] > 0.0f && d[3] > 0.0f) { key = make_key(ov, j); pending = true; }
+        if (S.mode) { if (has) pending = eval_candidate_f64(S, rl, j, &key); }
+        else {
+            float4 q = __ldg(tsegs + j);
+            float4 rA = S.rowA[rl], rB = S.rowB[rl];
+            bool inv;
+            float ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
+            if (has && ov > epi && ov >= S.row_thr[rl]) {      // below the current k-th best it can never be selected
+                SegRays s = load_rays(cache, src_base + rl), t = load_rays(cache, toff + j);
+                float d[4];
+                exact_depths(s, t, Cs, Ct, d);
+                if (d[0] > 0.0f && d[1] > 0.0f && d[2] > 0.0f && d[3] > 0.0f) { key = make_key(ov, j); pending = true; }
+            }
         }
     }
     while (true) {
@@ -155,9 +198,16 @@ __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int
         const int rank = rank_in_row(S.lists[rl], n, key);
         if (lane < n && rank < knn) {
             unsigned int j = key_tgt(key);
-            SegRays s = load_rays(S.cache, S.src_base + rl), t = load_rays(S.cache, S.toff + j);
             float d[4];
-            exact_depths(s, t, S.Cs, S.Ct, d);
+            if (S.mode) {
+                const SegRaysD s = load_rays_d(S.cache_d, S.src_base + rl), t = load_rays_d(S.cache_d, S.toff + j);
+                double dd[4];
+                exact_depths_f64(s, t, S.Csd, S.Ctd, dd);
+                d[0] = (float)dd[0]; d[1] = (float)dd[1]; d[2] = (float)dd[2]; d[3] = (float)dd[3];     // Match stores floats (commons.h:186-203)
+            } else {
+                SegRays s = load_rays(S.cache, S.src_base + rl), t = load_rays(S.cache, S.toff + j);
+                exact_depths(s, t, S.Cs, S.Ct, d);
+            }
             l3d_match_rec rec;
             rec.tgt_seg = j; rec.overlap = key_overlap(key);
             rec.d_p1 = d[0]; rec.d_p2 = d[1]; rec.d_q1 = d[2]; rec.d_q2 = d[3];
@@ -169,7 +219,7 @@ __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int
 __global__ void __launch_bounds__(MK_THREADS, MK_MINB)
 k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
              const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
-             int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out)
+             int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MatchSmem& S = *reinterpret_cast<MatchSmem*>(smem_raw);
@@ -188,6 +238,11 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
     if (tid == 0) {
         S.tsegs = tsegs; S.cache = cache; S.src_base = soff + row0; S.toff = toff; S.epi = epi; S.knn = knn; S.Nt = Nt;
         S.Cs = make_float3(vs->C[0], vs->C[1], vs->C[2]); S.Ct = make_float3(vt->C[0], vt->C[1], vt->C[2]);
+        S.mode = cache_d != nullptr; S.cache_d = cache_d; S.ssegs = segs + soff + row0;
+        if (cache_d) {
+            for (int i = 0; i < 9; ++i) S.Fd[i] = P->Fd[i];
+            S.Csd = d3(vs->C_d[0], vs->C_d[1], vs->C_d[2]); S.Ctd = d3(vt->C_d[0], vt->C_d[1], vt->C_d[2]);
+        }
         for (int i = 0; i < MK_STAGES; ++i) mbar_init(&S.bars[i], 1);
         mbar_fence_init();
         for (int i = 0; i < MK_STAGES && i < nchunks; ++i) {           // whole ring in flight while the rows are set up

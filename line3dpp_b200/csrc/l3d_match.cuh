@@ -44,7 +44,9 @@ __global__ void k_prep_segments(const float4* __restrict__ segs, const L3DViewDe
 __global__ void k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache,
                              const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
                              const int2* __restrict__ tiles, int knn, float epi, int* __restrict__ counts_out,
-                             l3d_match_rec* __restrict__ recs_out);
+                             l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d /* non-null: REF_CPU */);
+__global__ void k_prep_segments_f64(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int num_views,
+                                    long long total, double* __restrict__ cache);
 __global__ void k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
                               const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F, float3 Cs,
                               float3 Ct, float epi, float4* __restrict__ depths, float* __restrict__ overlaps);

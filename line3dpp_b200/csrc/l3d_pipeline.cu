@@ -13,6 +13,7 @@
 // operation (same libdevice expf/acosf), the double parts repeat the host code of view.cc / line3D.cc as restated in
 // oracle/l3d_oracle.cc (IEEE double, no contraction).
 #include "l3d_ctx.cuh"
+#include "l3d_device_f64.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -23,28 +24,10 @@
 #include <cstring>
 #include <numeric>
 
-#define L3D_EPS_D 1e-12
 #define L3D_PI_1_32_F 0.098174771f
 #define L3D_PI_31_32_F 3.043417886f
 #define L3D_PI_D 3.14159265358979323846
 
-// ---------------------------------------------------------------------------------------------- double helpers
-struct D3 { double x, y, z; };
-__device__ __forceinline__ D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ D3 dsub(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ double dnorm(D3 a) { return sqrt(ddot(a, a)); }
-__device__ __forceinline__ D3 dnormalized(D3 a)
-{
-    double n2 = ddot(a, a);
-    if (n2 > 0) { double n = sqrt(n2); return d3(a.x / n, a.y / n, a.z / n); }
-    return a;
-}
-// View::getNormalizedRay (view.cc:317-321)
-__device__ __forceinline__ D3 dray(const double* M, double x, double y)
-{
-    return dnormalized(d3(M[0] * x + M[1] * y + M[2] * 1.0, M[3] * x + M[4] * y + M[5] * 1.0, M[6] * x + M[7] * y + M[8] * 1.0));
-}
 // View::unprojectSegment + Segment3D ctor (view.cc:356-371, segment3D.h:48-66): degenerate segments collapse to zero
 struct DSeg { D3 P1, P2, dir; float length; };
 __device__ __forceinline__ DSeg dunproject(const L3DViewDev* v, float4 s, float d1, float d2)

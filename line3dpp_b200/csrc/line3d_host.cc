@@ -183,6 +183,7 @@ struct Line3D::Impl {
     int kNN = 10;
     bool fixed3Dreg = false, perform_RDD = false, matched = false;
     Vector3d translation;
+    int shard_rank = 0, shard_world = 1; Line3D::MatchExchangeFn exchange = nullptr; void* exchange_user = nullptr;
     // index maps (rebuilt at matchImages)
     std::vector<HostView*> vlist;                         // by view index (ascending camID)
     std::map<unsigned int, int> index_of;
@@ -321,6 +322,14 @@ Line3D::~Line3D() { if (p_) { l3d_ctx_destroy(p_->ctx); delete p_; } }
 const Line3DStats& Line3D::stats() const { return p_->st; }
 const char* Line3D::lastError() const { return p_->err.c_str(); }
 void Line3D::setVerbose(bool v) { p_->verbose = v; }
+void Line3D::setShard(int rank, int world, MatchExchangeFn fn, void* user)
+{
+    Impl& P = *p_;
+    std::lock_guard<std::mutex> g(P.mtx);
+    P.err.clear();
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) { P.fail("setShard: need 0 <= rank < world and an exchange function"); return; }
+    P.shard_rank = rank; P.shard_world = world; P.exchange = fn; P.exchange_user = user;
+}
 size_t Line3D::numImages() { std::lock_guard<std::mutex> g(p_->mtx); return p_->views.size(); }
 
 void Line3D::addImage(const unsigned int camID, const int w, const int h, const Matrix3d& K, const Matrix3d& R, const Vector3d& t,
@@ -403,8 +412,23 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
     std::vector<const float*> segp(P.vlist.size());
     for (size_t i = 0; i < P.vlist.size(); ++i) segp[i] = &P.vlist[i]->lines[0].v[0];
     auto t0 = std::chrono::steady_clock::now();
-    bool ok = P.chk(l3d_set_views(P.ctx, (int)d.size(), d.data(), segp.data()), "l3d_set_views") &&
-              P.chk(l3d_match_pairs(P.ctx, npairs, P.pairs.data(), F.data(), P.epi, P.kNN), "l3d_match_pairs") && P.chk(l3d_sync(P.ctx), "l3d_sync");
+    bool ok = P.chk(l3d_set_views(P.ctx, (int)d.size(), d.data(), segp.data()), "l3d_set_views");
+    if (ok && P.shard_world > 1) {
+        // this rank's contiguous share of the pair list, balanced by Ns*Nt; the same split on every rank
+        std::vector<long long> cost((size_t)npairs), row_off((size_t)npairs + 1), row_bounds((size_t)P.shard_world + 1);
+        for (int i = 0; i < npairs; ++i) cost[i] = (long long)P.vlist[P.pairs[2 * i]]->lines.size() * (long long)P.vlist[P.pairs[2 * i + 1]]->lines.size();
+        std::vector<int32_t> bounds((size_t)P.shard_world + 1);
+        ok = P.chk(l3d_balanced_split(cost.data(), npairs, P.shard_world, bounds.data()), "l3d_balanced_split") &&
+             P.chk(l3d_match_pairs_range(P.ctx, npairs, P.pairs.data(), F.data(), P.epi, P.kNN, bounds[P.shard_rank], bounds[P.shard_rank + 1]), "l3d_match_pairs_range") &&
+             P.chk(l3d_sync(P.ctx), "l3d_sync") && P.chk(l3d_pair_row_offsets(P.ctx, row_off.data()), "l3d_pair_row_offsets");
+        void *dc = nullptr, *dr = nullptr;
+        ok = ok && P.chk(l3d_match_device_buffers(P.ctx, &dc, &dr), "l3d_match_device_buffers");
+        if (ok) {
+            for (int r = 0; r <= P.shard_world; ++r) row_bounds[r] = row_off[bounds[r]];
+            if (P.exchange(P.exchange_user, dc, dr, row_bounds.data(), P.shard_world, P.kNN) != 0) { P.fail("matchImages: the match exchange callback failed"); ok = false; }
+        }
+    } else
+        ok = ok && P.chk(l3d_match_pairs(P.ctx, npairs, P.pairs.data(), F.data(), P.epi, P.kNN), "l3d_match_pairs") && P.chk(l3d_sync(P.ctx), "l3d_sync");
     auto t1 = std::chrono::steady_clock::now();
     ok = ok && P.chk(l3d_score_sweep(P.ctx, P.two_sigA_sqr, MIN_SIMILARITY_3D, MIN_BEST_SCORE_3D, MIN_BEST_SCORE_PERC), "l3d_score_sweep");
     auto t2 = std::chrono::steady_clock::now();
@@ -738,6 +762,8 @@ int l3dpp_match_images(void* h, float sp, float sa, unsigned int nn, float epi, 
 { Line3D* L = (Line3D*)h; L->matchImages(sp, sa, nn, epi, knn, crd); return L->lastError()[0] ? -1 : 0; }
 int l3dpp_reconstruct(void* h, unsigned int vis, int diffusion, float collin)
 { Line3D* L = (Line3D*)h; L->reconstruct3Dlines(vis, diffusion != 0, collin, false, 0); return L->lastError()[0] ? -1 : 0; }
+int l3dpp_set_shard(void* h, int rank, int world, Line3D::MatchExchangeFn fn, void* user)
+{ Line3D* L = (Line3D*)h; L->setShard(rank, world, fn, user); return L->lastError()[0] ? -1 : 0; }
 int l3dpp_stats(void* h, Line3DStats* out) { *out = ((Line3D*)h)->stats(); return 0; }
 int l3dpp_view_index(void* h, unsigned int cam) { auto& m = ((Line3D*)h)->impl()->index_of; auto it = m.find(cam); return it == m.end() ? -1 : it->second; }
 int l3dpp_view_info(void* h, unsigned int cam, float* k, float* md)

@@ -69,3 +69,51 @@ def test_shard_helpers():
         assert 4900 <= len(p) <= 5100          # balanced: ~5000 view pairs per GPU (BASELINE.json configs[3] per GPU)
         seen += len(p)
     assert seen == len(pairs) == 20000
+
+
+def test_balanced_split_is_contiguous_complete_and_balanced():
+    from line3dpp_b200 import dist as l3dist
+    rng = np.random.default_rng(5)
+    for n, parts in ((0, 3), (1, 4), (7, 7), (1000, 8), (5000, 3)):
+        cost = rng.integers(0, 9_000_000, n)
+        b = l3dist.balanced_split(cost, parts)
+        assert b[0] == 0 and b[-1] == n and (np.diff(b) >= 0).all()
+        if n >= 1000:
+            share = np.array([cost[b[r]:b[r + 1]].sum() for r in range(parts)], float)
+            assert share.max() <= share.mean() + cost.max()          # never worse than one item off the ideal
+    b = l3dist.balanced_split(np.zeros(10, np.int64), 4)                # all-empty views: split by count
+    assert b[0] == 0 and b[-1] == 10 and (np.diff(b) >= 2).all()
+    b = l3dist.balanced_split([5, 0, 0, 0, 5], 2)
+    assert list(b) in ([0, 1, 5], [0, 2, 5], [0, 3, 5], [0, 4, 5])
+
+
+EXCHANGE_WORKER = textwrap.dedent("""
+    import os, sys, numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    from line3dpp_b200 import dist as l3dist
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rows, knn = 1000, 3
+    rng = np.random.default_rng(11)
+    full_counts = rng.integers(0, knn + 1, rows).astype(np.int32)
+    full_recs = rng.integers(0, 255, (rows * knn, l3dist.REC_BYTES)).astype(np.uint8)
+    bounds = [0, 0, rows] if %r else [0, 377, rows]              # an empty share must be fine
+    counts, recs = np.zeros_like(full_counts), np.zeros_like(full_recs)
+    a, b = bounds[rank], bounds[rank + 1]
+    counts[a:b] = full_counts[a:b]; recs[a * knn:b * knn] = full_recs[a * knn:b * knn]
+    ct, rt = torch.from_numpy(counts.view(np.uint8)), torch.from_numpy(recs.reshape(-1))
+    l3dist.exchange_rows(ct, rt, bounds, knn)
+    assert np.array_equal(counts, full_counts) and np.array_equal(recs, full_recs), "rows missing after the exchange"
+    dist.barrier(); dist.destroy_process_group()
+    print("rank", rank, "exchange ok")
+""")
+
+
+def test_two_rank_gloo_match_row_exchange(tmp_path):
+    for empty_share in (False, True):
+        script = tmp_path / f"xworker_{int(empty_share)}.py"
+        script.write_text(EXCHANGE_WORKER % (ROOT, empty_share))
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", str(_free_port()), str(script)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
