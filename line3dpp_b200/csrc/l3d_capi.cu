@@ -54,6 +54,7 @@ int l3d_ctx_create(int device, l3d_ctx** out)
     cudaGetDeviceProperties(&prop, device);
     c->num_sms = prop.multiProcessorCount;
     e = cudaFuncSetAttribute(k_match_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3d_match_smem_bytes());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_topk_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3d_match_smem_bytes());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3d_dense_smem_bytes());
     if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return L3D_ERR_CUDA; }
     *out = c;
@@ -234,9 +235,14 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
     }
     c->semantics = Fd ? L3D_SEM_REF_CPU : L3D_SEM_REF_GPU;
     if (!c->h_tiles.empty()) {
-        k_match_topk<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
-            c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, knn,
-            epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, cache_d);
+        if (cache_d)
+            k_match_topk_f64<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
+                c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, knn,
+                epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, cache_d);
+        else
+            k_match_topk<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
+                c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, knn,
+                epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p);
         ++c->launches;
         L3D_CUDA(c, cudaGetLastError(), "k_match_topk");
     }

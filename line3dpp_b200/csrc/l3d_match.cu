@@ -71,8 +71,7 @@ struct MatchSmem {
     long long src_base, toff;
     float3 Cs, Ct;
     float epi; int knn, Nt;
-    // REF_CPU semantics (mode 1): the exact path is matchingCPU's double arithmetic; the float filter stays the same
-    int mode;
+    // REF_CPU semantics (k_match_topk_f64): the exact path is matchingCPU's double arithmetic; the float filter stays the same
     const double* cache_d; const float4* ssegs;
     double Fd[9]; D3 Csd, Ctd;
 };
@@ -126,6 +125,7 @@ __device__ __noinline__ bool eval_candidate_f64(const MatchSmem& S, int rl, unsi
 
 // exact evaluation of up to 32 queued candidates (one per lane).  Out of line on purpose: the hot filter loop must
 // stay inside the instruction cache (the first version inlined this 5x -> 64 KB of SASS, 55 % "no instruction" stalls).
+template <int MODE>
 __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool has, int lane)
 {
     const float4* __restrict__ tsegs = S.tsegs; const float4* __restrict__ cache = S.cache;
@@ -139,7 +139,7 @@ __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool 
         rl = (int)(entry >> 24);
         unsigned int j = entry & 0xFFFFFFu;
         if (j >= (unsigned int)S.Nt) j = 0u, has = false;         // padding segment of a partial stage
-        if (S.mode) { if (has) pending = eval_candidate_f64(S, rl, j, &key); }
+        if (MODE) { if (has) pending = eval_candidate_f64(S, rl, j, &key); }
         else {
             float4 q = __ldg(tsegs + j);
             float4 rA = S.rowA[rl], rB = S.rowB[rl];
@@ -183,6 +183,7 @@ __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool 
 }
 
 // select the k best survivors of each of this warp's rows and write them once (once per CTA: out of line)
+template <int MODE>
 __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int nrows, long long R0, int* __restrict__ counts_out,
                                            l3d_match_rec* __restrict__ recs_out)
 {
@@ -199,7 +200,7 @@ __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int
         if (lane < n && rank < knn) {
             unsigned int j = key_tgt(key);
             float d[4];
-            if (S.mode) {
+            if (MODE) {
                 const SegRaysD s = load_rays_d(S.cache_d, S.src_base + rl), t = load_rays_d(S.cache_d, S.toff + j);
                 double dd[4];
                 exact_depths_f64(s, t, S.Csd, S.Ctd, dd);
@@ -216,8 +217,8 @@ __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int
     }
 }
 
-__global__ void __launch_bounds__(MK_THREADS, MK_MINB)
-k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
+template <int MODE>
+__device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
              const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
              int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d)
 {
@@ -238,8 +239,8 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
     if (tid == 0) {
         S.tsegs = tsegs; S.cache = cache; S.src_base = soff + row0; S.toff = toff; S.epi = epi; S.knn = knn; S.Nt = Nt;
         S.Cs = make_float3(vs->C[0], vs->C[1], vs->C[2]); S.Ct = make_float3(vt->C[0], vt->C[1], vt->C[2]);
-        S.mode = cache_d != nullptr; S.cache_d = cache_d; S.ssegs = segs + soff + row0;
-        if (cache_d) {
+        S.cache_d = cache_d; S.ssegs = segs + soff + row0;
+        if (MODE) {
             for (int i = 0; i < 9; ++i) S.Fd[i] = P->Fd[i];
             S.Csd = d3(vs->C_d[0], vs->C_d[1], vs->C_d[2]); S.Ctd = d3(vt->C_d[0], vt->C_d[1], vt->C_d[2]);
         }
@@ -312,7 +313,7 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
                         __syncwarp();
                         while (qn >= 32) {
                             qn -= 32;
-                            exact_batch(S, S.queue[warp][qn + lane], true, lane);
+                            exact_batch<MODE>(S, S.queue[warp][qn + lane], true, lane);
                         }
                     }
                 }
@@ -330,12 +331,25 @@ k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, 
     }
     if (qn > 0) {
         bool has = lane < qn;
-        exact_batch(S, has ? S.queue[warp][lane] : 0u, has, lane);
+        exact_batch<MODE>(S, has ? S.queue[warp][lane] : 0u, has, lane);
     }
     __syncwarp();
 
-    finalize_rows(S, warp, lane, nrows, P->row_off + row0, counts_out, recs_out);
+    finalize_rows<MODE>(S, warp, lane, nrows, P->row_off + row0, counts_out, recs_out);
 }
+
+__global__ void __launch_bounds__(MK_THREADS, MK_MINB)
+k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
+             const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
+             int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out)
+{ match_topk_body<0>(segs, cache, views, pairs, tiles, knn, epi, counts_out, recs_out, nullptr); }
+
+// REF_CPU semantics: same tiling, staging and filter; the exact path is matchingCPU's double arithmetic
+__global__ void __launch_bounds__(MK_THREADS, MK_MINB)
+k_match_topk_f64(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
+                 const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
+                 int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d)
+{ match_topk_body<1>(segs, cache, views, pairs, tiles, knn, epi, counts_out, recs_out, cache_d); }
 
 // ------------------------------------------------------------------------------------------------ dense contract
 // K_match_lines' device contract: depths[Ns][Nt] (float4) + overlaps[Ns][Nt] (float) for EVERY cell, 20 B written per

@@ -44,7 +44,11 @@ __global__ void k_prep_segments(const float4* __restrict__ segs, const L3DViewDe
 __global__ void k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache,
                              const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
                              const int2* __restrict__ tiles, int knn, float epi, int* __restrict__ counts_out,
-                             l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d /* non-null: REF_CPU */);
+                             l3d_match_rec* __restrict__ recs_out);
+__global__ void k_match_topk_f64(const float4* __restrict__ segs, const float4* __restrict__ cache,
+                                 const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
+                                 const int2* __restrict__ tiles, int knn, float epi, int* __restrict__ counts_out,
+                                 l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d);
 __global__ void k_prep_segments_f64(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int num_views,
                                     long long total, double* __restrict__ cache);
 __global__ void k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
