@@ -138,6 +138,16 @@ class Context:
                   "l3d_match_pairs_range")
         self._knn = int(knn)
 
+    def match_pairs_f64(self, pairs, Fd, epi_overlap=0.25, knn=10, first=0, last=None):
+        """REF_CPU semantics: matchingCPU's double arithmetic (line3D.cc:900-1015) with double fundamental matrices"""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        Fd = np.ascontiguousarray(Fd, np.float64).reshape(-1, 9)
+        assert len(pairs) == len(Fd)
+        last = len(pairs) if last is None else last
+        self._chk(self.L.l3d_match_pairs_f64(self.h, len(pairs), _p(pairs), _p(Fd), C.c_float(epi_overlap), int(knn), int(first), int(last)),
+                  "l3d_match_pairs_f64")
+        self._knn = int(knn)
+
     def match_device_buffers(self):
         """(counts_ptr, recs_ptr) device addresses of the last match result"""
         a, b = C.c_void_p(), C.c_void_p()

@@ -16,13 +16,13 @@ struct SweepState {
     long long total = 0;
     DevBuf d_slot_score, d_keys, d_keys2, d_vals, d_vals2, d_reg, d_dir, d_meta, d_dep, d_os, d_kept, d_ranges, d_est_best, d_est_P,
         d_M, d_vmax, d_work, d_camrank, d_viewofrank, d_sort_tmp, d_aff_sim, d_aff_flag, d_aff_gi, d_aff_gj, d_aff_pos, d_aff_oi, d_aff_oj,
-        d_aff_ow, d_order, d_rankofview, d_region_off, d_reg_of_view, d_est_pos, d_est_out_best, d_est_out_P;
+        d_aff_ow, d_order, d_rankofview, d_region_off, d_reg_of_view, d_est_pos, d_est_out_best, d_est_out_P, d_slot_pos, d_dir64;
     long long n_est = 0;
     std::vector<DevBuf*> bufs()
     { return {&d_slot_score, &d_keys, &d_keys2, &d_vals, &d_vals2, &d_reg, &d_dir, &d_meta, &d_dep, &d_os, &d_kept, &d_ranges, &d_est_best,
               &d_est_P, &d_M, &d_vmax, &d_work, &d_camrank, &d_viewofrank, &d_sort_tmp, &d_aff_sim, &d_aff_flag, &d_aff_gi, &d_aff_gj,
               &d_aff_pos, &d_aff_oi, &d_aff_oj, &d_aff_ow, &d_order, &d_rankofview, &d_region_off, &d_reg_of_view, &d_est_pos,
-              &d_est_out_best, &d_est_out_P}; }
+              &d_est_out_best, &d_est_out_P, &d_slot_pos, &d_dir64}; }
 };
 
 // device state of the affinity-matrix bookkeeping (l3d_affinity.cu)

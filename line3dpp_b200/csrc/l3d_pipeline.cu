@@ -45,7 +45,11 @@ __device__ __forceinline__ DSeg dunproject(const L3DViewDev* v, float4 s, float 
 
 // sort key of a candidate match: (segment | rank of the target camera | target segment), packed as tightly as the
 // problem allows so that the radix sort touches few bits; bit `end_bit-1` is reserved for "invalid" (all ones)
-struct KeyBits { int seg_shift, cam_shift, end_bit; unsigned long long cam_mask, tgt_mask; };
+// REF_CPU semantics (mode 1): scoringCPU does not sort (only scoringGPU calls sortMatches, line3D.cc:1311), so the list
+// order of a segment is the order the matches were appended: first the inverse matches stored by the earlier views (in
+// those views' processing and list order = their global slot in the match store), then the direct matches in pair / kNN
+// order (= record index).  Key = (segment | direct? | origin index).
+struct KeyBits { int seg_shift, cam_shift, end_bit; unsigned long long cam_mask, tgt_mask; int mode; };
 static int bits_for(long long n) { int b = 1; while ((1ll << b) < n) ++b; return b; }
 
 // ---------------------------------------------------------------------------------------------- kernels
@@ -55,7 +59,8 @@ __global__ void __launch_bounds__(256)
 k_gather(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
          const int* __restrict__ counts, const l3d_match_rec* __restrict__ recs, const float* __restrict__ slot_score,
          const int4* __restrict__ work, int nwork, int v, int knn, const int* __restrict__ cam_rank,
-         unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals, int U, int* __restrict__ Mcount, KeyBits kb)
+         unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals, int U, int* __restrict__ Mcount, KeyBits kb,
+         const int* __restrict__ slot_pos, const long long* __restrict__ region_of_view)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
@@ -85,7 +90,10 @@ k_gather(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, 
                 double ang = acos(fmin(fmax(ddot(r1, S3.dir), -1.0), 1.0));
                 if (ang > (double)L3D_PI_1_32_F && ang < (double)L3D_PI_31_32_F) {
                     valid = true;
-                    key = ((unsigned long long)seg << kb.seg_shift) | ((unsigned long long)cam_rank[tgt_view] << kb.cam_shift) | (unsigned long long)tgt_seg;
+                    if (kb.mode == 0)
+                        key = ((unsigned long long)seg << kb.seg_shift) | ((unsigned long long)cam_rank[tgt_view] << kb.cam_shift) | (unsigned long long)tgt_seg;
+                    else if (!wk.y) key = ((unsigned long long)seg << kb.seg_shift) | (1ull << kb.cam_shift) | (unsigned long long)g;
+                    else key = ((unsigned long long)seg << kb.seg_shift) | (unsigned long long)(region_of_view[tgt_view] + slot_pos[g]);
                     val = (unsigned int)g | (wk.y ? 0x80000000u : 0u);
                 }
             }
@@ -103,16 +111,25 @@ k_build(const float4* __restrict__ segs, const float4* __restrict__ cache, const
         int v, int knn, const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals,
         const int* __restrict__ Mcount, const int* __restrict__ view_of_camrank,
         int4* __restrict__ m_meta, float4* __restrict__ m_dep, float2* __restrict__ m_os, float2* __restrict__ m_reg,
-        float4* __restrict__ m_dir, int2* __restrict__ ranges, KeyBits kb)
+        float4* __restrict__ m_dir, int2* __restrict__ ranges, KeyBits kb, int num_pairs, double4* __restrict__ m_dir64)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int M = *Mcount;
     if (x >= M) return;
     const unsigned long long key = keys[x];
-    const int seg = (int)(key >> kb.seg_shift), tgt_view = view_of_camrank[(int)((key >> kb.cam_shift) & kb.cam_mask)], tgt_seg = (int)(key & kb.tgt_mask);
+    const int seg = (int)(key >> kb.seg_shift);
     const unsigned int val = vals[x];
     const bool inv = (val & 0x80000000u) != 0u;
     const l3d_match_rec rec = recs[val & 0x7FFFFFFFu];
+    int tgt_view, tgt_seg;
+    if (kb.mode == 0) { tgt_view = view_of_camrank[(int)((key >> kb.cam_shift) & kb.cam_mask)]; tgt_seg = (int)(key & kb.tgt_mask); }
+    else {      // the key carries the list position, not the target: find the record's pair by its row
+        const long long row = (long long)(val & 0x7FFFFFFFu) / knn;
+        int lo = 0, hi = num_pairs - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pairs[mid].row_off <= row) lo = mid; else hi = mid - 1; }
+        tgt_view = inv ? pairs[lo].src : pairs[lo].tgt;
+        tgt_seg = inv ? (int)(row - pairs[lo].row_off) : (int)rec.tgt_seg;
+    }
     float4 dep = inv ? make_float4(rec.d_q1, rec.d_q2, rec.d_p1, rec.d_p2) : make_float4(rec.d_p1, rec.d_p2, rec.d_q1, rec.d_q2);
     m_meta[x] = make_int4(seg, tgt_view, tgt_seg, (int)val);
     m_dep[x] = dep;
@@ -120,12 +137,13 @@ k_build(const float4* __restrict__ segs, const float4* __restrict__ cache, const
     const L3DViewDev* V = views + v;
     const L3DViewDev* T = views + tgt_view;
     const float4 s = segs[V->seg_off + seg];
-    {   // regularizers_tgt (line3D.cc:1350-1352): |P - C_tgt| * k_tgt in double, stored as float
+    {   // regularizers_tgt (line3D.cc:1350-1352) == View::regularizerFrom3Dpoint (view.cc:445-448): |P - C_tgt| * k_tgt in double, stored as float
         DSeg S3 = dunproject(V, s, dep.x, dep.y);
         D3 Ct = d3(T->C_d[0], T->C_d[1], T->C_d[2]);
         m_reg[x] = make_float2((float)(dnorm(dsub(S3.P1, Ct)) * (double)T->k), (float)(dnorm(dsub(S3.P2, Ct)) * (double)T->k));
+        if (kb.mode) m_dir64[x] = make_double4(S3.dir.x, S3.dir.y, S3.dir.z, (double)S3.length);     // scoringCPU works on the double 3D segment
     }
-    {   // D_unproject x2 + D_line_direction_3D (cudawrapper.cu:167-171, 40-43) with the cached float rays
+    if (kb.mode == 0) {   // D_unproject x2 + D_line_direction_3D (cudawrapper.cu:167-171, 40-43) with the cached float rays
         SegRays R = load_rays(cache, V->seg_off + seg);
         float3 C = make_float3(V->C[0], V->C[1], V->C[2]);
         float3 P1 = make_float3(C.x + dep.x * R.r1.x, C.y + dep.x * R.r1.y, C.z + dep.x * R.r1.z);
@@ -192,18 +210,70 @@ k_score(const L3DViewDev* __restrict__ views, int v, const int* __restrict__ Mco
     m_os[x].y = score3D;
 }
 
+// G3 (REF_CPU): scoringCPU (line3D.cc:1208-1294) + similarityForScoring (1417-1446) + angleBetweenSeg3D (1571-1583), one
+// thread per match.  The score is the sum over target cameras of the best similarity among that camera's matches, built
+// with the reference's running update (add the first value of a camera, replace it when a larger one arrives) in list order.
+#define SC_MAP 48
+__global__ void __launch_bounds__(128)
+k_score_cpu(const L3DViewDev* __restrict__ views, int v, const int* __restrict__ Mcount, const int4* __restrict__ m_meta,
+            const float4* __restrict__ m_dep, const float2* __restrict__ m_reg, const double4* __restrict__ m_dir64,
+            const int2* __restrict__ ranges, float angle_reg, float sim_t, float2* __restrict__ m_os)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= *Mcount) return;
+    const float k = views[v].k;
+    const int4 me = m_meta[x];
+    const float4 dep = m_dep[x];
+    const double4 D1 = m_dir64[x];
+    const float sig1 = dep.x * k, sig2 = dep.y * k;
+    float reg1 = 2.0f * sig1 * sig1, reg2 = 2.0f * sig2 * sig2;
+    const float2 rg = m_reg[x];
+    reg1 = 0.5f * (reg1 + 2.0f * rg.x * rg.x); reg2 = 0.5f * (reg2 + 2.0f * rg.y * rg.y);
+    const int2 rng = ranges[me.x];
+    auto sim_of = [&](int i) -> float {
+        const double4 D2 = m_dir64[i];
+        if ((float)D1.w < L3D_EPS_D || (float)D2.w < L3D_EPS_D) return 0.0f;
+        const float dot_p = (float)(D1.x * D2.x + D1.y * D2.y + D1.z * D2.z);
+        float angle = (float)((double)acosf(fmaxf(fminf(dot_p, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
+        if (angle > 90.0f) angle = 180.0f - angle;
+        const float sim_a = expf(-angle * angle / angle_reg);
+        const float4 d2 = m_dep[i];
+        const float e1 = dep.x - d2.x, e2 = dep.y - d2.y;
+        const float sim_p = fminf(expf(-e1 * e1 / reg1), expf(-e2 * e2 / reg2));
+        const float sm = fminf(sim_a, sim_p);
+        return sm > sim_t ? sm : 0.0f;
+    };
+    int cams[SC_MAP]; float best[SC_MAP]; int ncam = 0;
+    float score3D = 0.0f;
+    for (int i = rng.x; i <= rng.y; ++i) {
+        const int cam = m_meta[i].y;
+        if (cam == me.y) continue;
+        const float sim = sim_of(i);
+        int slot = -1;
+        for (int j = 0; j < ncam; ++j) if (cams[j] == cam) { slot = j; break; }
+        if (slot >= 0) { if (sim > best[slot]) { score3D -= best[slot]; score3D += sim; best[slot] = sim; } }
+        else if (ncam < SC_MAP) { score3D += sim; cams[ncam] = cam; best[ncam] = sim; ++ncam; }
+        else {      // more target cameras than map slots: recover this camera's running maximum from the earlier entries
+            bool seen = false; float cur = 0.0f;
+            for (int j = rng.x; j < i; ++j) if (m_meta[j].y == cam) { const float sj = sim_of(j); if (!seen) { cur = sj; seen = true; } else if (sj > cur) cur = sj; }
+            if (seen) { if (sim > cur) { score3D -= cur; score3D += sim; } } else score3D += sim;
+        }
+    }
+    m_os[x].y = score3D;
+}
+
 // G4: publish the scores of direct matches to their record slots (read later by the target views as inverse matches)
 //     and reduce the view's maximum score.
 __global__ void __launch_bounds__(256)
 k_post_score(const int* __restrict__ Mcount, const int4* __restrict__ m_meta, const float2* __restrict__ m_os,
-             float* __restrict__ slot_score, int* __restrict__ view_max_bits)
+             float* __restrict__ slot_score, int* __restrict__ view_max_bits, int* __restrict__ slot_pos /* REF_CPU only */)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     float s = 0.0f;
     if (x < *Mcount) {
         s = m_os[x].y;
         const unsigned int val = (unsigned int)m_meta[x].w;
-        if (!(val & 0x80000000u)) slot_score[val] = s;
+        if (!(val & 0x80000000u)) { slot_score[val] = s; if (slot_pos) slot_pos[val] = x; }
     }
     s = fmaxf(s, 0.0f);
     for (int o = 16; o; o >>= 1) s = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, o));
@@ -310,17 +380,22 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
         nseg_max = std::max(nseg_max, c->h_views[v].nseg);
     }
     S.region_off[V] = total; S.total = total;
+    const long long slots = c->total_rows * knn;
+    const bool cpu_sem = c->semantics == L3D_SEM_REF_CPU;
     KeyBits kb;
-    {
+    if (!cpu_sem) {
         const int bt = bits_for(nseg_max), bc = bits_for(V);
         kb.cam_shift = bt; kb.seg_shift = bt + bc; kb.end_bit = bt + bc + bt + 1;
-        kb.cam_mask = (1ull << bc) - 1ull; kb.tgt_mask = (1ull << bt) - 1ull;
-        if (kb.end_bit > 64) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: views x segments too large for a 64-bit sort key");
+        kb.cam_mask = (1ull << bc) - 1ull; kb.tgt_mask = (1ull << bt) - 1ull; kb.mode = 0;
+    } else {
+        const int bo = bits_for(std::max(total, slots) + 1), bt = bits_for(nseg_max);
+        kb.cam_shift = bo; kb.seg_shift = bo + 1; kb.end_bit = bo + 1 + bt + 1;
+        kb.cam_mask = 1ull; kb.tgt_mask = (1ull << bo) - 1ull; kb.mode = 1;
     }
+    if (kb.end_bit > 64) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: views x segments too large for a 64-bit sort key");
     if (Umax >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: view with more than 2^31 candidates");
 
     int rc;
-    const long long slots = c->total_rows * knn;
 #define RES(buf, bytes, what) if ((rc = l3d_reserve(c, buf, (size_t)std::max<long long>((long long)(bytes), 16), what))) return rc
     RES(S.d_slot_score, sizeof(float) * slots, "slot scores");
     RES(S.d_keys, 8 * Umax, "keys"); RES(S.d_keys2, 8 * Umax, "keys2"); RES(S.d_vals, 4 * Umax, "vals"); RES(S.d_vals2, 4 * Umax, "vals2");
@@ -329,6 +404,8 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     RES(S.d_ranges, 8 * c->total_segs, "ranges"); RES(S.d_est_best, 4 * c->total_segs, "estimates"); RES(S.d_est_P, 48 * c->total_segs, "estimate points");
     RES(S.d_M, 4 * (size_t)V, "match counts"); RES(S.d_vmax, 4 * (size_t)V, "view max"); RES(S.d_work, 16 * (size_t)wmax, "work items");
     RES(S.d_camrank, 4 * (size_t)V, "cam rank"); RES(S.d_viewofrank, 4 * (size_t)V, "view of rank");
+    RES(S.d_reg_of_view, 8 * (size_t)V, "region of view");
+    if (cpu_sem) { RES(S.d_slot_pos, 4 * slots, "slot positions"); RES(S.d_dir64, 32 * Umax, "double directions"); }
     size_t sort_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)Umax, 0, kb.end_bit, c->stream);
     RES(S.d_sort_tmp, sort_bytes, "sort temp");
@@ -340,7 +417,10 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     L3D_CUDA(c, cudaMemsetAsync(S.d_vmax.p, 0, 4 * (size_t)V, st), "init maxima");
     L3D_CUDA(c, cudaMemcpyAsync(S.d_camrank.p, rank.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "cam rank");
     L3D_CUDA(c, cudaMemcpyAsync(S.d_viewofrank.p, view_of_rank.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "view of rank");
-    L3D_CUDA(c, cudaStreamSynchronize(st), "sync");   // rank/view_of_rank are stack-scoped
+    std::vector<long long> reg_of_view(V);
+    for (int i = 0; i < V; ++i) reg_of_view[S.order[i]] = S.region_off[i];
+    L3D_CUDA(c, cudaMemcpyAsync(S.d_reg_of_view.p, reg_of_view.data(), 8 * (size_t)V, cudaMemcpyHostToDevice, st), "region of view");
+    L3D_CUDA(c, cudaStreamSynchronize(st), "sync");   // rank/view_of_rank/reg_of_view are stack-scoped
 
     // shortcut thresholds of k_score (see there); disabled (never true) when sim_t <= 0 or the margins do not apply
     float q_thr = INFINITY, cos_thr = -1.0f;
@@ -373,16 +453,20 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
         const int nb = (U + 255) / 256;
         k_gather<<<nb, 256, 0, st>>>(segs, views, pairs, counts, recs, (const float*)S.d_slot_score.p, (const int4*)S.d_work.p + work_off[i],
                                      work_off[i + 1] - work_off[i], v, knn, (const int*)S.d_camrank.p, (unsigned long long*)S.d_keys.p,
-                                     (unsigned int*)S.d_vals.p, U, Mc, kb);
+                                     (unsigned int*)S.d_vals.p, U, Mc, kb, cpu_sem ? (const int*)S.d_slot_pos.p : nullptr, (const long long*)S.d_reg_of_view.p);
         size_t tb = S.d_sort_tmp.cap;
         cub::DeviceRadixSort::SortPairs(S.d_sort_tmp.p, tb, (const unsigned long long*)S.d_keys.p, (unsigned long long*)S.d_keys2.p,
                                         (const unsigned int*)S.d_vals.p, (unsigned int*)S.d_vals2.p, U, 0, kb.end_bit, st);
         k_build<<<nb, 256, 0, st>>>(segs, cache, views, pairs, recs, v, knn, (const unsigned long long*)S.d_keys2.p,
                                     (const unsigned int*)S.d_vals2.p, Mc, (const int*)S.d_viewofrank.p, m_meta, m_dep, m_os,
-                                    (float2*)S.d_reg.p, (float4*)S.d_dir.p, ranges, kb);
-        k_score<<<(U + 127) / 128, 128, 0, st>>>(views, v, Mc, m_meta, m_dep, (const float2*)S.d_reg.p, (const float4*)S.d_dir.p, ranges,
-                                                two_sigA_sqr, min_similarity, q_thr, cos_thr, m_os);
-        k_post_score<<<nb, 256, 0, st>>>(Mc, m_meta, m_os, (float*)S.d_slot_score.p, vmax);
+                                    (float2*)S.d_reg.p, (float4*)S.d_dir.p, ranges, kb, NP, cpu_sem ? (double4*)S.d_dir64.p : nullptr);
+        if (cpu_sem)
+            k_score_cpu<<<(U + 127) / 128, 128, 0, st>>>(views, v, Mc, m_meta, m_dep, (const float2*)S.d_reg.p, (const double4*)S.d_dir64.p, ranges,
+                                                        two_sigA_sqr, min_similarity, m_os);
+        else
+            k_score<<<(U + 127) / 128, 128, 0, st>>>(views, v, Mc, m_meta, m_dep, (const float2*)S.d_reg.p, (const float4*)S.d_dir.p, ranges,
+                                                    two_sigA_sqr, min_similarity, q_thr, cos_thr, m_os);
+        k_post_score<<<nb, 256, 0, st>>>(Mc, m_meta, m_os, (float*)S.d_slot_score.p, vmax, cpu_sem ? (int*)S.d_slot_pos.p : nullptr);
         k_filter<<<(nseg + 255) / 256, 256, 0, st>>>(segs, views, v, ranges, m_meta, m_dep, m_os, vmax, min_best_score, min_best_perc, kept,
                                                     (int*)S.d_est_best.p, (double*)S.d_est_P.p);
         c->launches += 5 + 8;   // + cub radix sort passes (histogram + 7 onesweep passes for 64-bit keys)
@@ -399,11 +483,7 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     // compact the estimates on the device: flags -> exclusive scan -> gather (best match record + P1,P2)
     {
         const long long N = c->total_segs;
-        std::vector<long long> reg_of_view(V);
-        for (int i = 0; i < V; ++i) reg_of_view[S.order[i]] = S.region_off[i];
-        if ((rc = l3d_reserve(c, S.d_reg_of_view, 8 * (size_t)V, "region of view"))) return rc;
         if ((rc = l3d_reserve(c, S.d_est_pos, 8 * (size_t)(N + 1), "estimate positions"))) return rc;
-        L3D_CUDA(c, cudaMemcpyAsync(S.d_reg_of_view.p, reg_of_view.data(), 8 * (size_t)V, cudaMemcpyHostToDevice, st), "region of view");
         cub::TransformInputIterator<long long, HasEstimate, const int*> flags((const int*)S.d_est_best.p, HasEstimate());
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, (long long*)S.d_est_pos.p, N, st);

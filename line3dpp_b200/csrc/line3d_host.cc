@@ -394,7 +394,7 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
     }
     // view pairs in the reference's order (computeMatches line3D.cc:704-741) + float fundamental matrices
     P.pairs.clear();
-    std::vector<float> F;
+    std::vector<float> F; std::vector<double> Fdbl;
     std::set<std::pair<unsigned int, unsigned int> > done;
     for (auto& kv : P.visual_neighbors)
         for (unsigned int n : kv.second) {
@@ -403,7 +403,7 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
             done.insert(std::make_pair(std::min(s, n), std::max(s, n)));
             P.pairs.push_back(P.index_of[s]); P.pairs.push_back(P.index_of[n]);
             const Matrix3d Fd = P.fundamental(P.views[s], P.views[n]);
-            for (int i = 0; i < 9; ++i) F.push_back((float)Fd.m[i]);                    // eigen2dataArray line3D.cc:2775-2781
+            for (int i = 0; i < 9; ++i) { F.push_back((float)Fd.m[i]); Fdbl.push_back(Fd.m[i]); }   // eigen2dataArray line3D.cc:2775-2781
         }
     const int npairs = (int)(P.pairs.size() / 2);
     if (P.kNN <= 0) { P.fail("kNN <= 0 (keep all matches) is not supported by the B200 matching kernel yet"); P.untranslate(); return; }
@@ -413,13 +413,19 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
     for (size_t i = 0; i < P.vlist.size(); ++i) segp[i] = &P.vlist[i]->lines[0].v[0];
     auto t0 = std::chrono::steady_clock::now();
     bool ok = P.chk(l3d_set_views(P.ctx, (int)d.size(), d.data(), segp.data()), "l3d_set_views");
+    // use_GPU selects the reference's semantics, not the processor (line3D.cc:708-757): true = K_match_lines / K_score_matches
+    // float arithmetic, false = matchingCPU / scoringCPU double arithmetic.  Both run on the B200.
+    auto match_range = [&](int first, int last) {
+        return P.use_gpu ? P.chk(l3d_match_pairs_range(P.ctx, npairs, P.pairs.data(), F.data(), P.epi, P.kNN, first, last), "l3d_match_pairs_range")
+                         : P.chk(l3d_match_pairs_f64(P.ctx, npairs, P.pairs.data(), Fdbl.data(), P.epi, P.kNN, first, last), "l3d_match_pairs_f64");
+    };
     if (ok && P.shard_world > 1) {
         // this rank's contiguous share of the pair list, balanced by Ns*Nt; the same split on every rank
         std::vector<long long> cost((size_t)npairs), row_off((size_t)npairs + 1), row_bounds((size_t)P.shard_world + 1);
         for (int i = 0; i < npairs; ++i) cost[i] = (long long)P.vlist[P.pairs[2 * i]]->lines.size() * (long long)P.vlist[P.pairs[2 * i + 1]]->lines.size();
         std::vector<int32_t> bounds((size_t)P.shard_world + 1);
         ok = P.chk(l3d_balanced_split(cost.data(), npairs, P.shard_world, bounds.data()), "l3d_balanced_split") &&
-             P.chk(l3d_match_pairs_range(P.ctx, npairs, P.pairs.data(), F.data(), P.epi, P.kNN, bounds[P.shard_rank], bounds[P.shard_rank + 1]), "l3d_match_pairs_range") &&
+             match_range(bounds[P.shard_rank], bounds[P.shard_rank + 1]) &&
              P.chk(l3d_sync(P.ctx), "l3d_sync") && P.chk(l3d_pair_row_offsets(P.ctx, row_off.data()), "l3d_pair_row_offsets");
         void *dc = nullptr, *dr = nullptr;
         ok = ok && P.chk(l3d_match_device_buffers(P.ctx, &dc, &dr), "l3d_match_device_buffers");
@@ -428,7 +434,7 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
             if (P.exchange(P.exchange_user, dc, dr, row_bounds.data(), P.shard_world, P.kNN) != 0) { P.fail("matchImages: the match exchange callback failed"); ok = false; }
         }
     } else
-        ok = ok && P.chk(l3d_match_pairs(P.ctx, npairs, P.pairs.data(), F.data(), P.epi, P.kNN), "l3d_match_pairs") && P.chk(l3d_sync(P.ctx), "l3d_sync");
+        ok = ok && match_range(0, npairs) && P.chk(l3d_sync(P.ctx), "l3d_sync");
     auto t1 = std::chrono::steady_clock::now();
     ok = ok && P.chk(l3d_score_sweep(P.ctx, P.two_sigA_sqr, MIN_SIMILARITY_3D, MIN_BEST_SCORE_3D, MIN_BEST_SCORE_PERC), "l3d_score_sweep");
     auto t2 = std::chrono::steady_clock::now();
