@@ -85,7 +85,9 @@ int l3d_update_view_params(l3d_ctx* ctx, int num_views, const l3d_view_desc* vie
  * F[9*i..] = float fundamental matrix of pair i, row-major, (float)F_double like eigen2dataArray line3D.cc:2775.
  * For every src segment the kNN tgt segments with the highest epipolar overlap among those with
  * overlap > epi_overlap and all four depths > 0 are kept (cudawrapper.cu:605-645); ties: smaller tgt_seg first.
- * 1 <= knn <= 32.  Results stay on the device; fetch with the l3d_get_* calls. */
+ * 1 <= knn <= 32: the kNN best per src segment.  knn <= 0: keep ALL matches like the reference does (cudawrapper.cu:628-636),
+ * in ascending tgt_seg order; the record array then uses the row stride l3d_match_stride() = the largest row of the job
+ * (memory: total_rows * stride * 24 B).  Results stay on the device; fetch with the l3d_get_* calls. */
 int l3d_match_pairs(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn);
 /* sharded form (view pairs are independent given all segment lists): the whole pair list is staged, so
  * row offsets and buffer sizes are those of the full job, but only pairs [first_pair, last_pair) are evaluated here;
@@ -100,6 +102,8 @@ int l3d_match_pairs_range(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, con
  * and keeps the match lists in the reference's unsorted list order.  There is still no CPU fallback. */
 int l3d_match_pairs_f64(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const double* Fd, float epi_overlap, int knn,
                         int first_pair, int last_pair);
+/* slots per row of the record array of the last match result: knn, or the largest row when knn <= 0 was asked for */
+int l3d_match_stride(const l3d_ctx* ctx);
 #define L3D_SEM_REF_GPU 0
 #define L3D_SEM_REF_CPU 1
 /* semantics of the last match result (L3D_SEM_*), or < 0 */

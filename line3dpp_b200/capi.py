@@ -127,7 +127,7 @@ class Context:
         assert len(pairs) == len(F)
         self._chk(self.L.l3d_match_pairs(self.h, len(pairs), _p(pairs), _p(F), C.c_float(epi_overlap), int(knn)),
                   "l3d_match_pairs")
-        self._knn = int(knn)
+        self._knn = int(self.L.l3d_match_stride(self.h))
 
     def match_pairs_range(self, pairs, F, first, last, epi_overlap=0.25, knn=10):
         """sharded form: stage all pairs, evaluate only [first, last) here (include/l3d_capi.h)"""
@@ -136,7 +136,7 @@ class Context:
         assert len(pairs) == len(F)
         self._chk(self.L.l3d_match_pairs_range(self.h, len(pairs), _p(pairs), _p(F), C.c_float(epi_overlap), int(knn), int(first), int(last)),
                   "l3d_match_pairs_range")
-        self._knn = int(knn)
+        self._knn = int(self.L.l3d_match_stride(self.h))
 
     def match_pairs_f64(self, pairs, Fd, epi_overlap=0.25, knn=10, first=0, last=None):
         """REF_CPU semantics: matchingCPU's double arithmetic (line3D.cc:900-1015) with double fundamental matrices"""
@@ -146,7 +146,7 @@ class Context:
         last = len(pairs) if last is None else last
         self._chk(self.L.l3d_match_pairs_f64(self.h, len(pairs), _p(pairs), _p(Fd), C.c_float(epi_overlap), int(knn), int(first), int(last)),
                   "l3d_match_pairs_f64")
-        self._knn = int(knn)
+        self._knn = int(self.L.l3d_match_stride(self.h))
 
     def match_device_buffers(self):
         """(counts_ptr, recs_ptr) device addresses of the last match result"""

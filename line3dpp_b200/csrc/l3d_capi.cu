@@ -3,10 +3,12 @@
 // l3d_pipeline.cu.  There is no CPU fallback: every entry needs a live CUDA context and fails loudly otherwise.
 #include "l3d_ctx.cuh"
 
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 
@@ -54,6 +56,7 @@ int l3d_ctx_create(int device, l3d_ctx** out)
     cudaGetDeviceProperties(&prop, device);
     c->num_sms = prop.multiProcessorCount;
     e = cudaFuncSetAttribute(k_match_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3d_match_smem_bytes());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3d_match_smem_bytes());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_topk_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3d_match_smem_bytes());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3d_dense_smem_bytes());
     if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return L3D_ERR_CUDA; }
@@ -193,7 +196,7 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
     if (!c->have_views) return l3d_fail(c, L3D_ERR_STATE, "l3d_match_pairs: call l3d_set_views first");
     if (num_pairs < 0 || (num_pairs && (!pairs || (!F && !Fd)))) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs: bad arguments");
     if (first_pair < 0 || last_pair < first_pair || last_pair > num_pairs) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs_range: bad pair range");
-    if (knn <= 0) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: kNN <= 0 (keep all matches) is not implemented; use l3d_match_dense");
+    const bool keep_all = knn <= 0;
     if (knn > 32) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: kNN > 32 not implemented");
     cudaSetDevice(c->device);
     L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync before pair staging");   // h_pairs/h_tiles may still be in flight
@@ -221,7 +224,7 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
     if ((rc = l3d_reserve(c, c->d_pairs, sizeof(L3DPairDev) * (size_t)std::max(num_pairs, 1), "pairs"))) return rc;
     if ((rc = l3d_reserve(c, c->d_tiles, sizeof(int2) * std::max<size_t>(c->h_tiles.size(), 1), "tiles"))) return rc;
     if ((rc = l3d_reserve(c, c->d_counts, sizeof(int) * (size_t)std::max<long long>(rows, 1), "match counts"))) return rc;
-    if ((rc = l3d_reserve(c, c->d_recs, sizeof(l3d_match_rec) * (size_t)std::max<long long>(rows, 1) * knn, "match records"))) return rc;
+    if (!keep_all && (rc = l3d_reserve(c, c->d_recs, sizeof(l3d_match_rec) * (size_t)std::max<long long>(rows, 1) * knn, "match records"))) return rc;
     if (num_pairs) L3D_CUDA(c, cudaMemcpyAsync(c->d_pairs.p, c->h_pairs.data(), sizeof(L3DPairDev) * num_pairs, cudaMemcpyHostToDevice, c->stream), "upload pairs");
     if (!c->h_tiles.empty()) L3D_CUDA(c, cudaMemcpyAsync(c->d_tiles.p, c->h_tiles.data(), sizeof(int2) * c->h_tiles.size(), cudaMemcpyHostToDevice, c->stream), "upload tiles");
     if (rows) L3D_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(int) * rows, c->stream), "clear counts");   // rows of pairs with Nt == 0
@@ -234,7 +237,45 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
         cache_d = (const double*)c->d_cache_d.p;
     }
     c->semantics = Fd ? L3D_SEM_REF_CPU : L3D_SEM_REF_GPU;
-    if (!c->h_tiles.empty()) {
+    if (keep_all) {
+        // "keep all matches" (cudawrapper.cu:628-636, line3D.cc:988-996): count pass -> row stride = largest row -> store pass -> sort rows
+        int stride = 1;
+        if (!c->h_tiles.empty()) {
+            k_match_all<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
+                c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, 0,
+                epi_overlap, (int*)c->d_counts.p, nullptr, cache_d);
+            ++c->launches;
+            L3D_CUDA(c, cudaGetLastError(), "k_match_all (count)");
+            size_t tb = 0;
+            cub::DeviceReduce::Max(nullptr, tb, (const int*)c->d_counts.p, (int*)nullptr, (int)std::min<long long>(rows, INT_MAX), c->stream);
+            if (rows > INT_MAX) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: more than 2^31 rows with kNN <= 0");
+            if ((rc = l3d_reserve(c, c->d_scan_tmp, tb, "reduce temp"))) return rc;
+            if ((rc = l3d_reserve(c, c->d_rowptr, 16, "row max"))) return rc;
+            int* d_max = (int*)c->d_rowptr.p;
+            L3D_CUDA(c, cub::DeviceReduce::Max(c->d_scan_tmp.p, tb, (const int*)c->d_counts.p, d_max, (int)rows, c->stream), "row maximum");
+            c->launches += 1;
+            L3D_CUDA(c, cudaMemcpyAsync(&stride, d_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream), "row maximum");
+            L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync");
+            stride = std::max(stride, 1);
+        }
+        knn = stride; c->knn = stride;
+        if ((rc = l3d_reserve(c, c->d_recs, sizeof(l3d_match_rec) * (size_t)std::max<long long>(rows, 1) * stride, "match records"))) return rc;
+        if (!c->h_tiles.empty()) {
+            const size_t per_warp = sizeof(l3d_match_rec) * (size_t)stride;
+            int wpb = 4;
+            while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+            if (per_warp * wpb > 200 * 1024) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: a row with more than 8500 matches (kNN <= 0)");
+            k_match_all<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
+                c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, stride,
+                epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, cache_d);
+            L3D_CUDA(c, cudaGetLastError(), "k_match_all (store)");
+            L3D_CUDA(c, cudaFuncSetAttribute(k_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)), "k_sort_rows smem");
+            const long long blocks = std::min<long long>((rows + wpb - 1) / wpb, (long long)c->num_sms * 16);
+            k_sort_rows<<<(unsigned int)blocks, wpb * 32, per_warp * wpb, c->stream>>>((const int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, stride, rows);
+            L3D_CUDA(c, cudaGetLastError(), "k_sort_rows");
+            c->launches += 2;
+        }
+    } else if (!c->h_tiles.empty()) {
         if (cache_d)
             k_match_topk_f64<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
                 c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, knn,
@@ -287,6 +328,7 @@ int l3d_balanced_split(const long long* cost, int n, int parts, int32_t* bounds)
     return L3D_OK;
 }
 
+int l3d_match_stride(const l3d_ctx* c) { return c && c->have_matches ? c->knn : L3D_ERR_STATE; }
 int l3d_match_semantics(const l3d_ctx* c) { return c && c->have_matches ? c->semantics : L3D_ERR_STATE; }
 long long l3d_match_total_rows(const l3d_ctx* c) { return c && c->have_matches ? c->total_rows : -1; }
 long long l3d_match_pair_evals(const l3d_ctx* c) { return c && c->have_matches ? c->pair_evals : -1; }

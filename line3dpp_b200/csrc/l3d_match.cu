@@ -74,6 +74,8 @@ struct MatchSmem {
     // REF_CPU semantics (k_match_topk_f64): the exact path is matchingCPU's double arithmetic; the float filter stays the same
     const double* cache_d; const float4* ssegs;
     double Fd[9]; D3 Csd, Ctd;
+    // keep-all modes (kNN <= 0, cudawrapper.cu:628-636): output row base / record array; knn then holds the row stride
+    long long R0; l3d_match_rec* recs_out;
 };
 size_t l3d_match_smem_bytes() { return sizeof(MatchSmem); }
 
@@ -108,7 +110,7 @@ __device__ __noinline__ void prune_row(MatchSmem& S, int row, int lane)
 }
 
 // matchingCPU's evaluation of one candidate (line3D.cc:925-1003): double overlap, double depths > 1e-12
-__device__ __noinline__ bool eval_candidate_f64(const MatchSmem& S, int rl, unsigned int j, unsigned long long* key)
+__device__ __noinline__ bool eval_candidate_f64(const MatchSmem& S, int rl, unsigned int j, float* ov_out, float* dep)
 {
     const float4 sp = __ldg(S.ssegs + rl);
     const D3 e1 = dmulmat(S.Fd, d3((double)sp.x, (double)sp.y, 1.0)), e2 = dmulmat(S.Fd, d3((double)sp.z, (double)sp.w, 1.0));
@@ -119,13 +121,16 @@ __device__ __noinline__ bool eval_candidate_f64(const MatchSmem& S, int rl, unsi
     double d[4];
     exact_depths_f64(s, t, S.Csd, S.Ctd, d);
     if (!(d[0] > L3D_EPS_D && d[1] > L3D_EPS_D && d[2] > L3D_EPS_D && d[3] > L3D_EPS_D)) return false;
-    *key = make_key(ov, j);
+    *ov_out = ov;
+    dep[0] = (float)d[0]; dep[1] = (float)d[1]; dep[2] = (float)d[2]; dep[3] = (float)d[3];     // Match stores floats (commons.h:186-203)
     return true;
 }
 
 // exact evaluation of up to 32 queued candidates (one per lane).  Out of line on purpose: the hot filter loop must
 // stay inside the instruction cache (the first version inlined this 5x -> 64 KB of SASS, 55 % "no instruction" stalls).
-template <int MODE>
+// KEEP: 0 = keep the kNN best per row; 1 = only count the survivors of every row; 2 = store every survivor (row stride
+// S.knn, slot = arrival order; k_sort_rows puts the rows into the reference's ascending-target order afterwards)
+template <int MODE, int KEEP>
 __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool has, int lane)
 {
     const float4* __restrict__ tsegs = S.tsegs; const float4* __restrict__ cache = S.cache;
@@ -139,21 +144,33 @@ __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool 
         rl = (int)(entry >> 24);
         unsigned int j = entry & 0xFFFFFFu;
         if (j >= (unsigned int)S.Nt) j = 0u, has = false;         // padding segment of a partial stage
-        if (MODE) { if (has) pending = eval_candidate_f64(S, rl, j, &key); }
+        float ov = 0.0f, d[4];
+        bool ok = false;
+        if (MODE) { if (has) ok = eval_candidate_f64(S, rl, j, &ov, d); }
         else {
             float4 q = __ldg(tsegs + j);
             float4 rA = S.rowA[rl], rB = S.rowB[rl];
             bool inv;
-            float ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
+            ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
             if (has && ov > epi && ov >= S.row_thr[rl]) {      // below the current k-th best it can never be selected
                 SegRays s = load_rays(cache, src_base + rl), t = load_rays(cache, toff + j);
-                float d[4];
                 exact_depths(s, t, Cs, Ct, d);
-                if (d[0] > 0.0f && d[1] > 0.0f && d[2] > 0.0f && d[3] > 0.0f) { key = make_key(ov, j); pending = true; }
+                ok = d[0] > 0.0f && d[1] > 0.0f && d[2] > 0.0f && d[3] > 0.0f;
+            }
+        }
+        if (ok) {
+            if (KEEP == 0) { key = make_key(ov, j); pending = true; }
+            else {
+                const int slot = atomicAdd(&S.list_cnt[rl], 1);         // a row belongs to one warp: no cross-warp contention
+                if (KEEP == 2 && slot < knn) {
+                    l3d_match_rec rec;
+                    rec.tgt_seg = j; rec.overlap = ov; rec.d_p1 = d[0]; rec.d_p2 = d[1]; rec.d_q1 = d[2]; rec.d_q2 = d[3];
+                    S.recs_out[(S.R0 + rl) * knn + slot] = rec;
+                }
             }
         }
     }
-    while (true) {
+    while (KEEP == 0) {
         if (pending) {
             int slot = atomicAdd(&S.list_cnt[rl], 1);
             if (slot < MK_CAP) { S.lists[rl][slot] = key; pending = false; }
@@ -183,7 +200,7 @@ __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool 
 }
 
 // select the k best survivors of each of this warp's rows and write them once (once per CTA: out of line)
-template <int MODE>
+template <int MODE, int KEEP>
 __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int nrows, long long R0, int* __restrict__ counts_out,
                                            l3d_match_rec* __restrict__ recs_out)
 {
@@ -191,8 +208,9 @@ __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int
     for (int r = 0; r < MK_RPW; ++r) {
         const int rl = warp * MK_RPW + r;
         if (rl >= nrows) break;
-        const int n = min(S.list_cnt[rl], MK_CAP);
         const long long R = R0 + rl;
+        if (KEEP != 0) { if (lane == 0) counts_out[R] = S.list_cnt[rl]; continue; }
+        const int n = min(S.list_cnt[rl], MK_CAP);
         if (lane == 0) counts_out[R] = min(n, knn);
         if (n == 0) continue;
         const unsigned long long key = lane < n ? S.lists[rl][lane] : 0ull;
@@ -204,7 +222,7 @@ __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int
                 const SegRaysD s = load_rays_d(S.cache_d, S.src_base + rl), t = load_rays_d(S.cache_d, S.toff + j);
                 double dd[4];
                 exact_depths_f64(s, t, S.Csd, S.Ctd, dd);
-                d[0] = (float)dd[0]; d[1] = (float)dd[1]; d[2] = (float)dd[2]; d[3] = (float)dd[3];     // Match stores floats (commons.h:186-203)
+                d[0] = (float)dd[0]; d[1] = (float)dd[1]; d[2] = (float)dd[2]; d[3] = (float)dd[3];
             } else {
                 SegRays s = load_rays(S.cache, S.src_base + rl), t = load_rays(S.cache, S.toff + j);
                 exact_depths(s, t, S.Cs, S.Ct, d);
@@ -217,7 +235,7 @@ __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int
     }
 }
 
-template <int MODE>
+template <int MODE, int KEEP>
 __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
              const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
              int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d)
@@ -239,7 +257,7 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
     if (tid == 0) {
         S.tsegs = tsegs; S.cache = cache; S.src_base = soff + row0; S.toff = toff; S.epi = epi; S.knn = knn; S.Nt = Nt;
         S.Cs = make_float3(vs->C[0], vs->C[1], vs->C[2]); S.Ct = make_float3(vt->C[0], vt->C[1], vt->C[2]);
-        S.cache_d = cache_d; S.ssegs = segs + soff + row0;
+        S.cache_d = cache_d; S.ssegs = segs + soff + row0; S.R0 = P->row_off + row0; S.recs_out = recs_out;
         if (MODE) {
             for (int i = 0; i < 9; ++i) S.Fd[i] = P->Fd[i];
             S.Csd = d3(vs->C_d[0], vs->C_d[1], vs->C_d[2]); S.Ctd = d3(vt->C_d[0], vt->C_d[1], vt->C_d[2]);
@@ -313,7 +331,7 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
                         __syncwarp();
                         while (qn >= 32) {
                             qn -= 32;
-                            exact_batch<MODE>(S, S.queue[warp][qn + lane], true, lane);
+                            exact_batch<MODE, KEEP>(S, S.queue[warp][qn + lane], true, lane);
                         }
                     }
                 }
@@ -331,25 +349,65 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
     }
     if (qn > 0) {
         bool has = lane < qn;
-        exact_batch<MODE>(S, has ? S.queue[warp][lane] : 0u, has, lane);
+        exact_batch<MODE, KEEP>(S, has ? S.queue[warp][lane] : 0u, has, lane);
     }
     __syncwarp();
 
-    finalize_rows<MODE>(S, warp, lane, nrows, P->row_off + row0, counts_out, recs_out);
+    finalize_rows<MODE, KEEP>(S, warp, lane, nrows, P->row_off + row0, counts_out, recs_out);
 }
 
 __global__ void __launch_bounds__(MK_THREADS, MK_MINB)
 k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
              const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
              int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out)
-{ match_topk_body<0>(segs, cache, views, pairs, tiles, knn, epi, counts_out, recs_out, nullptr); }
+{ match_topk_body<0, 0>(segs, cache, views, pairs, tiles, knn, epi, counts_out, recs_out, nullptr); }
 
 // REF_CPU semantics: same tiling, staging and filter; the exact path is matchingCPU's double arithmetic
 __global__ void __launch_bounds__(MK_THREADS, MK_MINB)
 k_match_topk_f64(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
                  const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
                  int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d)
-{ match_topk_body<1>(segs, cache, views, pairs, tiles, knn, epi, counts_out, recs_out, cache_d); }
+{ match_topk_body<1, 0>(segs, cache, views, pairs, tiles, knn, epi, counts_out, recs_out, cache_d); }
+
+// kNN <= 0 ("keep all matches", cudawrapper.cu:628-636 / line3D.cc:988-996): pass 1 counts the survivors of every row
+// (stride == 0), pass 2 stores them with the row stride found by pass 1.  cache_d != nullptr selects REF_CPU arithmetic.
+__global__ void __launch_bounds__(MK_THREADS, MK_MINB)
+k_match_all(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
+            const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int stride, float epi,
+            int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d)
+{
+    if (cache_d) {
+        if (stride == 0) match_topk_body<1, 1>(segs, cache, views, pairs, tiles, 0, epi, counts_out, recs_out, cache_d);
+        else match_topk_body<1, 2>(segs, cache, views, pairs, tiles, stride, epi, counts_out, recs_out, cache_d);
+    } else {
+        if (stride == 0) match_topk_body<0, 1>(segs, cache, views, pairs, tiles, 0, epi, counts_out, recs_out, nullptr);
+        else match_topk_body<0, 2>(segs, cache, views, pairs, tiles, stride, epi, counts_out, recs_out, nullptr);
+    }
+}
+
+// keep-all rows arrive in queue order; the reference appends them in ascending target order.  One warp per row, the row
+// staged in shared memory (stride * 24 B per warp), rank = number of smaller target indices (unique per row).
+__global__ void __launch_bounds__(128) k_sort_rows(const int* __restrict__ counts, l3d_match_rec* __restrict__ recs, int stride, long long rows)
+{
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    l3d_match_rec* buf = reinterpret_cast<l3d_match_rec*>(sort_smem) + (size_t)warp * stride;
+    for (long long row = (long long)blockIdx.x * wpb + warp; row < rows; row += (long long)gridDim.x * wpb) {
+        const int n = min(counts[row], stride);
+        if (n > 1) {
+            l3d_match_rec* g = recs + row * stride;
+            for (int i = lane; i < n; i += 32) buf[i] = g[i];
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                const unsigned int t = buf[i].tgt_seg;
+                int r = 0;
+                for (int j = 0; j < n; ++j) r += buf[j].tgt_seg < t;
+                g[r] = buf[i];
+            }
+        }
+        __syncwarp();
+    }
+}
 
 // ------------------------------------------------------------------------------------------------ dense contract
 // K_match_lines' device contract: depths[Ns][Nt] (float4) + overlaps[Ns][Nt] (float) for EVERY cell, 20 B written per

@@ -406,7 +406,6 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
             for (int i = 0; i < 9; ++i) { F.push_back((float)Fd.m[i]); Fdbl.push_back(Fd.m[i]); }   // eigen2dataArray line3D.cc:2775-2781
         }
     const int npairs = (int)(P.pairs.size() / 2);
-    if (P.kNN <= 0) { P.fail("kNN <= 0 (keep all matches) is not supported by the B200 matching kernel yet"); P.untranslate(); return; }
     // ---- device: upload, match all pairs, scoring sweep
     std::vector<l3d_view_desc> d = P.descs();
     std::vector<const float*> segp(P.vlist.size());
@@ -419,6 +418,7 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
         return P.use_gpu ? P.chk(l3d_match_pairs_range(P.ctx, npairs, P.pairs.data(), F.data(), P.epi, P.kNN, first, last), "l3d_match_pairs_range")
                          : P.chk(l3d_match_pairs_f64(P.ctx, npairs, P.pairs.data(), Fdbl.data(), P.epi, P.kNN, first, last), "l3d_match_pairs_f64");
     };
+    if (ok && P.shard_world > 1 && P.kNN <= 0) { P.fail("matchImages: kNN <= 0 (keep all matches) cannot be sharded: the row stride is only known after matching"); ok = false; }
     if (ok && P.shard_world > 1) {
         // this rank's contiguous share of the pair list, balanced by Ns*Nt; the same split on every rank
         std::vector<long long> cost((size_t)npairs), row_off((size_t)npairs + 1), row_bounds((size_t)P.shard_world + 1);

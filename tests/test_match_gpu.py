@@ -75,6 +75,57 @@ def test_topk_vs_reference_wrapper(loaded, scene, oracle, ref_nofma):
         assert nties <= 2
 
 
+@pytest.mark.parametrize("f64", [False, True])
+def test_keep_all_matches(loaded, scene, oracle, ref_nofma, f64):
+    """kNN <= 0: every cell with overlap > epi and positive depths is kept, in ascending target order
+    (cudawrapper.cu:628-636 / line3D.cc:988-996) -- against the verbatim wrapper (float) and the oracle's matchingCPU (double)"""
+    pairs = np.array(PAIRS[:3], np.int32)
+    if f64:
+        Fd = np.stack([synth.fundamental(scene.K[s], scene.R[s], scene.t[s], scene.K[t], scene.R[t], scene.t[t]).reshape(9) for s, t in pairs])
+        loaded.match_pairs_f64(pairs, Fd, 0.25, 0)
+    else:
+        loaded.match_pairs(pairs, util.pair_F(scene, pairs), 0.25, -1)
+    stride = loaded.L.l3d_match_stride(loaded.h)
+    assert stride > 10
+    biggest = 0
+    for p, (src, tgt) in enumerate(pairs):
+        pi = util.pair_inputs(scene, src, tgt)
+        if f64:
+            RtKinv, C = synth.camera_blocks(scene)
+            rcounts, rout, rtotal, _ = oracle.match_lines(oracle.lib().orc_match_lines_f64, pi["ls"], pi["lt"], Fd[p], RtKinv[src].reshape(9),
+                                                          RtKinv[tgt].reshape(9), C[src], C[tgt], src, tgt, 0.25, 0, f64=True)
+        else:
+            rcounts, rout, rtotal, _ = oracle.match_lines(ref_nofma.ref_match_lines, pi["ls"], pi["lt"], pi["F"], pi["Rs"], pi["Rt"], pi["Cs"],
+                                                          pi["Ct"], src, tgt, 0.25, 0)
+        counts, recs = loaded.pair_matches(p, len(pi["ls"]))
+        assert np.array_equal(counts, rcounts) and rtotal == counts.sum()
+        biggest = max(biggest, int(counts.max()))
+        for r in range(len(counts)):
+            a, b = recs[r, :counts[r]], rout[r, :counts[r]]
+            for f in ("tgt_seg", "overlap", "d_p1", "d_p2", "d_q1", "d_q2"):
+                assert a[f].tobytes() == b[f].tobytes(), (src, tgt, r, f)          # same members, same ORDER, bit-exact payload
+    assert biggest <= stride
+
+
+def test_keep_all_pipeline_vs_reference_kernels(oracle, ref_nofma):
+    """matchImages(kNN = -1) end to end: scored matches bit-identical to the reference kernels behind the oracle host logic"""
+    from line3dpp_b200 import line3d
+    sc = synth.make_scene(6, 250, 13, "ring2")
+    L = line3d.Line3D(neighbors_by_worldpoints=False)
+    L.add_scene(sc); L.match_images(knn=-1)
+    P = oracle.OraclePipeline(False, True, backend=ref_nofma)
+    P.add_scene(sc); P.match_images(knn=-1)
+    n = 0
+    for cam in sc.cam_ids:
+        g, o = L.view_matches(cam, False), P.scored(cam)
+        assert g.tobytes() == o.tobytes(), f"view {cam}"
+        n += len(g)
+    assert n > 3000
+    L.reconstruct_3d_lines(3, False); assert P.reconstruct(3, False) == 0
+    assert L.stats()["lines3D"] == P.num_lines() > 20
+    L.close()
+
+
 def test_topk_matches_csr_and_counts(loaded, scene):
     pairs = np.array(PAIRS, np.int32)
     loaded.match_pairs(pairs, util.pair_F(scene, pairs), 0.25, 10)
@@ -211,7 +262,8 @@ def test_capi_error_behaviour(gpu_ctx):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 10) == -1         # view index out of range
     pairs[0, 1] = 1
-    assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 0) == -4          # kNN <= 0: unsupported
+    assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 0) == 0           # kNN <= 0: keep all (here: none)
+    assert L.l3d_match_stride(fresh.h) == 1
     assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 33) == -4
     assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 5) == 0           # F = 0: valid call, no matches
     counts, total = fresh.match_counts()
