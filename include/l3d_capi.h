@@ -95,6 +95,12 @@ int l3d_match_pairs(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const flo
  * before l3d_score_sweep. l3d_match_pairs == the range [0, num_pairs). */
 int l3d_match_pairs_range(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn,
                           int first_pair, int last_pair);
+/* l3d_match_pairs + download in ONE call, overlapped (the shape of match_lines_GPU, which returns host lists): the pair
+ * list is evaluated in `chunks` launches (1..64) and the counts / fixed-slot records of every finished chunk are copied to the
+ * HOST arrays counts_out[total_rows], recs_out[total_rows*knn] on a second stream while the next chunk computes (page-locked
+ * host memory needed for real overlap).  Asynchronous like the rest: l3d_sync() before reading.  1 <= knn <= 32. */
+int l3d_match_pairs_host(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn,
+                         int32_t* counts_out, l3d_match_rec* recs_out, int chunks);
 /* REF_CPU semantics (the reference built without CUDA or constructed with use_GPU=false, line3D.cc:49-53): matchingCPU's
  * double-precision twin of the path (line3D.cc:900-1015: mutualOverlap 1086-1165, triangulationDepths 1168-1193, depths
  * must exceed 1e-12) on the GPU.  Fd[9*i..] = the DOUBLE fundamental matrix of pair i.  Same outputs and accessors as

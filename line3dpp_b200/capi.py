@@ -148,6 +148,15 @@ class Context:
                   "l3d_match_pairs_f64")
         self._knn = int(self.L.l3d_match_stride(self.h))
 
+    def match_pairs_host(self, pairs, F, counts_ptr: int, recs_ptr: int, epi_overlap=0.25, knn=10, chunks=8):
+        """match + overlapped download into host memory at the given addresses (pinned for real overlap); asynchronous"""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        F = np.ascontiguousarray(F, np.float32).reshape(-1, 9)
+        assert len(pairs) == len(F)
+        self._chk(self.L.l3d_match_pairs_host(self.h, len(pairs), _p(pairs), _p(F), C.c_float(epi_overlap), int(knn),
+                                              C.c_void_p(counts_ptr), C.c_void_p(recs_ptr), int(chunks)), "l3d_match_pairs_host")
+        self._knn = int(knn)
+
     def match_device_buffers(self):
         """(counts_ptr, recs_ptr) device addresses of the last match result"""
         a, b = C.c_void_p(), C.c_void_p()

@@ -71,6 +71,8 @@ void l3d_ctx_destroy(l3d_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : c->all_bufs()) if (b->p) cudaFree(b->p);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -178,7 +180,9 @@ int l3d_update_view_params(l3d_ctx* c, int V, const l3d_view_desc* views)
 int l3d_match_pairs(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn)
 { return l3d_match_pairs_range(c, num_pairs, pairs, F, epi_overlap, knn, 0, num_pairs); }
 
-static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, const double* Fd, float epi_overlap, int knn, int first_pair, int last_pair);
+struct HostOut { int32_t* counts; l3d_match_rec* recs; int chunks; };
+static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, const double* Fd, float epi_overlap, int knn, int first_pair, int last_pair,
+                      const HostOut* host = nullptr);
 
 int l3d_match_pairs_range(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn, int first_pair, int last_pair)
 { return match_impl(c, num_pairs, pairs, F, nullptr, epi_overlap, knn, first_pair, last_pair); }
@@ -190,7 +194,18 @@ int l3d_match_pairs_f64(l3d_ctx* c, int num_pairs, const int32_t* pairs, const d
     return match_impl(c, num_pairs, pairs, nullptr, Fd, epi_overlap, knn, first_pair, last_pair);
 }
 
-static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, const double* Fd, float epi_overlap, int knn, int first_pair, int last_pair)
+int l3d_match_pairs_host(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn, int32_t* counts_out,
+                         l3d_match_rec* recs_out, int chunks)
+{
+    if (!c) return L3D_ERR_INVALID;
+    if (!counts_out || !recs_out || chunks < 1) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs_host: bad arguments");
+    if (knn <= 0) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs_host: kNN <= 0 has no fixed row stride; use l3d_match_pairs + l3d_get_pair_matches");
+    HostOut h = {counts_out, recs_out, std::min(chunks, 64)};
+    return match_impl(c, num_pairs, pairs, F, nullptr, epi_overlap, knn, 0, num_pairs, &h);
+}
+
+static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const float* F, const double* Fd, float epi_overlap, int knn, int first_pair, int last_pair,
+                      const HostOut* host)
 {
     if (!c) return L3D_ERR_INVALID;
     if (!c->have_views) return l3d_fail(c, L3D_ERR_STATE, "l3d_match_pairs: call l3d_set_views first");
@@ -275,17 +290,50 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
             L3D_CUDA(c, cudaGetLastError(), "k_sort_rows");
             c->launches += 2;
         }
-    } else if (!c->h_tiles.empty()) {
-        if (cache_d)
-            k_match_topk_f64<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
-                c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, knn,
-                epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, cache_d);
-        else
-            k_match_topk<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
-                c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, knn,
-                epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p);
-        ++c->launches;
-        L3D_CUDA(c, cudaGetLastError(), "k_match_topk");
+    } else {
+        // One launch, or (l3d_match_pairs_host) `chunks` launches over contiguous tile ranges with the D2H copy of every finished
+        // chunk's rows queued on a second stream, so that the PCIe transfer of chunk k hides behind the arithmetic of chunk k+1.
+        const size_t ntiles = c->h_tiles.size();
+        const int chunks = host ? std::max(1, std::min<int>(host->chunks, (int)std::max<size_t>(ntiles, 1))) : 1;
+        if (host) {
+            if (!c->copy_stream) L3D_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "copy stream");
+            while ((int)c->events.size() < chunks + 1) {
+                cudaEvent_t e; L3D_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
+                c->events.push_back(e);
+            }
+        }
+        auto row_of_tile = [&](size_t t) { return t >= ntiles ? rows : c->h_pairs[c->h_tiles[t].x].row_off + c->h_tiles[t].y; };
+        long long row_done = 0;
+        for (int k = 0; k < chunks; ++k) {
+            const size_t t0 = ntiles * (size_t)k / chunks, t1 = ntiles * (size_t)(k + 1) / chunks;
+            if (t1 > t0) {
+                if (cache_d)
+                    k_match_topk_f64<<<(unsigned int)(t1 - t0), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
+                        c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p + t0, knn,
+                        epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, cache_d);
+                else
+                    k_match_topk<<<(unsigned int)(t1 - t0), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
+                        c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p + t0, knn,
+                        epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p);
+                ++c->launches;
+                L3D_CUDA(c, cudaGetLastError(), "k_match_topk");
+            }
+            if (host) {
+                const long long r1 = k == chunks - 1 ? rows : row_of_tile(t1);      // rows [row_done, r1) are final after this launch
+                if (r1 > row_done) {
+                    L3D_CUDA(c, cudaEventRecord(c->events[k], c->stream), "event record");
+                    L3D_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->events[k], 0), "event wait");
+                    L3D_CUDA(c, cudaMemcpyAsync(host->counts + row_done, (const int*)c->d_counts.p + row_done, sizeof(int) * (size_t)(r1 - row_done), cudaMemcpyDeviceToHost, c->copy_stream), "download counts");
+                    L3D_CUDA(c, cudaMemcpyAsync(host->recs + row_done * knn, (const l3d_match_rec*)c->d_recs.p + row_done * knn,
+                                                sizeof(l3d_match_rec) * (size_t)(r1 - row_done) * knn, cudaMemcpyDeviceToHost, c->copy_stream), "download records");
+                    row_done = r1;
+                }
+            }
+        }
+        if (host) {     // the context's stream (the one callers time and synchronise) completes only after the last copy
+            L3D_CUDA(c, cudaEventRecord(c->events[chunks], c->copy_stream), "event record");
+            L3D_CUDA(c, cudaStreamWaitEvent(c->stream, c->events[chunks], 0), "event wait");
+        }
     }
     c->have_matches = true; c->sweep.valid = false;
     return L3D_OK;

@@ -45,7 +45,8 @@ struct RddState {
 
 struct l3d_ctx {
     int device = 0, num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;      // copy_stream: D2H of finished chunks (l3d_match_pairs_host)
+    std::vector<cudaEvent_t> events;
     std::string err;
     long long launches = 0;
 
