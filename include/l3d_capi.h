@@ -159,17 +159,35 @@ long long l3d_get_view_matches(l3d_ctx* ctx, int view, int kept_only, l3d_match*
  * the working frame of C_d).  Returns the count. */
 long long l3d_get_estimates(l3d_ctx* ctx, l3d_match* best_out, double* p1p2_out, long long cap);
 
+/* ---- collinear 2D segments (optional, reconstruct3Dlines' collinearity_t > 0): replaces find_collinear_segments_GPU
+ * (cudawrapper.h:76-78, K_collinearity cudawrapper.cu:370-429) called from View::findCollinGPU (view.cc:187) and the
+ * host scan of its dense N x N char matrix (view.cc:192-203), for ALL views in one call.  Two segments of a view are
+ * potentially collinear when neither endpoint of one projects onto the other and the larger of the mutual endpoint-to-
+ * line distances is < dist_t pixels.  semantics: L3D_SEM_REF_GPU = the float kernel, L3D_SEM_REF_CPU = View::findCollinCPU
+ * (view.cc:212-263, double geometry).  The result (View::collin_, ascending ids per segment) stays on the device: while it
+ * is valid, l3d_affinity_matrix / l3d_affinity_edges add the collinearity links of computingAffinityMatrix
+ * (line3D.cc:1904-1937, 1941-1974).  dist_t <= 1e-12 switches the links off again (line3D.cc:1752, 1905). */
+int l3d_find_collinear(l3d_ctx* ctx, float dist_t, int semantics);
+/* total number of list entries over all views (0 if off) */
+long long l3d_collinear_total(const l3d_ctx* ctx);
+/* collin_ of one view as CSR: row_ptr_out[nseg+1] relative to the view, idx_out[row_ptr_out[nseg]] segment ids.
+ * Returns the view's entry count (even if > cap; then idx_out is not written). */
+long long l3d_get_collinear(l3d_ctx* ctx, int view, long long* row_ptr_out, int32_t* idx_out, long long cap);
+
 /* ---- affinity: Line3D::similarity (line3D.cc:1467-1553) for every kept match whose two segments have a 3D estimate,
  * i.e. the arithmetic of computingAffinityMatrix (line3D.cc:1852-1979).  Emits, in the reference's emission order,
  * the candidates with similarity > min_affinity (L3D_DEF_MIN_AFFINITY 0.5) as (global seg i, global seg j, w); the
  * "unused" de-duplication and local-id assignment stay on the host (line3D.cc:1881-1900, 1982-2023).  Needs
- * views[].median_depth to be current (l3d_update_view_params).  Returns the number of edges (even if > cap). */
+ * views[].median_depth to be current (l3d_update_view_params).  Returns the number of edges (even if > cap).
+ * With collinearity links on (l3d_find_collinear) the list also holds the collinear candidates, each of which only
+ * counts if its parent edge passed unused(): use l3d_affinity_matrix, which resolves that on the device. */
 long long l3d_affinity_edges(l3d_ctx* ctx, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity,
                              long long* out_gi, long long* out_gj, float* out_w, long long cap);
 
 /* The complete affinity matrix on the device: the candidates of l3d_affinity_edges, then the reference's "unused" pair
  * filter (line3D.cc:1982-2002: only the first candidate of an unordered segment pair, in emission order) and first-come
- * local ids (line3D.cc:2005-2023), reproduced with stable sorts and atomic minima instead of mutex-protected maps.
+ * local ids (line3D.cc:2005-2023), reproduced with stable sorts and atomic minima instead of mutex-protected maps; with
+ * collinearity links the order-dependent "only if the parent edge was new" rule is resolved by a device fixpoint.
  * out_i/out_j/out_w: the CLEdge list A_ in the reference's order ((id1,id2,w),(id2,id1,w) per accepted edge);
  * out_local2global[id] = global segment index.  Returns the number of list entries (even if the capacities are too
  * small; then nothing is copied) and sets *num_ids. */

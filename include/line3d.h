@@ -97,7 +97,7 @@ struct FinalLine3D {   /* segment3D.h:155-163 */
 /* counters the reference prints to stdout (SURVEY.md §5 "Metrics / logging"); handy parity checkpoints */
 struct Line3DStats {
     long long view_pairs, pair_evaluations, matches_after_knn, estimates, affinity_entries, affinity_rows, clusters_total,
-        clusters_valid, lines3D;
+        clusters_valid, lines3D, collinear_entries;
     double ms_match, ms_score, ms_affinity, ms_diffusion, ms_cluster;
 };
 

@@ -41,7 +41,7 @@ def lib():
         L.l3d_last_error.restype = C.c_char_p
         L.l3d_stream.restype = C.c_void_p
         for n in ("l3d_launch_count", "l3d_match_total_rows", "l3d_match_pair_evals", "l3d_get_match_counts",
-                  "l3d_get_matches_csr"):
+                  "l3d_get_matches_csr", "l3d_collinear_total", "l3d_get_collinear"):
             getattr(L, n).restype = C.c_longlong
         _lib = L
     return _lib
@@ -210,6 +210,20 @@ class Context:
         self._chk(self.L.l3d_rdd(self.h, int(n), C.c_longlong(len(ei)), _p(ei), _p(ej), _p(ew), int(iters), _p(oi), _p(oj), _p(ow),
                                  C.byref(ms)), "l3d_rdd")
         return oi, oj, ow, ms.value
+
+    def find_collinear(self, dist_t: float, semantics: int = 0):
+        """l3d_find_collinear for all views (semantics 0 = REF_GPU float kernel, 1 = REF_CPU); dist_t <= 0 switches the links off"""
+        self._chk(self.L.l3d_find_collinear(self.h, C.c_float(dist_t), int(semantics)), "l3d_find_collinear")
+        return int(self.L.l3d_collinear_total(self.h))
+
+    def collinear(self, view: int, nseg: int):
+        """View::collin_ of one view as CSR (row_ptr[nseg+1], idx)"""
+        row_ptr = np.zeros(nseg + 1, np.int64)
+        n = self._chk(self.L.l3d_get_collinear(self.h, int(view), _p(row_ptr), None, C.c_longlong(0)), "l3d_get_collinear")
+        idx = np.zeros(max(int(n), 1), np.int32)
+        if n > 0:
+            self._chk(self.L.l3d_get_collinear(self.h, int(view), _p(row_ptr), _p(idx), C.c_longlong(int(n))), "l3d_get_collinear")
+        return row_ptr, idx[:int(n)]
 
     def fp32_peak_tflops(self) -> float:
         v = C.c_double(0)

@@ -14,6 +14,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #define L3D_EPS_D 1e-12
@@ -51,6 +52,31 @@ __device__ __forceinline__ float dist_p2l(const ASeg& s, A3 P)
     return (float)anorm(asub(hp, P));
 }
 
+// Line3D::similarity(s1, m1, seg2, truncate = false) (line3D.cc:1467-1553) for two segments that both have a 3D estimate:
+// P1/P2 = their estimates (6 doubles each), m1/m2 = depths of their best matches, v1/v2 = their views
+__device__ __forceinline__ float aff_similarity(const L3DViewDev* v1, const L3DViewDev* v2, const double* P1, const double* P2, float4 m1, float4 m2,
+                                                float two_sigA_sqr, float med_scene_depth_lines)
+{
+    const ASeg s1 = make_seg(P1), s2 = make_seg(P2);
+    if (s1.length < L3D_EPS_D || s2.length < L3D_EPS_D) return 0.0f;
+    float dot_p = (float)adot(s1.dir, s2.dir);                               // angleBetweenSeg3D (line3D.cc:1571-1583)
+    float angle = (float)((double)acosf(fmaxf(fminf(dot_p, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
+    if (angle > 90.0f) angle = 180.0f - angle;
+    float sim_a = expf(-angle * angle / two_sigA_sqr);
+    float cutoff1 = v1->median_depth, cutoff2 = v2->median_depth;
+    if (med_scene_depth_lines > L3D_EPS_D) { cutoff1 = fminf(cutoff1, med_scene_depth_lines); cutoff2 = fminf(cutoff2, med_scene_depth_lines); }
+    float d11 = dist_p2l(s2, s1.P1), d12 = dist_p2l(s2, s1.P2), d21 = dist_p2l(s1, s2.P1), d22 = dist_p2l(s1, s2.P2);
+    float sig11 = m1.x > cutoff1 ? cutoff1 * v1->k : m1.x * v1->k;
+    float sig12 = m1.y > cutoff1 ? cutoff1 * v1->k : m1.y * v1->k;
+    float reg11 = 2.0f * sig11 * sig11, reg12 = 2.0f * sig12 * sig12;
+    float sig21 = m2.x > cutoff2 ? cutoff2 * v2->k : m2.x * v2->k;
+    float sig22 = m2.y > cutoff2 ? cutoff2 * v2->k : m2.y * v2->k;
+    float reg21 = 2.0f * sig21 * sig21, reg22 = 2.0f * sig22 * sig22;
+    float sim_p1 = fminf(expf(-d11 * d11 / reg11), expf(-d12 * d12 / reg12));
+    float sim_p2 = fminf(expf(-d21 * d21 / reg21), expf(-d22 * d22 / reg22));
+    return fminf(sim_a, fminf(sim_p1, sim_p2));
+}
+
 __global__ void __launch_bounds__(256)
 k_affinity(const L3DViewDev* __restrict__ views, const long long* __restrict__ region_off, const int* __restrict__ order,
            const int* __restrict__ rank_of_view, int V, long long total, const unsigned char* __restrict__ kept,
@@ -71,30 +97,82 @@ k_affinity(const L3DViewDev* __restrict__ views, const long long* __restrict__ r
         gi = v1->seg_off + me.x; gj = v2->seg_off + me.z;
         const int b1 = est_best[gi], b2 = est_best[gj];
         if (b1 >= 0 && b2 >= 0) {
-            const ASeg s1 = make_seg(est_P + 6 * gi), s2 = make_seg(est_P + 6 * gj);
-            if (!(s1.length < L3D_EPS_D || s2.length < L3D_EPS_D)) {
-                const float4 m1 = m_dep[region_off[lo] + b1], m2 = m_dep[region_off[rank_of_view[me.y]] + b2];
-                float dot_p = (float)adot(s1.dir, s2.dir);                               // angleBetweenSeg3D (line3D.cc:1571-1583)
-                float angle = (float)((double)acosf(fmaxf(fminf(dot_p, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
-                if (angle > 90.0f) angle = 180.0f - angle;
-                float sim_a = expf(-angle * angle / two_sigA_sqr);
-                float cutoff1 = v1->median_depth, cutoff2 = v2->median_depth;
-                if (med_scene_depth_lines > L3D_EPS_D) { cutoff1 = fminf(cutoff1, med_scene_depth_lines); cutoff2 = fminf(cutoff2, med_scene_depth_lines); }
-                float d11 = dist_p2l(s2, s1.P1), d12 = dist_p2l(s2, s1.P2), d21 = dist_p2l(s1, s2.P1), d22 = dist_p2l(s1, s2.P2);
-                float sig11 = m1.x > cutoff1 ? cutoff1 * v1->k : m1.x * v1->k;
-                float sig12 = m1.y > cutoff1 ? cutoff1 * v1->k : m1.y * v1->k;
-                float reg11 = 2.0f * sig11 * sig11, reg12 = 2.0f * sig12 * sig12;
-                float sig21 = m2.x > cutoff2 ? cutoff2 * v2->k : m2.x * v2->k;
-                float sig22 = m2.y > cutoff2 ? cutoff2 * v2->k : m2.y * v2->k;
-                float reg21 = 2.0f * sig21 * sig21, reg22 = 2.0f * sig22 * sig22;
-                float sim_p1 = fminf(expf(-d11 * d11 / reg11), expf(-d12 * d12 / reg12));
-                float sim_p2 = fminf(expf(-d21 * d21 / reg21), expf(-d22 * d22 / reg22));
-                sim = fminf(sim_a, fminf(sim_p1, sim_p2));
-                flag = sim > min_affinity ? 1 : 0;
-            }
+            sim = aff_similarity(v1, v2, est_P + 6 * gi, est_P + 6 * gj, m_dep[region_off[lo] + b1], m_dep[region_off[rank_of_view[me.y]] + b2],
+                                 two_sigA_sqr, med_scene_depth_lines);
+            flag = sim > min_affinity ? 1 : 0;
         }
     }
     sim_out[x] = sim; flag_out[x] = flag; gi_out[x] = gi; gj_out[x] = gj;
+}
+
+// ---- affinity candidates WITH collinearity links (line3D.cc:1904-1974), one thread per segment in estimate order ----
+// Events of estimate i, in the reference's order: for every kept match with sim > min_affinity the direct edge, then one
+// edge to every segment collinear with the match's target (if that one has an estimate and sim > min_affinity); after
+// the matches, if any direct edge exists, the edges to the segments collinear with i itself.  Whether an event really
+// enters A_ depends on unused() and, for the collinear ones, on their parent having passed unused() - that is resolved
+// by l3d_affinity_matrix.  par: -1 direct, >= 0 index of the parent direct event, -2 "any direct event of my source".
+// FILL = false counts (evcnt[t]); FILL = true writes at evptr[t].
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_aff_events(const L3DViewDev* __restrict__ views, const long long* __restrict__ region_off, const int* __restrict__ order,
+             const int* __restrict__ rank_of_view, const long long* __restrict__ segrank_off, int V, long long N,
+             const unsigned char* __restrict__ kept, const int4* __restrict__ m_meta, const float4* __restrict__ m_dep,
+             const int2* __restrict__ ranges, const int* __restrict__ est_best, const double* __restrict__ est_P,
+             const float* __restrict__ sim_slot, const int* __restrict__ flag_slot, const long long* __restrict__ cptr,
+             const int* __restrict__ cidx, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity, int* __restrict__ evcnt,
+             const long long* __restrict__ evptr, long long* __restrict__ out_i, long long* __restrict__ out_j, float* __restrict__ out_w,
+             int* __restrict__ out_par)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    int lo = 0, hi = V - 1;                      // processing rank of segment t
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (segrank_off[mid] <= t) lo = mid; else hi = mid - 1; }
+    const int v1i = order[lo];
+    const L3DViewDev* v1 = views + v1i;
+    const long long g = v1->seg_off + (t - segrank_off[lo]);
+    const int b1 = est_best[g];
+    long long n = 0;
+    const long long base = FILL ? evptr[t] : 0;
+    if (b1 >= 0) {
+        const long long ro = region_off[lo];
+        const int2 rng = ranges[g];
+        const double* P1 = est_P + 6 * g;
+        const float4 m1 = m_dep[ro + b1];
+        bool found = false;
+        for (int i = rng.x; i <= rng.y && rng.x >= 0; ++i) {
+            const long long x = ro + i;
+            if (!kept[x] || !flag_slot[x]) continue;
+            const int4 me = m_meta[x];
+            const L3DViewDev* v2 = views + me.y;
+            const long long gj = v2->seg_off + me.z;
+            const long long parent = base + n;
+            if (FILL) { out_i[parent] = g; out_j[parent] = gj; out_w[parent] = sim_slot[x]; out_par[parent] = -1; }
+            ++n; found = true;
+            const long long ro2 = region_off[rank_of_view[me.y]];
+            for (long long q = cptr[gj]; q < cptr[gj + 1]; ++q) {                  // collinear with the target (line3D.cc:1904-1937)
+                const long long g2 = v2->seg_off + cidx[q];
+                const int b2 = est_best[g2];
+                if (b2 < 0) continue;
+                const float s2 = aff_similarity(v1, v2, P1, est_P + 6 * g2, m1, m_dep[ro2 + b2], two_sigA_sqr, med_scene_depth_lines);
+                if (s2 > min_affinity) {
+                    if (FILL) { out_i[base + n] = g; out_j[base + n] = g2; out_w[base + n] = s2; out_par[base + n] = (int)parent; }
+                    ++n;
+                }
+            }
+        }
+        if (found)
+            for (long long q = cptr[g]; q < cptr[g + 1]; ++q) {                    // collinear with the source (line3D.cc:1941-1974)
+                const long long g2 = v1->seg_off + cidx[q];
+                const int b2 = est_best[g2];
+                if (b2 < 0) continue;
+                const float s2 = aff_similarity(v1, v1, P1, est_P + 6 * g2, m1, m_dep[ro + b2], two_sigA_sqr, med_scene_depth_lines);
+                if (s2 > min_affinity) {
+                    if (FILL) { out_i[base + n] = g; out_j[base + n] = g2; out_w[base + n] = s2; out_par[base + n] = -2; }
+                    ++n;
+                }
+            }
+    }
+    if (!FILL) evcnt[t] = (int)n;
 }
 
 __global__ void __launch_bounds__(256)
@@ -233,71 +311,96 @@ __global__ void __launch_bounds__(128) k_rdd_normalize4(int n, const int* __rest
         row[k4] = v;
     }
 }
-// per-entry walk descriptors, built once (the structure is constant over the iterations): everything the step needs is
-// then read with coalesced 16-byte loads instead of eight dependent scattered pointer look-ups per entry
-//   x = first float4 of P.row(r)   y = first float4 of W.col(c)   z = walk length min(len_r, len_c)   w = own padded slot
-// and dst = padded slot of the transposed entry P'(r,c) (or -1)
+// ---- fused diffusion iteration, organised by DESTINATION row ---------------------------------------------------
+// K_sparseMat_diffusion_step (cudawrapper.cu:480-544) lets the thread of entry (a,b) produce P'(b,a) = max(eps, P(a,b) *
+// sum_k P.row(b)[k] * W.col(a)[k]) and scatter it into row b; K_sparseMat_row_normalization (432-477) then re-reads every
+// row.  Here a group of G lanes owns destination row b: it streams its own row P.row(b) (the left factor of all its
+// entries), gathers W.col(a) and the single value P(a,b) for each of its columns a, and - because it ends up holding the
+// whole new row - normalises it before the only store.  One kernel per iteration instead of two, no scattered stores,
+// 16 B/nnz of streamed descriptors (column, transposed slot, value in, value out) instead of 24 + a second pass.
+// Arithmetic order is the reference's: products added in k order per entry, the row sum in slot order, IEEE divide.
+//   colinfo[a] = (first float4 of W.col(a), length of W.col(a));   rowinfo[b] = (rowptr[b], first float4 of P.row(b))
+//   src[s]     = padded slot of the transposed entry P(a,b) for destination slot s = (b,a), -1 if (a,b) does not exist or
+//                s is not the first slot of (b,a) in its row (the reference then never writes the slot: it keeps the
+//                value it had two iterations ago, cudawrapper.cu:524-542 - reproduced by re-normalising the stale value)
 __global__ void __launch_bounds__(256)
-k_rdd_plan(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr, const int* __restrict__ colptr,
-           const int* __restrict__ rp4, const int* __restrict__ cp4, const int* __restrict__ tslot, int4* __restrict__ plan, int* __restrict__ dst)
+k_rdd_rowinfo(int n, const int* __restrict__ rowptr, const int* __restrict__ rp4, const int* __restrict__ colptr, const int* __restrict__ cp4,
+              int2* __restrict__ rowinfo, int2* __restrict__ colinfo)
 {
-    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= nnz) return;
-    const int c = prow[y], r = pcol[y];                 // "transpose" (cudawrapper.cu:493-495)
-    const int rs = rowptr[r], m = min(rowptr[r + 1] - rs, colptr[c + 1] - colptr[c]);
-    plan[y] = make_int4(rp4[r], cp4[c], m, 4 * rp4[c] + (int)(y - rowptr[c]));
-    const int t = tslot[y];
-    dst[y] = t >= 0 ? 4 * rp4[r] + (t - rs) : -1;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    rowinfo[r] = make_int2(rowptr[r], rp4[r]);
+    if (r < n) colinfo[r] = make_int2(cp4[r], colptr[r + 1] - colptr[r]);
 }
-// K_sparseMat_diffusion_step on the padded arrays: entry y = (a,b) of P produces P'(b,a).
-// A thread owns RDD_ITEMS entries (strided by the block size, so the descriptor loads stay coalesced) and walks them
-// k-step by k-step together: the float4 gathers of the different entries are independent, which is the memory-level
-// parallelism this latency-bound gather needs; every entry still accumulates its own products strictly in k order.
-#define RDD_ITEMS 4
 __global__ void __launch_bounds__(256)
-k_rdd_step4(long long nnz, const int4* __restrict__ plan, const int* __restrict__ dst, const float* __restrict__ Pp, const float* __restrict__ Wp,
-            float* __restrict__ Pnp)
+k_rdd_src(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr, const int* __restrict__ rp4,
+          const int* __restrict__ tslot, int* __restrict__ src)
 {
-    const long long y0 = (long long)blockIdx.x * (256 * RDD_ITEMS) + threadIdx.x;
-    int4 pl[RDD_ITEMS];
-    int d[RDD_ITEMS];
-    float own[RDD_ITEMS], mul[RDD_ITEMS];
-    int mmax = 0;
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nnz) return;
+    const int b = prow[s], a = pcol[s];
+    const bool first = s == rowptr[b] || pcol[s - 1] != a;     // tslot of the writers points at the first (b,a) slot
+    const int t = tslot[s];                                     // first slot of (a,b) in row a
+    src[s] = (first && t >= 0) ? 4 * rp4[a] + (t - rowptr[a]) : -1;
+}
+
+template <int G, bool NORMALIZE>
+__global__ void __launch_bounds__(256)
+k_rdd_fused(int n, const int2* __restrict__ rowinfo, const int2* __restrict__ colinfo, const int* __restrict__ pcol, const int* __restrict__ src,
+            const float* __restrict__ Pp, const float* __restrict__ Wp, float* __restrict__ Pnp)
+{
+    const int gl = threadIdx.x & (G - 1);                                   // lane within the row group
+    const long long b = ((long long)blockIdx.x * 256 + threadIdx.x) / G;    // destination row
+    const unsigned int gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+    if (b >= n) return;                                                     // whole groups leave together
+    const int2 ri = rowinfo[b];
+    const int rs = ri.x, len = rowinfo[b + 1].x - rs;
+    if (len == 0) return;
+    const float4* prow4 = reinterpret_cast<const float4*>(Pp) + ri.y;
+    float* outrow = Pnp + 4ll * ri.y;
+    float sum = 0.0f, v = 0.0f;
+    for (int t0 = 0; t0 < len; t0 += G) {
+        const int t = t0 + gl;
+        v = 0.0f;
+        if (t < len) {
+            const int a = pcol[rs + t], sp = src[rs + t];
+            if (sp >= 0) {
+                const float own = Pp[sp];                                   // P(a,b)
+                const int2 ci = colinfo[a];
+                const float4* wcol4 = reinterpret_cast<const float4*>(Wp) + ci.x;
+                const int m = min(len, ci.y), n4 = (m + 3) >> 2;
+                float mul = 0.0f;
+                for (int k0 = 0; k0 < n4; k0 += 4) {
+                    float4 pv[4], wv[4];
 #pragma unroll
-    for (int i = 0; i < RDD_ITEMS; ++i) {
-        const long long y = y0 + 256ll * i;
-        const bool ok = y < nnz;
-        pl[i] = ok ? plan[y] : make_int4(0, 0, 0, 0);
-        d[i] = ok ? dst[y] : -1;
-        mmax = max(mmax, pl[i].z);
-        mul[i] = 0.0f;
-    }
+                    for (int j = 0; j < 4; ++j)
+                        if (k0 + j < n4) { pv[j] = prow4[k0 + j]; wv[j] = wcol4[k0 + j]; }
 #pragma unroll
-    for (int i = 0; i < RDD_ITEMS; ++i) own[i] = pl[i].z > 0 || d[i] >= 0 ? Pp[pl[i].w] : 0.0f;
-    for (int k4 = 0; 4 * k4 < mmax; ++k4) {
-        float4 pv[RDD_ITEMS], wv[RDD_ITEMS];
-#pragma unroll
-        for (int i = 0; i < RDD_ITEMS; ++i)
-            if (4 * k4 < pl[i].z) {
-                pv[i] = (reinterpret_cast<const float4*>(Pp) + pl[i].x)[k4];
-                wv[i] = (reinterpret_cast<const float4*>(Wp) + pl[i].y)[k4];
-            }
-#pragma unroll
-        for (int i = 0; i < RDD_ITEMS; ++i) {
-            const int rem = pl[i].z - 4 * k4;
-            if (rem > 0) {
-                mul[i] += pv[i].x * wv[i].x;
-                if (rem > 1) mul[i] += pv[i].y * wv[i].y;
-                if (rem > 2) mul[i] += pv[i].z * wv[i].z;
-                if (rem > 3) mul[i] += pv[i].w * wv[i].w;
-            }
+                    for (int j = 0; j < 4; ++j) {
+                        const int rem = m - 4 * (k0 + j);
+                        if (rem > 0) {
+                            mul += pv[j].x * wv[j].x;
+                            if (rem > 1) mul += pv[j].y * wv[j].y;
+                            if (rem > 2) mul += pv[j].z * wv[j].z;
+                            if (rem > 3) mul += pv[j].w * wv[j].w;
+                        }
+                    }
+                }
+                mul *= own;
+                if (mul < L3D_EPS_F) mul = L3D_EPS_F;
+                v = mul;
+            } else v = outrow[t];                                           // never written by the reference: stale value
         }
+        if (NORMALIZE) {
+            const int cnt = min(G, len - t0);
+            for (int j = 0; j < cnt; ++j) sum += __shfl_sync(gmask, v, j, G);   // row sum in slot order (cudawrapper.cu:452-459)
+            if (len > G && t < len) outrow[t] = v;                          // long row: park the raw values, divide below
+        } else if (t < len) outrow[t] = v;
     }
-#pragma unroll
-    for (int i = 0; i < RDD_ITEMS; ++i) {
-        float m = mul[i] * own[i];                      // times P(a,b) itself
-        if (m < L3D_EPS_F) m = L3D_EPS_F;
-        if (d[i] >= 0) Pnp[d[i]] = m;
+    if (NORMALIZE) {
+        if (sum < L3D_EPS_F) sum = L3D_EPS_F;
+        if (len <= G) { if (gl < len) outrow[gl] = v / sum; }
+        else for (int t = gl; t < len; t += G) outrow[t] = outrow[t] / sum;
     }
 }
 
@@ -317,11 +420,39 @@ __global__ void __launch_bounds__(256) k_aff_keys(long long ne, const long long*
     const unsigned long long a = (unsigned long long)min(gi[e], gj[e]), b = (unsigned long long)max(gi[e], gj[e]);
     key[e] = (a << 32) | b; val[e] = (unsigned int)e;
 }
-__global__ void __launch_bounds__(256) k_aff_first(long long ne, const unsigned long long* __restrict__ key, const unsigned int* __restrict__ val, int* __restrict__ keep)
+// unused() with conditional events (line3D.cc:1881-1974): event e enters A_ iff its parent did (direct events have none)
+// and no EARLIER event of the same unordered pair did.  All dependencies point to earlier events, so iterating
+//   acc[e] = parent_ok(e, acc_prev) && no earlier event e' of the same pair with parent_ok(e', acc_prev)
+// from acc = 0 reaches the sequential answer after (longest dependency chain) rounds and then stays.  Without
+// collinearity links every event is direct and the first round is already final (head of every run of the stable sort).
+__device__ __forceinline__ bool aff_parent_ok(int e, const int* __restrict__ par, const long long* __restrict__ gi, const int* __restrict__ acc_prev,
+                                              const int* __restrict__ found_prev)
+{
+    if (!par) return true;
+    const int p = par[e];
+    return p == -1 ? true : p >= 0 ? acc_prev[p] != 0 : found_prev[gi[e]] != 0;
+}
+__global__ void __launch_bounds__(256)
+k_aff_round(long long ne, const unsigned long long* __restrict__ key, const unsigned int* __restrict__ val, const int* __restrict__ par,
+            const long long* __restrict__ gi, const int* __restrict__ acc_prev, const int* __restrict__ found_prev, int* __restrict__ acc_new,
+            int* __restrict__ changed)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ne) return;
+    const int e = (int)val[j];
+    bool a = aff_parent_ok(e, par, gi, acc_prev, found_prev);
+    const unsigned long long k = key[j];
+    for (long long jj = j - 1; a && jj >= 0 && key[jj] == k; --jj)          // stable sort: earlier position = earlier in emission order
+        if (aff_parent_ok((int)val[jj], par, gi, acc_prev, found_prev)) a = false;
+    acc_new[e] = a ? 1 : 0;
+    if ((acc_prev[e] != 0) != a) *changed = 1;
+}
+// found_aff of every source segment (line3D.cc:1900): some DIRECT event of it was accepted
+__global__ void __launch_bounds__(256)
+k_aff_found(long long ne, const int* __restrict__ par, const long long* __restrict__ gi, const int* __restrict__ acc, int* __restrict__ found)
 {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= ne) return;
-    if (e == 0 || key[e - 1] != key[e]) keep[val[e]] = 1;      // stable sort: the head of a run is the first in emission order
+    if (e < ne && acc[e] && par[e] == -1) found[gi[e]] = 1;
 }
 __global__ void __launch_bounds__(256) k_aff_time(long long ne, const int* __restrict__ keep, const long long* __restrict__ q, const long long* __restrict__ gi,
                                                   const long long* __restrict__ gj, unsigned long long* __restrict__ time)
@@ -392,6 +523,47 @@ static long long affinity_candidates(l3d_ctx* c, float two_sigA_sqr, float med_s
                                    (const unsigned char*)S.d_kept.p, (const int4*)S.d_meta.p, (const float4*)S.d_dep.p, (const int*)S.d_est_best.p,
                                    (const double*)S.d_est_P.p, two_sigA_sqr, med_scene_depth_lines, min_affinity, (float*)d_sim.p, (int*)d_flag.p,
                                    (long long*)d_gi.p, (long long*)d_gj.p);
+    if (c->collin.valid) {
+        // collinearity links on: events per segment in estimate order (count, scan, fill), each with its parent
+        const CollinState& K = c->collin;
+        const long long N = c->total_segs;
+        std::vector<long long> segrank_off((size_t)V + 1, 0);
+        for (int i = 0; i < V; ++i) segrank_off[i + 1] = segrank_off[i] + c->h_views[S.order[i]].nseg;
+        if ((rc = l3d_reserve(c, S.d_segrank_off, 8 * ((size_t)V + 1), "segment rank offsets"))) return rc;
+        if ((rc = l3d_reserve(c, S.d_evcnt, 4 * (size_t)(N + 1), "event counts"))) return rc;
+        if ((rc = l3d_reserve(c, S.d_evptr, 8 * (size_t)(N + 1), "event offsets"))) return rc;
+        L3D_CUDA(c, cudaMemcpyAsync(S.d_segrank_off.p, segrank_off.data(), 8 * ((size_t)V + 1), cudaMemcpyHostToDevice, st), "segment rank offsets");
+        L3D_CUDA(c, cudaMemsetAsync(S.d_evcnt.p, 0, 4 * (size_t)(N + 1), st), "event counts");
+        const unsigned int nbs = (unsigned int)((N + 127) / 128);
+#define EV_ARGS c->views(), (const long long*)S.d_region_off.p, (const int*)S.d_order.p, (const int*)S.d_rankofview.p, (const long long*)S.d_segrank_off.p, V, N, \
+                (const unsigned char*)S.d_kept.p, (const int4*)S.d_meta.p, (const float4*)S.d_dep.p, (const int2*)S.d_ranges.p, (const int*)S.d_est_best.p,       \
+                (const double*)S.d_est_P.p, (const float*)d_sim.p, (const int*)d_flag.p, (const long long*)K.d_ptr.p, (const int*)K.d_idx.p, two_sigA_sqr,          \
+                med_scene_depth_lines, min_affinity
+        k_aff_events<false><<<nbs, 128, 0, st>>>(EV_ARGS, (int*)S.d_evcnt.p, nullptr, nullptr, nullptr, nullptr, nullptr);
+        size_t tbe = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tbe, (const int*)nullptr, (long long*)nullptr, N + 1, st);
+        if ((rc = l3d_reserve(c, S.d_sort_tmp, tbe, "scan temp"))) return rc;
+        tbe = S.d_sort_tmp.cap;
+        L3D_CUDA(c, cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tbe, (const int*)S.d_evcnt.p, (long long*)S.d_evptr.p, N + 1, st), "event scan");
+        long long nev = 0;
+        L3D_CUDA(c, cudaMemcpyAsync(&nev, (long long*)S.d_evptr.p + N, 8, cudaMemcpyDeviceToHost, st), "event count");
+        L3D_CUDA(c, cudaStreamSynchronize(st), "affinity events");
+        c->launches += 4;
+        if (nev == 0) return 0;
+        if (nev >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "affinity: more than 2^31 candidate events");
+        if ((rc = l3d_reserve(c, S.d_aff_oi, 8 * (size_t)nev, "edges i"))) return rc;
+        if ((rc = l3d_reserve(c, S.d_aff_oj, 8 * (size_t)nev, "edges j"))) return rc;
+        if ((rc = l3d_reserve(c, S.d_aff_ow, 4 * (size_t)nev, "edges w"))) return rc;
+        if ((rc = l3d_reserve(c, S.d_aff_par, 4 * (size_t)nev, "edge parents"))) return rc;
+        k_aff_events<true><<<nbs, 128, 0, st>>>(EV_ARGS, nullptr, (const long long*)S.d_evptr.p, (long long*)S.d_aff_oi.p, (long long*)S.d_aff_oj.p,
+                                                (float*)S.d_aff_ow.p, (int*)S.d_aff_par.p);
+#undef EV_ARGS
+        ++c->launches;
+        L3D_CUDA(c, cudaGetLastError(), "k_aff_events");
+        S.aff_has_parents = true;
+        return nev;
+    }
+    S.aff_has_parents = false;
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)d_flag.p, (long long*)d_pos.p, total, st);
     if ((rc = l3d_reserve(c, S.d_sort_tmp, tb, "scan temp"))) return rc;
@@ -475,8 +647,30 @@ long long l3d_affinity_matrix(l3d_ctx* c, float two_sigA_sqr, float med_scene_de
             k_aff_keys<<<nbe, 256, 0, st>>>(ne, (const long long*)S.d_aff_oi.p, (const long long*)S.d_aff_oj.p, (unsigned long long*)A.d_key.p, (unsigned int*)A.d_val.p);
             size_t tb = S.d_sort_tmp.cap;
             cub::DeviceRadixSort::SortPairs(S.d_sort_tmp.p, tb, (const unsigned long long*)A.d_key.p, (unsigned long long*)A.d_key2.p, (const unsigned int*)A.d_val.p, (unsigned int*)A.d_val2.p, (int)ne, 0, 32 + bseg, st);
-            L3D_CUDA(c, cudaMemsetAsync(A.d_keep.p, 0, 4 * ne, st), "clear keep");
-            k_aff_first<<<nbe, 256, 0, st>>>(ne, (const unsigned long long*)A.d_key2.p, (const unsigned int*)A.d_val2.p, (int*)A.d_keep.p);
+            {   // unused(): fixpoint over the conditional events (one round + one confirming round without collinearity links)
+                const int* par = S.aff_has_parents ? (const int*)S.d_aff_par.p : nullptr;
+                RES(A.d_keep2, 4 * ne, "keep flags"); RES(A.d_found, 4 * N, "found flags"); RES(A.d_changed, 16, "changed flag");
+                L3D_CUDA(c, cudaMemsetAsync(A.d_keep.p, 0, 4 * ne, st), "clear keep");
+                L3D_CUDA(c, cudaMemsetAsync(A.d_found.p, 0, 4 * N, st), "clear found");
+                int* acc_prev = (int*)A.d_keep.p; int* acc_new = (int*)A.d_keep2.p;
+                for (int round = 0;; ++round) {
+                    if (round > 100000) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_affinity_matrix: unused() fixpoint did not converge");
+                    L3D_CUDA(c, cudaMemsetAsync(A.d_changed.p, 0, 4, st), "clear changed");
+                    k_aff_round<<<nbe, 256, 0, st>>>(ne, (const unsigned long long*)A.d_key2.p, (const unsigned int*)A.d_val2.p, par, (const long long*)S.d_aff_oi.p,
+                                                     acc_prev, (const int*)A.d_found.p, acc_new, (int*)A.d_changed.p);
+                    std::swap(acc_prev, acc_new);
+                    ++c->launches;
+                    if (!par) break;                 // all events direct: the head of every run, final after one round
+                    L3D_CUDA(c, cudaMemsetAsync(A.d_found.p, 0, 4 * N, st), "clear found");
+                    k_aff_found<<<nbe, 256, 0, st>>>(ne, par, (const long long*)S.d_aff_oi.p, acc_prev, (int*)A.d_found.p);
+                    int changed = 0;
+                    L3D_CUDA(c, cudaMemcpyAsync(&changed, A.d_changed.p, 4, cudaMemcpyDeviceToHost, st), "changed flag");
+                    L3D_CUDA(c, cudaStreamSynchronize(st), "affinity fixpoint");
+                    ++c->launches;
+                    if (!changed) break;
+                }
+                if (acc_prev != (int*)A.d_keep.p) L3D_CUDA(c, cudaMemcpyAsync(A.d_keep.p, acc_prev, 4 * ne, cudaMemcpyDeviceToDevice, st), "keep flags");
+            }
             tb = S.d_sort_tmp.cap;
             cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tb, (const int*)A.d_keep.p, (long long*)A.d_q.p, ne, st);
             L3D_CUDA(c, cudaMemsetAsync(A.d_time.p, 0xFF, 8 * N, st), "init times");
@@ -581,10 +775,13 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     k_rdd_pad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, (const float*)R.d_P.p, (float*)R.d_Pp.p);
     k_rdd_pad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_wmaj.p, (const int*)R.d_colptr.p, (const int*)R.d_cp4.p, (const float*)R.d_W.p, (float*)R.d_Wp.p);
     if (4ll * std::max(tot4[0], tot4[1]) >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_rdd: padded matrix too large for 32-bit slots");
-    if ((rc = l3d_reserve(c, R.d_plan, 16 * (size_t)nnz, "rdd plan"))) return rc;
-    if ((rc = l3d_reserve(c, R.d_dst, 4 * (size_t)nnz, "rdd dst"))) return rc;
-    k_rdd_plan<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_colptr.p,
-                                   (const int*)R.d_rp4.p, (const int*)R.d_cp4.p, (const int*)R.d_tslot.p, (int4*)R.d_plan.p, (int*)R.d_dst.p);
+    if ((rc = l3d_reserve(c, R.d_rowinfo, 8 * ((size_t)n + 1), "rdd rowinfo"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_colinfo, 8 * ((size_t)n + 1), "rdd colinfo"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_src, 4 * (size_t)nnz, "rdd src"))) return rc;
+    k_rdd_rowinfo<<<(n + 256) / 256, 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, (const int*)R.d_colptr.p, (const int*)R.d_cp4.p,
+                                                   (int2*)R.d_rowinfo.p, (int2*)R.d_colinfo.p);
+    k_rdd_src<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p,
+                                  (const int*)R.d_tslot.p, (int*)R.d_src.p);
     // P' starts as a copy of the un-normalised P (cudawrapper.cu:724), then P is row-normalised (727)
     L3D_CUDA(c, cudaMemcpyAsync(R.d_Pnp.p, R.d_Pp.p, pbytes, cudaMemcpyDeviceToDevice, st), "rdd copy");
     const unsigned int nbr = (unsigned int)((n + 127) / 128);
@@ -592,14 +789,25 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     float* P = (float*)R.d_Pp.p; float* Pn = (float*)R.d_Pnp.p;
+    // lanes per destination row: the smallest power of two that covers the average row (longer rows take several passes)
+    const double avg = (double)nnz / (double)n;
+    int G = avg > 16.0 ? 32 : avg > 8.0 ? 16 : avg > 4.0 ? 8 : 4;
+    if (const char* g = getenv("L3D_RDD_G")) { const int v = atoi(g); if (v == 4 || v == 8 || v == 16 || v == 32) G = v; }   // tuning knob
+    const unsigned int nbf = (unsigned int)(((long long)n * G + 255) / 256);
     for (int it = 0; it < iters; ++it) {
-        k_rdd_step4<<<(unsigned int)((nnz + 256 * RDD_ITEMS - 1) / (256 * RDD_ITEMS)), 256, 0, st>>>(nnz, (const int4*)R.d_plan.p, (const int*)R.d_dst.p, P, (const float*)R.d_Wp.p, Pn);
+        const bool norm = it < iters - 1;       // no normalisation after the last step (cudawrapper.cu:751)
+#define RDD_LAUNCH(GG)                                                                                                                        \
+        do { if (norm) k_rdd_fused<GG, true><<<nbf, 256, 0, st>>>(n, (const int2*)R.d_rowinfo.p, (const int2*)R.d_colinfo.p, (const int*)R.d_pcol.p, \
+                                                                   (const int*)R.d_src.p, P, (const float*)R.d_Wp.p, Pn);                           \
+             else k_rdd_fused<GG, false><<<nbf, 256, 0, st>>>(n, (const int2*)R.d_rowinfo.p, (const int2*)R.d_colinfo.p, (const int*)R.d_pcol.p,    \
+                                                              (const int*)R.d_src.p, P, (const float*)R.d_Wp.p, Pn); } while (0)
+        if (G == 32) RDD_LAUNCH(32); else if (G == 16) RDD_LAUNCH(16); else if (G == 8) RDD_LAUNCH(8); else RDD_LAUNCH(4);
+#undef RDD_LAUNCH
         std::swap(P, Pn);
-        if (it < iters - 1) k_rdd_normalize4<<<nbr, 128, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, P);
     }
     if (kernel_ms) cudaEventRecord(e1, st);
     k_rdd_unpad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, P, (float*)R.d_P.p);
-    c->launches += 9 + 16 + 10 + 2 * iters;
+    c->launches += 9 + 16 + 11 + iters;
     L3D_CUDA(c, cudaGetLastError(), "rdd kernels");
     L3D_CUDA(c, cudaMemcpyAsync(out_w, R.d_P.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
     L3D_CUDA(c, cudaMemcpyAsync(out_i, R.d_prow.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");

@@ -117,7 +117,7 @@ static int finish_views(l3d_ctx* c)
         ++c->launches;
         L3D_CUDA(c, cudaGetLastError(), "k_prep_segments");
     }
-    c->have_views = true; c->have_matches = false; c->sweep.valid = false;
+    c->have_views = true; c->have_matches = false; c->sweep.valid = false; c->collin.valid = false; c->aff.valid = false;
     return L3D_OK;
 }
 
@@ -466,11 +466,12 @@ static int match_dense_impl(l3d_ctx* c, int sv, int tv, const float* F, float ep
     }
     L3DMat3 Fm; memcpy(Fm.m, F, sizeof(Fm.m));
     dim3 grid((Nt + DK_THREADS - 1) / DK_THREADS, (Ns + DKN_ROWS - 1) / DKN_ROWS);
-    dim3 gridf((Nt + DK_WARPS * DK_T * 32 - 1) / (DK_WARPS * DK_T * 32), (Ns + DK_ROWS - 1) / DK_ROWS);
+    const int R = l3d_dense_rows_per_cta(Ns, Nt, c->num_sms);
+    dim3 gridf((Nt + DK_WARPS * DK_T * 32 - 1) / (DK_WARPS * DK_T * 32), (Ns + R - 1) / R);
     const float4* cache = (const float4*)c->d_cache.p;
     if (filter)
         k_match_dense<<<gridf, DK_THREADS, l3d_dense_smem_bytes(), c->stream>>>(c->segs() + vs.seg_off, Ns, c->segs() + vt.seg_off, Nt, cache + 3 * vs.seg_off, cache + 3 * vt.seg_off, Fm,
-                                                          make_float3(vs.C[0], vs.C[1], vs.C[2]), make_float3(vt.C[0], vt.C[1], vt.C[2]), epi, d_dep, d_ov);
+                                                          make_float3(vs.C[0], vs.C[1], vs.C[2]), make_float3(vt.C[0], vt.C[1], vt.C[2]), epi, d_dep, d_ov, R);
     else
         k_match_dense_nofilter<<<grid, DK_THREADS, 0, c->stream>>>(c->segs() + vs.seg_off, Ns, c->segs() + vt.seg_off, Nt, cache + 3 * vs.seg_off, cache + 3 * vt.seg_off, Fm,
                                                                    make_float3(vs.C[0], vs.C[1], vs.C[2]), make_float3(vt.C[0], vt.C[1], vt.C[2]), epi, d_dep, d_ov);

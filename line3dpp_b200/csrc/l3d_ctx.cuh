@@ -16,31 +16,39 @@ struct SweepState {
     long long total = 0;
     DevBuf d_slot_score, d_keys, d_keys2, d_vals, d_vals2, d_reg, d_dir, d_meta, d_dep, d_os, d_kept, d_ranges, d_est_best, d_est_P,
         d_M, d_vmax, d_work, d_camrank, d_viewofrank, d_sort_tmp, d_aff_sim, d_aff_flag, d_aff_gi, d_aff_gj, d_aff_pos, d_aff_oi, d_aff_oj,
-        d_aff_ow, d_order, d_rankofview, d_region_off, d_reg_of_view, d_est_pos, d_est_out_best, d_est_out_P, d_slot_pos, d_dir64;
+        d_aff_ow, d_order, d_rankofview, d_region_off, d_reg_of_view, d_est_pos, d_est_out_best, d_est_out_P, d_slot_pos, d_dir64, d_segrank_off, d_evcnt, d_evptr, d_aff_par;
     long long n_est = 0;
+    bool aff_has_parents = false;           // d_aff_par valid: candidates carry parents (collinearity links)
     std::vector<DevBuf*> bufs()
     { return {&d_slot_score, &d_keys, &d_keys2, &d_vals, &d_vals2, &d_reg, &d_dir, &d_meta, &d_dep, &d_os, &d_kept, &d_ranges, &d_est_best,
               &d_est_P, &d_M, &d_vmax, &d_work, &d_camrank, &d_viewofrank, &d_sort_tmp, &d_aff_sim, &d_aff_flag, &d_aff_gi, &d_aff_gj,
               &d_aff_pos, &d_aff_oi, &d_aff_oj, &d_aff_ow, &d_order, &d_rankofview, &d_region_off, &d_reg_of_view, &d_est_pos,
-              &d_est_out_best, &d_est_out_P, &d_slot_pos, &d_dir64}; }
+              &d_est_out_best, &d_est_out_P, &d_slot_pos, &d_dir64, &d_segrank_off, &d_evcnt, &d_evptr, &d_aff_par}; }
 };
 
 // device state of the affinity-matrix bookkeeping (l3d_affinity.cu)
 struct AffinityState {
     bool valid = false; float two_sigA_sqr = 0.f, med = 0.f, min_aff = 0.f; long long K = 0, n_ids = 0;
-    DevBuf d_key, d_key2, d_val, d_val2, d_keep, d_q, d_time, d_nflag, d_npos, d_idof, d_nkey, d_nkey2, d_nval, d_nval2, d_l2g, d_ei, d_ej, d_ew;
+    DevBuf d_key, d_key2, d_val, d_val2, d_keep, d_keep2, d_found, d_changed, d_q, d_time, d_nflag, d_npos, d_idof, d_nkey, d_nkey2, d_nval, d_nval2, d_l2g, d_ei, d_ej, d_ew;
     std::vector<DevBuf*> bufs()
-    { return {&d_key, &d_key2, &d_val, &d_val2, &d_keep, &d_q, &d_time, &d_nflag, &d_npos, &d_idof, &d_nkey, &d_nkey2, &d_nval, &d_nval2, &d_l2g,
+    { return {&d_key, &d_key2, &d_val, &d_val2, &d_keep, &d_keep2, &d_found, &d_changed, &d_q, &d_time, &d_nflag, &d_npos, &d_idof, &d_nkey, &d_nkey2, &d_nval, &d_nval2, &d_l2g,
               &d_ei, &d_ej, &d_ew}; }
+};
+
+// per-view lists of potentially collinear segments (l3d_collinear.cu), CSR over the global segment index
+struct CollinState {
+    bool valid = false; float dist_t = 0.f; int sem = 0; long long total = 0;
+    DevBuf d_tiles, d_cnt, d_ptr, d_idx, d_tmp;
+    std::vector<DevBuf*> bufs() { return {&d_tiles, &d_cnt, &d_ptr, &d_idx, &d_tmp}; }
 };
 
 // device buffers of the diffusion (l3d_affinity.cu)
 struct RddState {
     DevBuf d_ei, d_ej, d_ew, d_krow, d_kcol, d_k2, d_idx, d_idx2, d_P, d_Pn, d_W, d_prow, d_pcol, d_wmaj, d_wmin, d_rowptr, d_colptr, d_tslot, d_tmp, d_len4, d_rp4, d_cp4,
-        d_Pp, d_Pnp, d_Wp, d_plan, d_dst;
+        d_Pp, d_Pnp, d_Wp, d_rowinfo, d_colinfo, d_src;
     std::vector<DevBuf*> bufs()
     { return {&d_ei, &d_ej, &d_ew, &d_krow, &d_kcol, &d_k2, &d_idx, &d_idx2, &d_P, &d_Pn, &d_W, &d_prow, &d_pcol, &d_wmaj, &d_wmin, &d_rowptr,
-              &d_colptr, &d_tslot, &d_tmp, &d_len4, &d_rp4, &d_cp4, &d_Pp, &d_Pnp, &d_Wp, &d_plan, &d_dst}; }
+              &d_colptr, &d_tslot, &d_tmp, &d_len4, &d_rp4, &d_cp4, &d_Pp, &d_Pnp, &d_Wp, &d_rowinfo, &d_colinfo, &d_src}; }
 };
 
 struct l3d_ctx {
@@ -72,6 +80,7 @@ struct l3d_ctx {
     SweepState sweep;
     RddState rdd;
     AffinityState aff;
+    CollinState collin;
 
     const float4* segs() const { return segs_ext ? segs_ext : (const float4*)d_segs.p; }
     const L3DViewDev* views() const { return (const L3DViewDev*)d_views.p; }
@@ -81,6 +90,7 @@ struct l3d_ctx {
         for (DevBuf* x : sweep.bufs()) b.push_back(x);
         for (DevBuf* x : rdd.bufs()) b.push_back(x);
         for (DevBuf* x : aff.bufs()) b.push_back(x);
+        for (DevBuf* x : collin.bufs()) b.push_back(x);
         return b;
     }
 };

@@ -425,6 +425,21 @@ struct DenseSmem {
     float epi; int Nt, row0;
 };
 size_t l3d_dense_smem_bytes() { return sizeof(DenseSmem); }
+// Rows per CTA (8..DK_ROWS) such that the tile count fills whole waves of the 3 resident CTAs per SM: a 3000 x 3000 pair
+// with the former fixed 16 rows gave 564 CTAs = 1.27 waves on 148 SMs, i.e. a second wave that is 73 % idle.
+int l3d_dense_rows_per_cta(int Ns, int Nt, int num_sms)
+{
+    const long long slots = 3ll * (num_sms > 0 ? num_sms : 148);
+    const long long colb = (Nt + DK_WARPS * DK_T * 32 - 1) / (DK_WARPS * DK_T * 32);
+    int best = 16; double best_eff = -1.0;
+    for (int R = 8; R <= DK_ROWS; ++R) {
+        const long long tiles = colb * ((Ns + R - 1) / R);
+        const long long waves = (tiles + slots - 1) / slots;
+        const double eff = (double)tiles / (double)(waves * slots);
+        if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && R > best)) { best_eff = eff; best = R; }
+    }
+    return best;
+}
 
 __device__ __forceinline__ SegRays rays_from_smem(const float4* p)
 {
@@ -457,13 +472,13 @@ __device__ __noinline__ void dense_exact_batch(DenseSmem& S, unsigned int entry,
 __global__ void __launch_bounds__(DK_THREADS, 3)
 k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
               const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F, float3 Cs, float3 Ct,
-              float epi, float4* __restrict__ depths, float* __restrict__ overlaps)
+              float epi, float4* __restrict__ depths, float* __restrict__ overlaps, int rows_per_cta)
 {
     extern __shared__ __align__(128) unsigned char dense_smem_raw[];
     DenseSmem& S = *reinterpret_cast<DenseSmem*>(dense_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row0 = blockIdx.y * DK_ROWS;
-    const int nrows = min(DK_ROWS, Ns - row0);
+    const int row0 = blockIdx.y * rows_per_cta;
+    const int nrows = min(rows_per_cta, Ns - row0);
     if (tid == 0) { S.depths = depths; S.overlaps = overlaps; S.Cs = Cs; S.Ct = Ct; S.epi = epi; S.Nt = Nt; S.row0 = row0; }
     if (tid < nrows) {
         float4 s = __ldg(ssegs + row0 + tid);

@@ -30,7 +30,8 @@
 
 #define DK_THREADS 256
 #define DK_WARPS 8
-#define DK_ROWS 16                      /* source rows per CTA of the dense kernel */
+#define DK_ROWS 32                      /* MAXIMUM source rows per CTA of the dense kernel; the launch picks 8..32 so that the tile
+                                           count fills whole waves of 3 CTAs per SM (l3d_dense_rows_per_cta) */
 #define DK_T 4                          /* target columns per lane: a CTA covers DK_ROWS x (8*4*32 = 1024) cells */
 #define DKN_ROWS 32                     /* rows per CTA of the unfiltered test kernel */
 
@@ -58,7 +59,8 @@ __global__ void k_prep_segments_f64(const float4* __restrict__ segs, const L3DVi
                                     long long total, double* __restrict__ cache);
 __global__ void k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
                               const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F, float3 Cs,
-                              float3 Ct, float epi, float4* __restrict__ depths, float* __restrict__ overlaps);
+                              float3 Ct, float epi, float4* __restrict__ depths, float* __restrict__ overlaps, int rows_per_cta);
+int l3d_dense_rows_per_cta(int Ns, int Nt, int num_sms);
 __global__ void k_match_dense_nofilter(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
                                        const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F,
                                        float3 Cs, float3 Ct, float epi, float4* __restrict__ depths,

@@ -561,7 +561,6 @@ void Line3D::reconstruct3Dlines(const unsigned int visibility_t, const bool perf
     P.lines3D.clear(); P.collin_t = collinearity_t;
     P.perform_RDD = perform_diffusion && P.use_gpu;                                       // line3D.cc:1729
     if (use_CERES) P.log("CERES optimisation is not part of this library; no optimisation will be performed");
-    if (collinearity_t > EPS) P.log("collinearity links (collinearity_t > 0) are not implemented yet; ignored");
     P.translate();
     // median scene depth for lines (line3D.cc:1759-1774)
     std::vector<float> sd;
@@ -570,6 +569,10 @@ void Line3D::reconstruct3Dlines(const unsigned int visibility_t, const bool perf
     std::vector<l3d_view_desc> d = P.descs();
     auto t0 = std::chrono::steady_clock::now();
     bool ok = P.chk(l3d_update_view_params(P.ctx, (int)d.size(), d.data()), "l3d_update_view_params");
+    // potentially collinear segments of every view (findCollinearSegments line3D.cc:1751-1756, 1827-1849); the affinity matrix
+    // below then adds the collinearity links (line3D.cc:1904-1974).  collinearity_t <= eps switches them off.
+    ok = ok && P.chk(l3d_find_collinear(P.ctx, collinearity_t > EPS ? collinearity_t : 0.0f, P.use_gpu ? L3D_SEM_REF_GPU : L3D_SEM_REF_CPU), "l3d_find_collinear");
+    P.st.collinear_entries = ok ? l3d_collinear_total(P.ctx) : 0;
     // affinity matrix incl. the "unused" pair filter and first-come local ids (line3D.cc:1881-1900, 1982-2023), on the device
     long long nids = 0;
     long long nA = ok ? l3d_affinity_matrix(P.ctx, P.two_sigA_sqr, P.med_scene_depth_lines, MIN_AFFINITY, nullptr, nullptr, nullptr, 0, nullptr, 0, &nids) : -1;

@@ -15,7 +15,7 @@ RESID_DT = np.dtype([("line", "<i4"), ("cam", "<u4"), ("seg", "<u4")])
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("view_pairs", "pair_evaluations", "matches_after_knn", "estimates", "affinity_entries",
-                                            "affinity_rows", "clusters_total", "clusters_valid", "lines3D")] + \
+                                            "affinity_rows", "clusters_total", "clusters_valid", "lines3D", "collinear_entries")] + \
                [(n, C.c_double) for n in ("ms_match", "ms_score", "ms_affinity", "ms_diffusion", "ms_cluster")]
 
 
@@ -104,6 +104,18 @@ class Line3D:
         if n > 0:
             self.L.l3d_get_estimates(self.ctx, _p(best), _p(p), C.c_longlong(n))
         return best, p
+
+    def ctx_collinear(self, view_index, nseg):
+        """View::collin_ of the view_index-th added view as CSR (row_ptr, idx), straight from the C ABI"""
+        row_ptr = np.zeros(nseg + 1, np.int64)
+        self.L.l3d_get_collinear.restype = C.c_longlong
+        n = self.L.l3d_get_collinear(self.ctx, int(view_index), _p(row_ptr), None, C.c_longlong(0))
+        if n < 0:
+            raise capi.L3DError("l3d_get_collinear failed")
+        idx = np.zeros(max(int(n), 1), np.int32)
+        if n > 0:
+            self.L.l3d_get_collinear(self.ctx, int(view_index), _p(row_ptr), _p(idx), C.c_longlong(int(n)))
+        return row_ptr, idx[:int(n)]
 
     def affinity(self, raw=False):
         n = self.L.l3dpp_get_affinity(self.h, int(raw), None, None, None, C.c_longlong(0))

@@ -69,7 +69,9 @@ def make_scene_views(num_views, segs_per_view, seed, neighbors, views, noise_px:
 
 
 def make_scene(num_views: int, segs_per_view: int, seed: int, neighbors: str | int = "ring5",
-               noise_px: float = 0.5, only_views=None) -> Scene:
+               noise_px: float = 0.5, only_views=None, collinear: bool = False) -> Scene:
+    """collinear=True: every odd 3D line continues the even line before it on the same infinite line after a gap
+    (broken edges, the case reconstruct3Dlines' collinearity_t is for); the default scenes are unchanged."""
     rng = np.random.default_rng(seed)
     V, N = num_views, segs_per_view
     L = 2 * N
@@ -78,7 +80,14 @@ def make_scene(num_views: int, segs_per_view: int, seed: int, neighbors: str | i
     d = rng.normal(size=(L, 3))
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     length = rng.uniform(0.05, 0.5, size=(L, 1))
-    P2 = np.clip(P1 + d * length, -1.0, 1.0)
+    if collinear:
+        gap = rng.uniform(0.03, 0.15, size=(L // 2, 1))
+        P1 = P1 * 0.6
+        d[1::2] = d[0::2]
+        P1[1::2] = P1[0::2] + d[0::2] * (length[0::2] + gap)
+        P2 = P1 + d * length
+    else:
+        P2 = np.clip(P1 + d * length, -1.0, 1.0)
     lines3d = np.concatenate([P1, P2], axis=1)
 
     Kmat = np.array([[FOCAL, 0, WIDTH / 2.0], [0, FOCAL, HEIGHT / 2.0], [0, 0, 1.0]])

@@ -199,6 +199,8 @@ struct View {
     float C_f3[3], RtKinv_f[9];               // view.cc:35-40 (set once at construction: NOT updated by translate())
     float k, median_depth, median_sigma, initial_median_depth, diagonal, min_line_length;
     std::vector<f4> lines;
+    float collin_t = 0.0f;                     // View::collin_t_ (view.cc:29)
+    std::vector<std::list<uint32_t> > collin;  // View::collin_ (view.h), filled by findCollinGPU / findCollinCPU
 
     void init()                               // View::View view.cc:6-42
     {
@@ -355,11 +357,67 @@ void rdd_step(const Sparse& P, const Sparse& W, Sparse& Pp)
     }
 }
 
+// K_collinearity (cudawrapper.cu:370-429) for one ordered cell: l1 = lines[x], l2 = lines[y], x > y; float arithmetic,
+// D_point_on_segment_2D_f3 (80-86), cross (helper_math.h:1420), D_distance_p2l_2D_f3 (34-37)
+inline float dist_p2l_f(f3 line, f3 p) { return fabsf((line.x * p.x + line.y * p.y + line.z) / sqrtf(line.x * line.x + line.y * line.y)); }
+inline unsigned char collinear_cell_f32(f4 l1, f4 l2, float dist_t)
+{
+    f3 p0 = mk3(l1.x, l1.y, 1.0f), p1 = mk3(l1.z, l1.w, 1.0f), q0 = mk3(l2.x, l2.y, 1.0f), q1 = mk3(l2.z, l2.w, 1.0f);
+    if (on_seg(p0, p1, q0) || on_seg(p0, p1, q1) || on_seg(q0, q1, p0) || on_seg(q0, q1, p1)) return 0;
+    f3 line1 = cross3(p0, p1), line2 = cross3(q0, q1);
+    float d1 = fmaxf(dist_p2l_f(line1, q0), dist_p2l_f(line1, q1));
+    float d2 = fmaxf(dist_p2l_f(line2, p0), dist_p2l_f(line2, p1));
+    return fmaxf(d1, d2) < dist_t ? 1 : 0;
+}
+// View::findCollinCPU (view.cc:212-263) for one (r, c) cell: double geometry, float distances
+// (View::distance_point2line_2D view.cc:266-269 returns float and takes sqrtf of the double sum; pointOnSegment 290-296)
+inline bool on_seg_d(V3 p1, V3 p2, V3 x) { return ((p1.x - x.x) * (p2.x - x.x) + (p1.y - x.y) * (p2.y - x.y)) < L3D_EPS; }
+inline float dist_p2l_d(V3 line, V3 p) { return (float)std::fabs((line.x * p.x + line.y * p.y + line.z) / sqrtf((float)(line.x * line.x + line.y * line.y))); }
+inline unsigned char collinear_cell_f64(f4 l1, f4 l2, float dist_t)
+{
+    V3 p0 = V(l1.x, l1.y, 1.0f), p1 = V(l1.z, l1.w, 1.0f), q0 = V(l2.x, l2.y, 1.0f), q1 = V(l2.z, l2.w, 1.0f);
+    V3 line1 = crossd(p0, p1), line2 = crossd(q0, q1);
+    if (on_seg_d(p0, p1, q0) || on_seg_d(p0, p1, q1) || on_seg_d(q0, q1, p0) || on_seg_d(q0, q1, p1)) return 0;
+    float d1 = fmaxf(dist_p2l_d(line1, q0), dist_p2l_d(line1, q1));
+    float d2 = fmaxf(dist_p2l_d(line2, p0), dist_p2l_d(line2, p1));
+    return fmaxf(d1, d2) < dist_t ? 1 : 0;
+}
+
+typedef int (*collinear_fn_t)(const float*, int, float, unsigned char*, float*);
+
 } // namespace
 
 extern "C" {
 
 void orc_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+
+// find_collinear_segments_GPU (cudawrapper.cu:689-705) + K_collinearity: dense N x N char matrix, C[y*N+x]; the kernel
+// evaluates the cells x >= y with l1 = lines[x], l2 = lines[y] and mirrors them (cudawrapper.cu:376-427)
+int orc_collinear_f32(const float* lines, int N, float dist_t, unsigned char* C_out, float* kernel_ms)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    const f4* L = (const f4*)lines;
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic, 16)
+    for (int y = 0; y < N; ++y)
+        for (int x = y; x < N; ++x) {
+            unsigned char v = x == y ? 0 : collinear_cell_f32(L[x], L[y], dist_t);
+            C_out[(size_t)y * N + x] = v; C_out[(size_t)x * N + y] = v;
+        }
+    if (kernel_ms) *kernel_ms = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+// View::findCollinCPU (view.cc:212-263) written as the same dense matrix: C[r*N+c] = 1 iff c is pushed to collin_[r]
+int orc_collinear_f64(const float* lines, int N, float dist_t, unsigned char* C_out, float* kernel_ms)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    const f4* L = (const f4*)lines;
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int r = 0; r < N; ++r)
+        for (int c2 = 0; c2 < N; ++c2)
+            C_out[(size_t)r * N + c2] = r == c2 ? 0 : collinear_cell_f64(L[r], L[c2], dist_t);
+    if (kernel_ms) *kernel_ms = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
 
 int orc_match_dense_f32(const float* lines_src, int Ns, const float* lines_tgt, int Nt, const float* F,
                         const float* RtKinv_src, const float* RtKinv_tgt, const float* C_src, const float* C_tgt,
@@ -600,7 +658,7 @@ struct FinalLine {
 
 struct orc_ctx {
     bool by_wps, use_gpu;
-    match_lines_fn_t match_fn; score_matches_fn_t score_fn; rdd_fn_t rdd_fn;
+    match_lines_fn_t match_fn; score_matches_fn_t score_fn; rdd_fn_t rdd_fn; collinear_fn_t collin_fn;
     std::map<uint32_t, View*> views; std::vector<uint32_t> view_order;
     std::map<uint32_t, std::vector<std::list<orc_match_t> > > matches;
     std::map<uint32_t, std::vector<orc_match_t> > scored;    // dump: flattened matches right after scoring
@@ -937,12 +995,36 @@ int local_id(orc_ctx* c, const Seg2D& s)   // line3D.cc:2005-2023
     return id;
 }
 
-void computing_affinity_matrix(orc_ctx* c)   // line3D.cc:1852-1979 (collinearity_t <= 0 branch; collinearity is §8f-3)
+// View::findCollinearSegments (view.cc:152-171) -> findCollinGPU (173-209: dense char matrix from the kernel, scanned per
+// row in ascending column order) or findCollinCPU (212-263)
+void view_find_collinear(orc_ctx* c, View* v, float dist_t, bool useGPU)
+{
+    if (std::fabs(dist_t - v->collin_t) < L3D_EPS) return;      // already computed
+    if (!(dist_t > L3D_EPS)) return;
+    v->collin_t = dist_t;
+    const int N = (int)v->lines.size();
+    v->collin.assign(N, std::list<uint32_t>());
+    if (N == 0) return;
+    std::vector<unsigned char> C((size_t)N * N);
+    if (useGPU) c->collin_fn((const float*)v->lines.data(), N, dist_t, C.data(), nullptr);
+    else orc_collinear_f64((const float*)v->lines.data(), N, dist_t, C.data(), nullptr);
+    for (int i = 0; i < N; ++i)
+        for (int x = 0; x < N; ++x)
+            if (C[(size_t)i * N + x] == 1) v->collin[i].push_back((uint32_t)x);
+}
+std::list<uint32_t> collinear_segments(View* v, uint32_t seg)   // View::collinearSegments view.cc:281-287
+{
+    if (v->collin.size() == v->lines.size() && seg < v->lines.size()) return v->collin[seg];
+    return std::list<uint32_t>();
+}
+
+void computing_affinity_matrix(orc_ctx* c)   // line3D.cc:1852-1979
 {
     c->A.clear(); c->global2local.clear(); c->local2global.clear(); c->localID = 0; c->used.clear();
+    const bool collin = c->collin_t > L3D_EPS;
     for (size_t i = 0; i < c->est.size(); ++i) {
         const Seg3D& s = c->est[i].first; const orc_match_t& m = c->est[i].second;
-        Seg2D seg = {m.src_cam, m.src_seg}; int id1 = -1;
+        Seg2D seg = {m.src_cam, m.src_seg}; int id1 = -1; bool found_aff = false;
         const std::list<orc_match_t>& L = c->matches[m.src_cam][m.src_seg];
         for (std::list<orc_match_t>::const_iterator it = L.begin(); it != L.end(); ++it) {
             Seg2D seg2 = {it->tgt_cam, it->tgt_seg};
@@ -952,6 +1034,31 @@ void computing_affinity_matrix(orc_ctx* c)   // line3D.cc:1852-1979 (collinearit
                 int id2 = local_id(c, seg2);
                 CLEdge e = {id1, id2, sim}; c->A.push_back(e);
                 CLEdge e2 = {id2, id1, sim}; c->A.push_back(e2);
+                found_aff = true;
+                if (collin) {            // links to the segments collinear with the target (line3D.cc:1904-1937)
+                    std::list<uint32_t> coll = collinear_segments(c->views[seg2.cam], seg2.seg);
+                    for (std::list<uint32_t>::const_iterator cit = coll.begin(); cit != coll.end(); ++cit) {
+                        Seg2D sc = {seg2.cam, *cit};
+                        float simc = similarity(c, s, m, sc, false);
+                        if (simc > MIN_AFFINITY && unused_pair(c, seg, sc)) {
+                            int idc = local_id(c, sc);
+                            CLEdge a = {id1, idc, simc}; c->A.push_back(a);
+                            CLEdge b = {idc, id1, simc}; c->A.push_back(b);
+                        }
+                    }
+                }
+            }
+        }
+        if (found_aff && id1 >= 0 && collin) {   // links to the segments collinear with the source (line3D.cc:1941-1974)
+            std::list<uint32_t> coll = collinear_segments(c->views[seg.cam], seg.seg);
+            for (std::list<uint32_t>::const_iterator cit = coll.begin(); cit != coll.end(); ++cit) {
+                Seg2D sc = {seg.cam, *cit};
+                float simc = similarity(c, s, m, sc, false);
+                if (simc > MIN_AFFINITY && unused_pair(c, seg, sc)) {
+                    int idc = local_id(c, sc);
+                    CLEdge a = {id1, idc, simc}; c->A.push_back(a);
+                    CLEdge b = {idc, id1, simc}; c->A.push_back(b);
+                }
             }
         }
     }
@@ -1101,6 +1208,7 @@ orc_ctx* orc_create(int neighbors_by_worldpoints, int use_gpu)
     orc_ctx* c = new orc_ctx();
     c->by_wps = neighbors_by_worldpoints != 0; c->use_gpu = use_gpu != 0;
     c->match_fn = (match_lines_fn_t)orc_match_lines_f32; c->score_fn = (score_matches_fn_t)orc_score_matches_f32; c->rdd_fn = (rdd_fn_t)orc_rdd_f32;
+    c->collin_fn = (collinear_fn_t)orc_collinear_f32;
     c->num_lines_total = 0; c->pair_evals = 0; c->collin_t = -1.0f; c->localID = 0;
     c->translation = V(0, 0, 0); c->med_scene_depth = -1.0f; c->med_scene_depth_lines = 0.0f;
     c->fixed3Dreg = false; c->perform_RDD = false; c->visibility_t = 3; c->num_neighbors = 10; c->kNN = 10;
@@ -1118,6 +1226,7 @@ void orc_set_backend(orc_ctx* c, void* m, void* s, void* r)
     if (s) c->score_fn = (score_matches_fn_t)s;
     if (r) c->rdd_fn = (rdd_fn_t)r;
 }
+void orc_set_collinear_backend(orc_ctx* c, void* f) { c->collin_fn = f ? (collinear_fn_t)f : (collinear_fn_t)orc_collinear_f32; }
 
 int orc_add_view(orc_ctx* c, uint32_t cam_id, int width, int height, const double* K, const double* R, const double* t,
                  float median_depth, const uint32_t* list, int n_list, const float* segs, int nseg)
@@ -1182,9 +1291,13 @@ int orc_reconstruct(orc_ctx* c, uint32_t visibility_t, int perform_diffusion, fl
 {
     if (c->est.empty()) return -1;
     c->visibility_t = (unsigned)std::max(int(visibility_t), 3);
-    c->clusters3D.clear(); c->lines3D.clear(); c->collin_t = collinearity_t;
+    c->clusters3D.clear(); c->lines3D.clear();
+    const float prev_collin_t = c->collin_t;
+    c->collin_t = collinearity_t;
     c->perform_RDD = perform_diffusion && c->use_gpu;
     translate(c);
+    if (c->collin_t > L3D_EPS && (prev_collin_t < L3D_EPS || std::fabs(prev_collin_t - c->collin_t) > L3D_EPS))   // line3D.cc:1751-1756, 1827-1849
+        for (std::map<uint32_t, View*>::iterator v = c->views.begin(); v != c->views.end(); ++v) view_find_collinear(c, v->second, c->collin_t, c->use_gpu);
     std::vector<float> sd;
     for (std::map<uint32_t, View*>::const_iterator v = c->views.begin(); v != c->views.end(); ++v)
         if (v->second->median_depth > L3D_EPS) sd.push_back(v->second->median_depth);
@@ -1265,6 +1378,20 @@ int orc_get_local2global(orc_ctx* c, uint32_t* cs, int cap)
 {
     for (size_t i = 0; i < c->l2g_dump.size() && (int)i < cap; ++i) { cs[2 * i] = c->l2g_dump[i].cam; cs[2 * i + 1] = c->l2g_dump[i].seg; }
     return (int)c->l2g_dump.size();
+}
+// collinear lists of a view as CSR: row_ptr[nseg+1], idx[row_ptr[nseg]]; returns the number of entries (even if > cap)
+long long orc_get_collinear(orc_ctx* c, uint32_t cam, long long* row_ptr, int* idx, long long cap)
+{
+    if (!c->views.count(cam)) return -1;
+    View* v = c->views[cam];
+    long long n = 0;
+    for (size_t i = 0; i < v->lines.size(); ++i) {
+        if (row_ptr) row_ptr[i] = n;
+        if (i < v->collin.size())
+            for (std::list<uint32_t>::const_iterator it = v->collin[i].begin(); it != v->collin[i].end(); ++it) { if (idx && n < cap) idx[n] = (int)*it; ++n; }
+    }
+    if (row_ptr) row_ptr[v->lines.size()] = n;
+    return n;
 }
 int orc_num_lines(orc_ctx* c) { return (int)c->lines3D.size(); }
 long long orc_get_segments3d(orc_ctx* c, orc_seg3d_t* out, long long cap)

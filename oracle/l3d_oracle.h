@@ -46,6 +46,10 @@ int orc_score_matches_f32(const float* lines, int Ns, const float* matches, int 
                           float min_similarity, float* scores_out, float* kernel_ms);
 int orc_rdd_f32(int nedges, const int* ei, const int* ej, const float* ew, int n, int* out_i, int* out_j,
                 float* out_w, double* wall_ms);
+/* find_collinear_segments_GPU + K_collinearity (cudawrapper.cu:370-429, 689-705) / View::findCollinCPU (view.cc:212-263):
+ * dense N x N char matrix C[r*N+c] = 1 iff segment c is collinear with segment r (distance threshold dist_t, px) */
+int orc_collinear_f32(const float* lines, int N, float dist_t, unsigned char* C_out, float* kernel_ms);
+int orc_collinear_f64(const float* lines, int N, float dist_t, unsigned char* C_out, float* kernel_ms);
 int orc_cluster(int nedges, const int* ei, const int* ej, const float* ew, int n, float c, int* labels_out);
 
 /* ---- pipeline: restatement of L3DPP::Line3D (line3D.h:80-233) ---- */
@@ -57,6 +61,8 @@ void orc_destroy(orc_ctx*);
  * (e.g. the verbatim reference kernels from oracle/_ref on a GPU box).  NULL keeps the CPU emulation. */
 void orc_set_backend(orc_ctx*, void* match_lines_fn, void* score_matches_fn, void* rdd_fn);
 void orc_set_threads(int n);
+/* same for find_collinear_segments_GPU (signature of ref_collinear / orc_collinear_f32); NULL restores the CPU emulation */
+void orc_set_collinear_backend(orc_ctx*, void* collinear_fn);
 /* addImage with explicit line segments (line3D.cc:112-226); image itself is not needed */
 int orc_add_view(orc_ctx*, uint32_t cam_id, int width, int height, const double* K, const double* R, const double* t,
                  float median_depth, const uint32_t* wps_or_neighbors, int n_list, const float* segs, int nseg);
@@ -75,6 +81,7 @@ long long orc_get_estimates(orc_ctx*, orc_match_t* best, double* p1p2 /*6 per es
 long long orc_get_affinity(orc_ctx*, int* ei, int* ej, float* ew, long long cap); /* A_ handed to clustering */
 long long orc_get_affinity_raw(orc_ctx*, int* ei, int* ej, float* ew, long long cap); /* A_ before diffusion */
 int orc_get_local2global(orc_ctx*, uint32_t* cam_seg /*2 per id*/, int cap);
+long long orc_get_collinear(orc_ctx*, uint32_t cam, long long* row_ptr, int* idx, long long cap); /* View::collin_ as CSR */
 int orc_num_lines(orc_ctx*);
 long long orc_get_segments3d(orc_ctx*, orc_seg3d_t* out, long long cap);
 long long orc_get_residuals(orc_ctx*, orc_residual_t* out, long long cap);

@@ -50,7 +50,7 @@ def lib():
         L.orc_match_lines_f32.restype = C.c_longlong
         L.orc_match_lines_f64.restype = C.c_longlong
         for n in ("orc_pair_evals", "orc_get_matches", "orc_get_scored", "orc_get_estimates", "orc_get_affinity",
-                  "orc_get_affinity_raw", "orc_get_segments3d", "orc_get_residuals"):
+                  "orc_get_affinity_raw", "orc_get_segments3d", "orc_get_residuals", "orc_get_collinear"):
             getattr(L, n).restype = C.c_longlong
         _lib = L
     return _lib
@@ -123,6 +123,17 @@ def rdd(fn, ei, ej, ew, n):
     return oi, oj, ow, ms.value
 
 
+def collinear(fn, lines, dist_t):
+    """fn = lib().orc_collinear_f32 / orc_collinear_f64 / ref_lib().ref_collinear.  Returns (C[N,N] uint8, ms)."""
+    lines = _f32(lines)
+    N = len(lines)
+    Cm = np.zeros((N, N), np.uint8)
+    ms = C.c_float(0)
+    rc = fn(_p(lines), N, C.c_float(dist_t), _p(Cm), C.byref(ms))
+    assert rc == 0, rc
+    return Cm, ms.value
+
+
 def cluster(fn, ei, ej, ew, n, c=3.0):
     ei, ej = np.ascontiguousarray(ei, np.int32), np.ascontiguousarray(ej, np.int32)
     lab = np.zeros(n, np.int32)
@@ -141,6 +152,8 @@ class OraclePipeline:
         if backend is not None:   # verbatim reference kernels (oracle/_ref) instead of the CPU emulation
             g = lambda n: C.cast(getattr(backend, n), C.c_void_p)
             self.L.orc_set_backend(self.ctx, g("ref_match_lines"), g("ref_score_matches"), g("ref_rdd"))
+            if hasattr(backend, "ref_collinear"):
+                self.L.orc_set_collinear_backend(self.ctx, g("ref_collinear"))
 
     def __del__(self):
         if getattr(self, "ctx", None):
@@ -170,6 +183,15 @@ class OraclePipeline:
 
     def pair_evals(self):
         return int(self.L.orc_pair_evals(self.ctx))
+
+    def collinear(self, cam, nseg):
+        """View::collin_ of a view as CSR (row_ptr[nseg+1], idx)"""
+        row_ptr = np.zeros(nseg + 1, np.int64)
+        n = self.L.orc_get_collinear(self.ctx, C.c_uint(int(cam)), _p(row_ptr), None, C.c_longlong(0))
+        idx = np.zeros(max(int(n), 1), np.int32)
+        if n > 0:
+            self.L.orc_get_collinear(self.ctx, C.c_uint(int(cam)), _p(row_ptr), _p(idx), C.c_longlong(int(n)))
+        return row_ptr, idx[:max(int(n), 0)]
 
     def pairs(self):
         n = self.L.orc_get_pairs(self.ctx, None, 0)

@@ -12,6 +12,7 @@
 //     scoringGPU    line3D.cc:1357-1368  (upload ranges/matches/reg_tgt, launch, download scores)
 //     performRDD    line3D.cc:2026-2036  (SparseMatrix(A_, n) -> replicator_dynamics_diffusion_GPU -> download)
 //     clusterSegments line3D.cc:2089     (performClustering(A_, n, 3.0f))
+//     findCollinGPU   view.cc:173-209    (char N x N buffer -> find_collinear_segments_GPU -> download)
 #include "cudawrapper.cu"
 #include "sparsematrix.cc"
 #include "clustering.cc"
@@ -102,6 +103,32 @@ int ref_match_dense(const float* lines_src, int Ns, const float* lines_tgt, int 
             }
     }
     delete ls; delete lt; delete dF; delete dRs; delete dRt; delete buffer; delete overlaps;
+    return st == cudaSuccess ? 0 : -(int)st;
+}
+
+// Verbatim find_collinear_segments_GPU (cudawrapper.cu:689-705) staged like View::findCollinGPU (view.cc:173-209):
+// C_out[i*N + c] = buffer->dataCPU(c,i)[0], the char the reference tests against 1 when it builds collin_[i].
+// (every cell is written: thread (x,y), x >= y, stores C[y][x] and its mirror C[x][y], cudawrapper.cu:376-427)
+int ref_collinear(const float* lines, int N, float dist_t, unsigned char* C_out, float* kernel_ms)
+{
+    L3DPP::DataArray<float4>* ls = lines_to_da(lines, N);
+    L3DPP::DataArray<char>* buffer = new L3DPP::DataArray<char>(N, N, true);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    L3DPP::find_collinear_segments_GPU(buffer, ls, dist_t);
+    cudaEventRecord(e1);
+    cudaError_t st = cudaDeviceSynchronize();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (kernel_ms) *kernel_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (C_out) {
+        buffer->download();
+        for (int i = 0; i < N; ++i)
+            for (int c = 0; c < N; ++c) C_out[(size_t)i * N + c] = (unsigned char)buffer->dataCPU(c, i)[0];
+    }
+    delete ls; delete buffer;
     return st == cudaSuccess ? 0 : -(int)st;
 }
 

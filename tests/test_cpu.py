@@ -163,6 +163,63 @@ def test_scene_shards_are_consistent():
     assert len(part.segs[0]) == 0 and np.array_equal(full.K, part.K) and np.array_equal(full.R, part.R)
 
 
+
+# ---------------------------------------------------------------------------------------------- collinearity
+GOLD_COLLIN = os.path.join(ROOT, "tests", "golden", "ref_collinear_v1.npz")
+
+
+@pytest.mark.parametrize("name", ["v0", "v2", "edge"])
+def test_oracle_collinear_vs_reference_golden(oracle, name):
+    """orc_collinear_f32 == the UNMODIFIED K_collinearity run on a B200 (tests/golden/make_golden_collinear.py)"""
+    if not os.path.exists(GOLD_COLLIN):
+        pytest.skip("collinearity golden vectors not generated yet (tests/golden/make_golden_collinear.py on a GPU box)")
+    g = np.load(GOLD_COLLIN)
+    segs = g[f"{name}_segs"]
+    if name != "edge":
+        v, n, seed = [int(x) for x in g["scene_args"]]
+        sc = synth.make_scene(v, n, seed, "ring1", collinear=True)
+        assert np.array_equal(sc.segs[int(name[1:])], segs), "synthetic scene generator changed: regenerate the golden file"
+    for t in (0.5, 2.0, 6.0):
+        Cm, _ = oracle.collinear(oracle.lib().orc_collinear_f32, segs, t)
+        assert np.array_equal(np.argwhere(Cm == 1).astype(np.int32), g[f"{name}_t{t}"]), (name, t)
+
+
+def test_oracle_collinear_properties(oracle):
+    """symmetric, empty diagonal, monotone in the threshold, float and double paths agree on well-conditioned input,
+    and the fragments of a broken 3D line are found"""
+    sc = synth.make_scene(4, 300, 95, "ring1", collinear=True)
+    L = oracle.lib()
+    prev = None
+    for t in (1.0, 2.0, 5.0):
+        a, _ = oracle.collinear(L.orc_collinear_f32, sc.segs[1], t)
+        b, _ = oracle.collinear(L.orc_collinear_f64, sc.segs[1], t)
+        assert np.array_equal(a, a.T) and not a.diagonal().any() and np.array_equal(a, b)
+        if prev is not None:
+            assert np.all(a >= prev)
+        prev = a
+    ids = sc.line_ids[1]
+    frag = {(i, j) for i in range(len(ids)) for j in range(len(ids)) if i != j and ids[i] // 2 == ids[j] // 2}
+    found = {tuple(x) for x in np.argwhere(prev == 1)}
+    assert len(frag) > 20 and len(frag & found) >= 0.9 * len(frag)
+    e, _ = oracle.collinear(L.orc_collinear_f32, np.zeros((0, 4), np.float32), 2.0)
+    assert e.shape == (0, 0)
+
+
+@pytest.mark.parametrize("use_gpu", [1, 0])
+def test_oracle_collinearity_links_merge_fragments(oracle, use_gpu):
+    sc = synth.make_scene(8, 300, 3, "ring2", collinear=True)
+    out = {}
+    for ct in (-1.0, 2.0):
+        P = oracle.OraclePipeline(False, use_gpu)
+        P.add_scene(sc)
+        P.match_images()
+        assert P.reconstruct(3, bool(use_gpu), ct) == 0
+        out[ct] = (P.num_lines(), len(P.affinity_raw()[0]), sum(len(P.collinear(c, len(s))[1]) for c, s in zip(sc.cam_ids, sc.segs)))
+        s = P.segments3d()
+        assert np.median(_dist_to_gt(s["p1"], sc.lines3d)) < 5e-3
+    assert out[-1.0][2] == 0 and out[2.0][2] > 300
+    assert out[2.0][1] > out[-1.0][1] and out[2.0][0] < out[-1.0][0]
+
 # ---------------------------------------------------------------------------------------------- product library surface
 def test_capi_library_loads_and_exports_every_declared_symbol():
     from line3dpp_b200 import build
