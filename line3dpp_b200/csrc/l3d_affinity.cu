@@ -264,13 +264,15 @@ k_rdd_step(long long nnz, const int* __restrict__ prow, const int* __restrict__ 
 // ---- 16-byte-aligned rows --------------------------------------------------------------------------------------------
 // The lock-step walk reads a run of P.row(r) and a run of W.col(c) per entry.  With 4-byte loads every thread of a warp
 // touches a different 128-byte line on every step (one L1 wavefront per thread and step: the first version was bound by
-// exactly that).  Values are therefore kept in PADDED arrays whose rows/columns start on float4 boundaries (rp4/cp4 =
-// start in float4 units, rows padded with zeros to a multiple of 4); the walk loads float4 and still adds the products
-// strictly in k order, so the sums round exactly like the reference's.
+// exactly that).  Values are therefore kept in PADDED arrays whose rows/columns start on 32-byte boundaries (rp4/cp4 =
+// start in float4 units, always even; rows padded with zeros to a multiple of 8); the walk loads float4 and still adds
+// the products strictly in k order, so the sums round exactly like the reference's.
 __global__ void __launch_bounds__(256) k_rdd_len4(int n, const int* __restrict__ ptr, int* __restrict__ len4)
 {
+    // rows padded to a multiple of EIGHT floats: every row starts on a 32-byte sector boundary, so the back-to-back float4
+    // loads of a walk use whole sectors (with 16-byte alignment half of every gathered sector was wasted L2 bandwidth)
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) len4[r] = (ptr[r + 1] - ptr[r] + 3) >> 2;
+    if (r < n) len4[r] = 2 * ((ptr[r + 1] - ptr[r] + 7) >> 3);
 }
 __global__ void __launch_bounds__(256) k_rdd_pad(long long nnz, const int* __restrict__ major, const int* __restrict__ ptr, const int* __restrict__ p4,
                                                  const float* __restrict__ val, float* __restrict__ padded)
@@ -319,22 +321,20 @@ __global__ void __launch_bounds__(128) k_rdd_normalize4(int n, const int* __rest
 // whole new row - normalises it before the only store.  One kernel per iteration instead of two, no scattered stores,
 // 16 B/nnz of streamed descriptors (column, transposed slot, value in, value out) instead of 24 + a second pass.
 // Arithmetic order is the reference's: products added in k order per entry, the row sum in slot order, IEEE divide.
-//   colinfo[a] = (first float4 of W.col(a), length of W.col(a));   rowinfo[b] = (rowptr[b], first float4 of P.row(b))
+//   rowinfo[b] = (rowptr[b], first float4 of P.row(b));   desc[s] = (first float4 of W.col(a), walk length) for slot s = (b,a)
 //   src[s]     = padded slot of the transposed entry P(a,b) for destination slot s = (b,a), -1 if (a,b) does not exist or
 //                s is not the first slot of (b,a) in its row (the reference then never writes the slot: it keeps the
 //                value it had two iterations ago, cudawrapper.cu:524-542 - reproduced by re-normalising the stale value)
 __global__ void __launch_bounds__(256)
-k_rdd_rowinfo(int n, const int* __restrict__ rowptr, const int* __restrict__ rp4, const int* __restrict__ colptr, const int* __restrict__ cp4,
-              int2* __restrict__ rowinfo, int2* __restrict__ colinfo)
+k_rdd_rowinfo(int n, const int* __restrict__ rowptr, const int* __restrict__ rp4, int2* __restrict__ rowinfo)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > n) return;
-    rowinfo[r] = make_int2(rowptr[r], rp4[r]);
-    if (r < n) colinfo[r] = make_int2(cp4[r], colptr[r + 1] - colptr[r]);
+    if (r <= n) rowinfo[r] = make_int2(rowptr[r], rp4[r]);
 }
+// per destination slot s = (b,a): desc = (first float4 of W.col(a), walk length min(len P.row(b), len W.col(a))) and src
 __global__ void __launch_bounds__(256)
-k_rdd_src(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr, const int* __restrict__ rp4,
-          const int* __restrict__ tslot, int* __restrict__ src)
+k_rdd_desc(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr, const int* __restrict__ rp4,
+           const int* __restrict__ colptr, const int* __restrict__ cp4, const int* __restrict__ tslot, int2* __restrict__ desc, int* __restrict__ src)
 {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nnz) return;
@@ -342,11 +342,12 @@ k_rdd_src(long long nnz, const int* __restrict__ prow, const int* __restrict__ p
     const bool first = s == rowptr[b] || pcol[s - 1] != a;     // tslot of the writers points at the first (b,a) slot
     const int t = tslot[s];                                     // first slot of (a,b) in row a
     src[s] = (first && t >= 0) ? 4 * rp4[a] + (t - rowptr[a]) : -1;
+    desc[s] = make_int2(cp4[a], min(rowptr[b + 1] - rowptr[b], colptr[a + 1] - colptr[a]));
 }
 
 template <int G, bool NORMALIZE>
 __global__ void __launch_bounds__(256)
-k_rdd_fused(int n, const int2* __restrict__ rowinfo, const int2* __restrict__ colinfo, const int* __restrict__ pcol, const int* __restrict__ src,
+k_rdd_fused(int n, const int2* __restrict__ rowinfo, const int2* __restrict__ desc, const int* __restrict__ src,
             const float* __restrict__ Pp, const float* __restrict__ Wp, float* __restrict__ Pnp)
 {
     const int gl = threadIdx.x & (G - 1);                                   // lane within the row group
@@ -363,12 +364,12 @@ k_rdd_fused(int n, const int2* __restrict__ rowinfo, const int2* __restrict__ co
         const int t = t0 + gl;
         v = 0.0f;
         if (t < len) {
-            const int a = pcol[rs + t], sp = src[rs + t];
+            const int sp = src[rs + t];
             if (sp >= 0) {
+                const int2 ds = desc[rs + t];
                 const float own = Pp[sp];                                   // P(a,b)
-                const int2 ci = colinfo[a];
-                const float4* wcol4 = reinterpret_cast<const float4*>(Wp) + ci.x;
-                const int m = min(len, ci.y), n4 = (m + 3) >> 2;
+                const float4* wcol4 = reinterpret_cast<const float4*>(Wp) + ds.x;
+                const int m = ds.y, n4 = (m + 3) >> 2;
                 float mul = 0.0f;
                 for (int k0 = 0; k0 < n4; k0 += 4) {
                     float4 pv[4], wv[4];
@@ -776,12 +777,11 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     k_rdd_pad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_wmaj.p, (const int*)R.d_colptr.p, (const int*)R.d_cp4.p, (const float*)R.d_W.p, (float*)R.d_Wp.p);
     if (4ll * std::max(tot4[0], tot4[1]) >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_rdd: padded matrix too large for 32-bit slots");
     if ((rc = l3d_reserve(c, R.d_rowinfo, 8 * ((size_t)n + 1), "rdd rowinfo"))) return rc;
-    if ((rc = l3d_reserve(c, R.d_colinfo, 8 * ((size_t)n + 1), "rdd colinfo"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_desc, 8 * (size_t)nnz, "rdd desc"))) return rc;
     if ((rc = l3d_reserve(c, R.d_src, 4 * (size_t)nnz, "rdd src"))) return rc;
-    k_rdd_rowinfo<<<(n + 256) / 256, 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, (const int*)R.d_colptr.p, (const int*)R.d_cp4.p,
-                                                   (int2*)R.d_rowinfo.p, (int2*)R.d_colinfo.p);
-    k_rdd_src<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p,
-                                  (const int*)R.d_tslot.p, (int*)R.d_src.p);
+    k_rdd_rowinfo<<<(n + 256) / 256, 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, (int2*)R.d_rowinfo.p);
+    k_rdd_desc<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p,
+                                   (const int*)R.d_colptr.p, (const int*)R.d_cp4.p, (const int*)R.d_tslot.p, (int2*)R.d_desc.p, (int*)R.d_src.p);
     // P' starts as a copy of the un-normalised P (cudawrapper.cu:724), then P is row-normalised (727)
     L3D_CUDA(c, cudaMemcpyAsync(R.d_Pnp.p, R.d_Pp.p, pbytes, cudaMemcpyDeviceToDevice, st), "rdd copy");
     const unsigned int nbr = (unsigned int)((n + 127) / 128);
@@ -797,10 +797,10 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     for (int it = 0; it < iters; ++it) {
         const bool norm = it < iters - 1;       // no normalisation after the last step (cudawrapper.cu:751)
 #define RDD_LAUNCH(GG)                                                                                                                        \
-        do { if (norm) k_rdd_fused<GG, true><<<nbf, 256, 0, st>>>(n, (const int2*)R.d_rowinfo.p, (const int2*)R.d_colinfo.p, (const int*)R.d_pcol.p, \
-                                                                   (const int*)R.d_src.p, P, (const float*)R.d_Wp.p, Pn);                           \
-             else k_rdd_fused<GG, false><<<nbf, 256, 0, st>>>(n, (const int2*)R.d_rowinfo.p, (const int2*)R.d_colinfo.p, (const int*)R.d_pcol.p,    \
-                                                              (const int*)R.d_src.p, P, (const float*)R.d_Wp.p, Pn); } while (0)
+        do { if (norm) k_rdd_fused<GG, true><<<nbf, 256, 0, st>>>(n, (const int2*)R.d_rowinfo.p, (const int2*)R.d_desc.p, (const int*)R.d_src.p, P, \
+                                                                   (const float*)R.d_Wp.p, Pn);                                                     \
+             else k_rdd_fused<GG, false><<<nbf, 256, 0, st>>>(n, (const int2*)R.d_rowinfo.p, (const int2*)R.d_desc.p, (const int*)R.d_src.p, P,    \
+                                                              (const float*)R.d_Wp.p, Pn); } while (0)
         if (G == 32) RDD_LAUNCH(32); else if (G == 16) RDD_LAUNCH(16); else if (G == 8) RDD_LAUNCH(8); else RDD_LAUNCH(4);
 #undef RDD_LAUNCH
         std::swap(P, Pn);

@@ -45,10 +45,10 @@ struct CollinState {
 // device buffers of the diffusion (l3d_affinity.cu)
 struct RddState {
     DevBuf d_ei, d_ej, d_ew, d_krow, d_kcol, d_k2, d_idx, d_idx2, d_P, d_Pn, d_W, d_prow, d_pcol, d_wmaj, d_wmin, d_rowptr, d_colptr, d_tslot, d_tmp, d_len4, d_rp4, d_cp4,
-        d_Pp, d_Pnp, d_Wp, d_rowinfo, d_colinfo, d_src;
+        d_Pp, d_Pnp, d_Wp, d_rowinfo, d_desc, d_src;
     std::vector<DevBuf*> bufs()
     { return {&d_ei, &d_ej, &d_ew, &d_krow, &d_kcol, &d_k2, &d_idx, &d_idx2, &d_P, &d_Pn, &d_W, &d_prow, &d_pcol, &d_wmaj, &d_wmin, &d_rowptr,
-              &d_colptr, &d_tslot, &d_tmp, &d_len4, &d_rp4, &d_cp4, &d_Pp, &d_Pnp, &d_Wp, &d_rowinfo, &d_colinfo, &d_src}; }
+              &d_colptr, &d_tslot, &d_tmp, &d_len4, &d_rp4, &d_cp4, &d_Pp, &d_Pnp, &d_Wp, &d_rowinfo, &d_desc, &d_src}; }
 };
 
 struct l3d_ctx {

@@ -418,18 +418,19 @@ struct DenseSmem {
     float4 rowA[DK_ROWS], rowB[DK_ROWS];
     float4 sray[DK_ROWS][3];                       // cached rays / plane normal of the CTA's source rows
     float4 tq[DK_WARPS][32 * DK_T];                // target segments of each warp's columns
-    float4 tray[DK_WARPS][32 * DK_T][3];           // their cached rays / plane normals
     unsigned int queue[DK_WARPS][64];
     float4* depths; float* overlaps;
+    const float4* tcache;                          // cached rays / plane normals of the target view: only the ~1 % of cells whose
+                                                   // overlap exceeds the threshold read them (L2), not worth 48 KB of shared memory
     float3 Cs, Ct;
     float epi; int Nt, row0;
 };
 size_t l3d_dense_smem_bytes() { return sizeof(DenseSmem); }
-// Rows per CTA (8..DK_ROWS) such that the tile count fills whole waves of the 3 resident CTAs per SM: a 3000 x 3000 pair
+// Rows per CTA (8..DK_ROWS) such that the tile count fills whole waves of the 4 resident CTAs per SM: a 3000 x 3000 pair
 // with the former fixed 16 rows gave 564 CTAs = 1.27 waves on 148 SMs, i.e. a second wave that is 73 % idle.
 int l3d_dense_rows_per_cta(int Ns, int Nt, int num_sms)
 {
-    const long long slots = 3ll * (num_sms > 0 ? num_sms : 148);
+    const long long slots = (long long)DK_MINB * (num_sms > 0 ? num_sms : 148);
     const long long colb = (Nt + DK_WARPS * DK_T * 32 - 1) / (DK_WARPS * DK_T * 32);
     int best = 16; double best_eff = -1.0;
     for (int R = 8; R <= DK_ROWS; ++R) {
@@ -459,7 +460,7 @@ __device__ __noinline__ void dense_exact_batch(DenseSmem& S, unsigned int entry,
     bool inv;
     const float ov = exact_overlap(q, make_float3(rA.x, rA.y, rA.z), make_float3(rA.w, rB.x, rB.y), &inv);
     if (ov > S.epi) {
-        const SegRays s = rays_from_smem(S.sray[r]), t = rays_from_smem(S.tray[warp][col]);
+        const SegRays s = rays_from_smem(S.sray[r]), t = load_rays(S.tcache, x);
         float d[4];
         exact_depths(s, t, S.Cs, S.Ct, d);
         res = make_float4(d[0], d[1], d[2], d[3]);
@@ -469,7 +470,7 @@ __device__ __noinline__ void dense_exact_batch(DenseSmem& S, unsigned int entry,
     __stcs(S.overlaps + o, ov);
 }
 
-__global__ void __launch_bounds__(DK_THREADS, 3)
+__global__ void __launch_bounds__(DK_THREADS, DK_MINB)
 k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
               const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F, float3 Cs, float3 Ct,
               float epi, float4* __restrict__ depths, float* __restrict__ overlaps, int rows_per_cta)
@@ -479,7 +480,7 @@ k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = blockIdx.y * rows_per_cta;
     const int nrows = min(rows_per_cta, Ns - row0);
-    if (tid == 0) { S.depths = depths; S.overlaps = overlaps; S.Cs = Cs; S.Ct = Ct; S.epi = epi; S.Nt = Nt; S.row0 = row0; }
+    if (tid == 0) { S.depths = depths; S.overlaps = overlaps; S.tcache = tcache; S.Cs = Cs; S.Ct = Ct; S.epi = epi; S.Nt = Nt; S.row0 = row0; }
     if (tid < nrows) {
         float4 s = __ldg(ssegs + row0 + tid);
         float3 e1 = mulmat_h(F.m, s.x, s.y), e2 = mulmat_h(F.m, s.z, s.w);
@@ -497,10 +498,6 @@ k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict
         ok[t] = x < Nt;
         q[t] = __ldg(tsegs + (ok[t] ? x : 0));
         S.tq[warp][t * 32 + lane] = q[t];
-    }
-    {   // this warp's 32*DK_T columns x 3 float4 of cached rays, coalesced
-        const int ncol = max(0, min(32 * DK_T, Nt - x0));
-        for (int i = lane; i < 3 * ncol; i += 32) (&S.tray[warp][0][0])[i] = __ldg(tcache + 3 * (size_t)x0 + i);
     }
     __syncthreads();
     if (x0 >= Nt) return;

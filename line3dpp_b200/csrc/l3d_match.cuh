@@ -29,9 +29,12 @@
 #endif
 
 #define DK_THREADS 256
+#ifndef DK_MINB
+#define DK_MINB 4                       /* resident CTAs per SM of the dense kernel (register budget 64) */
+#endif
 #define DK_WARPS 8
 #define DK_ROWS 32                      /* MAXIMUM source rows per CTA of the dense kernel; the launch picks 8..32 so that the tile
-                                           count fills whole waves of 3 CTAs per SM (l3d_dense_rows_per_cta) */
+                                           count fills whole waves of 4 CTAs per SM (l3d_dense_rows_per_cta) */
 #define DK_T 4                          /* target columns per lane: a CTA covers DK_ROWS x (8*4*32 = 1024) cells */
 #define DKN_ROWS 32                     /* rows per CTA of the unfiltered test kernel */
 

@@ -414,6 +414,7 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     L3D_CUDA(c, cudaMemsetAsync(S.d_slot_score.p, 0xFF, sizeof(float) * slots, st), "init slot scores");        // NaN: "not scored" (never > 0)
     L3D_CUDA(c, cudaMemsetAsync(S.d_ranges.p, 0xFF, 8 * c->total_segs, st), "init ranges");                      // (-1,-1)
     L3D_CUDA(c, cudaMemsetAsync(S.d_M.p, 0, 4 * (size_t)V, st), "init counts");
+    L3D_CUDA(c, cudaMemsetAsync(S.d_kept.p, 0, (size_t)total, st), "init kept flags");     // slots [M_v, U_v) of a region are never written: k_affinity scans them all
     L3D_CUDA(c, cudaMemsetAsync(S.d_vmax.p, 0, 4 * (size_t)V, st), "init maxima");
     L3D_CUDA(c, cudaMemcpyAsync(S.d_camrank.p, rank.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "cam rank");
     L3D_CUDA(c, cudaMemcpyAsync(S.d_viewofrank.p, view_of_rank.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "view of rank");
