@@ -202,6 +202,26 @@ long long l3d_affinity_matrix(l3d_ctx* ctx, float two_sigA_sqr, float med_scene_
 int l3d_rdd(l3d_ctx* ctx, int n, long long nnz, const int* ei, const int* ej, const float* ew, int iters, int* out_i,
             int* out_j, float* out_w, float* kernel_ms);
 
+/* ---- line bundling (optional, reconstruct3Dlines' use_CERES): replaces LineOptimizer::optimize (optimization.h:174-190,
+ * optimization.cc:8-303; called from Line3D::optimizeClusters line3D.cc:2269-2275), i.e. the Ceres problem the reference
+ * builds from LineReprojectionError (optimization.h:52-171) with every camera / intrinsic block constant.  Only the four
+ * Cayley parameters of each line are free, so the system is block diagonal: residuals, exact derivatives, the 4x4
+ * Levenberg-Marquardt solves and the candidate costs run on the device for all lines at once; the host plays Ceres'
+ * trust-region controller (one radius, its default tolerances).  Ceres itself is not needed.
+ *   p1p2        6 doubles per line: the cluster's 3D segment in the working (translated) frame   optimization.cc:36-39
+ *   res_ptr     num_lines+1 offsets into the residual arrays
+ *   res_cam     per residual: index into cams
+ *   res_xy      per residual: x1 y1 x2 y2 of the observed 2D segment (View::getLineSegment2D)     optimization.cc:155-166
+ *   cams        16 doubles per camera: R (row-major), C (working frame), fx, fy, px, py           optimization.cc:108-141
+ *   max_iter    L3D_DEF_CERES_MAX_ITER 250 (commons.h:88)
+ *   p1p2_out    updated segments (unit direction around the old mid point, optimization.cc:259-277); may alias p1p2
+ *   valid_out   0 where the reference drops the cluster (optimization.cc:293-298)
+ *   summary     optional, 8 doubles: iterations, initial cost, final cost, termination (0 convergence, 1 max_iter reached,
+ *               2 failure), successful steps, free lines, final trust-region radius, kernels launched */
+int l3d_optimize_lines(l3d_ctx* ctx, int num_lines, const double* p1p2, const long long* res_ptr, const int32_t* res_cam,
+                       const double* res_xy, int num_cams, const double* cams, int max_iter, double* p1p2_out, int32_t* valid_out,
+                       double* summary);
+
 /* stable ascending argsort of float keys on the device: the weight sort of performClustering (clustering.cc:13-14) for
  * large edge lists.  perm_out[i] = index of the i-th smallest key, ties in input order. */
 int l3d_argsort_f32(l3d_ctx* ctx, long long n, const float* keys, unsigned int* perm_out);

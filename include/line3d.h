@@ -97,8 +97,8 @@ struct FinalLine3D {   /* segment3D.h:155-163 */
 /* counters the reference prints to stdout (SURVEY.md §5 "Metrics / logging"); handy parity checkpoints */
 struct Line3DStats {
     long long view_pairs, pair_evaluations, matches_after_knn, estimates, affinity_entries, affinity_rows, clusters_total,
-        clusters_valid, lines3D, collinear_entries;
-    double ms_match, ms_score, ms_affinity, ms_diffusion, ms_cluster;
+        clusters_valid, lines3D, collinear_entries, opt_iterations;
+    double ms_match, ms_score, ms_affinity, ms_diffusion, ms_cluster, opt_cost_before, opt_cost_after;
 };
 
 class Line3D {
@@ -122,7 +122,8 @@ public:
                      const unsigned int num_neighbors = L3D_DEF_MATCHING_NEIGHBORS, const float epipolar_overlap = L3D_DEF_EPIPOLAR_OVERLAP,
                      const int kNN = L3D_DEF_KNN, const float const_regularization_depth = -1.0f);
 
-    /* line3D.h:162-166 (use_CERES is accepted and ignored with a warning: Ceres bundling is out of scope) */
+    /* line3D.h:162-166.  use_CERES: the bundling of optimization.cc runs on the GPU (l3d_optimize_lines); Ceres is not needed,
+     * so the flag is honoured in every build (the reference silently drops it when it was built without Ceres, line3D.cc:1738-1744) */
     void reconstruct3Dlines(const unsigned int visibility_t = L3D_DEF_MIN_VISIBILITY_T, const bool perform_diffusion = L3D_DEF_PERFORM_RDD,
                             const float collinearity_t = L3D_DEF_COLLINEARITY_T, const bool use_CERES = L3D_DEF_USE_CERES,
                             const unsigned int max_iter_CERES = L3D_DEF_CERES_MAX_ITER);

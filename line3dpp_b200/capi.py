@@ -225,6 +225,17 @@ class Context:
             self._chk(self.L.l3d_get_collinear(self.h, int(view), _p(row_ptr), _p(idx), C.c_longlong(int(n))), "l3d_get_collinear")
         return row_ptr, idx[:int(n)]
 
+    def optimize_lines(self, p1p2, res_ptr, res_cam, res_xy, cams, max_iter=250):
+        """l3d_optimize_lines: returns (p1p2_out[L,6], valid[L], summary[8])"""
+        f64 = lambda a: np.ascontiguousarray(a, np.float64)
+        p1p2, res_xy, cams = f64(p1p2), f64(res_xy), f64(cams)
+        res_ptr = np.ascontiguousarray(res_ptr, np.int64); res_cam = np.ascontiguousarray(res_cam, np.int32)
+        L = len(p1p2)
+        out = np.zeros((L, 6), np.float64); valid = np.zeros(L, np.int32); summ = np.zeros(8, np.float64)
+        self._chk(self.L.l3d_optimize_lines(self.h, L, _p(p1p2), _p(res_ptr), _p(res_cam), _p(res_xy), len(cams), _p(cams), int(max_iter),
+                                            _p(out), _p(valid), _p(summ)), "l3d_optimize_lines")
+        return out, valid, summ
+
     def fp32_peak_tflops(self) -> float:
         v = C.c_double(0)
         self._chk(self.L.l3d_fp32_peak_probe(self.h, C.byref(v)), "l3d_fp32_peak_probe")

@@ -290,119 +290,112 @@ __global__ void __launch_bounds__(256) k_rdd_unpad(long long nnz, const int* __r
     const int r = major[y];
     val[y] = padded[4ll * p4[r] + (y - ptr[r])];
 }
-// K_sparseMat_row_normalization on the padded array
-__global__ void __launch_bounds__(128) k_rdd_normalize4(int n, const int* __restrict__ rowptr, const int* __restrict__ rp4, float* __restrict__ Pp)
+// per-entry walk descriptors, built once (the structure is constant over the iterations): everything the step needs is
+// then read with coalesced 16-byte loads instead of eight dependent scattered pointer look-ups per entry
+//   x = first float4 of P.row(r)   y = first float4 of W.col(c)   z = walk length min(len_r, len_c)   w = own padded slot
+// and dst = padded slot of the transposed entry P'(r,c) (or -1)
+__global__ void __launch_bounds__(256)
+k_rdd_plan(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr, const int* __restrict__ colptr,
+           const int* __restrict__ rp4, const int* __restrict__ cp4, const int* __restrict__ tslot, int4* __restrict__ plan, int* __restrict__ dst)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= nnz) return;
+    const int c = prow[y], r = pcol[y];                 // "transpose" (cudawrapper.cu:493-495)
+    const int rs = rowptr[r], m = min(rowptr[r + 1] - rs, colptr[c + 1] - colptr[c]);
+    plan[y] = make_int4(rp4[r], cp4[c], m, 4 * rp4[c] + (int)(y - rowptr[c]));
+    const int t = tslot[y];
+    dst[y] = t >= 0 ? 4 * rp4[r] + (t - rs) : -1;
+}
+// K_sparseMat_diffusion_step (cudawrapper.cu:480-544) on the padded arrays: entry y = (a,b) of P produces P'(b,a).
+// A thread owns RDD_ITEMS entries (strided by the block size, so the descriptor loads stay coalesced) and walks them in
+// steps of EIGHT values = one whole 32-byte sector of P.row(b) and of W.col(a) per entry and step (two back-to-back float4
+// loads each); the gathers of the different entries are independent, which is the memory-level parallelism this latency-
+// bound gather needs.  No per-element guards: beyond the walk length min(len_r, len_c) at least one of the two factors
+// lies in its row's zero padding (rows are padded to 8), the product is +0 and `mul + 0 == mul` exactly, so every entry
+// still accumulates exactly the reference's products in the reference's k order (weights and P are finite).
+#ifndef RDD_ITEMS
+#define RDD_ITEMS 2
+#endif
+// one whole 32-byte sector per lane and instruction (LDG.E.256, new on sm_100): with divergent addresses the L1 looks up
+// about one sector per cycle and SM, so two 16-byte loads of the same sector cost twice as much as one 32-byte load -
+// the first float4 version of this kernel sat at 80 % L1 throughput for exactly that reason
+struct __align__(32) F8 { float v[8]; };
+__device__ __forceinline__ F8 ld256(const float* p)
+{
+    F8 r;
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+    return r;
+}
+__global__ void __launch_bounds__(256)
+k_rdd_step8(long long nnz, const int4* __restrict__ plan, const int* __restrict__ dst, const float* __restrict__ Pp, const float* __restrict__ Wp,
+            float* __restrict__ Pnp)
+{
+    const long long y0 = (long long)blockIdx.x * (256 * RDD_ITEMS) + threadIdx.x;
+    int4 pl[RDD_ITEMS];
+    int d[RDD_ITEMS];
+    float own[RDD_ITEMS], mul[RDD_ITEMS];
+    int mmax = 0;
+#pragma unroll
+    for (int i = 0; i < RDD_ITEMS; ++i) {
+        const long long y = y0 + 256ll * i;
+        const bool ok = y < nnz;
+        pl[i] = ok ? plan[y] : make_int4(0, 0, 0, 0);
+        d[i] = ok ? dst[y] : -1;
+        mmax = max(mmax, pl[i].z);
+        mul[i] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < RDD_ITEMS; ++i) own[i] = pl[i].z > 0 || d[i] >= 0 ? Pp[pl[i].w] : 0.0f;
+    for (int k8 = 0; 8 * k8 < mmax; ++k8) {
+        F8 pv[RDD_ITEMS], wv[RDD_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RDD_ITEMS; ++i)
+            if (8 * k8 < pl[i].z) { pv[i] = ld256(Pp + 4ll * pl[i].x + 8 * k8); wv[i] = ld256(Wp + 4ll * pl[i].y + 8 * k8); }
+#pragma unroll
+        for (int i = 0; i < RDD_ITEMS; ++i)
+            if (8 * k8 < pl[i].z) {
+                float m = mul[i];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) m += pv[i].v[e] * wv[i].v[e];
+                mul[i] = m;
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < RDD_ITEMS; ++i) {
+        float m = mul[i] * own[i];                      // times P(a,b) itself
+        if (m < L3D_EPS_F) m = L3D_EPS_F;
+        if (d[i] >= 0) Pnp[d[i]] = m;
+    }
+}
+// K_sparseMat_row_normalization (cudawrapper.cu:432-477), 4 lanes per row, one float4 each per pass: coalesced loads and
+// stores, and the row sum is still added strictly in slot order - the running sum is handed from lane to lane (lane j adds
+// its four values to what lane j-1 produced).  No guards: padding slots hold +0 (x + 0 == x exactly, 0 / sum == 0).
+__global__ void __launch_bounds__(256)
+k_rdd_normalize_q(int n, const int* __restrict__ rowptr, const int* __restrict__ rp4, float* __restrict__ Pp)
+{
+    const int gl = threadIdx.x & 3;
+    const long long r = ((long long)blockIdx.x * 256 + threadIdx.x) >> 2;
+    const unsigned int gmask = 0xFu << ((threadIdx.x & 31) & ~3);
     if (r >= n) return;
     const int len = rowptr[r + 1] - rowptr[r];
     if (len == 0) return;
     float4* row = reinterpret_cast<float4*>(Pp) + rp4[r];
-    const int n4 = (len + 3) >> 2;
+    const int n4 = 2 * ((len + 7) >> 3);                 // float4 per padded row (k_rdd_len4)
     float sum = 0.0f;
-    for (int k4 = 0; k4 < n4; ++k4) {
-        const float4 v = row[k4];
-        const int rem = len - 4 * k4;
-        sum += v.x; if (rem > 1) sum += v.y; if (rem > 2) sum += v.z; if (rem > 3) sum += v.w;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = 0; c0 < n4; c0 += 4) {
+        v = c0 + gl < n4 ? row[c0 + gl] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float s = sum;
+            if (gl == j) { s += v.x; s += v.y; s += v.z; s += v.w; }
+            sum = __shfl_sync(gmask, s, j, 4);
+        }
     }
     if (sum < L3D_EPS_F) sum = L3D_EPS_F;
-    for (int k4 = 0; k4 < n4; ++k4) {
-        float4 v = row[k4];
-        const int rem = len - 4 * k4;
-        v.x /= sum; if (rem > 1) v.y /= sum; if (rem > 2) v.z /= sum; if (rem > 3) v.w /= sum;
-        row[k4] = v;
-    }
-}
-// ---- fused diffusion iteration, organised by DESTINATION row ---------------------------------------------------
-// K_sparseMat_diffusion_step (cudawrapper.cu:480-544) lets the thread of entry (a,b) produce P'(b,a) = max(eps, P(a,b) *
-// sum_k P.row(b)[k] * W.col(a)[k]) and scatter it into row b; K_sparseMat_row_normalization (432-477) then re-reads every
-// row.  Here a group of G lanes owns destination row b: it streams its own row P.row(b) (the left factor of all its
-// entries), gathers W.col(a) and the single value P(a,b) for each of its columns a, and - because it ends up holding the
-// whole new row - normalises it before the only store.  One kernel per iteration instead of two, no scattered stores,
-// 16 B/nnz of streamed descriptors (column, transposed slot, value in, value out) instead of 24 + a second pass.
-// Arithmetic order is the reference's: products added in k order per entry, the row sum in slot order, IEEE divide.
-//   rowinfo[b] = (rowptr[b], first float4 of P.row(b));   desc[s] = (first float4 of W.col(a), walk length) for slot s = (b,a)
-//   src[s]     = padded slot of the transposed entry P(a,b) for destination slot s = (b,a), -1 if (a,b) does not exist or
-//                s is not the first slot of (b,a) in its row (the reference then never writes the slot: it keeps the
-//                value it had two iterations ago, cudawrapper.cu:524-542 - reproduced by re-normalising the stale value)
-__global__ void __launch_bounds__(256)
-k_rdd_rowinfo(int n, const int* __restrict__ rowptr, const int* __restrict__ rp4, int2* __restrict__ rowinfo)
-{
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r <= n) rowinfo[r] = make_int2(rowptr[r], rp4[r]);
-}
-// per destination slot s = (b,a): desc = (first float4 of W.col(a), walk length min(len P.row(b), len W.col(a))) and src
-__global__ void __launch_bounds__(256)
-k_rdd_desc(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr, const int* __restrict__ rp4,
-           const int* __restrict__ colptr, const int* __restrict__ cp4, const int* __restrict__ tslot, int2* __restrict__ desc, int* __restrict__ src)
-{
-    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nnz) return;
-    const int b = prow[s], a = pcol[s];
-    const bool first = s == rowptr[b] || pcol[s - 1] != a;     // tslot of the writers points at the first (b,a) slot
-    const int t = tslot[s];                                     // first slot of (a,b) in row a
-    src[s] = (first && t >= 0) ? 4 * rp4[a] + (t - rowptr[a]) : -1;
-    desc[s] = make_int2(cp4[a], min(rowptr[b + 1] - rowptr[b], colptr[a + 1] - colptr[a]));
-}
-
-template <int G, bool NORMALIZE>
-__global__ void __launch_bounds__(256)
-k_rdd_fused(int n, const int2* __restrict__ rowinfo, const int2* __restrict__ desc, const int* __restrict__ src,
-            const float* __restrict__ Pp, const float* __restrict__ Wp, float* __restrict__ Pnp)
-{
-    const int gl = threadIdx.x & (G - 1);                                   // lane within the row group
-    const long long b = ((long long)blockIdx.x * 256 + threadIdx.x) / G;    // destination row
-    const unsigned int gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-    if (b >= n) return;                                                     // whole groups leave together
-    const int2 ri = rowinfo[b];
-    const int rs = ri.x, len = rowinfo[b + 1].x - rs;
-    if (len == 0) return;
-    const float4* prow4 = reinterpret_cast<const float4*>(Pp) + ri.y;
-    float* outrow = Pnp + 4ll * ri.y;
-    float sum = 0.0f, v = 0.0f;
-    for (int t0 = 0; t0 < len; t0 += G) {
-        const int t = t0 + gl;
-        v = 0.0f;
-        if (t < len) {
-            const int sp = src[rs + t];
-            if (sp >= 0) {
-                const int2 ds = desc[rs + t];
-                const float own = Pp[sp];                                   // P(a,b)
-                const float4* wcol4 = reinterpret_cast<const float4*>(Wp) + ds.x;
-                const int m = ds.y, n4 = (m + 3) >> 2;
-                float mul = 0.0f;
-                for (int k0 = 0; k0 < n4; k0 += 4) {
-                    float4 pv[4], wv[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (k0 + j < n4) { pv[j] = prow4[k0 + j]; wv[j] = wcol4[k0 + j]; }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int rem = m - 4 * (k0 + j);
-                        if (rem > 0) {
-                            mul += pv[j].x * wv[j].x;
-                            if (rem > 1) mul += pv[j].y * wv[j].y;
-                            if (rem > 2) mul += pv[j].z * wv[j].z;
-                            if (rem > 3) mul += pv[j].w * wv[j].w;
-                        }
-                    }
-                }
-                mul *= own;
-                if (mul < L3D_EPS_F) mul = L3D_EPS_F;
-                v = mul;
-            } else v = outrow[t];                                           // never written by the reference: stale value
-        }
-        if (NORMALIZE) {
-            const int cnt = min(G, len - t0);
-            for (int j = 0; j < cnt; ++j) sum += __shfl_sync(gmask, v, j, G);   // row sum in slot order (cudawrapper.cu:452-459)
-            if (len > G && t < len) outrow[t] = v;                          // long row: park the raw values, divide below
-        } else if (t < len) outrow[t] = v;
-    }
-    if (NORMALIZE) {
-        if (sum < L3D_EPS_F) sum = L3D_EPS_F;
-        if (len <= G) { if (gl < len) outrow[gl] = v / sum; }
-        else for (int t = gl; t < len; t += G) outrow[t] = outrow[t] / sum;
-    }
+    if (n4 <= 4) { if (gl < n4) { v.x /= sum; v.y /= sum; v.z /= sum; v.w /= sum; row[gl] = v; } }
+    else for (int c = gl; c < n4; c += 4) { float4 w = row[c]; w.x /= sum; w.y /= sum; w.z /= sum; w.w /= sum; row[c] = w; }
 }
 
 __global__ void __launch_bounds__(256) k_iota(long long n, unsigned int* __restrict__ idx)
@@ -776,38 +769,26 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     k_rdd_pad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, (const float*)R.d_P.p, (float*)R.d_Pp.p);
     k_rdd_pad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_wmaj.p, (const int*)R.d_colptr.p, (const int*)R.d_cp4.p, (const float*)R.d_W.p, (float*)R.d_Wp.p);
     if (4ll * std::max(tot4[0], tot4[1]) >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_rdd: padded matrix too large for 32-bit slots");
-    if ((rc = l3d_reserve(c, R.d_rowinfo, 8 * ((size_t)n + 1), "rdd rowinfo"))) return rc;
-    if ((rc = l3d_reserve(c, R.d_desc, 8 * (size_t)nnz, "rdd desc"))) return rc;
-    if ((rc = l3d_reserve(c, R.d_src, 4 * (size_t)nnz, "rdd src"))) return rc;
-    k_rdd_rowinfo<<<(n + 256) / 256, 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, (int2*)R.d_rowinfo.p);
-    k_rdd_desc<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p,
-                                   (const int*)R.d_colptr.p, (const int*)R.d_cp4.p, (const int*)R.d_tslot.p, (int2*)R.d_desc.p, (int*)R.d_src.p);
+    if ((rc = l3d_reserve(c, R.d_plan, 16 * (size_t)nnz, "rdd plan"))) return rc;
+    if ((rc = l3d_reserve(c, R.d_dst, 4 * (size_t)nnz, "rdd dst"))) return rc;
+    k_rdd_plan<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (const int*)R.d_colptr.p,
+                                   (const int*)R.d_rp4.p, (const int*)R.d_cp4.p, (const int*)R.d_tslot.p, (int4*)R.d_plan.p, (int*)R.d_dst.p);
     // P' starts as a copy of the un-normalised P (cudawrapper.cu:724), then P is row-normalised (727)
     L3D_CUDA(c, cudaMemcpyAsync(R.d_Pnp.p, R.d_Pp.p, pbytes, cudaMemcpyDeviceToDevice, st), "rdd copy");
-    const unsigned int nbr = (unsigned int)((n + 127) / 128);
-    k_rdd_normalize4<<<nbr, 128, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, (float*)R.d_Pp.p);
+    const unsigned int nbn = (unsigned int)((4ll * n + 255) / 256);
+    auto normalize = [&](float* Pbuf) { k_rdd_normalize_q<<<nbn, 256, 0, st>>>(n, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, Pbuf); };
+    normalize((float*)R.d_Pp.p);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     float* P = (float*)R.d_Pp.p; float* Pn = (float*)R.d_Pnp.p;
-    // lanes per destination row: the smallest power of two that covers the average row (longer rows take several passes)
-    const double avg = (double)nnz / (double)n;
-    int G = avg > 16.0 ? 32 : avg > 8.0 ? 16 : avg > 4.0 ? 8 : 4;
-    if (const char* g = getenv("L3D_RDD_G")) { const int v = atoi(g); if (v == 4 || v == 8 || v == 16 || v == 32) G = v; }   // tuning knob
-    const unsigned int nbf = (unsigned int)(((long long)n * G + 255) / 256);
     for (int it = 0; it < iters; ++it) {
-        const bool norm = it < iters - 1;       // no normalisation after the last step (cudawrapper.cu:751)
-#define RDD_LAUNCH(GG)                                                                                                                        \
-        do { if (norm) k_rdd_fused<GG, true><<<nbf, 256, 0, st>>>(n, (const int2*)R.d_rowinfo.p, (const int2*)R.d_desc.p, (const int*)R.d_src.p, P, \
-                                                                   (const float*)R.d_Wp.p, Pn);                                                     \
-             else k_rdd_fused<GG, false><<<nbf, 256, 0, st>>>(n, (const int2*)R.d_rowinfo.p, (const int2*)R.d_desc.p, (const int*)R.d_src.p, P,    \
-                                                              (const float*)R.d_Wp.p, Pn); } while (0)
-        if (G == 32) RDD_LAUNCH(32); else if (G == 16) RDD_LAUNCH(16); else if (G == 8) RDD_LAUNCH(8); else RDD_LAUNCH(4);
-#undef RDD_LAUNCH
+        k_rdd_step8<<<(unsigned int)((nnz + 256 * RDD_ITEMS - 1) / (256 * RDD_ITEMS)), 256, 0, st>>>(nnz, (const int4*)R.d_plan.p, (const int*)R.d_dst.p, P, (const float*)R.d_Wp.p, Pn);
         std::swap(P, Pn);
+        if (it < iters - 1) normalize(P);       // no normalisation after the last step (cudawrapper.cu:751)
     }
     if (kernel_ms) cudaEventRecord(e1, st);
     k_rdd_unpad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, P, (float*)R.d_P.p);
-    c->launches += 9 + 16 + 11 + iters;
+    c->launches += 9 + 16 + 10 + 2 * iters;
     L3D_CUDA(c, cudaGetLastError(), "rdd kernels");
     L3D_CUDA(c, cudaMemcpyAsync(out_w, R.d_P.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
     L3D_CUDA(c, cudaMemcpyAsync(out_i, R.d_prow.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");

@@ -42,13 +42,20 @@ struct CollinState {
     std::vector<DevBuf*> bufs() { return {&d_tiles, &d_cnt, &d_ptr, &d_idx, &d_tmp}; }
 };
 
+// device state of the line bundling (l3d_optimize.cu)
+struct OptState {
+    DevBuf d_p, d_pout, d_valid, d_resptr, d_rescam, d_resxy, d_obs, d_cams, d_x, d_xc, d_g, d_H, d_S, d_diag, d_free, d_part, d_tot;
+    std::vector<DevBuf*> bufs()
+    { return {&d_p, &d_pout, &d_valid, &d_resptr, &d_rescam, &d_resxy, &d_obs, &d_cams, &d_x, &d_xc, &d_g, &d_H, &d_S, &d_diag, &d_free, &d_part, &d_tot}; }
+};
+
 // device buffers of the diffusion (l3d_affinity.cu)
 struct RddState {
     DevBuf d_ei, d_ej, d_ew, d_krow, d_kcol, d_k2, d_idx, d_idx2, d_P, d_Pn, d_W, d_prow, d_pcol, d_wmaj, d_wmin, d_rowptr, d_colptr, d_tslot, d_tmp, d_len4, d_rp4, d_cp4,
-        d_Pp, d_Pnp, d_Wp, d_rowinfo, d_desc, d_src;
+        d_Pp, d_Pnp, d_Wp, d_plan, d_dst;
     std::vector<DevBuf*> bufs()
     { return {&d_ei, &d_ej, &d_ew, &d_krow, &d_kcol, &d_k2, &d_idx, &d_idx2, &d_P, &d_Pn, &d_W, &d_prow, &d_pcol, &d_wmaj, &d_wmin, &d_rowptr,
-              &d_colptr, &d_tslot, &d_tmp, &d_len4, &d_rp4, &d_cp4, &d_Pp, &d_Pnp, &d_Wp, &d_rowinfo, &d_desc, &d_src}; }
+              &d_colptr, &d_tslot, &d_tmp, &d_len4, &d_rp4, &d_cp4, &d_Pp, &d_Pnp, &d_Wp, &d_plan, &d_dst}; }
 };
 
 struct l3d_ctx {
@@ -81,6 +88,7 @@ struct l3d_ctx {
     RddState rdd;
     AffinityState aff;
     CollinState collin;
+    OptState opt;
 
     const float4* segs() const { return segs_ext ? segs_ext : (const float4*)d_segs.p; }
     const L3DViewDev* views() const { return (const L3DViewDev*)d_views.p; }
@@ -91,6 +99,7 @@ struct l3d_ctx {
         for (DevBuf* x : rdd.bufs()) b.push_back(x);
         for (DevBuf* x : aff.bufs()) b.push_back(x);
         for (DevBuf* x : collin.bufs()) b.push_back(x);
+        for (DevBuf* x : opt.bufs()) b.push_back(x);
         return b;
     }
 };

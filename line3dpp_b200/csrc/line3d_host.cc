@@ -180,6 +180,7 @@ struct Line3D::Impl {
     unsigned int num_neighbors = 10, visibility_t = 3;
     float sigma_p = 2.5f, sigma_a = 10.f, two_sigA_sqr = 200.f, epi = 0.25f, const_reg_depth = -1.f, med_scene_depth = -1.f,
           med_scene_depth_lines = 0.f, collin_t = -1.f;
+    bool use_ceres = false;
     int kNN = 10;
     bool fixed3Dreg = false, perform_RDD = false, matched = false;
     Vector3d translation;
@@ -551,7 +552,7 @@ std::list<Segment3D> Line3D::Impl::collinear_segments(const LineCluster3D& cl) c
 }
 
 void Line3D::reconstruct3Dlines(const unsigned int visibility_t, const bool perform_diffusion, const float collinearity_t, const bool use_CERES,
-                                const unsigned int)
+                                const unsigned int max_iter_CERES)
 {
     Impl& P = *p_;
     std::lock_guard<std::mutex> g(P.mtx);
@@ -560,7 +561,6 @@ void Line3D::reconstruct3Dlines(const unsigned int visibility_t, const bool perf
     P.visibility_t = (unsigned int)std::max(int(visibility_t), 3);
     P.lines3D.clear(); P.collin_t = collinearity_t;
     P.perform_RDD = perform_diffusion && P.use_gpu;                                       // line3D.cc:1729
-    if (use_CERES) P.log("CERES optimisation is not part of this library; no optimisation will be performed");
     P.translate();
     // median scene depth for lines (line3D.cc:1759-1774)
     std::vector<float> sd;
@@ -634,6 +634,46 @@ void Line3D::reconstruct3Dlines(const unsigned int visibility_t, const bool perf
             if (cams[cl].size() >= P.visibility_t) { LineCluster3D LC; if (P.line_from_cluster(members[cl], LC)) clusters.push_back(LC); }
     }
     P.st.clusters_valid = (long long)clusters.size();
+    // optimizeClusters (line3D.cc:1800-1805, 2269-2275): bundle the cluster lines against their 2D residuals.  The reference
+    // needs Ceres for this (optimization.cc); here the same problem is minimised on the GPU (l3d_optimize_lines).
+    P.st.opt_iterations = 0; P.st.opt_cost_before = P.st.opt_cost_after = 0.0;
+    if (use_CERES && !clusters.empty()) {
+        const int Lc = (int)clusters.size(), nc = (int)P.vlist.size();
+        std::vector<double> p((size_t)6 * Lc), cams((size_t)16 * nc), xy;
+        std::vector<long long> ptr((size_t)Lc + 1, 0);
+        std::vector<int> rcam;
+        for (int v = 0; v < nc; ++v) {
+            const HostView& hv = *P.vlist[v];
+            double* cm = &cams[(size_t)16 * v];
+            for (int r = 0; r < 3; ++r) for (int c2 = 0; c2 < 3; ++c2) cm[3 * r + c2] = hv.R(r, c2);
+            cm[9] = hv.C.x; cm[10] = hv.C.y; cm[11] = hv.C.z;
+            cm[12] = hv.K(0, 0); cm[13] = hv.K(1, 1); cm[14] = hv.K(0, 2); cm[15] = hv.K(1, 2);
+        }
+        for (int i = 0; i < Lc; ++i) {
+            const Segment3D s3 = clusters[i].seg3D();
+            p[6 * i] = s3.P1().x; p[6 * i + 1] = s3.P1().y; p[6 * i + 2] = s3.P1().z; p[6 * i + 3] = s3.P2().x; p[6 * i + 4] = s3.P2().y; p[6 * i + 5] = s3.P2().z;
+            for (const Segment2D& s2 : *clusters[i].residuals()) {
+                const int vi = P.index_of.at(s2.camID());
+                const Vec4f& ln = P.vlist[vi]->lines[s2.segID()];
+                rcam.push_back(vi);
+                for (int k = 0; k < 4; ++k) xy.push_back((double)ln.v[k]);
+            }
+            ptr[i + 1] = (long long)rcam.size();
+        }
+        std::vector<int> valid((size_t)Lc);
+        double summ[8];
+        if (!P.chk(l3d_optimize_lines(P.ctx, Lc, p.data(), ptr.data(), rcam.data(), xy.data(), nc, cams.data(), (int)max_iter_CERES, p.data(), valid.data(), summ),
+                   "l3d_optimize_lines")) { P.untranslate(); return; }
+        std::vector<LineCluster3D> kept;
+        for (int i = 0; i < Lc; ++i) {
+            if (!valid[i]) continue;                        // optimization.cc:293-298
+            clusters[i].update3Dline(Segment3D(Vector3d(p[6 * i], p[6 * i + 1], p[6 * i + 2]), Vector3d(p[6 * i + 3], p[6 * i + 4], p[6 * i + 5])));
+            kept.push_back(clusters[i]);
+        }
+        clusters.swap(kept);
+        P.st.opt_iterations = (long long)summ[0]; P.st.opt_cost_before = summ[1]; P.st.opt_cost_after = summ[2];
+    }
+    P.use_ceres = use_CERES;
     // computeFinal3Dsegments + filterTinySegments (line3D.cc:2278-2339)
     for (const LineCluster3D& cl : clusters) {
         std::list<Segment3D> col = P.collinear_segments(cl);
@@ -676,6 +716,7 @@ std::string Line3D::createOutputFilename()   // line3D.cc:2855-2894
     s << "N_" << P.num_neighbors << "__" << "sigmaP_" << P.sigma_p << "__" << "sigmaA_" << P.sigma_a << "__" << "epiOverlap_" << P.epi << "__";
     if (P.kNN > 0) s << "kNN_" << P.kNN << "__";
     if (P.collin_t > EPS) s << "COLLIN_" << P.collin_t << "__";
+    if (P.use_ceres) s << "OPTIMIZED__";                                   // line3D.cc:2889-2890
     if (P.fixed3Dreg) { s << "FXD_SIGMA_P__"; if (P.const_reg_depth > 0.0f) s << "REG_DEPTH_" << P.const_reg_depth << "__"; }
     if (P.perform_RDD) s << "DIFFUSION__";
     s << "vis_" << P.visibility_t;
@@ -771,6 +812,8 @@ int l3dpp_match_images(void* h, float sp, float sa, unsigned int nn, float epi, 
 { Line3D* L = (Line3D*)h; L->matchImages(sp, sa, nn, epi, knn, crd); return L->lastError()[0] ? -1 : 0; }
 int l3dpp_reconstruct(void* h, unsigned int vis, int diffusion, float collin)
 { Line3D* L = (Line3D*)h; L->reconstruct3Dlines(vis, diffusion != 0, collin, false, 0); return L->lastError()[0] ? -1 : 0; }
+int l3dpp_reconstruct_opt(void* h, unsigned int vis, int diffusion, float collin, int use_ceres, unsigned int max_iter)
+{ Line3D* L = (Line3D*)h; L->reconstruct3Dlines(vis, diffusion != 0, collin, use_ceres != 0, max_iter); return L->lastError()[0] ? -1 : 0; }
 int l3dpp_set_shard(void* h, int rank, int world, Line3D::MatchExchangeFn fn, void* user)
 { Line3D* L = (Line3D*)h; L->setShard(rank, world, fn, user); return L->lastError()[0] ? -1 : 0; }
 int l3dpp_stats(void* h, Line3DStats* out) { *out = ((Line3D*)h)->stats(); return 0; }

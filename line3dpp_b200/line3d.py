@@ -15,8 +15,8 @@ RESID_DT = np.dtype([("line", "<i4"), ("cam", "<u4"), ("seg", "<u4")])
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("view_pairs", "pair_evaluations", "matches_after_knn", "estimates", "affinity_entries",
-                                            "affinity_rows", "clusters_total", "clusters_valid", "lines3D", "collinear_entries")] + \
-               [(n, C.c_double) for n in ("ms_match", "ms_score", "ms_affinity", "ms_diffusion", "ms_cluster")]
+                                            "affinity_rows", "clusters_total", "clusters_valid", "lines3D", "collinear_entries", "opt_iterations")] + \
+               [(n, C.c_double) for n in ("ms_match", "ms_score", "ms_affinity", "ms_diffusion", "ms_cluster", "opt_cost_before", "opt_cost_after")]
 
 
 def _p(a):
@@ -67,9 +67,9 @@ class Line3D:
         self._chk(self.L.l3dpp_match_images(self.h, C.c_float(sigma_p), C.c_float(sigma_a), C.c_uint(num_neighbors), C.c_float(epi_overlap),
                                             C.c_int(knn), C.c_float(const_reg_depth)), "matchImages")
 
-    def reconstruct_3d_lines(self, visibility_t=3, perform_diffusion=False, collinearity_t=-1.0):
-        self._chk(self.L.l3dpp_reconstruct(self.h, C.c_uint(visibility_t), int(perform_diffusion), C.c_float(collinearity_t)),
-                  "reconstruct3Dlines")
+    def reconstruct_3d_lines(self, visibility_t=3, perform_diffusion=False, collinearity_t=-1.0, use_ceres=False, max_iter_ceres=250):
+        self._chk(self.L.l3dpp_reconstruct_opt(self.h, C.c_uint(visibility_t), int(perform_diffusion), C.c_float(collinearity_t),
+                                               int(use_ceres), C.c_uint(max_iter_ceres)), "reconstruct3Dlines")
 
     # ---- dumps
     def stats(self):

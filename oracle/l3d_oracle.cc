@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <list>
 #include <map>
 #include <queue>
@@ -648,6 +649,302 @@ int orc_cluster(int nedges, const int* ei, const int* ej, const float* ew, int n
 
 } // extern "C"
 
+// ================================================================================================ line bundling
+// LineOptimizer::optimize (optimization.cc:8-303) with LineReprojectionError (optimization.h:52-171).  The reference hands
+// the problem to Ceres (third-party, NOT in /root/reference; CMake accepts any installed Ceres, CMakeLists.txt:120-134):
+// cameras and intrinsics are set constant (optimization.cc:178-188), so only the 4 Cayley parameters of every line are
+// free and the Jacobian is block diagonal (one 4-column block per line).  Restated here from Ceres' PUBLISHED algorithm
+// (solver defaults of ceres-solver 1.13-2.1: trust_region_minimizer.cc, levenberg_marquardt_strategy.cc, corrector.cc,
+// loss_function.cc): Levenberg-Marquardt trust region with ONE radius for the whole problem, Jacobi scaling fixed at
+// iteration 0, Huber loss through the Triggs corrector, the function / gradient / parameter tolerances 1e-6 / 1e-10 /
+// 1e-8, min_relative_decrease 1e-3, initial radius 1e4.  SPARSE_SCHUR on a block-diagonal system is a 4x4 Cholesky per
+// line.  Exact derivatives by forward-mode dual numbers like ceres::AutoDiffCostFunction.
+// Pinned against the reference's own before/after result fixtures (tests/golden/line3dpp_ref_opt_pairs_v1.npz).
+namespace {
+
+struct Jet4 { double a; double v[4]; };
+inline Jet4 J(double a) { Jet4 r; r.a = a; r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.0; return r; }
+inline Jet4 operator+(Jet4 x, Jet4 y) { Jet4 r; r.a = x.a + y.a; for (int i = 0; i < 4; ++i) r.v[i] = x.v[i] + y.v[i]; return r; }
+inline Jet4 operator-(Jet4 x, Jet4 y) { Jet4 r; r.a = x.a - y.a; for (int i = 0; i < 4; ++i) r.v[i] = x.v[i] - y.v[i]; return r; }
+inline Jet4 operator-(Jet4 x) { Jet4 r; r.a = -x.a; for (int i = 0; i < 4; ++i) r.v[i] = -x.v[i]; return r; }
+inline Jet4 operator*(Jet4 x, Jet4 y) { Jet4 r; r.a = x.a * y.a; for (int i = 0; i < 4; ++i) r.v[i] = x.a * y.v[i] + x.v[i] * y.a; return r; }
+inline Jet4 operator/(Jet4 x, Jet4 y)
+{ Jet4 r; const double inv = 1.0 / y.a, q = x.a * inv; r.a = q; for (int i = 0; i < 4; ++i) r.v[i] = (x.v[i] - q * y.v[i]) * inv; return r; }
+inline Jet4 operator*(double s, Jet4 x) { return J(s) * x; }
+inline Jet4 operator*(Jet4 x, double s) { return x * J(s); }
+inline Jet4 jsqrt(Jet4 x) { Jet4 r; r.a = std::sqrt(x.a); const double t = 1.0 / (2.0 * r.a); for (int i = 0; i < 4; ++i) r.v[i] = x.v[i] * t; return r; }
+inline Jet4 jacos(Jet4 x) { Jet4 r; r.a = std::acos(x.a); const double t = -1.0 / std::sqrt(1.0 - x.a * x.a); for (int i = 0; i < 4; ++i) r.v[i] = x.v[i] * t; return r; }
+inline Jet4 jexp(Jet4 x) { Jet4 r; r.a = std::exp(x.a); for (int i = 0; i < 4; ++i) r.v[i] = r.a * x.v[i]; return r; }
+inline bool jfinite(Jet4 x) { bool f = std::isfinite(x.a); for (int i = 0; i < 4; ++i) f = f && std::isfinite(x.v[i]); return f; }
+
+struct OptCam { double R[9], C[3], fx, fy, px, py; };
+struct OptObs { double x1, y1, x2, y2, nx, ny; };   // observed end points and NORMAL direction (-dir.y, dir.x), optimization.cc:160-166
+
+// LineReprojectionError::operator() (optimization.h:66-162); line = (omega, sx, sy, sz).  AngleAxisRotatePoint(camera, m)
+// with the angle-axis of R (optimization.cc:118-128) is R*m.
+bool reprojection_error(const OptCam& cam, const OptObs& o, const Jet4 line[4], Jet4 res[2])
+{
+    const Jet4 omega = line[0], sx = line[1], sy = line[2], sz = line[3];
+    const Jet4 nm = sx * sx + sy * sy + sz * sz;
+    const Jet4 div = J(1.0) / (J(1.0) + nm);
+    Jet4 l[3], m[3];
+    l[0] = div * (J(1.0) - nm + J(2.0) * sx * sx);
+    l[1] = div * (J(2.0) * sz + J(2.0) * sy * sx);
+    l[2] = div * (J(-2.0) * sy + J(2.0) * sz * sx);
+    m[0] = omega * div * (J(-2.0) * sz + J(2.0) * sx * sy);
+    m[1] = omega * div * (J(1.0) - nm + J(2.0) * sy * sy);
+    m[2] = omega * div * (J(2.0) * sx + J(2.0) * sz * sy);
+    if (std::fabs(omega.a) < 1e-12) { res[0] = res[1] = J(0.0); return false; }
+    Jet4 Ccl[3];
+    Ccl[0] = cam.C[1] * l[2] - cam.C[2] * l[1];
+    Ccl[1] = -(cam.C[0] * l[2] - cam.C[2] * l[0]);
+    Ccl[2] = cam.C[0] * l[1] - cam.C[1] * l[0];
+    m[0] = m[0] - Ccl[0]; m[1] = m[1] - Ccl[1]; m[2] = m[2] - Ccl[2];
+    Jet4 q[3];
+    for (int i = 0; i < 3; ++i) q[i] = cam.R[3 * i] * m[0] + cam.R[3 * i + 1] * m[1] + cam.R[3 * i + 2] * m[2];
+    Jet4 pl[3];
+    pl[0] = cam.fy * q[0];
+    pl[1] = cam.fx * q[1];
+    pl[2] = (-cam.fy * cam.px) * q[0] - (cam.fx * cam.py) * q[1] + (cam.fx * cam.fy) * q[2];
+    const Jet4 d = jsqrt(pl[0] * pl[0] + pl[1] * pl[1]);
+    if (d.a < 1e-12) { res[0] = res[1] = J(0.0); return false; }
+    Jet4 aw = J(1.0);
+    if (d.a > 1e-12) {
+        const Jet4 dx = pl[0] / d, dy = pl[1] / d;
+        const Jet4 dotp = dx * o.nx + dy * o.ny;
+        Jet4 angle = jacos(dotp);
+        if (jfinite(angle)) {
+            if (angle.a > M_PI_2) angle = J(M_PI) - angle;
+            aw = jexp(2.0 * angle);
+        }
+    }
+    res[0] = (pl[0] * o.x1 + pl[1] * o.y1 + pl[2]) / d * aw;
+    res[1] = (pl[0] * o.x2 + pl[1] * o.y2 + pl[2]) / d * aw;
+    return true;
+}
+
+// 0.5 * sum rho(|r|^2) over the residual blocks of line i, its gradient g = J'r and H = J'J (robustified, UNscaled).
+// HuberLoss(2) (loss_function.cc): rho = s, rho' = 1 for s <= 4; rho = 4 sqrt(s) - 4, rho' = 2/sqrt(s), rho'' < 0 beyond;
+// Corrector (corrector.cc:88-111) with rho'' <= 0: residual and Jacobian are both scaled by sqrt(rho').
+bool eval_line(const OptCam* cams, const int* res_cam, const OptObs* obs, long long r0, long long r1, const double x[4], double* cost,
+               double g[4], double H[10])
+{
+    Jet4 line[4];
+    for (int k = 0; k < 4; ++k) { line[k] = J(x[k]); line[k].v[k] = 1.0; }
+    double c = 0.0;
+    if (g) for (int k = 0; k < 4; ++k) g[k] = 0.0;
+    if (H) for (int k = 0; k < 10; ++k) H[k] = 0.0;
+    for (long long r = r0; r < r1; ++r) {
+        Jet4 res[2];
+        if (!reprojection_error(cams[res_cam[r]], obs[r], line, res)) return false;
+        const double s = res[0].a * res[0].a + res[1].a * res[1].a;
+        double rho, rho1;
+        if (s > 4.0) { const double sr = std::sqrt(s); rho = 2.0 * 2.0 * sr - 4.0; rho1 = std::max(std::numeric_limits<double>::min(), 2.0 / sr); }
+        else { rho = s; rho1 = 1.0; }
+        c += 0.5 * rho;
+        if (g) {
+            const double w = std::sqrt(rho1);
+            for (int e = 0; e < 2; ++e) {
+                const double rr = w * res[e].a;
+                double jr[4];
+                for (int k = 0; k < 4; ++k) jr[k] = w * res[e].v[k];
+                int idx = 0;
+                for (int a = 0; a < 4; ++a) { g[a] += jr[a] * rr; for (int b = a; b < 4; ++b) H[idx++] += jr[a] * jr[b]; }
+            }
+        }
+    }
+    *cost = c;
+    return true;
+}
+
+// (A + diag(D2)) y = b for symmetric 4x4 A (upper triangle, row-wise: 00 01 02 03 11 12 13 22 23 33), Cholesky
+bool solve4(const double A[10], const double D2[4], const double b[4], double y[4])
+{
+    double M[4][4];
+    int idx = 0;
+    for (int a = 0; a < 4; ++a) for (int c = a; c < 4; ++c) { M[a][c] = M[c][a] = A[idx++]; }
+    for (int a = 0; a < 4; ++a) M[a][a] += D2[a];
+    double L[4][4] = {{0}};
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = M[i][j];
+            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+            if (i == j) { if (!(s > 0.0)) return false; L[i][i] = std::sqrt(s); } else L[i][j] = s / L[j][j];
+        }
+    double z[4];
+    for (int i = 0; i < 4; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * z[k]; z[i] = s / L[i][i]; }
+    for (int i = 3; i >= 0; --i) { double s = z[i]; for (int k = i + 1; k < 4; ++k) s -= L[k][i] * y[k]; y[i] = s / L[i][i]; }
+    for (int i = 0; i < 4; ++i) if (!std::isfinite(y[i])) return false;
+    return true;
+}
+
+// Pluecker -> Cayley (optimization.cc:34-91).  false: "symmetric line coords... do not bundle" (kept constant)
+bool cayley_from_segment(const double* p, double x[4])
+{
+    V3 P1 = V(p[0], p[1], p[2]), P2 = V(p[3], p[4], p[5]);
+    V3 l = normalized(P2 - P1);
+    V3 m = crossd((P1 + P2) * 0.5, l);
+    V3 e1, e2;
+    if (normd(m) < L3D_EPS) {
+        // the reference takes Eigen's FullPivLU kernel of l' here (a line through the origin of the translated frame, a set
+        // of measure zero); any basis of the plane normal to l spans the same family of Cayley rotations
+        V3 t = std::fabs(l.x) < 0.9 ? V(1, 0, 0) : V(0, 1, 0);
+        e1 = normalized(crossd(l, t)); e2 = crossd(l, e1);
+    } else { e1 = normalized(m); e2 = normalized(crossd(l, m)); }
+    M3 Q, Qm, Qp;
+    Q(0, 0) = l.x; Q(0, 1) = e1.x; Q(0, 2) = e2.x; Q(1, 0) = l.y; Q(1, 1) = e1.y; Q(1, 2) = e2.y; Q(2, 0) = l.z; Q(2, 1) = e1.z; Q(2, 2) = e2.z;
+    for (int i = 0; i < 9; ++i) { Qm.m[i] = Q.m[i]; Qp.m[i] = Q.m[i]; }
+    for (int i = 0; i < 3; ++i) { Qm(i, i) -= 1.0; Qp(i, i) += 1.0; }
+    M3 sx = mul(Qm, inverse(Qp));
+    x[0] = normd(m); x[1] = sx(2, 1); x[2] = sx(0, 2); x[3] = sx(1, 0);
+    return !(std::isnan(x[0]) || std::isnan(x[1]) || std::isnan(x[2]) || std::isnan(x[3]));
+}
+
+// Cayley -> end points (optimization.cc:213-291); false if the new segment has no length (cluster dropped, 293-298)
+bool segment_from_cayley(const double x[4], const double* old, double* out)
+{
+    V3 P1o = V(old[0], old[1], old[2]), P2o = V(old[3], old[4], old[5]), P1 = P1o, P2 = P2o;
+    const double omega = x[0];
+    if (!(omega < 0.0 || std::fabs(omega) < L3D_EPS)) {
+        const double s0 = x[1], s1 = x[2], s2 = x[3], nm = s0 * s0 + s1 * s1 + s2 * s2, f = 1.0 / (1.0 + nm);
+        // Q = f * ((1-nm) I + 2 [s]x + 2 s s')
+        double Q[3][3] = {{(1.0 - nm) + 2.0 * s0 * s0, 2.0 * -s2 + 2.0 * s0 * s1, 2.0 * s1 + 2.0 * s0 * s2},
+                          {2.0 * s2 + 2.0 * s1 * s0, (1.0 - nm) + 2.0 * s1 * s1, 2.0 * -s0 + 2.0 * s1 * s2},
+                          {2.0 * -s1 + 2.0 * s2 * s0, 2.0 * s0 + 2.0 * s2 * s1, (1.0 - nm) + 2.0 * s2 * s2}};
+        V3 l = V(f * Q[0][0], f * Q[1][0], f * Q[2][0]), m = V(f * Q[0][1], f * Q[1][1], f * Q[2][1]) * omega;
+        if (std::fabs(l.x) > L3D_EPS || std::fabs(l.y) > L3D_EPS || std::fabs(l.z) > L3D_EPS) {
+            V3 Pm = (P1o + P2o) * 0.5;
+            double x1, x2, x3;
+            if (std::fabs(l.x) > std::fabs(l.y) && std::fabs(l.x) > std::fabs(l.z)) { x1 = Pm.x; x3 = (-m.y - x1 * l.z) / -l.x; x2 = (m.z - x1 * l.y) / -l.x; }
+            else if (std::fabs(l.y) > std::fabs(l.x) && std::fabs(l.y) > std::fabs(l.z)) { x2 = Pm.y; x3 = (m.x - x2 * l.z) / -l.y; x1 = (m.z + x2 * l.x) / l.y; }
+            else { x3 = Pm.z; x2 = (m.x + x3 * l.y) / l.z; x1 = (-m.y + x3 * l.x) / l.z; }
+            Pm = V(x1, x2, x3);
+            P1 = Pm + l; P2 = Pm - l;
+        }
+    }
+    out[0] = P1.x; out[1] = P1.y; out[2] = P1.z; out[3] = P2.x; out[4] = P2.y; out[5] = P2.z;
+    return normd(P1 - P2) > L3D_EPS;
+}
+
+} // namespace
+
+extern "C" {
+
+// LineOptimizer::optimize.  cams: 16 doubles per camera (R row-major, C, fx, fy, px, py); res_xy: x1 y1 x2 y2 per residual
+// (the float segment coordinates, optimization.cc:155-157); res_ptr[num_lines+1].  p1p2_out / valid_out per line
+// (valid 0 = the cluster is dropped, optimization.cc:293-298).  summary (optional, 8 doubles): iterations, initial cost,
+// final cost, termination (0 convergence, 1 no convergence, 2 failure), successful steps, free lines, final radius, 0.
+int orc_optimize_lines(int num_lines, const double* p1p2, const long long* res_ptr, const int* res_cam, const double* res_xy, int num_cams,
+                       const double* cams, int max_iter, double* p1p2_out, int* valid_out, double* summary)
+{
+    const int L = num_lines;
+    std::vector<OptCam> C(num_cams);
+    for (int i = 0; i < num_cams; ++i) {
+        for (int k = 0; k < 9; ++k) C[i].R[k] = cams[16 * i + k];
+        for (int k = 0; k < 3; ++k) C[i].C[k] = cams[16 * i + 9 + k];
+        C[i].fx = cams[16 * i + 12]; C[i].fy = cams[16 * i + 13]; C[i].px = cams[16 * i + 14]; C[i].py = cams[16 * i + 15];
+    }
+    const long long NR = res_ptr[L];
+    std::vector<OptObs> obs((size_t)NR);
+    for (long long r = 0; r < NR; ++r) {
+        OptObs& o = obs[(size_t)r];
+        o.x1 = res_xy[4 * r]; o.y1 = res_xy[4 * r + 1]; o.x2 = res_xy[4 * r + 2]; o.y2 = res_xy[4 * r + 3];
+        double dx = o.x2 - o.x1, dy = o.y2 - o.y1; const double n2 = dx * dx + dy * dy;
+        if (n2 > 0) { const double n = std::sqrt(n2); dx /= n; dy /= n; }       // Eigen normalized()
+        o.nx = -dy; o.ny = dx;
+    }
+    std::vector<double> x(4 * (size_t)L), xc(4 * (size_t)L), g(4 * (size_t)L), H(10 * (size_t)L), S(4 * (size_t)L, 1.0), diag(4 * (size_t)L), step(4 * (size_t)L);
+    std::vector<char> free_(L);
+    int nfree = 0;
+    for (int i = 0; i < L; ++i) {
+        free_[i] = cayley_from_segment(p1p2 + 6 * i, &x[4 * i]) && res_ptr[i + 1] > res_ptr[i];
+        if (!free_[i] && !(res_ptr[i + 1] > res_ptr[i])) { /* no residuals: parameter block unused */ }
+        else if (!free_[i]) { x[4 * i] = -1; x[4 * i + 1] = x[4 * i + 2] = x[4 * i + 3] = 0; }
+        nfree += free_[i];
+    }
+    double sum[8] = {0, 0, 0, 1, 0, (double)nfree, 1e4, 0};
+    auto finish = [&](int term, int iters, double c0, double c1, int nsucc, double radius) {
+        for (int i = 0; i < L; ++i) valid_out[i] = segment_from_cayley(&x[4 * i], p1p2 + 6 * i, p1p2_out + 6 * i) ? 1 : 0;
+        if (summary) { sum[0] = iters; sum[1] = c0; sum[2] = c1; sum[3] = term; sum[4] = nsucc; sum[5] = nfree; sum[6] = radius; for (int k = 0; k < 8; ++k) summary[k] = sum[k]; }
+        return 0;
+    };
+    if (nfree == 0 || max_iter < 0) return finish(0, 0, 0, 0, 0, 1e4);
+    // ---- iteration zero (trust_region_minimizer.cc: IterationZero)
+    auto evaluate = [&](const std::vector<double>& xx, bool jac, double* total) {
+        double c = 0.0; bool ok = true;
+        for (int i = 0; i < L; ++i) {
+            if (!free_[i]) continue;
+            double ci;
+            if (!eval_line(C.data(), res_cam, obs.data(), res_ptr[i], res_ptr[i + 1], &xx[4 * i], &ci, jac ? &g[4 * i] : nullptr, jac ? &H[10 * i] : nullptr)) { ok = false; continue; }
+            c += ci;
+        }
+        *total = c; return ok;
+    };
+    double cost;
+    if (!evaluate(x, true, &cost)) return finish(2, 0, 0, 0, 0, 1e4);
+    const double cost0 = cost;
+    static const int DI[4] = {0, 4, 7, 9};
+    for (int i = 0; i < L; ++i) if (free_[i]) for (int k = 0; k < 4; ++k) S[4 * i + k] = 1.0 / (1.0 + std::sqrt(H[10 * i + DI[k]]));   // jacobi scaling
+    auto grad_max = [&]() { double m = 0; for (int i = 0; i < L; ++i) if (free_[i]) for (int k = 0; k < 4; ++k) m = std::max(m, std::fabs(g[4 * i + k])); return m; };
+    if (grad_max() <= 1e-10) return finish(0, 0, cost0, cost, 0, 1e4);
+    double radius = 1e4, decrease_factor = 2.0; bool reuse_diagonal = false; int invalid = 0, nsucc = 0;
+    int it = 0;
+    for (;;) {
+        if (it >= max_iter) return finish(1, it, cost0, cost, nsucc, radius);
+        if (radius <= 1e-32) return finish(0, it, cost0, cost, nsucc, radius);
+        ++it;
+        // ---- LevenbergMarquardtStrategy::ComputeStep on the scaled system
+        bool solved = true; double model_change = 0.0, step_sq = 0.0, x_sq = 0.0;
+        for (int i = 0; i < L; ++i) {
+            if (!free_[i]) continue;
+            double Hs[10], gs[4], D2[4], y[4];
+            int idx = 0;
+            for (int a = 0; a < 4; ++a) { gs[a] = S[4 * i + a] * g[4 * i + a]; for (int b = a; b < 4; ++b) { Hs[idx] = S[4 * i + a] * S[4 * i + b] * H[10 * i + idx]; ++idx; } }
+            if (!reuse_diagonal) for (int k = 0; k < 4; ++k) diag[4 * i + k] = std::min(std::max(Hs[DI[k]], 1e-6), 1e32);
+            for (int k = 0; k < 4; ++k) D2[k] = diag[4 * i + k] / radius;
+            if (!solve4(Hs, D2, gs, y)) { solved = false; continue; }
+            double d[4], Hd[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; ++k) d[k] = -y[k];
+            double Hf[4][4]; idx = 0;
+            for (int a = 0; a < 4; ++a) for (int b = a; b < 4; ++b) { Hf[a][b] = Hf[b][a] = Hs[idx++]; }
+            for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) Hd[a] += Hf[a][b] * d[b];
+            double dg = 0, dHd = 0;
+            for (int k = 0; k < 4; ++k) { dg += d[k] * gs[k]; dHd += d[k] * Hd[k]; }
+            model_change += -(dg + 0.5 * dHd);            // -(J d)'(r + J d / 2)
+            for (int k = 0; k < 4; ++k) {
+                step[4 * i + k] = d[k] * S[4 * i + k];
+                xc[4 * i + k] = x[4 * i + k] + step[4 * i + k];
+                step_sq += step[4 * i + k] * step[4 * i + k]; x_sq += x[4 * i + k] * x[4 * i + k];
+            }
+        }
+        reuse_diagonal = true;
+        if (!solved || !(model_change > 0.0)) {            // HandleInvalidStep
+            if (++invalid >= 5) return finish(2, it, cost0, cost, nsucc, radius);
+            radius *= 0.5; reuse_diagonal = false;
+            continue;
+        }
+        invalid = 0;
+        double cand;
+        if (!evaluate(xc, false, &cand)) cand = std::numeric_limits<double>::max();
+        if (std::sqrt(step_sq) <= 1e-8 * (std::sqrt(x_sq) + 1e-8)) return finish(0, it, cost0, cost, nsucc, radius);      // parameter tolerance
+        if (std::fabs(cost - cand) <= 1e-6 * cost) return finish(0, it, cost0, cost, nsucc, radius);                     // function tolerance (the
+                                                                                                   // candidate is NOT applied: both checks precede the acceptance test)
+        const double quality = (cost - cand) / model_change;
+        if (quality > 1e-3) {                                 // HandleSuccessfulStep
+            for (int i = 0; i < L; ++i) if (free_[i]) for (int k = 0; k < 4; ++k) x[4 * i + k] = xc[4 * i + k];
+            ++nsucc;
+            if (!evaluate(x, true, &cost)) return finish(2, it, cost0, cost, nsucc, radius);
+            radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * quality - 1.0, 3));
+            radius = std::min(1e16, radius); decrease_factor = 2.0; reuse_diagonal = false;
+            if (grad_max() <= 1e-10) return finish(0, it, cost0, cost, nsucc, radius);
+        } else {                                              // HandleUnsuccessfulStep
+            radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        }
+    }
+}
+
+}  // extern "C"
+
 // ================================================================================================ pipeline
 struct FinalLine {
     std::list<Seg3D> collinear;       // FinalLine3D::collinear3Dsegments_
@@ -677,6 +974,7 @@ struct orc_ctx {
     std::list<CLEdge> A, A_raw, A_final; std::map<Seg2D, int> global2local; std::map<int, Seg2D> local2global; std::vector<Seg2D> l2g_dump; int localID;
     std::map<Seg2D, std::set<Seg2D> > used;
     std::vector<FinalLine> clusters3D, lines3D;
+    double opt_summary[8];
 };
 
 namespace {
@@ -1287,7 +1585,46 @@ int orc_match_images(orc_ctx* c, float sigma_position, float sigma_angle, uint32
     return 0;
 }
 
-int orc_reconstruct(orc_ctx* c, uint32_t visibility_t, int perform_diffusion, float collinearity_t)   // line3D.cc:1702-1824
+int orc_reconstruct_opt(orc_ctx* c, uint32_t visibility_t, int perform_diffusion, float collinearity_t, int use_ceres, uint32_t max_iter_ceres);
+int orc_reconstruct(orc_ctx* c, uint32_t visibility_t, int perform_diffusion, float collinearity_t)
+{ return orc_reconstruct_opt(c, visibility_t, perform_diffusion, collinearity_t, 0, 0); }
+
+// Line3D::optimizeClusters (line3D.cc:2269-2275) -> LineOptimizer::optimize
+static void optimize_clusters(orc_ctx* c, uint32_t max_iter)
+{
+    const int L = (int)c->clusters3D.size();
+    if (L == 0) return;
+    std::map<uint32_t, int> cam_local; std::vector<double> cams;
+    for (std::map<uint32_t, View*>::const_iterator v = c->views.begin(); v != c->views.end(); ++v) {     // optimization.cc:106-142
+        cam_local[v->first] = (int)cam_local.size();
+        const View* w = v->second;
+        for (int k = 0; k < 9; ++k) cams.push_back(w->R.m[k]);
+        cams.push_back(w->C.x); cams.push_back(w->C.y); cams.push_back(w->C.z);
+        cams.push_back(w->K(0, 0)); cams.push_back(w->K(1, 1)); cams.push_back(w->K(0, 2)); cams.push_back(w->K(1, 2));
+    }
+    std::vector<double> p((size_t)6 * L), xy; std::vector<long long> ptr((size_t)L + 1, 0); std::vector<int> rcam;
+    for (int i = 0; i < L; ++i) {
+        const Seg3D& s = c->clusters3D[i].cluster_seg;
+        p[6 * i] = s.P1.x; p[6 * i + 1] = s.P1.y; p[6 * i + 2] = s.P1.z; p[6 * i + 3] = s.P2.x; p[6 * i + 4] = s.P2.y; p[6 * i + 5] = s.P2.z;
+        for (std::list<Seg2D>::const_iterator it = c->clusters3D[i].residuals.begin(); it != c->clusters3D[i].residuals.end(); ++it) {
+            const f4& ln = c->views[it->cam]->lines[it->seg];
+            rcam.push_back(cam_local[it->cam]);
+            xy.push_back(ln.x); xy.push_back(ln.y); xy.push_back(ln.z); xy.push_back(ln.w);
+        }
+        ptr[i + 1] = (long long)rcam.size();
+    }
+    std::vector<int> valid(L);
+    orc_optimize_lines(L, p.data(), ptr.data(), rcam.data(), xy.data(), (int)cam_local.size(), cams.data(), (int)max_iter, p.data(), valid.data(), c->opt_summary);
+    std::vector<FinalLine> kept;
+    for (int i = 0; i < L; ++i) {
+        if (!valid[i]) continue;
+        c->clusters3D[i].cluster_seg = Seg3D(V(p[6 * i], p[6 * i + 1], p[6 * i + 2]), V(p[6 * i + 3], p[6 * i + 4], p[6 * i + 5]));
+        kept.push_back(c->clusters3D[i]);
+    }
+    c->clusters3D = kept;
+}
+
+int orc_reconstruct_opt(orc_ctx* c, uint32_t visibility_t, int perform_diffusion, float collinearity_t, int use_ceres, uint32_t max_iter_ceres)   // line3D.cc:1702-1824
 {
     if (c->est.empty()) return -1;
     c->visibility_t = (unsigned)std::max(int(visibility_t), 3);
@@ -1309,6 +1646,7 @@ int orc_reconstruct(orc_ctx* c, uint32_t visibility_t, int perform_diffusion, fl
     if (c->perform_RDD) perform_rdd(c);
     cluster_segments(c);
     c->global2local.clear(); c->local2global.clear();
+    if (use_ceres) optimize_clusters(c, max_iter_ceres);        // line3D.cc:1800-1805
     for (size_t i = 0; i < c->clusters3D.size(); ++i) {   // computeFinal3Dsegments line3D.cc:2278-2299
         std::list<Seg3D> col = find_collinear_segments(c, c->clusters3D[i]);
         if (!col.empty()) { FinalLine f = c->clusters3D[i]; f.collinear = col; c->lines3D.push_back(f); }
@@ -1330,6 +1668,7 @@ int orc_reconstruct(orc_ctx* c, uint32_t visibility_t, int perform_diffusion, fl
     return 0;
 }
 
+int orc_get_opt_summary(orc_ctx* c, double* s8) { for (int k = 0; k < 8; ++k) s8[k] = c->opt_summary[k]; return 0; }
 int orc_num_views(orc_ctx* c) { return (int)c->views.size(); }
 long long orc_pair_evals(orc_ctx* c) { return c->pair_evals; }
 int orc_get_pairs(orc_ctx* c, int* st, int cap)

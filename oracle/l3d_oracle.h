@@ -52,6 +52,14 @@ int orc_collinear_f32(const float* lines, int N, float dist_t, unsigned char* C_
 int orc_collinear_f64(const float* lines, int N, float dist_t, unsigned char* C_out, float* kernel_ms);
 int orc_cluster(int nedges, const int* ei, const int* ej, const float* ew, int n, float c, int* labels_out);
 
+/* LineOptimizer::optimize (optimization.cc:8-303) + LineReprojectionError (optimization.h:52-171) with Ceres' published
+ * Levenberg-Marquardt (Ceres itself is a third-party dependency absent from the reference tree).  cams: 16 doubles per
+ * camera (R row-major, C, fx, fy, px, py); res_cam indexes cams; res_xy = x1 y1 x2 y2 per residual; valid_out 0 = dropped.
+ * summary[8] (optional): iterations, initial cost, final cost, termination (0 conv, 1 max iter, 2 failure), successful steps,
+ * free lines, final radius, 0. */
+int orc_optimize_lines(int num_lines, const double* p1p2, const long long* res_ptr, const int* res_cam, const double* res_xy, int num_cams,
+                       const double* cams, int max_iter, double* p1p2_out, int* valid_out, double* summary);
+
 /* ---- pipeline: restatement of L3DPP::Line3D (line3D.h:80-233) ---- */
 typedef struct orc_ctx orc_ctx;
 /* use_gpu: 1 = REF_GPU semantics (float kernels, scoringGPU), 0 = REF_CPU (matchingCPU/scoringCPU)   line3D.cc:49-53 */
@@ -69,6 +77,9 @@ int orc_add_view(orc_ctx*, uint32_t cam_id, int width, int height, const double*
 int orc_match_images(orc_ctx*, float sigma_p, float sigma_a, uint32_t num_neighbors, float epi_overlap, int kNN,
                      float const_reg_depth);
 int orc_reconstruct(orc_ctx*, uint32_t visibility_t, int perform_diffusion, float collinearity_t);
+/* same with the bundling step of reconstruct3Dlines (use_CERES, max_iter_CERES; line3D.cc:1800-1805) */
+int orc_reconstruct_opt(orc_ctx*, uint32_t visibility_t, int perform_diffusion, float collinearity_t, int use_ceres, uint32_t max_iter_ceres);
+int orc_get_opt_summary(orc_ctx*, double* summary8);
 
 /* stage dumps (all in deterministic single-thread reference order) */
 int orc_num_views(orc_ctx*);

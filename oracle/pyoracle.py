@@ -177,9 +177,14 @@ class OraclePipeline:
         return self.L.orc_match_images(self.ctx, C.c_float(sigma_p), C.c_float(sigma_a), C.c_uint(num_neighbors),
                                        C.c_float(epi_overlap), C.c_int(knn), C.c_float(const_reg_depth))
 
-    def reconstruct(self, visibility_t=3, perform_diffusion=False, collinearity_t=-1.0):
-        return self.L.orc_reconstruct(self.ctx, C.c_uint(visibility_t), int(perform_diffusion),
-                                      C.c_float(collinearity_t))
+    def reconstruct(self, visibility_t=3, perform_diffusion=False, collinearity_t=-1.0, use_ceres=False, max_iter_ceres=250):
+        return self.L.orc_reconstruct_opt(self.ctx, C.c_uint(visibility_t), int(perform_diffusion),
+                                          C.c_float(collinearity_t), int(use_ceres), C.c_uint(max_iter_ceres))
+
+    def opt_summary(self):
+        s = np.zeros(8, np.float64)
+        self.L.orc_get_opt_summary(self.ctx, _p(s))
+        return s
 
     def pair_evals(self):
         return int(self.L.orc_pair_evals(self.ctx))
@@ -264,3 +269,16 @@ class OraclePipeline:
 
     def save_txt(self, path):
         return self.L.orc_save_txt(self.ctx, path.encode())
+
+
+def optimize_lines(fn, p1p2, res_ptr, res_cam, res_xy, cams, max_iter=250, handle=None):
+    """fn = lib().orc_optimize_lines (or the product's l3d_optimize_lines with handle = its context).
+    Returns (p1p2_out[L,6], valid[L], summary[8])."""
+    p1p2 = _f64(p1p2); res_xy = _f64(res_xy); cams = _f64(cams)
+    res_ptr = np.ascontiguousarray(res_ptr, np.int64); res_cam = np.ascontiguousarray(res_cam, np.int32)
+    L = len(p1p2)
+    out = np.zeros((L, 6), np.float64); valid = np.zeros(L, np.int32); summ = np.zeros(8, np.float64)
+    args = (L, _p(p1p2), _p(res_ptr), _p(res_cam), _p(res_xy), len(cams), _p(cams), int(max_iter), _p(out), _p(valid), _p(summ))
+    rc = fn(*args) if handle is None else fn(handle, *args)
+    assert rc == 0, rc
+    return out, valid, summ
