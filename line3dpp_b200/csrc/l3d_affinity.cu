@@ -307,15 +307,11 @@ k_rdd_plan(long long nnz, const int* __restrict__ prow, const int* __restrict__ 
     dst[y] = t >= 0 ? 4 * rp4[r] + (t - rs) : -1;
 }
 // K_sparseMat_diffusion_step (cudawrapper.cu:480-544) on the padded arrays: entry y = (a,b) of P produces P'(b,a).
-// A thread owns RDD_ITEMS entries (strided by the block size, so the descriptor loads stay coalesced) and walks them in
-// steps of EIGHT values = one whole 32-byte sector of P.row(b) and of W.col(a) per entry and step (two back-to-back float4
-// loads each); the gathers of the different entries are independent, which is the memory-level parallelism this latency-
-// bound gather needs.  No per-element guards: beyond the walk length min(len_r, len_c) at least one of the two factors
+// One thread per entry, walking in steps of EIGHT values = one whole 32-byte sector of P.row(b) and of W.col(a) per step
+// (one 256-bit load each); the first two steps are in flight together, which is the memory-level parallelism this
+// latency-bound gather needs at 6 resident CTAs per SM.  No per-element guards: beyond the walk length min(len_r, len_c) at least one of the two factors
 // lies in its row's zero padding (rows are padded to 8), the product is +0 and `mul + 0 == mul` exactly, so every entry
 // still accumulates exactly the reference's products in the reference's k order (weights and P are finite).
-#ifndef RDD_ITEMS
-#define RDD_ITEMS 2
-#endif
 // one whole 32-byte sector per lane and instruction (LDG.E.256, new on sm_100): with divergent addresses the L1 looks up
 // about one sector per cycle and SM, so two 16-byte loads of the same sector cost twice as much as one 32-byte load -
 // the first float4 version of this kernel sat at 80 % L1 throughput for exactly that reason
@@ -331,42 +327,35 @@ __global__ void __launch_bounds__(256)
 k_rdd_step8(long long nnz, const int4* __restrict__ plan, const int* __restrict__ dst, const float* __restrict__ Pp, const float* __restrict__ Wp,
             float* __restrict__ Pnp)
 {
-    const long long y0 = (long long)blockIdx.x * (256 * RDD_ITEMS) + threadIdx.x;
-    int4 pl[RDD_ITEMS];
-    int d[RDD_ITEMS];
-    float own[RDD_ITEMS], mul[RDD_ITEMS];
-    int mmax = 0;
+    const long long y = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (y >= nnz) return;
+    const int4 pl = plan[y];
+    const int d = dst[y];
+    const int n8 = (pl.z + 7) >> 3;
+    const float* pr = Pp + 4ll * pl.x;
+    const float* wc = Wp + 4ll * pl.y;
+    // the first two steps (16 values: most walks) are requested together, before anything waits on them
+    F8 p0, w0, p1, w1;
+    if (n8 > 0) { p0 = ld256(pr); w0 = ld256(wc); }
+    if (n8 > 1) { p1 = ld256(pr + 8); w1 = ld256(wc + 8); }
+    const float own = (pl.z > 0 || d >= 0) ? Pp[pl.w] : 0.0f;
+    float m = 0.0f;
+    if (n8 > 0) {
 #pragma unroll
-    for (int i = 0; i < RDD_ITEMS; ++i) {
-        const long long y = y0 + 256ll * i;
-        const bool ok = y < nnz;
-        pl[i] = ok ? plan[y] : make_int4(0, 0, 0, 0);
-        d[i] = ok ? dst[y] : -1;
-        mmax = max(mmax, pl[i].z);
-        mul[i] = 0.0f;
+        for (int e = 0; e < 8; ++e) m += p0.v[e] * w0.v[e];
     }
+    if (n8 > 1) {
 #pragma unroll
-    for (int i = 0; i < RDD_ITEMS; ++i) own[i] = pl[i].z > 0 || d[i] >= 0 ? Pp[pl[i].w] : 0.0f;
-    for (int k8 = 0; 8 * k8 < mmax; ++k8) {
-        F8 pv[RDD_ITEMS], wv[RDD_ITEMS];
-#pragma unroll
-        for (int i = 0; i < RDD_ITEMS; ++i)
-            if (8 * k8 < pl[i].z) { pv[i] = ld256(Pp + 4ll * pl[i].x + 8 * k8); wv[i] = ld256(Wp + 4ll * pl[i].y + 8 * k8); }
-#pragma unroll
-        for (int i = 0; i < RDD_ITEMS; ++i)
-            if (8 * k8 < pl[i].z) {
-                float m = mul[i];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) m += pv[i].v[e] * wv[i].v[e];
-                mul[i] = m;
-            }
+        for (int e = 0; e < 8; ++e) m += p1.v[e] * w1.v[e];
     }
+    for (int k8 = 2; k8 < n8; ++k8) {
+        const F8 pv = ld256(pr + 8 * k8), wv = ld256(wc + 8 * k8);
 #pragma unroll
-    for (int i = 0; i < RDD_ITEMS; ++i) {
-        float m = mul[i] * own[i];                      // times P(a,b) itself
-        if (m < L3D_EPS_F) m = L3D_EPS_F;
-        if (d[i] >= 0) Pnp[d[i]] = m;
+        for (int e = 0; e < 8; ++e) m += pv.v[e] * wv.v[e];
     }
+    m *= own;                                           // times P(a,b) itself
+    if (m < L3D_EPS_F) m = L3D_EPS_F;
+    if (d >= 0) Pnp[d] = m;
 }
 // K_sparseMat_row_normalization (cudawrapper.cu:432-477), 4 lanes per row, one float4 each per pass: coalesced loads and
 // stores, and the row sum is still added strictly in slot order - the running sum is handed from lane to lane (lane j adds
@@ -782,7 +771,7 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     float* P = (float*)R.d_Pp.p; float* Pn = (float*)R.d_Pnp.p;
     for (int it = 0; it < iters; ++it) {
-        k_rdd_step8<<<(unsigned int)((nnz + 256 * RDD_ITEMS - 1) / (256 * RDD_ITEMS)), 256, 0, st>>>(nnz, (const int4*)R.d_plan.p, (const int*)R.d_dst.p, P, (const float*)R.d_Wp.p, Pn);
+        k_rdd_step8<<<(unsigned int)((nnz + 255) / 256), 256, 0, st>>>(nnz, (const int4*)R.d_plan.p, (const int*)R.d_dst.p, P, (const float*)R.d_Wp.p, Pn);
         std::swap(P, Pn);
         if (it < iters - 1) normalize(P);       // no normalisation after the last step (cudawrapper.cu:751)
     }
