@@ -188,10 +188,10 @@ k_opt_init(int L, const double* __restrict__ p1p2, const long long* __restrict__
     double S[3][3];
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) S[r][c] = A[r][0] * Bi[0][c] + A[r][1] * Bi[1][c] + A[r][2] * Bi[2][c];
     double xi[4] = {dnorm(m), S[2][1], S[0][2], S[1][0]};
-    const bool ok = !(isnan(xi[0]) || isnan(xi[1]) || isnan(xi[2]) || isnan(xi[3])) && res_ptr[i + 1] > res_ptr[i];
-    if (!ok) { xi[0] = -1.0; xi[1] = xi[2] = xi[3] = 0.0; }
+    const bool ok = !(isnan(xi[0]) || isnan(xi[1]) || isnan(xi[2]) || isnan(xi[3]));
+    if (!ok) { xi[0] = -1.0; xi[1] = xi[2] = xi[3] = 0.0; }       // optimization.cc:72-84: kept constant, original end points survive
     for (int k = 0; k < 4; ++k) x[4 * i + k] = xi[k];
-    isfree[i] = ok ? 1 : 0;
+    isfree[i] = (ok && res_ptr[i + 1] > res_ptr[i]) ? 1 : 0;     // a block without residuals never enters the problem but is still written back
 }
 
 // per-line terms of one evaluation, reduced by k_opt_reduce:  part[0*L+i] cost  [1] |g|_inf  [2] failed
