@@ -348,6 +348,7 @@ def run_ours(args):
                          "traffic_note": "DRAM read+write bytes per launch from the committed ncu --set full capture of this command (profiles/traffic.json); "
                                          "algorithmic output is 24 B per emitted match + 4 B per (pair,row) count"},
             "roofline_hbm": extra.get("roofline_hbm"),
+            "extras": extra.get("extras"),
             "peaks": peaks,
         }
         cpu_v, cores, sample = cpu_matching_sample(12.0)
@@ -433,6 +434,35 @@ def roofline_legs(ctx, st, scene, torch):
                                     "algorithmic_bytes_per_nnz_per_iteration": RDD_BYTES_PER_NNZ})
     except Exception as e:   # noqa
         out["roofline_hbm"].append({"kernel": "k_rdd_step", "error": str(e)[:200]})
+    # the two optional stages around the path, timed once each; not part of `value`
+    out["extras"] = {}
+    try:
+        cells = float(sum(len(sg) ** 2 for sg in scene.segs))
+        ctx.find_collinear(2.0, 0); ctx.find_collinear(0.0, 0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st); entries = ctx.find_collinear(2.001, 0); e1.record(st); ctx.sync()
+        ms = e0.elapsed_time(e1)
+        ctx.find_collinear(0.0, 0)
+        out["extras"]["collinear"] = {"kernel": "k_collinear (count + scan + fill, all views in one launch pair)", "views": scene.num_views, "cells": cells, "ms": ms,
+                                      "cells_per_sec": cells / (ms * 1e-3), "list_entries": entries, "threshold_px": 2.0}
+    except Exception as e:   # noqa
+        out["extras"]["collinear"] = {"error": str(e)[:200]}
+    try:
+        from tests import nvm_util as nu
+        before, after, ptr, res = nu.load_opt_pairs()
+        cams, shift = nu.optimizer_inputs(nu.load_inputs())
+        rep = 40
+        p = np.tile(before + np.tile(shift, 2), (rep, 1))
+        pp = np.concatenate([[0], np.cumsum(np.tile(np.diff(ptr), rep))])
+        cam = np.tile(res[:, 0].astype(np.int32), rep); xy = np.tile(res[:, 2:6], (rep, 1))
+        for _ in range(2):
+            t0 = time.time(); _, _, summ = ctx.optimize_lines(p, pp, cam, xy, cams, 250); wall = time.time() - t0
+        out["extras"]["bundling"] = {"kernel": "l3d_optimize_lines (Ceres-equivalent LM, all lines per launch)", "lines": len(p), "residuals": len(cam),
+                                     "ms_wall_incl_copies": wall * 1e3, "lm_iterations": int(summ[0]), "kernels": int(summ[7]),
+                                     "cost_before": summ[1], "cost_after": summ[2],
+                                     "input": "the reference's own result clusters (testdata/Line3D++_ref), replicated x40"}
+    except Exception as e:   # noqa
+        out["extras"]["bundling"] = {"error": str(e)[:200]}
     return out
 
 
