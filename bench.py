@@ -437,7 +437,7 @@ def roofline_legs(ctx, st, scene, torch):
     # the two optional stages around the path, timed once each; not part of `value`
     out["extras"] = {}
     try:
-        cells = float(sum(len(sg) ** 2 for sg in scene.segs))
+        cells = float(scene.num_views) * SEGS_PER_VIEW * SEGS_PER_VIEW      # every view of the context (remote shards included)
         ctx.find_collinear(2.0, 0); ctx.find_collinear(0.0, 0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st); entries = ctx.find_collinear(2.001, 0); e1.record(st); ctx.sync()
