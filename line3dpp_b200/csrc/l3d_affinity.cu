@@ -315,6 +315,9 @@ k_rdd_plan(long long nnz, const int* __restrict__ prow, const int* __restrict__ 
 // one whole 32-byte sector per lane and instruction (LDG.E.256, new on sm_100): with divergent addresses the L1 looks up
 // about one sector per cycle and SM, so two 16-byte loads of the same sector cost twice as much as one 32-byte load -
 // the first float4 version of this kernel sat at 80 % L1 throughput for exactly that reason
+#ifndef RDD_MINB
+#define RDD_MINB 5
+#endif
 struct __align__(32) F8 { float v[8]; };
 __device__ __forceinline__ F8 ld256(const float* p)
 {
@@ -323,7 +326,7 @@ __device__ __forceinline__ F8 ld256(const float* p)
                  : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
     return r;
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RDD_MINB)
 k_rdd_step8(long long nnz, const int4* __restrict__ plan, const int* __restrict__ dst, const float* __restrict__ Pp, const float* __restrict__ Wp,
             float* __restrict__ Pnp)
 {
@@ -363,27 +366,29 @@ k_rdd_step8(long long nnz, const int4* __restrict__ plan, const int* __restrict_
 __global__ void __launch_bounds__(256)
 k_rdd_normalize_q(int n, const int* __restrict__ rowptr, const int* __restrict__ rp4, float* __restrict__ Pp)
 {
-    const int gl = threadIdx.x & 3;
+    // control flow is kept warp-uniform (trip count = the longest of the warp's 8 rows, no early exit) so that the shuffles can
+    // name the full warp: sub-warp masks compile to a WARPSYNC / collective sequence per shuffle, which made the first version
+    // of this kernel instruction-bound
+    const int lane = threadIdx.x & 31, gl = lane & 3, g0 = lane & ~3;
     const long long r = ((long long)blockIdx.x * 256 + threadIdx.x) >> 2;
-    const unsigned int gmask = 0xFu << ((threadIdx.x & 31) & ~3);
-    if (r >= n) return;
-    const int len = rowptr[r + 1] - rowptr[r];
-    if (len == 0) return;
-    float4* row = reinterpret_cast<float4*>(Pp) + rp4[r];
+    const int len = r < n ? rowptr[r + 1] - rowptr[r] : 0;
     const int n4 = 2 * ((len + 7) >> 3);                 // float4 per padded row (k_rdd_len4)
+    float4* row = reinterpret_cast<float4*>(Pp) + (r < n ? rp4[r] : 0);
+    const int n4max = __reduce_max_sync(0xffffffffu, n4);
     float sum = 0.0f;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c0 = 0; c0 < n4; c0 += 4) {
-        v = c0 + gl < n4 ? row[c0 + gl] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);         // this lane's float4 of the first chunk (rows of <= 16 values are done from it)
+    for (int c0 = 0; c0 < n4max; c0 += 4) {
+        const float4 v = c0 + gl < n4 ? row[c0 + gl] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 == 0) v0 = v;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float s = sum;
-            if (gl == j) { s += v.x; s += v.y; s += v.z; s += v.w; }
-            sum = __shfl_sync(gmask, s, j, 4);
+            float t = sum; t += v.x; t += v.y; t += v.z; t += v.w;          // what lane j of the group contributes, in slot order
+            sum = __shfl_sync(0xffffffffu, t, g0 + j);
         }
     }
+    if (len == 0) return;
     if (sum < L3D_EPS_F) sum = L3D_EPS_F;
-    if (n4 <= 4) { if (gl < n4) { v.x /= sum; v.y /= sum; v.z /= sum; v.w /= sum; row[gl] = v; } }
+    if (n4 <= 4) { if (gl < n4) { v0.x /= sum; v0.y /= sum; v0.z /= sum; v0.w /= sum; row[gl] = v0; } }
     else for (int c = gl; c < n4; c += 4) { float4 w = row[c]; w.x /= sum; w.y /= sum; w.z /= sum; w.w /= sum; row[c] = w; }
 }
 
