@@ -229,39 +229,7 @@ k_rdd_tslot(long long nnz, const int* __restrict__ prow, const int* __restrict__
     while (lo < hi) { int mid = (lo + hi) >> 1; if (pcol[mid] < a) lo = mid + 1; else hi = mid; }
     tslot[y] = (lo < end && pcol[lo] == a) ? lo : -1;
 }
-// K_sparseMat_row_normalization (cudawrapper.cu:432-477): sequential sum in slot order, clamp, divide
-__global__ void __launch_bounds__(128)
-k_rdd_normalize(int n, const int* __restrict__ rowptr, float* __restrict__ val)
-{
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const int s = rowptr[r], e = rowptr[r + 1];
-    if (s == e) return;
-    float sum = 0.0f;
-    for (int i = s; i < e; ++i) sum += val[i];
-    if (sum < L3D_EPS_F) sum = L3D_EPS_F;
-    for (int i = s; i < e; ++i) val[i] /= sum;
-}
-// K_sparseMat_diffusion_step (cudawrapper.cu:480-544): entry y = (a,b) of P produces P'(b,a) = max(eps, P(a,b) * sum_k P.row(b)[k] * W.col(a)[k])
-__global__ void __launch_bounds__(256)
-k_rdd_step(long long nnz, const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ rowptr,
-           const int* __restrict__ colptr, const float* __restrict__ P, const float* __restrict__ W,
-           const int* __restrict__ tslot, float* __restrict__ Pn)
-{
-    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= nnz) return;
-    const int c = prow[y], r = pcol[y];                 // "transpose" (cudawrapper.cu:493-495)
-    int sp = rowptr[r], sw = colptr[c];
-    const int ep = rowptr[r + 1], ew = colptr[c + 1];
-    float mul = 0.0f;
-    while (sp < ep && sw < ew) { mul += P[sp] * W[sw]; ++sp; ++sw; }
-    mul *= P[y];
-    if (mul < L3D_EPS_F) mul = L3D_EPS_F;
-    const int t = tslot[y];
-    if (t >= 0) Pn[t] = mul;
-}
-
-// ---- 16-byte-aligned rows --------------------------------------------------------------------------------------------
+// ---- sector-aligned rows ----------------------------------------------------------------------------------------------
 // The lock-step walk reads a run of P.row(r) and a run of W.col(c) per entry.  With 4-byte loads every thread of a warp
 // touches a different 128-byte line on every step (one L1 wavefront per thread and step: the first version was bound by
 // exactly that).  Values are therefore kept in PADDED arrays whose rows/columns start on 32-byte boundaries (rp4/cp4 =
