@@ -818,6 +818,25 @@ int l3dpp_set_shard(void* h, int rank, int world, Line3D::MatchExchangeFn fn, vo
 { Line3D* L = (Line3D*)h; L->setShard(rank, world, fn, user); return L->lastError()[0] ? -1 : 0; }
 int l3dpp_stats(void* h, Line3DStats* out) { *out = ((Line3D*)h)->stats(); return 0; }
 int l3dpp_view_index(void* h, unsigned int cam) { auto& m = ((Line3D*)h)->impl()->index_of; auto it = m.find(cam); return it == m.end() ? -1 : it->second; }
+// test hook for the cluster -> 3D segment tail: findCollinearSegments(cluster) (line3D.cc:2342-2452) on an explicit cluster
+// (line end points + (camID, segID) residuals of views added with addImage).  Returns the number of 3D segments.
+int l3dpp_collinear_from_cluster(void* h, const double* p1p2, int nres, const unsigned int* cams, const unsigned int* segs, double* out6, int cap)
+{
+    Line3D::Impl& P = *((Line3D*)h)->impl();
+    if (P.vlist.size() != P.views.size()) {                       // views are indexed at the start of matchImages: do it here too
+        P.vlist.clear(); P.index_of.clear();
+        for (auto& kv : P.views) { P.index_of[kv.first] = (int)P.vlist.size(); P.vlist.push_back(&kv.second); }
+    }
+    std::list<Segment2D> res;
+    for (int i = 0; i < nres; ++i) res.push_back(Segment2D(cams[i], segs[i]));
+    const LineCluster3D cl(Segment3D(Vector3d(p1p2[0], p1p2[1], p1p2[2]), Vector3d(p1p2[3], p1p2[4], p1p2[5])), res, nres ? cams[0] : 0);
+    int n = 0;
+    for (const Segment3D& sg : P.collinear_segments(cl)) {
+        if (n < cap) { double* o = out6 + 6 * n; o[0] = sg.P1().x; o[1] = sg.P1().y; o[2] = sg.P1().z; o[3] = sg.P2().x; o[4] = sg.P2().y; o[5] = sg.P2().z; }
+        ++n;
+    }
+    return n;
+}
 int l3dpp_view_info(void* h, unsigned int cam, float* k, float* md)
 { auto& v = ((Line3D*)h)->impl()->views; auto it = v.find(cam); if (it == v.end()) return -1; *k = it->second.k; *md = it->second.median_depth; return 0; }
 int l3dpp_get_pairs(void* h, int* out, int cap)   // (src cam, tgt cam) in match order

@@ -1732,6 +1732,20 @@ long long orc_get_collinear(orc_ctx* c, uint32_t cam, long long* row_ptr, int* i
     if (row_ptr) row_ptr[v->lines.size()] = n;
     return n;
 }
+// findCollinearSegments(cluster) (line3D.cc:2342-2452) on an explicit cluster: end points of the cluster line + (camID, segID)
+// residuals of views added with orc_add_view.  Returns the number of 3D segments (out6: 6 doubles each).
+int orc_collinear_from_cluster(orc_ctx* c, const double* p1p2, int nres, const uint32_t* cams, const uint32_t* segs, double* out6, int cap)
+{
+    FinalLine cl;
+    cl.cluster_seg = Seg3D(V(p1p2[0], p1p2[1], p1p2[2]), V(p1p2[3], p1p2[4], p1p2[5]));
+    for (int i = 0; i < nres; ++i) { Seg2D s = {cams[i], segs[i]}; cl.residuals.push_back(s); }
+    cl.reference_view = nres ? cams[0] : 0;
+    std::list<Seg3D> col = find_collinear_segments(c, cl);
+    int n = 0;
+    for (std::list<Seg3D>::const_iterator it = col.begin(); it != col.end(); ++it, ++n)
+        if (n < cap) { double* o = out6 + 6 * n; o[0] = it->P1.x; o[1] = it->P1.y; o[2] = it->P1.z; o[3] = it->P2.x; o[4] = it->P2.y; o[5] = it->P2.z; }
+    return n;
+}
 int orc_num_lines(orc_ctx* c) { return (int)c->lines3D.size(); }
 long long orc_get_segments3d(orc_ctx* c, orc_seg3d_t* out, long long cap)
 {

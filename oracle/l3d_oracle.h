@@ -93,6 +93,8 @@ long long orc_get_affinity(orc_ctx*, int* ei, int* ej, float* ew, long long cap)
 long long orc_get_affinity_raw(orc_ctx*, int* ei, int* ej, float* ew, long long cap); /* A_ before diffusion */
 int orc_get_local2global(orc_ctx*, uint32_t* cam_seg /*2 per id*/, int cap);
 long long orc_get_collinear(orc_ctx*, uint32_t cam, long long* row_ptr, int* idx, long long cap); /* View::collin_ as CSR */
+/* findCollinearSegments(cluster) (line3D.cc:2342-2452) on an explicit cluster of views added with orc_add_view */
+int orc_collinear_from_cluster(orc_ctx*, const double* p1p2, int nres, const uint32_t* cams, const uint32_t* segs, double* out6, int cap);
 int orc_num_lines(orc_ctx*);
 long long orc_get_segments3d(orc_ctx*, orc_seg3d_t* out, long long cap);
 long long orc_get_residuals(orc_ctx*, orc_residual_t* out, long long cap);

@@ -77,3 +77,50 @@ def dist_points_to_lines(P, L):
 def line_gap(A, B):
     """max distance of the two end points of A[i] to the infinite line B[i]"""
     return np.maximum(dist_points_to_lines(A[:, :3], B), dist_points_to_lines(A[:, 3:], B))
+
+
+def fixture_clusters():
+    """the reference's own result file as known-answer vectors for the cluster -> 3D segment tail (findCollinearSegments,
+    line3D.cc:2342-2452): per final line the infinite line through its 3D segments, its residuals (camera, per-camera segment
+    index into `cam_segs`) and the expected 3D segments.  Returns (cam_segs, clusters)."""
+    inp = load_inputs()
+    segs3d, seg_line, res = load_fixture()
+    cam_segs = [[] for _ in range(inp["V"])]
+    seg_id = {}
+    for r in res:
+        key = (int(r[1]), int(r[2]))
+        if key not in seg_id:
+            seg_id[key] = len(cam_segs[key[0]])
+            cam_segs[key[0]].append(r[3:7])
+    cam_segs = [np.array(c, np.float32) if c else np.zeros((1, 4), np.float32) for c in cam_segs]
+    clusters = []
+    order = np.argsort(res[:, 0], kind="stable")
+    bounds = np.searchsorted(res[order, 0], np.arange(int(res[:, 0].max()) + 2))
+    for ln in sorted(set(seg_line.tolist())):
+        S = segs3d[seg_line == ln]
+        pts = np.concatenate([S[:, :3], S[:, 3:]])
+        c = pts.mean(0)
+        d = np.linalg.svd(pts - c)[2][0]
+        t = (pts - c) @ d
+        rr = res[order[bounds[ln]:bounds[ln + 1]]]
+        clusters.append(dict(p1p2=np.concatenate([c + d * t.min(), c + d * t.max()]), cams=rr[:, 1].astype(np.uint32),
+                             segs=np.array([seg_id[(int(a), int(b))] for a, b in rr[:, 1:3]], np.uint32), expect=S))
+    return cam_segs, clusters
+
+
+def check_fixture_segments(run, clusters):
+    """run(cluster) -> (n,6) 3D segments; every segment of the reference output must be reproduced (text rounding ~5e-6)"""
+    total = matched = extra = 0
+    worst = 0.0
+    for cl in clusters:
+        mine = run(cl)
+        for s in cl["expect"]:
+            total += 1
+            if len(mine) == 0:
+                continue
+            e = np.minimum(np.abs(mine - s).max(1), np.abs(mine - np.r_[s[3:], s[:3]]).max(1)).min()
+            if e < 5e-5:
+                matched += 1
+                worst = max(worst, e)
+        extra += max(0, len(mine) - len(cl["expect"]))
+    return total, matched, extra, worst

@@ -323,6 +323,31 @@ def test_oracle_pipeline_with_bundling(oracle, use_gpu):
             assert sm[3] == 0 and sm[2] < sm[1] and sm[5] > 100
     assert abs(d[True][0] - d[False][0]) <= 2 and d[True][1] < d[False][1]          # closer to the ground-truth lines
 
+
+# ---------------------------------------------------------------------------------------------- cluster -> 3D segments
+def test_oracle_cluster_tail_reproduces_the_reference_result_file(oracle):
+    """findCollinearSegments(cluster) + project2DsegmentOnto3Dline (line3D.cc:2221-2266, 2342-2452) on the reference's OWN
+    clusters: from the line and the 2D residuals listed in testdata/Line3D++_ref/*.txt the oracle rebuilds every one of the
+    2501 3D segments of that file (end points to the text rounding); the few extra segments are the tiny ones the
+    reference removes afterwards (filterTinySegments needs the cluster's reference view, which the file does not record)."""
+    from tests import nvm_util as nu
+    inp = nu.load_inputs()
+    cam_segs, clusters = nu.fixture_clusters()
+    P = oracle.OraclePipeline(True, 1)
+    for i in range(inp["V"]):
+        w, h = inp["wh"][i]
+        assert P.add_view(i, int(w), int(h), inp["K"][i], inp["R"][i], inp["t"][i], inp["median_depth"][i], inp["wps"][i], cam_segs[i]) == 0
+    out = np.zeros((64, 6))
+    L = oracle.lib()
+
+    def run(cl):
+        n = L.orc_collinear_from_cluster(P.ctx, oracle._p(np.ascontiguousarray(cl["p1p2"])), len(cl["cams"]), oracle._p(cl["cams"]), oracle._p(cl["segs"]),
+                                         oracle._p(out), 64)
+        return out[:n].copy()
+    total, matched, extra, worst = nu.check_fixture_segments(run, clusters)
+    assert total == 2501 and matched == total and worst < 5e-5, (total, matched, worst)
+    assert extra <= 0.02 * total, extra
+
 # ---------------------------------------------------------------------------------------------- product library surface
 def test_capi_library_loads_and_exports_every_declared_symbol():
     from line3dpp_b200 import build

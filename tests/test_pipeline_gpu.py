@@ -209,3 +209,26 @@ def test_nvm_b200_vs_reference_kernels_and_fixture(oracle, ref_nofma):
     assert m1 < 0.005 * depth and m2 < 0.005 * depth, (m1, m2)
     print("nvm on B200:", st)
     L.close()
+
+
+def test_cluster_tail_reproduces_the_reference_result_file():
+    """the host-side cluster -> 3D segment tail of the product (csrc/line3d_host.cc, findCollinearSegments line3D.cc:2342-2452)
+    rebuilds every 3D segment of the reference's own result file from its lines + residuals"""
+    import ctypes as C
+    from tests import nvm_util as nu
+    inp = nu.load_inputs()
+    cam_segs, clusters = nu.fixture_clusters()
+    L = line3d.Line3D(neighbors_by_worldpoints=True, use_gpu=True)
+    for i in range(inp["V"]):
+        w, h = inp["wh"][i]
+        L.add_image(i, int(w), int(h), inp["K"][i], inp["R"][i], inp["t"][i], inp["median_depth"][i], inp["wps"][i], cam_segs[i])
+    out = np.zeros((64, 6))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def run(cl):
+        n = L.L.l3dpp_collinear_from_cluster(L.h, p(np.ascontiguousarray(cl["p1p2"])), len(cl["cams"]), p(cl["cams"]), p(cl["segs"]), p(out), 64)
+        return out[:n].copy()
+    total, matched, extra, worst = nu.check_fixture_segments(run, clusters)
+    assert total == 2501 and matched == total and worst < 5e-5, (total, matched, worst)
+    assert extra <= 0.02 * total, extra
+    L.close()
