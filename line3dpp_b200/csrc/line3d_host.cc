@@ -880,5 +880,29 @@ long long l3dpp_get_residuals(void* h, l3dpp_residual* out, long long cap)
         for (const Segment2D& s : *L[i].underlyingCluster_.residuals()) { if (out && n < cap) { out[n].line = (int)i; out[n].cam = s.camID(); out[n].seg = s.segID(); } ++n; }
     return n;
 }
+int l3dpp_save_obj(void* h, const char* folder) { Line3D* L = (Line3D*)h; L->saveResultAsOBJ(folder); return L->lastError()[0] ? -1 : 0; }
+int l3dpp_save_stl(void* h, const char* folder) { Line3D* L = (Line3D*)h; L->saveResultAsSTL(folder); return L->lastError()[0] ? -1 : 0; }
+int l3dpp_output_filename(void* h, char* buf, int cap)
+{ const std::string s = ((Line3D*)h)->createOutputFilename(); if ((int)s.size() + 1 > cap) return -1; memcpy(buf, s.c_str(), s.size() + 1); return (int)s.size(); }
+// test hook for the writers: replace the result by explicit lines (segments: 6 doubles each; residuals: camID, segID of added views)
+int l3dpp_set_lines(void* h, int nlines, const int* nseg, const double* segs6, const int* nres, const unsigned int* res_cam, const unsigned int* res_seg)
+{
+    Line3D::Impl& P = *((Line3D*)h)->impl();
+    std::lock_guard<std::mutex> g(P.mtx);
+    P.lines3D.clear();
+    size_t so = 0, ro = 0;
+    for (int i = 0; i < nlines; ++i) {
+        FinalLine3D f;
+        for (int k = 0; k < nseg[i]; ++k, ++so) {
+            const double* q = segs6 + 6 * so;
+            f.collinear3Dsegments_.push_back(Segment3D(Vector3d(q[0], q[1], q[2]), Vector3d(q[3], q[4], q[5])));
+        }
+        std::list<Segment2D> res;
+        for (int k = 0; k < nres[i]; ++k, ++ro) res.push_back(Segment2D(res_cam[ro], res_seg[ro]));
+        f.underlyingCluster_ = LineCluster3D(f.collinear3Dsegments_.empty() ? Segment3D() : f.collinear3Dsegments_.front(), res, nres[i] ? res.front().camID() : 0);
+        P.lines3D.push_back(f);
+    }
+    return 0;
+}
 int l3dpp_save_txt(void* h, const char* folder) { Line3D* L = (Line3D*)h; L->save3DLinesAsTXT(folder); return L->lastError()[0] ? -1 : 0; }
 }

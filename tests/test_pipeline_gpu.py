@@ -208,6 +208,10 @@ def test_nvm_b200_vs_reference_kernels_and_fixture(oracle, ref_nofma):
     m2, _ = nu.chamfer(nu.sample_points(fx), nu.sample_points(mine))
     assert m1 < 0.005 * depth and m2 < 0.005 * depth, (m1, m2)
     print("nvm on B200:", st)
+    import ctypes as C
+    buf = C.create_string_buffer(512)
+    assert L.L.l3dpp_output_filename(L.h, buf, 512) > 0
+    assert buf.value.decode() == "Line3D++__W_FULL__N_10__sigmaP_2.5__sigmaA_10__epiOverlap_0.25__kNN_10__vis_3"      # the reference's own file name
     L.close()
 
 
@@ -231,4 +235,45 @@ def test_cluster_tail_reproduces_the_reference_result_file():
     total, matched, extra, worst = nu.check_fixture_segments(run, clusters)
     assert total == 2501 and matched == total and worst < 5e-5, (total, matched, worst)
     assert extra <= 0.02 * total, extra
+    L.close()
+
+
+def test_writers_reproduce_the_reference_result_files_byte_for_byte(tmp_path):
+    """save3DLinesAsTXT / saveResultAsOBJ / saveResultAsSTL (line3D.cc:2465-2687) against the reference's own files
+    testdata/Line3D++_ref/*.{txt,obj,stl}: the lines parsed from those files are fed back into L3DPP::Line3D and the three
+    writers must reproduce them byte for byte (SHA-256 committed by tests/golden/make_writer_golden.py); the file name of the
+    nvm configuration is checked in test_nvm_b200_vs_reference_kernels_and_fixture"""
+    import ctypes as C
+    import hashlib
+    import os
+    from tests import nvm_util as nu
+    inp = nu.load_inputs()
+    segs3d, seg_line, res = nu.load_fixture()
+    gold = np.load(os.path.join(nu.G, "ref_writers_v1.npz"))
+    L = line3d.Line3D(neighbors_by_worldpoints=True, use_gpu=True)
+    for i in range(inp["V"]):                           # views whose 2D segments sit at the reference's own segment ids
+        r = res[res[:, 1] == i]
+        lines = np.zeros((int(r[:, 2].max()) + 1 if len(r) else 1, 4), np.float32)
+        lines[r[:, 2].astype(int)] = r[:, 3:7]
+        w, h = inp["wh"][i]
+        L.add_image(i, int(w), int(h), inp["K"][i], inp["R"][i], inp["t"][i], inp["median_depth"][i], inp["wps"][i], lines)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ids = sorted(set(seg_line.tolist()))
+    nseg = np.array([(seg_line == ln).sum() for ln in ids], np.int32)
+    nres = np.array([(res[:, 0] == ln).sum() for ln in ids], np.int32)
+    order = np.argsort(res[:, 0], kind="stable")
+    rc, rs = np.ascontiguousarray(res[order, 1], np.uint32), np.ascontiguousarray(res[order, 2], np.uint32)
+
+    def written(segs, save, ext):
+        assert L.L.l3dpp_set_lines(L.h, len(ids), p(nseg), p(np.ascontiguousarray(segs, np.float64)), p(nres), p(rc), p(rs)) == 0
+        d = tmp_path / ext
+        d.mkdir()
+        assert save(L.h, str(d).encode()) == 0
+        files = os.listdir(d)
+        assert len(files) == 1 and files[0].endswith("." + ext)
+        return hashlib.sha256(open(d / files[0], "rb").read()).hexdigest()
+    assert len(gold["stl_segs"]) == len(segs3d) == nseg.sum()
+    assert written(segs3d, L.L.l3dpp_save_txt, "txt") == str(gold["sha_txt"])
+    assert written(segs3d, L.L.l3dpp_save_obj, "obj") == str(gold["sha_obj"])
+    assert written(gold["stl_segs"], L.L.l3dpp_save_stl, "stl") == str(gold["sha_stl"])
     L.close()
