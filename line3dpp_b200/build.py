@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libl3d_b200.so")
-SOURCES = ["l3d_match.cu", "l3d_capi.cu", "l3d_pipeline.cu", "l3d_affinity.cu", "l3d_collinear.cu", "l3d_optimize.cu", "line3d_host.cc"]
+SOURCES = ["l3d_match.cu", "l3d_capi.cu", "l3d_pipeline.cu", "l3d_affinity.cu", "l3d_collinear.cu", "l3d_optimize.cu", "line3d_host.cc", "line3d_io.cc"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
          "-Xcompiler", "-fPIC,-Wno-deprecated-declarations", "-shared", "-ccbin", "/usr/bin/g++"]

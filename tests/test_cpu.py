@@ -348,6 +348,90 @@ def test_oracle_cluster_tail_reproduces_the_reference_result_file(oracle):
     assert total == 2501 and matched == total and worst < 5e-5, (total, matched, worst)
     assert extra <= 0.02 * total, extra
 
+
+# ---------------------------------------------------------------------------------------------- .nvm input format
+def _read_nvm_product(path):
+    from line3dpp_b200 import build
+    L = ctypes.CDLL(build.build())
+    L.l3dpp_nvm_open.restype = ctypes.c_void_p
+    err = ctypes.create_string_buffer(256)
+    h = L.l3dpp_nvm_open(str(path).encode(), err, 256)
+    if not h:
+        return None, err.value.decode()
+    h = ctypes.c_void_p(h)
+    cams = []
+    for i in range(L.l3dpp_nvm_num_cameras(h)):
+        R, t, Cc = np.zeros(9), np.zeros(3), np.zeros(3)
+        f, d, md, nw = ctypes.c_float(), ctypes.c_float(), ctypes.c_float(), ctypes.c_int()
+        name = ctypes.create_string_buffer(512)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        assert L.l3dpp_nvm_camera(h, i, p(R), p(t), p(Cc), ctypes.byref(f), ctypes.byref(d), ctypes.byref(md), ctypes.byref(nw), name, 512) == 0
+        w = np.zeros(max(nw.value, 1), np.uint32)
+        assert L.l3dpp_nvm_worldpoints(h, i, p(w), nw.value) == nw.value
+        cams.append(dict(R=R.reshape(3, 3), t=t, C=Cc, f=f.value, dist=d.value, md=md.value, wps=w[:nw.value], name=name.value.decode()))
+    L.l3dpp_nvm_close(h)
+    return cams, ""
+
+
+def test_nvm_reader_round_trip(tmp_path):
+    """L3DPP::readNVM (include/line3d_io.h; restates main_vsfm.cpp:143-310) on a synthetic NVM_V3 model"""
+    rng = np.random.default_rng(3)
+    V, NP = 5, 40
+    q = rng.normal(size=(V, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    Cc = rng.uniform(-3, 3, (V, 3)); f = rng.uniform(800, 2500, V); d = np.array([0, 0.01, 0, -0.02, 0])
+    pts = rng.uniform(-1, 1, (NP, 3))
+    vis = [sorted(rng.choice(V, size=rng.integers(2, V + 1), replace=False).tolist()) for _ in range(NP)]
+    lines = ["NVM_V3", "", str(V)]
+    for i in range(V):
+        lines.append(f"dir/img{i}.jpg\t{f[i]:.10f} {q[i,0]:.12f} {q[i,1]:.12f} {q[i,2]:.12f} {q[i,3]:.12f} {Cc[i,0]:.12f} {Cc[i,1]:.12f} {Cc[i,2]:.12f} {d[i]:.6f} 0")
+    lines += ["", str(NP)]
+    for j in range(NP):
+        meas = " ".join(f"{c} {7 * j + c} {10.5 + c} {-3.25 + j}" for c in vis[j])
+        lines.append(f"{pts[j,0]:.12f} {pts[j,1]:.12f} {pts[j,2]:.12f} 255 128 0 {len(vis[j])} {meas}")
+    path = tmp_path / "model.nvm"
+    path.write_text("\n".join(lines) + "\n0\n")
+    cams, err = _read_nvm_product(path)
+    assert cams is not None, err
+    assert len(cams) == V
+    for i, c in enumerate(cams):
+        qw, qx, qy, qz = [float(f"{v:.12f}") for v in q[i]]
+        R = np.array([[1 - 2 * qy * qy - 2 * qz * qz, 2 * qx * qy - 2 * qz * qw, 2 * qx * qz + 2 * qy * qw],
+                      [2 * qx * qy + 2 * qz * qw, 1 - 2 * qx * qx - 2 * qz * qz, 2 * qy * qz - 2 * qx * qw],
+                      [2 * qx * qz - 2 * qy * qw, 2 * qy * qz + 2 * qx * qw, 1 - 2 * qx * qx - 2 * qy * qy]])
+        Ci = np.array([float(f"{v:.12f}") for v in Cc[i]])
+        np.testing.assert_allclose(c["R"], R, atol=1e-14)
+        np.testing.assert_allclose(c["t"], -R @ Ci, atol=1e-13)
+        assert c["name"] == f"dir/img{i}.jpg" and abs(c["f"] - np.float32(f[i])) < 1e-3 and abs(c["dist"] - d[i]) < 1e-7
+        mine = [j for j in range(NP) if i in vis[j]]
+        assert c["wps"].tolist() == mine
+        dep = np.sort(np.array([np.float32(np.linalg.norm(np.array([float(f"{v:.12f}") for v in pts[j]]) - Ci)) for j in mine], np.float32))
+        assert c["md"] == (dep[len(dep) // 2] if len(dep) else 0.0)
+    bad, err = _read_nvm_product(tmp_path / "missing.nvm")
+    assert bad is None and "cannot open" in err
+    (tmp_path / "empty.nvm").write_text("NVM_V3\n\n0\n")
+    bad, err = _read_nvm_product(tmp_path / "empty.nvm")
+    assert bad is None and "No aligned cameras" in err
+
+
+def test_nvm_reader_on_the_reference_test_data():
+    """readNVM on the reference's own testdata/vsfm_result.nvm equals the committed inputs of the nvm configuration"""
+    path = "/root/reference/testdata/vsfm_result.nvm"
+    if not os.path.exists(path):
+        pytest.skip("reference test data only exists in the build container")
+    from tests import nvm_util as nu
+    inp = nu.load_inputs()
+    cams, err = _read_nvm_product(path)
+    assert cams is not None and len(cams) == inp["V"], err
+    from line3dpp_b200 import build
+    L = ctypes.CDLL(build.build())
+    for i, c in enumerate(cams):
+        np.testing.assert_allclose(c["R"], inp["R"][i], atol=1e-15)
+        np.testing.assert_allclose(c["t"], inp["t"][i], atol=1e-13)
+        assert c["md"] == inp["median_depth"][i] and np.array_equal(c["wps"], inp["wps"][i])
+        K = np.zeros(9)
+        L.l3dpp_intrinsics_from_focal(ctypes.c_float(c["f"]), int(inp["wh"][i][0]), int(inp["wh"][i][1]), K.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(K.reshape(3, 3), inp["K"][i])
+
 # ---------------------------------------------------------------------------------------------- product library surface
 def test_capi_library_loads_and_exports_every_declared_symbol():
     from line3dpp_b200 import build
