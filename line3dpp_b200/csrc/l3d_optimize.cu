@@ -30,7 +30,6 @@ struct Jet4 { double a; double v[4]; };
 __device__ __forceinline__ Jet4 J(double a) { Jet4 r; r.a = a; r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.0; return r; }
 __device__ __forceinline__ Jet4 operator+(const Jet4& x, const Jet4& y) { Jet4 r; r.a = x.a + y.a; for (int i = 0; i < 4; ++i) r.v[i] = x.v[i] + y.v[i]; return r; }
 __device__ __forceinline__ Jet4 operator-(const Jet4& x, const Jet4& y) { Jet4 r; r.a = x.a - y.a; for (int i = 0; i < 4; ++i) r.v[i] = x.v[i] - y.v[i]; return r; }
-__device__ __forceinline__ Jet4 operator-(const Jet4& x) { Jet4 r; r.a = -x.a; for (int i = 0; i < 4; ++i) r.v[i] = -x.v[i]; return r; }
 __device__ __forceinline__ Jet4 operator*(const Jet4& x, const Jet4& y) { Jet4 r; r.a = x.a * y.a; for (int i = 0; i < 4; ++i) r.v[i] = x.a * y.v[i] + x.v[i] * y.a; return r; }
 __device__ __forceinline__ Jet4 operator*(double s, const Jet4& x) { Jet4 r; r.a = s * x.a; for (int i = 0; i < 4; ++i) r.v[i] = s * x.v[i]; return r; }
 __device__ __forceinline__ Jet4 operator*(const Jet4& x, double s) { return s * x; }
