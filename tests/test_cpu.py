@@ -446,6 +446,28 @@ def test_capi_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, n)
 
 
+def test_cpp_frontend_compiles_against_the_public_headers(tmp_path):
+    """the drop-in boundary is plain C++: examples/vsfm_frontend.cpp (the reference's main_vsfm.cpp flow on include/line3d.h +
+    include/line3d_io.h) must compile warning-free with g++ alone, link against the in-tree library and - without a GPU - fail
+    loudly instead of computing on the CPU"""
+    from line3dpp_b200 import build
+    so = build.build()
+    exe = tmp_path / "vsfm_frontend"
+    cmd = ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", "vsfm_frontend.cpp"), "-I" + os.path.join(ROOT, "include"),
+           "-L" + os.path.dirname(so), "-ll3d_b200", "-Wl,-rpath," + os.path.dirname(so), "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    nvm = tmp_path / "m.nvm"
+    nvm.write_text("NVM_V3\n\n1\nimg0.jpg 1000 1 0 0 0 0 0 0 0 0\n\n1\n0 0 5 255 255 255 1 0 0 1.0 2.0\n")
+    r = subprocess.run([str(exe), str(nvm), str(tmp_path), str(tmp_path)], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 1 and "fewer than three usable images" in r.stderr, (r.returncode, r.stderr)
+    else:
+        assert r.returncode == 3 and "no usable CUDA device" in r.stderr, (r.returncode, r.stderr)
+
+
+
 def test_no_cpu_fallback_without_gpu():
     """without a CUDA device the product must fail loudly, not compute on the CPU"""
     import torch
