@@ -282,3 +282,160 @@ def optimize_lines(fn, p1p2, res_ptr, res_cam, res_xy, cams, max_iter=250, handl
     rc = fn(*args) if handle is None else fn(handle, *args)
     assert rc == 0, rc
     return out, valid, summ
+
+
+# ------------------------------------------------------------------------------------------- the reference's whole pipeline, verbatim
+def ref_full_lib(variant: str = "cpu"):
+    """oracle/_ref/libl3dref_full_{cpu,gpu}.so: /root/reference/line3D.cc + view.cc (+ the accelerator files) compiled verbatim
+    against oracle/ref_shim (oracle/ref_full_harness.cu).  None if it has not been built."""
+    path = os.path.join(HERE, "_ref", f"libl3dref_full_{variant}.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.rfl_create.restype = C.c_void_p
+    for n in ("rfl_get_matches", "rfl_get_scored", "rfl_get_estimates", "rfl_get_affinity", "rfl_get_affinity_raw", "rfl_get_segments3d",
+              "rfl_get_residuals", "rfl_get_collinear"):
+        getattr(L, n).restype = C.c_longlong
+    return L
+
+
+class RefFullPipeline:
+    """The UNMODIFIED L3DPP::Line3D (line3D.cc) behind the same dump interface as OraclePipeline.  variant "cpu": the
+    reference's CPU code path (use_GPU is forced off by line3D.cc:49-53); "gpu": its CUDA code path (needs a GPU)."""
+
+    def __init__(self, neighbors_by_worldpoints=False, use_gpu=False, variant="cpu", folder="/tmp/l3dref_full"):
+        self.L = ref_full_lib(variant)
+        if self.L is None:
+            raise RuntimeError(f"oracle/_ref/libl3dref_full_{variant}.so not built")
+        os.makedirs(folder, exist_ok=True)
+        self.folder = folder
+        self.ctx = C.c_void_p(self.L.rfl_create((folder.rstrip("/") + "/").encode(), int(neighbors_by_worldpoints), int(use_gpu)))
+
+    def __del__(self):
+        if getattr(self, "ctx", None):
+            self.L.rfl_destroy(self.ctx)
+            self.ctx = None
+
+    def add_view(self, cam, width, height, K, R, t, median_depth, wps_or_neighbors, segs):
+        lst = np.ascontiguousarray(wps_or_neighbors, np.uint32)
+        segs = _f32(segs)
+        return self.L.rfl_add_view(self.ctx, C.c_uint(int(cam)), int(width), int(height), _p(_f64(K)), _p(_f64(R)), _p(_f64(t)),
+                                   C.c_float(float(median_depth)), _p(lst), len(lst), _p(segs), len(segs))
+
+    def add_scene(self, scene):
+        for i in range(scene.num_views):
+            rc = self.add_view(scene.cam_ids[i], scene.width, scene.height, scene.K[i], scene.R[i], scene.t[i], scene.median_depth[i],
+                               scene.neighbors[i], scene.segs[i])
+            assert rc == 0, rc
+
+    def match_images(self, sigma_p=2.5, sigma_a=10.0, num_neighbors=10, epi_overlap=0.25, knn=10, const_reg_depth=-1.0):
+        return self.L.rfl_match_images(self.ctx, C.c_float(sigma_p), C.c_float(sigma_a), C.c_uint(num_neighbors), C.c_float(epi_overlap),
+                                       C.c_int(knn), C.c_float(const_reg_depth))
+
+    def reconstruct(self, visibility_t=3, perform_diffusion=False, collinearity_t=-1.0, use_ceres=False, max_iter_ceres=250):
+        return self.L.rfl_reconstruct_opt(self.ctx, C.c_uint(visibility_t), int(perform_diffusion), C.c_float(collinearity_t), int(use_ceres),
+                                          C.c_uint(max_iter_ceres))
+
+    def pairs(self):
+        n = self.L.rfl_get_pairs(self.ctx, None, 0)
+        a = np.zeros((n, 2), np.int32)
+        self.L.rfl_get_pairs(self.ctx, _p(a), n)
+        return a
+
+    def fundamental(self, src, tgt):
+        F = np.zeros((3, 3))
+        assert self.L.rfl_get_fundamental(self.ctx, C.c_uint(int(src)), C.c_uint(int(tgt)), _p(F)) == 0
+        return F
+
+    def neighbors(self, cam):
+        a = np.zeros(4096, np.uint32)
+        n = self.L.rfl_get_neighbors(self.ctx, C.c_uint(int(cam)), _p(a), len(a))
+        return a[:n].copy()
+
+    def _matches(self, fn, cam):
+        n = fn(self.ctx, C.c_uint(int(cam)), None, C.c_longlong(0))
+        a = np.zeros(max(n, 0), MATCH_DT)
+        if n > 0:
+            fn(self.ctx, C.c_uint(int(cam)), _p(a), C.c_longlong(n))
+        return a
+
+    def matches(self, cam):
+        return self._matches(self.L.rfl_get_matches, cam)
+
+    def scored(self, cam):
+        return self._matches(self.L.rfl_get_scored, cam)
+
+    def view_info(self, cam):
+        k, md = C.c_float(0), C.c_float(0)
+        self.L.rfl_get_view_info(self.ctx, C.c_uint(int(cam)), C.byref(k), C.byref(md))
+        return k.value, md.value
+
+    def view_geometry(self, cam):
+        M, Cc = np.zeros((3, 3)), np.zeros(3)
+        self.L.rfl_get_view_geometry(self.ctx, C.c_uint(int(cam)), _p(M), _p(Cc))
+        return M, Cc
+
+    def estimates(self):
+        n = self.L.rfl_get_estimates(self.ctx, None, None, C.c_longlong(0))
+        best, p = np.zeros(n, MATCH_DT), np.zeros((n, 6), np.float64)
+        if n:
+            self.L.rfl_get_estimates(self.ctx, _p(best), _p(p), C.c_longlong(n))
+        return best, p
+
+    def _edges(self, fn):
+        n = fn(self.ctx, None, None, None, C.c_longlong(0))
+        ei, ej, ew = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float32)
+        if n:
+            fn(self.ctx, _p(ei), _p(ej), _p(ew), C.c_longlong(n))
+        return ei, ej, ew
+
+    def affinity(self):
+        return self._edges(self.L.rfl_get_affinity)
+
+    def affinity_raw(self):
+        return self._edges(self.L.rfl_get_affinity_raw)
+
+    def local2global(self):
+        n = self.L.rfl_get_local2global(self.ctx, None, 0)
+        a = np.zeros((n, 2), np.uint32)
+        if n:
+            self.L.rfl_get_local2global(self.ctx, _p(a), n)
+        return a
+
+    def clusters(self):
+        n = self.L.rfl_get_clusters(self.ctx, None, None, None, 0)
+        p, nr, rv = np.zeros((n, 6)), np.zeros(n, np.int32), np.zeros(n, np.uint32)
+        if n:
+            self.L.rfl_get_clusters(self.ctx, _p(p), _p(nr), _p(rv), n)
+        return p, nr, rv
+
+    def collinear(self, cam, nseg):
+        row_ptr = np.zeros(nseg + 1, np.int64)
+        n = self.L.rfl_get_collinear(self.ctx, C.c_uint(int(cam)), _p(row_ptr), None, C.c_longlong(0))
+        idx = np.zeros(max(int(n), 1), np.int32)
+        if n > 0:
+            self.L.rfl_get_collinear(self.ctx, C.c_uint(int(cam)), _p(row_ptr), _p(idx), C.c_longlong(int(n)))
+        return row_ptr, idx[:max(int(n), 0)]
+
+    def num_lines(self):
+        return self.L.rfl_num_lines(self.ctx)
+
+    def segments3d(self):
+        n = self.L.rfl_get_segments3d(self.ctx, None, C.c_longlong(0))
+        a = np.zeros(n, SEG3D_DT)
+        if n:
+            self.L.rfl_get_segments3d(self.ctx, _p(a), C.c_longlong(n))
+        return a
+
+    def residuals(self):
+        n = self.L.rfl_get_residuals(self.ctx, None, C.c_longlong(0))
+        a = np.zeros(n, RESID_DT)
+        if n:
+            self.L.rfl_get_residuals(self.ctx, _p(a), C.c_longlong(n))
+        return a
+
+    def save(self, folder, txt=True, obj=False, stl=False):
+        """the reference's own writers; returns createOutputFilename()"""
+        buf = C.create_string_buffer(512)
+        self.L.rfl_save(self.ctx, folder.encode(), int(txt), int(obj), int(stl), buf, 512)
+        return buf.value.decode()
