@@ -9,6 +9,7 @@
 //                       so the result is bit-identical to the reference kernels; the linear search for the transposed
 //                       slot (cudawrapper.cu:524-542) is replaced by a precomputed permutation.
 #include "l3d_ctx.cuh"
+#include "l3d_sweep.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -77,27 +78,34 @@ __device__ __forceinline__ float aff_similarity(const L3DViewDev* v1, const L3DV
     return fminf(sim_a, fminf(sim_p1, sim_p2));
 }
 
+// everything a thread needs to read the sweep's match store (l3d_sweep.cuh)
+struct SwStore {
+    const SwView* vt; const L3DPairDev* pairs; const long long* row_off; int num_pairs, knn; const l3d_match_rec* recs;
+    const unsigned int* e_val; const unsigned char* e_flag;
+};
+// depths of the best match of global segment g (its estimate), b = est_best[g]
+__device__ __forceinline__ float4 sw_best_depths(const SwStore& M, int view, int b) { return sw_depths(M.e_val[M.vt[view].region_off + b], M.recs); }
+
 __global__ void __launch_bounds__(256)
 k_affinity(const L3DViewDev* __restrict__ views, const long long* __restrict__ region_off, const int* __restrict__ order,
-           const int* __restrict__ rank_of_view, int V, long long total, const unsigned char* __restrict__ kept,
-           const int4* __restrict__ m_meta, const float4* __restrict__ m_dep, const int* __restrict__ est_best,
+           int V, long long total, const SwStore M, const int* __restrict__ est_best,
            const double* __restrict__ est_P, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity,
            float* __restrict__ sim_out, int* __restrict__ flag_out, long long* __restrict__ gi_out, long long* __restrict__ gj_out)
 {
     const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= total) return;
     int flag = 0; float sim = 0.0f; long long gi = -1, gj = -1;
-    if (kept[x]) {
+    if (M.e_flag[x] & SW_KEPT) {
         int lo = 0, hi = V - 1;                  // processing rank whose region contains x
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (region_off[mid] <= x) lo = mid; else hi = mid - 1; }
         const int v1i = order[lo];
-        const int4 me = m_meta[x];
+        const SwEntry me = sw_decode(M.e_val[x], M.pairs, M.row_off, M.num_pairs, M.knn, M.recs);
         const L3DViewDev* v1 = views + v1i;
-        const L3DViewDev* v2 = views + me.y;
-        gi = v1->seg_off + me.x; gj = v2->seg_off + me.z;
+        const L3DViewDev* v2 = views + me.tgt_view;
+        gi = v1->seg_off + me.seg; gj = v2->seg_off + me.tgt_seg;
         const int b1 = est_best[gi], b2 = est_best[gj];
         if (b1 >= 0 && b2 >= 0) {
-            sim = aff_similarity(v1, v2, est_P + 6 * gi, est_P + 6 * gj, m_dep[region_off[lo] + b1], m_dep[region_off[rank_of_view[me.y]] + b2],
+            sim = aff_similarity(v1, v2, est_P + 6 * gi, est_P + 6 * gj, sw_best_depths(M, v1i, b1), sw_best_depths(M, me.tgt_view, b2),
                                  two_sigA_sqr, med_scene_depth_lines);
             flag = sim > min_affinity ? 1 : 0;
         }
@@ -115,8 +123,7 @@ k_affinity(const L3DViewDev* __restrict__ views, const long long* __restrict__ r
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_aff_events(const L3DViewDev* __restrict__ views, const long long* __restrict__ region_off, const int* __restrict__ order,
-             const int* __restrict__ rank_of_view, const long long* __restrict__ segrank_off, int V, long long N,
-             const unsigned char* __restrict__ kept, const int4* __restrict__ m_meta, const float4* __restrict__ m_dep,
+             const long long* __restrict__ segrank_off, int V, long long N, const SwStore M,
              const int2* __restrict__ ranges, const int* __restrict__ est_best, const double* __restrict__ est_P,
              const float* __restrict__ sim_slot, const int* __restrict__ flag_slot, const long long* __restrict__ cptr,
              const int* __restrict__ cidx, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity, int* __restrict__ evcnt,
@@ -137,23 +144,22 @@ k_aff_events(const L3DViewDev* __restrict__ views, const long long* __restrict__
         const long long ro = region_off[lo];
         const int2 rng = ranges[g];
         const double* P1 = est_P + 6 * g;
-        const float4 m1 = m_dep[ro + b1];
+        const float4 m1 = sw_best_depths(M, v1i, b1);
         bool found = false;
         for (int i = rng.x; i <= rng.y && rng.x >= 0; ++i) {
             const long long x = ro + i;
-            if (!kept[x] || !flag_slot[x]) continue;
-            const int4 me = m_meta[x];
-            const L3DViewDev* v2 = views + me.y;
-            const long long gj = v2->seg_off + me.z;
+            if (!(M.e_flag[x] & SW_KEPT) || !flag_slot[x]) continue;
+            const SwEntry me = sw_decode(M.e_val[x], M.pairs, M.row_off, M.num_pairs, M.knn, M.recs);
+            const L3DViewDev* v2 = views + me.tgt_view;
+            const long long gj = v2->seg_off + me.tgt_seg;
             const long long parent = base + n;
             if (FILL) { out_i[parent] = g; out_j[parent] = gj; out_w[parent] = sim_slot[x]; out_par[parent] = -1; }
             ++n; found = true;
-            const long long ro2 = region_off[rank_of_view[me.y]];
             for (long long q = cptr[gj]; q < cptr[gj + 1]; ++q) {                  // collinear with the target (line3D.cc:1904-1937)
                 const long long g2 = v2->seg_off + cidx[q];
                 const int b2 = est_best[g2];
                 if (b2 < 0) continue;
-                const float s2 = aff_similarity(v1, v2, P1, est_P + 6 * g2, m1, m_dep[ro2 + b2], two_sigA_sqr, med_scene_depth_lines);
+                const float s2 = aff_similarity(v1, v2, P1, est_P + 6 * g2, m1, sw_best_depths(M, me.tgt_view, b2), two_sigA_sqr, med_scene_depth_lines);
                 if (s2 > min_affinity) {
                     if (FILL) { out_i[base + n] = g; out_j[base + n] = g2; out_w[base + n] = s2; out_par[base + n] = (int)parent; }
                     ++n;
@@ -165,7 +171,7 @@ k_aff_events(const L3DViewDev* __restrict__ views, const long long* __restrict__
                 const long long g2 = v1->seg_off + cidx[q];
                 const int b2 = est_best[g2];
                 if (b2 < 0) continue;
-                const float s2 = aff_similarity(v1, v1, P1, est_P + 6 * g2, m1, m_dep[ro + b2], two_sigA_sqr, med_scene_depth_lines);
+                const float s2 = aff_similarity(v1, v1, P1, est_P + 6 * g2, m1, sw_best_depths(M, v1i, b2), two_sigA_sqr, med_scene_depth_lines);
                 if (s2 > min_affinity) {
                     if (FILL) { out_i[base + n] = g; out_j[base + n] = g2; out_w[base + n] = s2; out_par[base + n] = -2; }
                     ++n;
@@ -479,8 +485,10 @@ static long long affinity_candidates(l3d_ctx* c, float two_sigA_sqr, float med_s
     L3D_CUDA(c, cudaMemcpyAsync(S.d_rankofview.p, rank_of_view.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "rank of view");
     L3D_CUDA(c, cudaMemcpyAsync(S.d_region_off.p, S.region_off.data(), 8 * (size_t)(V + 1), cudaMemcpyHostToDevice, st), "region offsets");
     const unsigned int nb = (unsigned int)((total + 255) / 256);
-    k_affinity<<<nb, 256, 0, st>>>(c->views(), (const long long*)S.d_region_off.p, (const int*)S.d_order.p, (const int*)S.d_rankofview.p, V, total,
-                                   (const unsigned char*)S.d_kept.p, (const int4*)S.d_meta.p, (const float4*)S.d_dep.p, (const int*)S.d_est_best.p,
+    SwStore M;
+    M.vt = (const SwView*)S.d_vt.p; M.pairs = (const L3DPairDev*)c->d_pairs.p; M.row_off = (const long long*)S.d_rowoff.p; M.num_pairs = c->num_pairs; M.knn = c->knn;
+    M.recs = (const l3d_match_rec*)c->d_recs.p; M.e_val = (const unsigned int*)S.d_eval.p; M.e_flag = (const unsigned char*)S.d_eflag.p;
+    k_affinity<<<nb, 256, 0, st>>>(c->views(), (const long long*)S.d_region_off.p, (const int*)S.d_order.p, V, total, M, (const int*)S.d_est_best.p,
                                    (const double*)S.d_est_P.p, two_sigA_sqr, med_scene_depth_lines, min_affinity, (float*)d_sim.p, (int*)d_flag.p,
                                    (long long*)d_gi.p, (long long*)d_gj.p);
     if (c->collin.valid) {
@@ -495,8 +503,8 @@ static long long affinity_candidates(l3d_ctx* c, float two_sigA_sqr, float med_s
         L3D_CUDA(c, cudaMemcpyAsync(S.d_segrank_off.p, segrank_off.data(), 8 * ((size_t)V + 1), cudaMemcpyHostToDevice, st), "segment rank offsets");
         L3D_CUDA(c, cudaMemsetAsync(S.d_evcnt.p, 0, 4 * (size_t)(N + 1), st), "event counts");
         const unsigned int nbs = (unsigned int)((N + 127) / 128);
-#define EV_ARGS c->views(), (const long long*)S.d_region_off.p, (const int*)S.d_order.p, (const int*)S.d_rankofview.p, (const long long*)S.d_segrank_off.p, V, N, \
-                (const unsigned char*)S.d_kept.p, (const int4*)S.d_meta.p, (const float4*)S.d_dep.p, (const int2*)S.d_ranges.p, (const int*)S.d_est_best.p,       \
+#define EV_ARGS c->views(), (const long long*)S.d_region_off.p, (const int*)S.d_order.p, (const long long*)S.d_segrank_off.p, V, N, M,                      \
+                (const int2*)S.d_ranges.p, (const int*)S.d_est_best.p,                                                                                        \
                 (const double*)S.d_est_P.p, (const float*)d_sim.p, (const int*)d_flag.p, (const long long*)K.d_ptr.p, (const int*)K.d_idx.p, two_sigA_sqr,          \
                 med_scene_depth_lines, min_affinity
         k_aff_events<false><<<nbs, 128, 0, st>>>(EV_ARGS, (int*)S.d_evcnt.p, nullptr, nullptr, nullptr, nullptr, nullptr);

@@ -11,19 +11,20 @@ struct DevBuf { void* p = nullptr; size_t cap = 0; };   // grow-only device allo
 struct SweepState {
     bool valid = false;
     std::vector<int> order;                 // view indices in processing order (ascending camID)
-    std::vector<int> U, h_M;                // per view: candidate upper bound / number of scored matches (by processing rank for h_M)
-    std::vector<long long> region_off;      // per processing rank: first match slot of the view's region
+    std::vector<int> h_M;                   // per processing rank: number of matches in matches_[view] after scoring (active entries)
+    std::vector<long long> region_off;      // per processing rank (+1): first entry of the view's region
     long long total = 0;
-    DevBuf d_slot_score, d_keys, d_keys2, d_vals, d_vals2, d_reg, d_dir, d_meta, d_dep, d_os, d_kept, d_ranges, d_est_best, d_est_P,
-        d_M, d_vmax, d_work, d_camrank, d_viewofrank, d_sort_tmp, d_aff_sim, d_aff_flag, d_aff_gi, d_aff_gj, d_aff_pos, d_aff_oi, d_aff_oj,
-        d_aff_ow, d_order, d_rankofview, d_region_off, d_reg_of_view, d_est_pos, d_est_out_best, d_est_out_P, d_slot_pos, d_dir64, d_segrank_off, d_evcnt, d_evptr, d_aff_par;
+    // match store (l3d_sweep.cuh): view table, chunk descriptors, chunk offsets, entries
+    DevBuf d_vt, d_vp, d_pairc, d_rowoff, d_rays, d_rflag, d_invpos, d_csize, d_ccur, d_cstart, d_eval, d_escore, d_eflag, d_gstage, d_gpub, d_dir64, d_export, d_export_ok,
+        d_ranges, d_est_best, d_est_P, d_M, d_vmax, d_sort_tmp, d_aff_sim, d_aff_flag, d_aff_gi, d_aff_gj, d_aff_pos, d_aff_oi, d_aff_oj,
+        d_aff_ow, d_order, d_rankofview, d_region_off, d_est_pos, d_est_out_best, d_est_out_P, d_segrank_off, d_evcnt, d_evptr, d_aff_par;
     long long n_est = 0;
     bool aff_has_parents = false;           // d_aff_par valid: candidates carry parents (collinearity links)
     std::vector<DevBuf*> bufs()
-    { return {&d_slot_score, &d_keys, &d_keys2, &d_vals, &d_vals2, &d_reg, &d_dir, &d_meta, &d_dep, &d_os, &d_kept, &d_ranges, &d_est_best,
-              &d_est_P, &d_M, &d_vmax, &d_work, &d_camrank, &d_viewofrank, &d_sort_tmp, &d_aff_sim, &d_aff_flag, &d_aff_gi, &d_aff_gj,
-              &d_aff_pos, &d_aff_oi, &d_aff_oj, &d_aff_ow, &d_order, &d_rankofview, &d_region_off, &d_reg_of_view, &d_est_pos,
-              &d_est_out_best, &d_est_out_P, &d_slot_pos, &d_dir64, &d_segrank_off, &d_evcnt, &d_evptr, &d_aff_par}; }
+    { return {&d_vt, &d_vp, &d_pairc, &d_rowoff, &d_rays, &d_rflag, &d_invpos, &d_csize, &d_ccur, &d_cstart, &d_eval, &d_escore, &d_eflag, &d_gstage, &d_gpub, &d_dir64,
+              &d_export, &d_export_ok, &d_ranges, &d_est_best, &d_est_P, &d_M, &d_vmax, &d_sort_tmp, &d_aff_sim, &d_aff_flag, &d_aff_gi, &d_aff_gj,
+              &d_aff_pos, &d_aff_oi, &d_aff_oj, &d_aff_ow, &d_order, &d_rankofview, &d_region_off, &d_est_pos,
+              &d_est_out_best, &d_est_out_P, &d_segrank_off, &d_evcnt, &d_evptr, &d_aff_par}; }
 };
 
 // device state of the affinity-matrix bookkeeping (l3d_affinity.cu)

@@ -5,17 +5,28 @@
 // line3D.cc:811-858), sorts them by (tgt cam, tgt seg) and flattens them (scoringGPU, 1311-1355), scores them
 // (K_score_matches, cudawrapper.cu:256-367), hands the positively scored ones to the not-yet-processed target views as
 // inverse matches (storeInverseMatches, 1672-1699) and keeps the good ones + the best 3D estimate per segment
-// (filterMatches, 1586-1669).  The order dependence (a view sees the inverse matches of its earlier neighbours) is kept:
-// views are processed sequentially, but every step is a kernel over all matches / segments of the view and nothing
-// returns to the host in between.
+// (filterMatches, 1586-1669).
+//
+// What really depends on the view order is ONE bit per inverse match: "did its source score it > 0".  Everything else is
+// hoisted out of the chain and done for ALL views at once:
+//   k_sw_flags      orientation check of every record from both sides; sizes of the (view, segment, neighbour) chunks
+//   cub scan        chunk offsets = the final list layout of every view (l3d_sweep.cuh)
+//   k_sw_scatter    records -> their chunk(s);  k_sw_chunksort: the (<= kNN-ish) entries of a chunk into list order
+//   ---- chain: ONE launch per view, in camID order --------------------------------------------------------------
+//   k_sw_score      a warp per segment stages the segment's list in shared memory (3D direction, target regulariser,
+//                   depths: what scoringGPU's host pass + K_score_matches' prologue compute), scores every active entry
+//                   against it with K_score_matches' loop, publishes score3D, the view's maximum and - the only thing the
+//                   next views need - the "active" bit of the inverse entries it creates
+//   ---- after the chain, all views at once -----------------------------------------------------------------------
+//   k_sw_filter     filterMatches + the best 3D estimate per segment
 //
 // Arithmetic contract as in l3d_device.cuh (-fmad=false): the float parts repeat K_score_matches operation by
-// operation (same libdevice expf/acosf), the double parts repeat the host code of view.cc / line3D.cc as restated in
-// oracle/l3d_oracle.cc (IEEE double, no contraction).
+// operation (same libdevice expf/acosf), the double parts repeat the host code of view.cc / line3D.cc (IEEE double, no
+// contraction); pinned against the unmodified reference in tests/test_ref_full_gpu.py.
 #include "l3d_ctx.cuh"
 #include "l3d_device_f64.cuh"
+#include "l3d_sweep.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
@@ -43,211 +54,283 @@ __device__ __forceinline__ DSeg dunproject(const L3DViewDev* v, float4 s, float 
     return o;
 }
 
-// sort key of a candidate match: (segment | rank of the target camera | target segment), packed as tightly as the
-// problem allows so that the radix sort touches few bits; bit `end_bit-1` is reserved for "invalid" (all ones)
-// REF_CPU semantics (mode 1): scoringCPU does not sort (only scoringGPU calls sortMatches, line3D.cc:1311), so the list
-// order of a segment is the order the matches were appended: first the inverse matches stored by the earlier views (in
-// those views' processing and list order = their global slot in the match store), then the direct matches in pair / kNN
-// order (= record index).  Key = (segment | direct? | origin index).
-struct KeyBits { int seg_shift, cam_shift, end_bit; unsigned long long cam_mask, tgt_mask; int mode; };
-static int bits_for(long long n) { int b = 1; while ((1ll << b) < n) ++b; return b; }
-
-// ---------------------------------------------------------------------------------------------- kernels
-// G1: enumerate the candidate matches of view v (direct records of pairs with src == v, inverse records of pairs with
-//     tgt == v whose src was processed earlier and scored them > 0), apply the orientation check, emit sort keys.
+// per-segment double rays, computed once per sweep: View::getNormalizedRay (view.cc:317-321) of the two end points and of the
+// mid point (segmentQualityAngle, view.cc:466-484) - the same values dunproject / the orientation check would recompute per match
+struct SegRaysQ { D3 r1, r2, rm; };
 __global__ void __launch_bounds__(256)
-k_gather(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
-         const int* __restrict__ counts, const l3d_match_rec* __restrict__ recs, const float* __restrict__ slot_score,
-         const int4* __restrict__ work, int nwork, int v, int knn, const int* __restrict__ cam_rank,
-         unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals, int U, int* __restrict__ Mcount, KeyBits kb,
-         const int* __restrict__ slot_pos, const long long* __restrict__ region_of_view)
+k_sw_rays(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int V, long long N, double* __restrict__ rays)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = false;
-    unsigned long long key = ~0ull;
-    unsigned int val = 0u;
-    if (t < U) {
-        int w = 0;                                   // work item: (pair, inverse?, first candidate index, -)
-        while (w + 1 < nwork && work[w + 1].z <= t) ++w;
-        const int4 wk = work[w];
-        const L3DPairDev* P = pairs + wk.x;
-        const int local = t - wk.z;
-        const int r = local / knn, i = local - r * knn;
-        const long long row = P->row_off + r;
-        if (i < counts[row]) {
-            const long long g = row * knn + i;
-            const l3d_match_rec rec = recs[g];
-            int seg, tgt_view, tgt_seg; float d1, d2;
-            bool ok = true;
-            if (!wk.y) { seg = r; tgt_view = P->tgt; tgt_seg = (int)rec.tgt_seg; d1 = rec.d_p1; d2 = rec.d_p2; }
-            else { ok = slot_score[g] > 0.0f; seg = (int)rec.tgt_seg; tgt_view = P->src; tgt_seg = r; d1 = rec.d_q1; d2 = rec.d_q2; }
-            if (ok) {
-                const L3DViewDev* V = views + v;
-                const float4 s = segs[V->seg_off + seg];
-                DSeg S3 = dunproject(V, s, d1, d2);                                  // unprojectMatch (line3D.cc:1556)
-                double px = 0.5 * ((double)s.x + (double)s.z), py = 0.5 * ((double)s.y + (double)s.w);
-                D3 r1 = dray(V->RtKinv_d, px, py);                                   // segmentQualityAngle (view.cc:466-484)
-                double ang = acos(fmin(fmax(ddot(r1, S3.dir), -1.0), 1.0));
-                if (ang > (double)L3D_PI_1_32_F && ang < (double)L3D_PI_31_32_F) {
-                    valid = true;
-                    if (kb.mode == 0)
-                        key = ((unsigned long long)seg << kb.seg_shift) | ((unsigned long long)cam_rank[tgt_view] << kb.cam_shift) | (unsigned long long)tgt_seg;
-                    else if (!wk.y) key = ((unsigned long long)seg << kb.seg_shift) | (1ull << kb.cam_shift) | (unsigned long long)g;
-                    else key = ((unsigned long long)seg << kb.seg_shift) | (unsigned long long)(region_of_view[tgt_view] + slot_pos[g]);
-                    val = (unsigned int)g | (wk.y ? 0x80000000u : 0u);
-                }
-            }
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    int lo = 0, hi = V - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (views[mid].seg_off <= g) lo = mid; else hi = mid - 1; }
+    const L3DViewDev* Vw = views + lo;
+    const float4 s = segs[g];
+    const D3 r1 = dray(Vw->RtKinv_d, (double)s.x, (double)s.y), r2 = dray(Vw->RtKinv_d, (double)s.z, (double)s.w);
+    const D3 rm = dray(Vw->RtKinv_d, 0.5 * ((double)s.x + (double)s.z), 0.5 * ((double)s.y + (double)s.w));
+    double* o = rays + 9 * g;
+    o[0] = r1.x; o[1] = r1.y; o[2] = r1.z; o[3] = r2.x; o[4] = r2.y; o[5] = r2.z; o[6] = rm.x; o[7] = rm.y; o[8] = rm.z;
+}
+__device__ __forceinline__ SegRaysQ sw_load_rays(const double* __restrict__ rays, long long g)
+{
+    const double* p = rays + 9 * g;
+    SegRaysQ q;
+    q.r1 = d3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); q.r2 = d3(__ldg(p + 3), __ldg(p + 4), __ldg(p + 5)); q.rm = d3(__ldg(p + 6), __ldg(p + 7), __ldg(p + 8));
+    return q;
+}
+// dunproject with the cached rays: same expressions, same results
+__device__ __forceinline__ void sw_unproject_pts(const L3DViewDev* v, const SegRaysQ& q, float d1, float d2, D3* P1, D3* P2)
+{
+    const D3 C = d3(v->C_d[0], v->C_d[1], v->C_d[2]);
+    *P1 = d3(C.x + q.r1.x * (double)d1, C.y + q.r1.y * (double)d1, C.z + q.r1.z * (double)d1);
+    *P2 = d3(C.x + q.r2.x * (double)d2, C.y + q.r2.y * (double)d2, C.z + q.r2.z * (double)d2);
+}
+// Segment3D's degeneracy test `(float)|P1-P2| > 1e-12` (segment3D.h:50-66); n2 = |P1-P2|^2
+__device__ __forceinline__ bool sw_nondegenerate(double n2) { return n2 > 1e-20 ? true : (double)(float)sqrt(n2) > L3D_EPS_D; }
+
+// checkMatchOrientation (line3D.cc:811-858) for the match (segment of view V with rays q, depths d1,d2): unprojectMatch
+// (1556-1568) + View::segmentQualityAngle (view.cc:466-484): keep iff pi/32 < acos(clamp(ray_mid . dir)) < 31 pi/32.
+// acos is monotonic: away from the two thresholds the decision follows from the cosine alone (margin 1e-9 >> the few ulps by
+// which the shortcut's cosine, one division instead of three, can differ from the reference's); inside the margins the
+// reference's own sequence decides.
+__device__ __forceinline__ bool sw_orientation_ok(const L3DViewDev* V, const SegRaysQ& q, float d1, float d2)
+{
+    D3 P1, P2;
+    sw_unproject_pts(V, q, d1, d2, &P1, &P2);
+    const D3 d = dsub(P2, P1);
+    const double n2 = ddot(d, d);
+    if (n2 > 1e-20) {
+        const double c = ddot(q.rm, d) / sqrt(n2);
+        const double c1 = 0.99518472667, c2 = -0.99518472667;       // cos(pi/32), cos(31 pi/32)
+        if (c < c1 - 1e-9 && c > c2 + 1e-9) return true;
+        if (c > c1 + 1e-9 || c < c2 - 1e-9) return false;
+    }
+    D3 dir = d3(0, 0, 0);
+    if (sw_nondegenerate(ddot(dsub(P1, P2), dsub(P1, P2)))) dir = dnormalized(d);
+    const double ang = acos(fmin(fmax(ddot(q.rm, dir), -1.0), 1.0));
+    return ang > (double)L3D_PI_1_32_F && ang < (double)L3D_PI_31_32_F;
+}
+
+// ---------------------------------------------------------------------------------------------- batched set-up kernels
+// P1: one thread per record slot.  rflag bit 0: the record survives the orientation check as a direct match of its source
+// view, bit 1: as an inverse match of its target view (only asked for when the target is processed after the source).
+__global__ void __launch_bounds__(256)
+k_sw_flags(const double* __restrict__ rays, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
+           const long long* __restrict__ row_off, int num_pairs, const int* __restrict__ counts, const l3d_match_rec* __restrict__ recs,
+           int knn, long long slots, const SwView* __restrict__ vt, const int2* __restrict__ pairc, unsigned char* __restrict__ rflag,
+           int* __restrict__ csize)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= slots) return;
+    const long long row = g / knn;
+    const int i = (int)(g - row * knn);
+    if (i >= counts[row]) return;
+    const int p = sw_pair_of_row(row_off, num_pairs, row);
+    const L3DPairDev* P = pairs + p;
+    const int r = (int)(row - __ldg(row_off + p));
+    const l3d_match_rec rec = recs[g];
+    const int2 pc = pairc[p];
+    unsigned char f = 0;
+    {
+        const L3DViewDev* S = views + P->src;
+        if (sw_orientation_ok(S, sw_load_rays(rays, S->seg_off + r), rec.d_p1, rec.d_p2)) {
+            f |= 1;
+            const SwView sv = vt[P->src];
+            atomicAdd(csize + sv.chunk_base + (long long)r * sv.np + pc.x, 1);
         }
-        keys[t] = key; vals[t] = val;
     }
-    unsigned int b = __ballot_sync(0xffffffffu, valid);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(Mcount, __popc(b));
+    if (pc.y >= 0) {
+        const L3DViewDev* T = views + P->tgt;
+        if (sw_orientation_ok(T, sw_load_rays(rays, T->seg_off + rec.tgt_seg), rec.d_q1, rec.d_q2)) {
+            f |= 2;
+            const SwView tv = vt[P->tgt];
+            atomicAdd(csize + tv.chunk_base + (long long)rec.tgt_seg * tv.np + pc.y, 1);
+        }
+    }
+    rflag[g] = f;
 }
 
-// G2: per sorted match: decode, fetch payload, target regulariser (double), unprojected 3D direction (float), ranges.
+// region_off of every view = offset of its first chunk; written into the view table and a flat array (rank order is the
+// order the chunk bases were assigned in, so the regions lie in processing order)
 __global__ void __launch_bounds__(256)
-k_build(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
-        const L3DPairDev* __restrict__ pairs, const l3d_match_rec* __restrict__ recs,
-        int v, int knn, const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals,
-        const int* __restrict__ Mcount, const int* __restrict__ view_of_camrank,
-        int4* __restrict__ m_meta, float4* __restrict__ m_dep, float2* __restrict__ m_os, float2* __restrict__ m_reg,
-        float4* __restrict__ m_dir, int2* __restrict__ ranges, KeyBits kb, int num_pairs, double4* __restrict__ m_dir64)
+k_sw_regions(int V, SwView* __restrict__ vt, const long long* __restrict__ cstart, long long num_chunks, const int* __restrict__ order,
+             long long* __restrict__ region_by_rank)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int M = *Mcount;
-    if (x >= M) return;
-    const unsigned long long key = keys[x];
-    const int seg = (int)(key >> kb.seg_shift);
-    const unsigned int val = vals[x];
-    const bool inv = (val & 0x80000000u) != 0u;
-    const l3d_match_rec rec = recs[val & 0x7FFFFFFFu];
-    int tgt_view, tgt_seg;
-    if (kb.mode == 0) { tgt_view = view_of_camrank[(int)((key >> kb.cam_shift) & kb.cam_mask)]; tgt_seg = (int)(key & kb.tgt_mask); }
-    else {      // the key carries the list position, not the target: find the record's pair by its row
-        const long long row = (long long)(val & 0x7FFFFFFFu) / knn;
-        int lo = 0, hi = num_pairs - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pairs[mid].row_off <= row) lo = mid; else hi = mid - 1; }
-        tgt_view = inv ? pairs[lo].src : pairs[lo].tgt;
-        tgt_seg = inv ? (int)(row - pairs[lo].row_off) : (int)rec.tgt_seg;
-    }
-    float4 dep = inv ? make_float4(rec.d_q1, rec.d_q2, rec.d_p1, rec.d_p2) : make_float4(rec.d_p1, rec.d_p2, rec.d_q1, rec.d_q2);
-    m_meta[x] = make_int4(seg, tgt_view, tgt_seg, (int)val);
-    m_dep[x] = dep;
-    m_os[x] = make_float2(rec.overlap, 0.0f);
-    const L3DViewDev* V = views + v;
-    const L3DViewDev* T = views + tgt_view;
-    const float4 s = segs[V->seg_off + seg];
-    {   // regularizers_tgt (line3D.cc:1350-1352) == View::regularizerFrom3Dpoint (view.cc:445-448): |P - C_tgt| * k_tgt in double, stored as float
-        DSeg S3 = dunproject(V, s, dep.x, dep.y);
-        D3 Ct = d3(T->C_d[0], T->C_d[1], T->C_d[2]);
-        m_reg[x] = make_float2((float)(dnorm(dsub(S3.P1, Ct)) * (double)T->k), (float)(dnorm(dsub(S3.P2, Ct)) * (double)T->k));
-        if (kb.mode) m_dir64[x] = make_double4(S3.dir.x, S3.dir.y, S3.dir.z, (double)S3.length);     // scoringCPU works on the double 3D segment
-    }
-    if (kb.mode == 0) {   // D_unproject x2 + D_line_direction_3D (cudawrapper.cu:167-171, 40-43) with the cached float rays
-        SegRays R = load_rays(cache, V->seg_off + seg);
-        float3 C = make_float3(V->C[0], V->C[1], V->C[2]);
-        float3 P1 = make_float3(C.x + dep.x * R.r1.x, C.y + dep.x * R.r1.y, C.z + dep.x * R.r1.z);
-        float3 P2 = make_float3(C.x + dep.y * R.r2.x, C.y + dep.y * R.r2.y, C.z + dep.y * R.r2.z);
-        float3 dir = normalize3(make_float3(P2.x - P1.x, P2.y - P1.y, P2.z - P1.z));
-        m_dir[x] = make_float4(dir.x, dir.y, dir.z, 0.f);
-    }
-    if (x == 0 || (int)(keys[x - 1] >> kb.seg_shift) != seg) ranges[seg].x = x;
-    if (x == M - 1 || (int)(keys[x + 1] >> kb.seg_shift) != seg) ranges[seg].y = x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > V) return;
+    if (i == V) { region_by_rank[V] = cstart[num_chunks]; return; }
+    const int v = order[i];
+    const long long ro = cstart[vt[v].chunk_base];
+    vt[v].region_off = ro;
+    region_by_rank[i] = ro;
 }
 
-// G3: K_score_matches (cudawrapper.cu:256-367), one thread per match, same operation order.
-__global__ void __launch_bounds__(128)
-k_score(const L3DViewDev* __restrict__ views, int v, const int* __restrict__ Mcount, const int4* __restrict__ m_meta,
-        const float4* __restrict__ m_dep, const float2* __restrict__ m_reg, const float4* __restrict__ m_dir,
-        const int2* __restrict__ ranges, float angle_reg, float sim_t, float q_thr, float cos_thr, float2* __restrict__ m_os)
+// P4: records -> entries of their chunk(s), in arbitrary order inside the chunk; key = what the chunk is sorted by
+// (REF_GPU: the target segment of the list entry, sortMatchesByIDs commons.h:206-214; REF_CPU: the record index = append order)
+__global__ void __launch_bounds__(256)
+k_sw_scatter(const L3DPairDev* __restrict__ pairs, const long long* __restrict__ row_off, int num_pairs, const l3d_match_rec* __restrict__ recs,
+             int knn, long long slots, const SwView* __restrict__ vt, const int2* __restrict__ pairc, const unsigned char* __restrict__ rflag,
+             const long long* __restrict__ cstart, int* __restrict__ ccur, unsigned int* __restrict__ e_key, unsigned int* __restrict__ e_val,
+             int cpu_sem)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= *Mcount) return;
-    const float k = views[v].k;
-    const int4 me = m_meta[x];
-    const int tgt_cam_src = me.y;
-    const float4 dep = m_dep[x];
-    const float d1_src = dep.x, d2_src = dep.y;
-    const float4 ds = m_dir[x];
-    const float3 dir_src = make_float3(ds.x, ds.y, ds.z);
-    float sig1 = k * d1_src, sig2 = k * d2_src;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= slots) return;
+    const unsigned char f = rflag[g];
+    if (!f) return;
+    const long long row = g / knn;
+    const int p = sw_pair_of_row(row_off, num_pairs, row);
+    const L3DPairDev* P = pairs + p;
+    const int r = (int)(row - __ldg(row_off + p));
+    const unsigned int tseg = recs[g].tgt_seg;
+    const int2 pc = pairc[p];
+    if (f & 1) {
+        const SwView sv = vt[P->src];
+        const long long ch = sv.chunk_base + (long long)r * sv.np + pc.x;
+        const long long x = cstart[ch] + atomicAdd(ccur + ch, 1);
+        e_key[x] = cpu_sem ? (unsigned int)g : tseg;
+        e_val[x] = (unsigned int)g;
+    }
+    if (f & 2) {
+        const SwView tv = vt[P->tgt];
+        const long long ch = tv.chunk_base + (long long)tseg * tv.np + pc.y;
+        const long long x = cstart[ch] + atomicAdd(ccur + ch, 1);
+        e_key[x] = cpu_sem ? (unsigned int)g : (unsigned int)r;
+        e_val[x] = (unsigned int)g | SW_INV;
+    }
+}
+
+// P5: one thread per chunk: insertion sort of its few entries by key (keys are unique inside a chunk), then the initial
+// flags (direct entries are active from the start) and, for inverse entries, where the source will find them
+__global__ void __launch_bounds__(256)
+k_sw_chunksort(long long num_chunks, const long long* __restrict__ cstart, unsigned int* __restrict__ e_key, unsigned int* __restrict__ e_val,
+               unsigned char* __restrict__ e_flag, unsigned int* __restrict__ invpos, int V, const long long* __restrict__ region_by_rank)
+{
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= num_chunks) return;
+    const long long a = cstart[ch], b = cstart[ch + 1];
+    if (a == b) return;
+    const int n = (int)(b - a);
+    if (n > 1 && n <= 32) {             // the usual case: sort in thread-local storage, one read and one write per entry
+        unsigned int k[32], v[32];
+        for (int i = 0; i < n; ++i) {
+            const unsigned int ki = e_key[a + i], vi = e_val[a + i];
+            int j = i - 1;
+            while (j >= 0 && k[j] > ki) { k[j + 1] = k[j]; v[j + 1] = v[j]; --j; }
+            k[j + 1] = ki; v[j + 1] = vi;
+        }
+        for (int i = 0; i < n; ++i) e_val[a + i] = v[i];
+    } else if (n > 32) {
+        for (long long i = a + 1; i < b; ++i) {
+            const unsigned int k = e_key[i], v = e_val[i];
+            long long j = i - 1;
+            while (j >= a && e_key[j] > k) { e_key[j + 1] = e_key[j]; e_val[j + 1] = e_val[j]; --j; }
+            e_key[j + 1] = k; e_val[j + 1] = v;
+        }
+    }
+    int lo = 0, hi = V - 1;                 // region (processing rank) that holds this chunk's entries
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (region_by_rank[mid] <= a) lo = mid; else hi = mid - 1; }
+    // regions of views without entries share their offset with the next one: any of them gives the same relative position
+    const long long ro = region_by_rank[lo];
+    for (long long i = a; i < b; ++i) {
+        const unsigned int v = e_val[i];
+        if (v & SW_INV) { e_flag[i] = 0; invpos[v & ~SW_INV] = (unsigned int)(i - ro); }
+        else e_flag[i] = SW_ACTIVE;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- the chain kernel
+#define SW_WARPS 4
+#define SW_CAP_GPU 160        // list entries of one segment staged in shared memory (longer lists: global scratch)
+#define SW_CAP_CPU 80
+
+struct SwStage { float4 dir_cam; float4 dep_reg; };      // (dir.xyz, target view or -1 if inactive), (depth1, depth2, reg1, reg2)
+
+template <bool CPU>
+struct SwScoreArgs {
+    const float4* segs; const float4* cache; const double* rays; const L3DViewDev* views; const L3DPairDev* pairs; const long long* row_off; int num_pairs;
+    const l3d_match_rec* recs; int knn; int v;
+    const SwView* vt; const SwChunk* vp; const int2* pairc; const long long* cstart;
+    const unsigned int* e_val; float* e_score; unsigned char* e_flag; const unsigned int* invpos;
+    int* view_max_bits; int* M;
+    SwStage* g_stage; double4* g_dir64; int* g_pub;           // global scratch for lists longer than the shared-memory capacity
+    float angle_reg, sim_t, q_thr, cos_thr;
+};
+
+// K_score_matches (cudawrapper.cu:256-367) for own entry `me` against the staged list of its segment
+__device__ __forceinline__ float sw_score_gpu(const SwStage* __restrict__ st, int n, int me, float k, float angle_reg, float sim_t, float q_thr,
+                                              float cos_thr)
+{
+    const float4 mine = st[me].dir_cam, md = st[me].dep_reg;
+    const int tgt_cam_src = __float_as_int(mine.w);
+    const float d1_src = md.x, d2_src = md.y;
+    const float sig1 = k * d1_src, sig2 = k * d2_src;
     float pos_reg1 = 2.0f * sig1 * sig1, pos_reg2 = 2.0f * sig2 * sig2;
-    const float2 rg = m_reg[x];
-    float pos_reg1_tgt = 2.0f * rg.x * rg.x, pos_reg2_tgt = 2.0f * rg.y * rg.y;
+    const float pos_reg1_tgt = 2.0f * md.z * md.z, pos_reg2_tgt = 2.0f * md.w * md.w;
     pos_reg1 = 0.5f * (pos_reg1 + pos_reg1_tgt);
     pos_reg2 = 0.5f * (pos_reg2 + pos_reg2_tgt);
-    const int2 rng = ranges[me.x];
     float score3D = 0.0f, current_max_sim = 0.0f;
     int current_cam = -1;
-    for (int i = rng.x; i <= rng.y; ++i) {
-        const int tgt_cam_tgt = m_meta[i].y;
-        if (tgt_cam_src != tgt_cam_tgt) {
-            const float4 d2 = m_dep[i];
-            const float4 dt = m_dir[i];
-            const float dp = dir_src.x * dt.x + dir_src.y * dt.y + dir_src.z * dt.z;
-            const float e1 = d1_src - d2.x, e2 = d2_src - d2.y;
-            float sim;
-            // Exact shortcut: sim = min(three terms), then truncated to 0 below sim_t.  If ONE term is certainly below
-            // sim_t the result is 0 whatever the others are (fminf ignores NaN).  exp(-q) < sim_t is certain when
-            // q > q_thr = 1.01 * -ln(sim_t) (1 % margin >> the rounding of the division and of expf), and the angular
-            // term is certainly below sim_t when |cos| < cos_thr (same margin on the angle).  Everything inside the
-            // margins takes the full, reference-order path.
-            if (e1 * e1 > q_thr * pos_reg1 || e2 * e2 > q_thr * pos_reg2 || fabsf(dp) < cos_thr) sim = 0.0f;
-            else {
-                // D_undirected_angle_3D_DEG (cudawrapper.cu:46-53): float acos, DOUBLE divide by pi, times 180, back to float
-                float angle = (float)((double)acosf(fmaxf(fminf(dp, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
-                if (angle > 90.0f) angle = 180.0f - angle;
-                float sim_a = expf(-angle * angle / angle_reg);
-                float sim_p1 = expf(-e1 * e1 / pos_reg1), sim_p2 = expf(-e2 * e2 / pos_reg2);
-                sim = fminf(sim_a, fminf(sim_p1, sim_p2));
-                if (sim < sim_t) sim = 0.0f;
-            }
-            current_max_sim = fmaxf(current_max_sim, sim);
-            if (current_cam != tgt_cam_tgt) { score3D += current_max_sim; current_max_sim = 0.0f; current_cam = tgt_cam_tgt; }
+    for (int i = 0; i < n; ++i) {
+        const float4 dt = st[i].dir_cam;
+        const int tgt_cam_tgt = __float_as_int(dt.w);
+        if (tgt_cam_tgt < 0 || tgt_cam_src == tgt_cam_tgt) continue;         // not (yet) in the list / same target camera
+        const float4 d2 = st[i].dep_reg;
+        const float dp = mine.x * dt.x + mine.y * dt.y + mine.z * dt.z;
+        const float e1 = d1_src - d2.x, e2 = d2_src - d2.y;
+        float sim;
+        // Exact shortcut: sim = min(three terms), then truncated to 0 below sim_t.  If ONE term is certainly below
+        // sim_t the result is 0 whatever the others are (fminf ignores NaN).  exp(-q) < sim_t is certain when
+        // q > q_thr = 1.01 * -ln(sim_t) (1 % margin >> the rounding of the division and of expf), and the angular
+        // term is certainly below sim_t when |cos| < cos_thr (same margin on the angle).  Everything inside the
+        // margins takes the full, reference-order path.
+        if (e1 * e1 > q_thr * pos_reg1 || e2 * e2 > q_thr * pos_reg2 || fabsf(dp) < cos_thr) sim = 0.0f;
+        else {
+            // D_undirected_angle_3D_DEG (cudawrapper.cu:46-53): float acos, DOUBLE divide by pi, times 180, back to float
+            float angle = (float)((double)acosf(fmaxf(fminf(dp, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
+            if (angle > 90.0f) angle = 180.0f - angle;
+            const float sim_a = expf(-angle * angle / angle_reg);
+            const float sim_p1 = expf(-e1 * e1 / pos_reg1), sim_p2 = expf(-e2 * e2 / pos_reg2);
+            sim = fminf(sim_a, fminf(sim_p1, sim_p2));
+            if (sim < sim_t) sim = 0.0f;
         }
+        current_max_sim = fmaxf(current_max_sim, sim);
+        if (current_cam != tgt_cam_tgt) { score3D += current_max_sim; current_max_sim = 0.0f; current_cam = tgt_cam_tgt; }
     }
     score3D += current_max_sim;
-    m_os[x].y = score3D;
+    return score3D;
 }
 
-// G3 (REF_CPU): scoringCPU (line3D.cc:1208-1294) + similarityForScoring (1417-1446) + angleBetweenSeg3D (1571-1583), one
-// thread per match.  The score is the sum over target cameras of the best similarity among that camera's matches, built
-// with the reference's running update (add the first value of a camera, replace it when a larger one arrives) in list order.
+// scoringCPU (line3D.cc:1208-1294) + similarityForScoring (1417-1446) + angleBetweenSeg3D (1571-1583): the score is the sum
+// over target cameras of the best similarity among that camera's matches, built with the reference's running update (add the
+// first value of a camera, replace it when a larger one arrives) in list order.
 #define SC_MAP 48
-__global__ void __launch_bounds__(128)
-k_score_cpu(const L3DViewDev* __restrict__ views, int v, const int* __restrict__ Mcount, const int4* __restrict__ m_meta,
-            const float4* __restrict__ m_dep, const float2* __restrict__ m_reg, const double4* __restrict__ m_dir64,
-            const int2* __restrict__ ranges, float angle_reg, float sim_t, float2* __restrict__ m_os)
+__device__ __forceinline__ float sw_score_cpu(const SwStage* __restrict__ st, const double4* __restrict__ d64, int n, int me, float k,
+                                              float angle_reg, float sim_t)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= *Mcount) return;
-    const float k = views[v].k;
-    const int4 me = m_meta[x];
-    const float4 dep = m_dep[x];
-    const double4 D1 = m_dir64[x];
-    const float sig1 = dep.x * k, sig2 = dep.y * k;
+    const float4 md = st[me].dep_reg;
+    const int my_cam = __float_as_int(st[me].dir_cam.w);
+    const double4 D1 = d64[me];
+    const float sig1 = md.x * k, sig2 = md.y * k;
     float reg1 = 2.0f * sig1 * sig1, reg2 = 2.0f * sig2 * sig2;
-    const float2 rg = m_reg[x];
-    reg1 = 0.5f * (reg1 + 2.0f * rg.x * rg.x); reg2 = 0.5f * (reg2 + 2.0f * rg.y * rg.y);
-    const int2 rng = ranges[me.x];
+    reg1 = 0.5f * (reg1 + 2.0f * md.z * md.z); reg2 = 0.5f * (reg2 + 2.0f * md.w * md.w);
     auto sim_of = [&](int i) -> float {
-        const double4 D2 = m_dir64[i];
+        const double4 D2 = d64[i];
         if ((float)D1.w < L3D_EPS_D || (float)D2.w < L3D_EPS_D) return 0.0f;
         const float dot_p = (float)(D1.x * D2.x + D1.y * D2.y + D1.z * D2.z);
         float angle = (float)((double)acosf(fmaxf(fminf(dot_p, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
         if (angle > 90.0f) angle = 180.0f - angle;
         const float sim_a = expf(-angle * angle / angle_reg);
-        const float4 d2 = m_dep[i];
-        const float e1 = dep.x - d2.x, e2 = dep.y - d2.y;
+        const float4 d2 = st[i].dep_reg;
+        const float e1 = md.x - d2.x, e2 = md.y - d2.y;
         const float sim_p = fminf(expf(-e1 * e1 / reg1), expf(-e2 * e2 / reg2));
         const float sm = fminf(sim_a, sim_p);
         return sm > sim_t ? sm : 0.0f;
     };
     int cams[SC_MAP]; float best[SC_MAP]; int ncam = 0;
     float score3D = 0.0f;
-    for (int i = rng.x; i <= rng.y; ++i) {
-        const int cam = m_meta[i].y;
-        if (cam == me.y) continue;
+    for (int i = 0; i < n; ++i) {
+        const int cam = __float_as_int(st[i].dir_cam.w);
+        if (cam < 0 || cam == my_cam) continue;
         const float sim = sim_of(i);
         int slot = -1;
         for (int j = 0; j < ncam; ++j) if (cams[j] == cam) { slot = j; break; }
@@ -255,73 +338,178 @@ k_score_cpu(const L3DViewDev* __restrict__ views, int v, const int* __restrict__
         else if (ncam < SC_MAP) { score3D += sim; cams[ncam] = cam; best[ncam] = sim; ++ncam; }
         else {      // more target cameras than map slots: recover this camera's running maximum from the earlier entries
             bool seen = false; float cur = 0.0f;
-            for (int j = rng.x; j < i; ++j) if (m_meta[j].y == cam) { const float sj = sim_of(j); if (!seen) { cur = sj; seen = true; } else if (sj > cur) cur = sj; }
+            for (int j = 0; j < i; ++j) if (__float_as_int(st[j].dir_cam.w) == cam) { const float sj = sim_of(j); if (!seen) { cur = sj; seen = true; } else if (sj > cur) cur = sj; }
             if (seen) { if (sim > cur) { score3D -= cur; score3D += sim; } } else score3D += sim;
         }
     }
-    m_os[x].y = score3D;
+    return score3D;
 }
 
-// G4: publish the scores of direct matches to their record slots (read later by the target views as inverse matches)
-//     and reduce the view's maximum score.
-__global__ void __launch_bounds__(256)
-k_post_score(const int* __restrict__ Mcount, const int4* __restrict__ m_meta, const float2* __restrict__ m_os,
-             float* __restrict__ slot_score, int* __restrict__ view_max_bits, int* __restrict__ slot_pos /* REF_CPU only */)
+template <bool CPU>
+__global__ void __launch_bounds__(32 * SW_WARPS, CPU ? 4 : 6)
+k_sw_score(const SwScoreArgs<CPU> A)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    float s = 0.0f;
-    if (x < *Mcount) {
-        s = m_os[x].y;
-        const unsigned int val = (unsigned int)m_meta[x].w;
-        if (!(val & 0x80000000u)) { slot_score[val] = s; if (slot_pos) slot_pos[val] = x; }
-    }
-    s = fmaxf(s, 0.0f);
-    for (int o = 16; o; o >>= 1) s = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, o));
-    if ((threadIdx.x & 31) == 0 && s > 0.0f) atomicMax(view_max_bits, __float_as_int(s));
-}
-
-// G5: filterMatches (line3D.cc:1586-1669): one thread per segment of the view.
-__global__ void __launch_bounds__(256)
-k_filter(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int v, const int2* __restrict__ ranges,
-         const int4* __restrict__ m_meta, const float4* __restrict__ m_dep, float2* __restrict__ m_os,
-         const int* __restrict__ view_max_bits, float min_best, float perc, unsigned char* __restrict__ kept,
-         int* __restrict__ est_best /*per global seg: index of best match in the view region or -1*/, double* __restrict__ est_P)
-{
-    const L3DViewDev* V = views + v;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int CAP = CPU ? SW_CAP_CPU : SW_CAP_GPU;
+    extern __shared__ __align__(16) unsigned char sw_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int s = blockIdx.x * SW_WARPS + wid;
+    const L3DViewDev* V = A.views + A.v;
     if (s >= V->nseg) return;
-    const long long gs = V->seg_off + s;
-    const int2 rng = ranges[s];
-    int best = -1;
-    if (rng.x >= 0) {
-        const float score_lim = perc * __int_as_float(*view_max_bits);
+    const SwView me = A.vt[A.v];
+    const long long ch0 = me.chunk_base + (long long)s * me.np;
+    const long long x0 = A.cstart[ch0], x1 = A.cstart[ch0 + me.np];
+    const int n = (int)(x1 - x0);
+    if (n == 0) return;
+    SwStage* st; double4* d64 = nullptr; int* pub;
+    if (n <= CAP) {
+        st = (SwStage*)sw_smem + wid * CAP;
+        pub = (int*)(sw_smem + sizeof(SwStage) * SW_WARPS * CAP) + wid * CAP;
+        if (CPU) d64 = (double4*)(sw_smem + (sizeof(SwStage) + sizeof(int)) * SW_WARPS * CAP) + wid * CAP;
+    } else {
+        const long long rel = x0 - me.region_off;
+        st = A.g_stage + rel; pub = A.g_pub + rel;
+        if (CPU) d64 = A.g_dir64 + rel;
+    }
+    const SegRays R = load_rays(A.cache, V->seg_off + s);
+    const SegRaysQ Q = sw_load_rays(A.rays, V->seg_off + s);
+    const float3 Cf = make_float3(V->C[0], V->C[1], V->C[2]);
+    // ---- stage the segment's list: what scoringGPU's host pass (line3D.cc:1311-1355) and K_score_matches' prologue compute
+    for (int j = lane; j < n; j += 32) {
+        const long long x = x0 + j;
+        const unsigned int val = A.e_val[x];
+        int lo = 0, hi = me.np - 1;             // chunk of x: last c with cstart[ch0 + c] <= x
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (A.cstart[ch0 + mid] <= x) lo = mid; else hi = mid - 1; }
+        const SwChunk ck = A.vp[me.vp_off + lo];
+        const l3d_match_rec rec = A.recs[val & ~SW_INV];
+        const bool inv = (val & SW_INV) != 0u;
+        const float d1 = inv ? rec.d_q1 : rec.d_p1, d2 = inv ? rec.d_q2 : rec.d_p2;
+        const bool active = inv ? (A.e_flag[x] & SW_ACTIVE) != 0 : true;
+        SwStage e;
+        {   // D_unproject x2 + D_line_direction_3D (cudawrapper.cu:167-171, 40-43) with the cached float rays
+            const float3 P1 = make_float3(Cf.x + d1 * R.r1.x, Cf.y + d1 * R.r1.y, Cf.z + d1 * R.r1.z);
+            const float3 P2 = make_float3(Cf.x + d2 * R.r2.x, Cf.y + d2 * R.r2.y, Cf.z + d2 * R.r2.z);
+            const float3 dir = normalize3(make_float3(P2.x - P1.x, P2.y - P1.y, P2.z - P1.z));
+            e.dir_cam = make_float4(dir.x, dir.y, dir.z, __int_as_float(active ? ck.other : -1));
+        }
+        float2 reg = make_float2(0.f, 0.f);
+        if (active) {   // regularizers_tgt (line3D.cc:1350-1352) == View::regularizerFrom3Dpoint (view.cc:445-448): |P - C_tgt| * k_tgt in double, stored as float
+            const L3DViewDev* T = A.views + ck.other;
+            D3 P1, P2;
+            sw_unproject_pts(V, Q, d1, d2, &P1, &P2);
+            const D3 dd = dsub(P1, P2);
+            const double n2 = ddot(dd, dd);
+            const bool nondeg = sw_nondegenerate(n2);
+            if (!nondeg) P1 = P2 = d3(0, 0, 0);                                   // Segment3D ctor (segment3D.h:58-63)
+            const D3 Ct = d3(T->C_d[0], T->C_d[1], T->C_d[2]);
+            reg = make_float2((float)(dnorm(dsub(P1, Ct)) * (double)T->k), (float)(dnorm(dsub(P2, Ct)) * (double)T->k));
+            if (CPU) {      // scoringCPU works on the double 3D segment: direction and (float) length
+                D3 dir = d3(0, 0, 0); float len = 0.0f;
+                if (nondeg) { dir = dnormalized(dsub(P2, P1)); len = (float)sqrt(n2); }
+                d64[j] = make_double4(dir.x, dir.y, dir.z, (double)len);
+            }
+        }
+        e.dep_reg = make_float4(d1, d2, reg.x, reg.y);
+        st[j] = e;
+        // where a positive score has to be announced: the target view, if it is still to be processed (line3D.cc:1680)
+        pub[j] = (!inv && A.pairc[ck.pair].y >= 0) ? ck.other : -1;
+    }
+    __syncwarp();
+    // ---- score the active entries, publish
+    const float k = V->k;
+    float vmax = 0.0f; int cnt = 0;
+    for (int j = lane; j < n; j += 32) {
+        const long long x = x0 + j;
+        float sc = 0.0f;
+        if (__float_as_int(st[j].dir_cam.w) >= 0) {
+            ++cnt;
+            sc = CPU ? sw_score_cpu(st, d64, n, j, k, A.angle_reg, A.sim_t) : sw_score_gpu(st, n, j, k, A.angle_reg, A.sim_t, A.q_thr, A.cos_thr);
+            const int T = pub[j];
+            if (T >= 0 && sc > 0.0f) {      // storeInverseMatches; an inverse match that fails T's orientation check has no entry there
+                const unsigned int ip = A.invpos[A.e_val[x]];
+                if (ip != 0xFFFFFFFFu) A.e_flag[A.vt[T].region_off + ip] = SW_ACTIVE;
+            }
+            vmax = fmaxf(vmax, sc);
+        }
+        A.e_score[x] = sc;
+    }
+    for (int o = 16; o; o >>= 1) { vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    if (lane == 0) {
+        if (vmax > 0.0f) atomicMax(A.view_max_bits + A.v, __float_as_int(vmax));
+        atomicAdd(A.M + A.v, cnt);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- after the chain
+// filterMatches (line3D.cc:1586-1669) for every segment of every view: one thread per global segment
+__global__ void __launch_bounds__(256)
+k_sw_filter(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int V, long long N, const SwView* __restrict__ vt,
+            const long long* __restrict__ cstart, const unsigned int* __restrict__ e_val, const float* __restrict__ e_score,
+            unsigned char* __restrict__ e_flag, const l3d_match_rec* __restrict__ recs, const int* __restrict__ view_max_bits, float min_best,
+            float perc, int2* __restrict__ ranges, int* __restrict__ est_best /*per global seg: index of best match in the view region or -1*/,
+            double* __restrict__ est_P)
+{
+    const long long gs = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gs >= N) return;
+    int lo = 0, hi = V - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (views[mid].seg_off <= gs) lo = mid; else hi = mid - 1; }
+    const L3DViewDev* Vw = views + lo;
+    const SwView me = vt[lo];
+    const int s = (int)(gs - Vw->seg_off);
+    const long long ch0 = me.chunk_base + (long long)s * me.np;
+    const long long x0 = me.np ? cstart[ch0] : 0, x1 = me.np ? cstart[ch0 + me.np] : 0;
+    long long best = -1;
+    if (x1 > x0) {
+        const float score_lim = perc * __int_as_float(view_max_bits[lo]);
         float best_score = 0.0f;
-        for (int i = rng.x; i <= rng.y; ++i) {
-            const float sc = m_os[i].y;
+        for (long long x = x0; x < x1; ++x) {
+            const unsigned char f = e_flag[x];
+            if (!(f & SW_ACTIVE)) continue;
+            const float sc = e_score[x];
             const bool keep = sc > 0.0f && sc > score_lim;
-            kept[i] = keep ? 1 : 0;
-            if (keep && sc > best_score) { best_score = sc; best = i; }
+            if (keep) { e_flag[x] = f | SW_KEPT; if (sc > best_score) { best_score = sc; best = x; } }
         }
         if (!(best_score > min_best)) {
             best = -1;
-            for (int i = rng.x; i <= rng.y; ++i) kept[i] = 0;
+            for (long long x = x0; x < x1; ++x) e_flag[x] &= (unsigned char)~SW_KEPT;
         }
-    }
-    est_best[gs] = best;
+        ranges[gs] = make_int2((int)(x0 - me.region_off), (int)(x1 - 1 - me.region_off));
+    } else ranges[gs] = make_int2(-1, -1);
+    est_best[gs] = best >= 0 ? (int)(best - me.region_off) : -1;
     if (best >= 0) {
-        const float4 dep = m_dep[best];
-        DSeg S3 = dunproject(V, segs[gs], dep.x, dep.y);       // unprojectMatch(best_match, true)
+        const float4 dep = sw_depths(e_val[best], recs);
+        const DSeg S3 = dunproject(Vw, segs[gs], dep.x, dep.y);       // unprojectMatch(best_match, true)
         double* o = est_P + 6 * gs;
         o[0] = S3.P1.x; o[1] = S3.P1.y; o[2] = S3.P1.z; o[3] = S3.P2.x; o[4] = S3.P2.y; o[5] = S3.P2.z;
     }
 }
 
+// the matches of one view as L3DPP::Match records (test / dump interface)
+__global__ void __launch_bounds__(256)
+k_sw_export(const L3DViewDev* __restrict__ views, int v, long long ro, int n, const L3DPairDev* __restrict__ pairs,
+            const long long* __restrict__ row_off, int num_pairs, int knn, const l3d_match_rec* __restrict__ recs,
+            const unsigned int* __restrict__ e_val, const float* __restrict__ e_score, const unsigned char* __restrict__ e_flag,
+            unsigned char want, l3d_match* __restrict__ out, unsigned char* __restrict__ ok)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long x = ro + i;
+    const bool take = (e_flag[x] & want) == want;
+    ok[i] = take ? 1 : 0;
+    if (!take) return;
+    const SwEntry e = sw_decode(e_val[x], pairs, row_off, num_pairs, knn, recs);
+    l3d_match m;
+    m.src_cam = views[v].cam_id; m.src_seg = (unsigned int)e.seg; m.tgt_cam = views[e.tgt_view].cam_id; m.tgt_seg = (unsigned int)e.tgt_seg;
+    m.overlap = e.overlap; m.score3D = e_score[x]; m.d_p1 = e.dep.x; m.d_p2 = e.dep.y; m.d_q1 = e.dep.z; m.d_q2 = e.dep.w;
+    out[i] = m;
+}
+
 // compact list of the segments that have a 3D estimate: their best match (L3DPP::Match layout) and P1,P2
 struct HasEstimate { __host__ __device__ long long operator()(int best) const { return best >= 0 ? 1ll : 0ll; } };
 __global__ void __launch_bounds__(256)
-k_collect_estimates(const L3DViewDev* __restrict__ views, int V, long long N, const long long* __restrict__ reg_of_view,
-                    const int* __restrict__ est_best, const long long* __restrict__ pos, const int4* __restrict__ m_meta,
-                    const float4* __restrict__ m_dep, const float2* __restrict__ m_os, const double* __restrict__ est_P,
+k_collect_estimates(const L3DViewDev* __restrict__ views, int V, long long N, const SwView* __restrict__ vt,
+                    const int* __restrict__ est_best, const long long* __restrict__ pos, const L3DPairDev* __restrict__ pairs,
+                    const long long* __restrict__ row_off, int num_pairs, int knn, const l3d_match_rec* __restrict__ recs,
+                    const unsigned int* __restrict__ e_val, const float* __restrict__ e_score, const double* __restrict__ est_P,
                     l3d_match* __restrict__ out_best, double* __restrict__ out_P)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -330,11 +518,11 @@ k_collect_estimates(const L3DViewDev* __restrict__ views, int V, long long N, co
     if (b < 0) return;
     int lo = 0, hi = V - 1;
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (views[mid].seg_off <= g) lo = mid; else hi = mid - 1; }
-    const long long x = reg_of_view[lo] + b;
-    const int4 me = m_meta[x]; const float4 dep = m_dep[x]; const float2 os = m_os[x];
+    const long long x = vt[lo].region_off + b;
+    const SwEntry e = sw_decode(e_val[x], pairs, row_off, num_pairs, knn, recs);
     l3d_match m;
-    m.src_cam = views[lo].cam_id; m.src_seg = (unsigned int)(g - views[lo].seg_off); m.tgt_cam = views[me.y].cam_id; m.tgt_seg = (unsigned int)me.z;
-    m.overlap = os.x; m.score3D = os.y; m.d_p1 = dep.x; m.d_p2 = dep.y; m.d_q1 = dep.z; m.d_q2 = dep.w;
+    m.src_cam = views[lo].cam_id; m.src_seg = (unsigned int)(g - views[lo].seg_off); m.tgt_cam = views[e.tgt_view].cam_id; m.tgt_seg = (unsigned int)e.tgt_seg;
+    m.overlap = e.overlap; m.score3D = e_score[x]; m.d_p1 = e.dep.x; m.d_p2 = e.dep.y; m.d_q1 = e.dep.z; m.d_q2 = e.dep.w;
     const long long p = pos[g];
     out_best[p] = m;
     for (int i = 0; i < 6; ++i) out_P[6 * p + i] = est_P[6 * g + i];
@@ -349,170 +537,184 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     if (!c->have_matches) return l3d_fail(c, L3D_ERR_STATE, "l3d_score_sweep: call l3d_match_pairs first");
     cudaSetDevice(c->device);
     const int V = c->num_views, NP = c->num_pairs, knn = c->knn;
-    if (V >= 65536) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: more than 65535 views");
-    if (c->total_rows * (long long)knn >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: more than 2^31 match slots");
+    const long long slots = c->total_rows * knn;
+    if (slots >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: more than 2^31 match slots");
     SweepState& S = c->sweep;
     S.valid = false; c->aff.valid = false;
+    const bool cpu_sem = c->semantics == L3D_SEM_REF_CPU;
     // processing order = ascending camID (std::map iteration, line3D.cc:704)
     S.order.resize(V);
     std::iota(S.order.begin(), S.order.end(), 0);
     std::stable_sort(S.order.begin(), S.order.end(), [&](int a, int b) { return c->h_views[a].cam_id < c->h_views[b].cam_id; });
-    std::vector<int> rank(V), view_of_rank(V);
-    for (int i = 0; i < V; ++i) { rank[S.order[i]] = i; view_of_rank[i] = S.order[i]; }
-    // per-view work items
-    std::vector<std::vector<int4> > work(V);
-    S.U.assign(V, 0); S.region_off.assign(V + 1, 0);
+    std::vector<int> rank(V);
+    for (int i = 0; i < V; ++i) rank[S.order[i]] = i;
+    // chunk descriptors of every view in list order: REF_GPU sorts a segment's matches by (tgt cam, tgt seg) (sortMatches,
+    // line3D.cc:1196-1205): chunks by the other view's camID.  REF_CPU keeps the append order (scoringCPU does not sort): first
+    // the inverse matches, stored by the earlier views in their processing order, then the direct ones in matching order.
+    std::vector<std::vector<SwChunk> > chunks(V);
     for (int p = 0; p < NP; ++p) {
         const L3DPairDev& P = c->h_pairs[p];
-        const int Ns = c->h_views[P.src].nseg;
-        work[P.src].push_back(make_int4(p, 0, S.U[P.src], 0));
-        S.U[P.src] += Ns * knn;
-        if (rank[P.tgt] > rank[P.src]) {      // tgt still unprocessed when src stores its inverse matches (line3D.cc:1680)
-            work[P.tgt].push_back(make_int4(p, 1, S.U[P.tgt], 0));
-            S.U[P.tgt] += Ns * knn;
-        }
+        chunks[P.src].push_back(SwChunk{p, 0, P.tgt, 0});
+        if (rank[P.tgt] > rank[P.src]) chunks[P.tgt].push_back(SwChunk{p, 1, P.src, 0});   // tgt still unprocessed when src stores its inverse matches (line3D.cc:1680)
     }
-    long long Umax = 1, total = 0; int wmax = 1, nseg_max = 1;
+    std::vector<SwChunk> vp; std::vector<SwView> vt(V); std::vector<int2> pairc(NP, make_int2(-1, -1));
+    long long NC = 0;
     for (int i = 0; i < V; ++i) {
         const int v = S.order[i];
-        S.region_off[i] = total; total += S.U[v];
-        Umax = std::max<long long>(Umax, S.U[v]); wmax = std::max<int>(wmax, (int)work[v].size());
-        nseg_max = std::max(nseg_max, c->h_views[v].nseg);
+        std::vector<SwChunk>& L = chunks[v];
+        if (!cpu_sem) std::stable_sort(L.begin(), L.end(), [&](const SwChunk& a, const SwChunk& b) { return rank[a.other] != rank[b.other] ? rank[a.other] < rank[b.other] : a.inv > b.inv; });
+        else std::stable_sort(L.begin(), L.end(), [&](const SwChunk& a, const SwChunk& b) {
+            if (a.inv != b.inv) return a.inv > b.inv;
+            return a.inv ? rank[a.other] < rank[b.other] : a.pair < b.pair; });
+        vt[v].vp_off = (int)vp.size(); vt[v].np = (int)L.size(); vt[v].chunk_base = NC; vt[v].region_off = 0;
+        for (int k = 0; k < (int)L.size(); ++k) { if (L[k].inv) pairc[L[k].pair].y = k; else pairc[L[k].pair].x = k; }
+        vp.insert(vp.end(), L.begin(), L.end());
+        NC += (long long)c->h_views[v].nseg * (long long)L.size();
     }
-    S.region_off[V] = total; S.total = total;
-    const long long slots = c->total_rows * knn;
-    const bool cpu_sem = c->semantics == L3D_SEM_REF_CPU;
-    KeyBits kb;
-    if (!cpu_sem) {
-        const int bt = bits_for(nseg_max), bc = bits_for(V);
-        kb.cam_shift = bt; kb.seg_shift = bt + bc; kb.end_bit = bt + bc + bt + 1;
-        kb.cam_mask = (1ull << bc) - 1ull; kb.tgt_mask = (1ull << bt) - 1ull; kb.mode = 0;
-    } else {
-        const int bo = bits_for(std::max(total, slots) + 1), bt = bits_for(nseg_max);
-        kb.cam_shift = bo; kb.seg_shift = bo + 1; kb.end_bit = bo + 1 + bt + 1;
-        kb.cam_mask = 1ull; kb.tgt_mask = (1ull << bo) - 1ull; kb.mode = 1;
-    }
-    if (kb.end_bit > 64) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: views x segments too large for a 64-bit sort key");
-    if (Umax >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: view with more than 2^31 candidates");
+    std::vector<long long> row_off(NP + 1);
+    for (int p = 0; p < NP; ++p) row_off[p] = c->h_pairs[p].row_off;
+    row_off[NP] = c->total_rows;
 
     int rc;
-#define RES(buf, bytes, what) if ((rc = l3d_reserve(c, buf, (size_t)std::max<long long>((long long)(bytes), 16), what))) return rc
-    RES(S.d_slot_score, sizeof(float) * slots, "slot scores");
-    RES(S.d_keys, 8 * Umax, "keys"); RES(S.d_keys2, 8 * Umax, "keys2"); RES(S.d_vals, 4 * Umax, "vals"); RES(S.d_vals2, 4 * Umax, "vals2");
-    RES(S.d_reg, 8 * Umax, "reg"); RES(S.d_dir, 16 * Umax, "dir");
-    RES(S.d_meta, 16 * total, "match meta"); RES(S.d_dep, 16 * total, "match depths"); RES(S.d_os, 8 * total, "match scores"); RES(S.d_kept, total, "kept flags");
-    RES(S.d_ranges, 8 * c->total_segs, "ranges"); RES(S.d_est_best, 4 * c->total_segs, "estimates"); RES(S.d_est_P, 48 * c->total_segs, "estimate points");
-    RES(S.d_M, 4 * (size_t)V, "match counts"); RES(S.d_vmax, 4 * (size_t)V, "view max"); RES(S.d_work, 16 * (size_t)wmax, "work items");
-    RES(S.d_camrank, 4 * (size_t)V, "cam rank"); RES(S.d_viewofrank, 4 * (size_t)V, "view of rank");
-    RES(S.d_reg_of_view, 8 * (size_t)V, "region of view");
-    if (cpu_sem) { RES(S.d_slot_pos, 4 * slots, "slot positions"); RES(S.d_dir64, 32 * Umax, "double directions"); }
-    size_t sort_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)Umax, 0, kb.end_bit, c->stream);
-    RES(S.d_sort_tmp, sort_bytes, "sort temp");
-#undef RES
     cudaStream_t st = c->stream;
-    L3D_CUDA(c, cudaMemsetAsync(S.d_slot_score.p, 0xFF, sizeof(float) * slots, st), "init slot scores");        // NaN: "not scored" (never > 0)
-    L3D_CUDA(c, cudaMemsetAsync(S.d_ranges.p, 0xFF, 8 * c->total_segs, st), "init ranges");                      // (-1,-1)
+#define RES(buf, bytes, what) if ((rc = l3d_reserve(c, buf, (size_t)std::max<long long>((long long)(bytes), 16), what))) return rc
+    RES(S.d_vt, sizeof(SwView) * (size_t)V, "view table"); RES(S.d_vp, sizeof(SwChunk) * vp.size(), "chunk descriptors"); RES(S.d_pairc, 8 * (size_t)NP, "pair chunks");
+    RES(S.d_rowoff, 8 * (size_t)(NP + 1), "pair row offsets"); RES(S.d_order, 4 * (size_t)V, "order"); RES(S.d_region_off, 8 * (size_t)(V + 1), "region offsets");
+    RES(S.d_rays, 72 * c->total_segs, "segment rays"); RES(S.d_rflag, slots, "record flags"); RES(S.d_invpos, 4 * slots, "inverse positions");
+    RES(S.d_csize, 4 * (NC + 1), "chunk sizes"); RES(S.d_ccur, 4 * (NC + 1), "chunk cursors"); RES(S.d_cstart, 8 * (NC + 1), "chunk offsets");
+    RES(S.d_ranges, 8 * c->total_segs, "ranges"); RES(S.d_est_best, 4 * c->total_segs, "estimates"); RES(S.d_est_P, 48 * c->total_segs, "estimate points");
+    RES(S.d_M, 4 * (size_t)V, "match counts"); RES(S.d_vmax, 4 * (size_t)V, "view max");
+    L3D_CUDA(c, cudaMemcpyAsync(S.d_vt.p, vt.data(), sizeof(SwView) * (size_t)V, cudaMemcpyHostToDevice, st), "view table");
+    if (!vp.empty()) L3D_CUDA(c, cudaMemcpyAsync(S.d_vp.p, vp.data(), sizeof(SwChunk) * vp.size(), cudaMemcpyHostToDevice, st), "chunk descriptors");
+    if (NP) L3D_CUDA(c, cudaMemcpyAsync(S.d_pairc.p, pairc.data(), 8 * (size_t)NP, cudaMemcpyHostToDevice, st), "pair chunks");
+    L3D_CUDA(c, cudaMemcpyAsync(S.d_rowoff.p, row_off.data(), 8 * (size_t)(NP + 1), cudaMemcpyHostToDevice, st), "pair row offsets");
+    L3D_CUDA(c, cudaMemcpyAsync(S.d_order.p, S.order.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "order");
+    L3D_CUDA(c, cudaMemsetAsync(S.d_csize.p, 0, 4 * (size_t)(NC + 1), st), "init chunk sizes");
+    L3D_CUDA(c, cudaMemsetAsync(S.d_ccur.p, 0, 4 * (size_t)(NC + 1), st), "init chunk cursors");
+    L3D_CUDA(c, cudaMemsetAsync(S.d_rflag.p, 0, (size_t)slots, st), "init record flags");
+    L3D_CUDA(c, cudaMemsetAsync(S.d_invpos.p, 0xFF, 4 * (size_t)slots, st), "init inverse positions");   // "no inverse entry"
     L3D_CUDA(c, cudaMemsetAsync(S.d_M.p, 0, 4 * (size_t)V, st), "init counts");
-    L3D_CUDA(c, cudaMemsetAsync(S.d_kept.p, 0, (size_t)total, st), "init kept flags");     // slots [M_v, U_v) of a region are never written: k_affinity scans them all
     L3D_CUDA(c, cudaMemsetAsync(S.d_vmax.p, 0, 4 * (size_t)V, st), "init maxima");
-    L3D_CUDA(c, cudaMemcpyAsync(S.d_camrank.p, rank.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "cam rank");
-    L3D_CUDA(c, cudaMemcpyAsync(S.d_viewofrank.p, view_of_rank.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "view of rank");
-    std::vector<long long> reg_of_view(V);
-    for (int i = 0; i < V; ++i) reg_of_view[S.order[i]] = S.region_off[i];
-    L3D_CUDA(c, cudaMemcpyAsync(S.d_reg_of_view.p, reg_of_view.data(), 8 * (size_t)V, cudaMemcpyHostToDevice, st), "region of view");
-    L3D_CUDA(c, cudaStreamSynchronize(st), "sync");   // rank/view_of_rank/reg_of_view are stack-scoped
 
-    // shortcut thresholds of k_score (see there); disabled (never true) when sim_t <= 0 or the margins do not apply
+    const float4* segs = c->segs(); const float4* cache = (const float4*)c->d_cache.p;
+    const L3DViewDev* views = c->views(); const L3DPairDev* pairs = (const L3DPairDev*)c->d_pairs.p;
+    const int* counts = (const int*)c->d_counts.p; const l3d_match_rec* recs = (const l3d_match_rec*)c->d_recs.p;
+    const SwView* d_vt = (const SwView*)S.d_vt.p; const int2* d_pairc = (const int2*)S.d_pairc.p; const long long* d_rowoff = (const long long*)S.d_rowoff.p;
+    const unsigned int nbs = (unsigned int)((slots + 255) / 256);
+    S.region_off.assign(V + 1, 0); S.total = 0;
+    if (NP > 0 && slots > 0) {
+        k_sw_rays<<<(unsigned int)((c->total_segs + 255) / 256), 256, 0, st>>>(segs, views, V, c->total_segs, (double*)S.d_rays.p);
+        k_sw_flags<<<nbs, 256, 0, st>>>((const double*)S.d_rays.p, views, pairs, d_rowoff, NP, counts, recs, knn, slots, d_vt, d_pairc, (unsigned char*)S.d_rflag.p, (int*)S.d_csize.p);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)S.d_csize.p, (long long*)S.d_cstart.p, NC + 1, st);
+        RES(S.d_sort_tmp, tb, "scan temp");
+        tb = S.d_sort_tmp.cap;
+        L3D_CUDA(c, cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tb, (const int*)S.d_csize.p, (long long*)S.d_cstart.p, NC + 1, st), "chunk scan");
+        k_sw_regions<<<(V + 256) / 256, 256, 0, st>>>(V, (SwView*)S.d_vt.p, (const long long*)S.d_cstart.p, NC, (const int*)S.d_order.p, (long long*)S.d_region_off.p);
+        L3D_CUDA(c, cudaMemcpyAsync(S.region_off.data(), S.d_region_off.p, 8 * (size_t)(V + 1), cudaMemcpyDeviceToHost, st), "region offsets");
+        L3D_CUDA(c, cudaStreamSynchronize(st), "score sweep set-up");
+        c->launches += 4;
+    } else {
+        L3D_CUDA(c, cudaMemsetAsync(S.d_cstart.p, 0, 8 * (size_t)(NC + 1), st), "chunk offsets");
+        L3D_CUDA(c, cudaMemsetAsync(S.d_region_off.p, 0, 8 * (size_t)(V + 1), st), "region offsets");
+    }
+    const long long total = S.region_off[V];
+    S.total = total;
+    long long Umax = 1;
+    for (int i = 0; i < V; ++i) Umax = std::max(Umax, S.region_off[i + 1] - S.region_off[i]);
+    if (Umax >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: view with more than 2^31 matches");
+    RES(S.d_eval, 4 * total, "entry records"); RES(S.d_escore, 4 * total, "entry scores"); RES(S.d_eflag, total, "entry flags");
+    RES(S.d_gstage, sizeof(SwStage) * Umax, "long-list scratch"); RES(S.d_gpub, 4 * Umax, "long-list scratch");
+    if (cpu_sem) RES(S.d_dir64, 32 * Umax, "long-list scratch");
+    unsigned int* e_val = (unsigned int*)S.d_eval.p; float* e_score = (float*)S.d_escore.p; unsigned char* e_flag = (unsigned char*)S.d_eflag.p;
+    if (total > 0) {
+        // the sort keys live in the score array until the chain starts
+        k_sw_scatter<<<nbs, 256, 0, st>>>(pairs, d_rowoff, NP, recs, knn, slots, d_vt, d_pairc, (const unsigned char*)S.d_rflag.p, (const long long*)S.d_cstart.p,
+                                          (int*)S.d_ccur.p, (unsigned int*)e_score, e_val, cpu_sem ? 1 : 0);
+        k_sw_chunksort<<<(unsigned int)((NC + 255) / 256), 256, 0, st>>>(NC, (const long long*)S.d_cstart.p, (unsigned int*)e_score, e_val, e_flag,
+                                                                         (unsigned int*)S.d_invpos.p, V, (const long long*)S.d_region_off.p);
+        c->launches += 2;
+    }
+
+    // shortcut thresholds of sw_score_gpu (see there); disabled (never true) when sim_t <= 0 or the margins do not apply
     float q_thr = INFINITY, cos_thr = -1.0f;
     if (min_similarity > 0.0f && min_similarity < 1.0f) {
         q_thr = 1.01f * -std::log(min_similarity);
         const double ang = std::sqrt((double)q_thr * (double)two_sigA_sqr);           // degrees
         cos_thr = ang < 89.0 ? (float)(std::cos(ang * L3D_PI_D / 180.0) * (1.0 - 1e-4)) : -1.0f;
     }
-    const float4* segs = c->segs(); const float4* cache = (const float4*)c->d_cache.p;
-    const L3DViewDev* views = c->views(); const L3DPairDev* pairs = (const L3DPairDev*)c->d_pairs.p;
-    const int* counts = (const int*)c->d_counts.p; const l3d_match_rec* recs = (const l3d_match_rec*)c->d_recs.p;
-    std::vector<int4> work_flat;   // all views' work items, uploaded once
-    std::vector<int> work_off(V + 1, 0);
-    for (int i = 0; i < V; ++i) { work_off[i] = (int)work_flat.size(); work_flat.insert(work_flat.end(), work[S.order[i]].begin(), work[S.order[i]].end()); }
-    work_off[V] = (int)work_flat.size();
-    if ((rc = l3d_reserve(c, S.d_work, 16 * std::max<size_t>(work_flat.size(), 1), "work items"))) return rc;
-    if (!work_flat.empty()) L3D_CUDA(c, cudaMemcpyAsync(S.d_work.p, work_flat.data(), 16 * work_flat.size(), cudaMemcpyHostToDevice, st), "work items");
-    L3D_CUDA(c, cudaStreamSynchronize(st), "sync");
-
-    for (int i = 0; i < V; ++i) {
-        const int v = S.order[i];
-        const int U = S.U[v];
-        const int nseg = c->h_views[v].nseg;
-        if (U == 0 || nseg == 0) continue;
-        const long long ro = S.region_off[i];
-        int* Mc = (int*)S.d_M.p + i; int* vmax = (int*)S.d_vmax.p + i;
-        int4* m_meta = (int4*)S.d_meta.p + ro; float4* m_dep = (float4*)S.d_dep.p + ro; float2* m_os = (float2*)S.d_os.p + ro;
-        unsigned char* kept = (unsigned char*)S.d_kept.p + ro;
-        int2* ranges = (int2*)S.d_ranges.p + c->h_views[v].seg_off;
-        const int nb = (U + 255) / 256;
-        k_gather<<<nb, 256, 0, st>>>(segs, views, pairs, counts, recs, (const float*)S.d_slot_score.p, (const int4*)S.d_work.p + work_off[i],
-                                     work_off[i + 1] - work_off[i], v, knn, (const int*)S.d_camrank.p, (unsigned long long*)S.d_keys.p,
-                                     (unsigned int*)S.d_vals.p, U, Mc, kb, cpu_sem ? (const int*)S.d_slot_pos.p : nullptr, (const long long*)S.d_reg_of_view.p);
-        size_t tb = S.d_sort_tmp.cap;
-        cub::DeviceRadixSort::SortPairs(S.d_sort_tmp.p, tb, (const unsigned long long*)S.d_keys.p, (unsigned long long*)S.d_keys2.p,
-                                        (const unsigned int*)S.d_vals.p, (unsigned int*)S.d_vals2.p, U, 0, kb.end_bit, st);
-        k_build<<<nb, 256, 0, st>>>(segs, cache, views, pairs, recs, v, knn, (const unsigned long long*)S.d_keys2.p,
-                                    (const unsigned int*)S.d_vals2.p, Mc, (const int*)S.d_viewofrank.p, m_meta, m_dep, m_os,
-                                    (float2*)S.d_reg.p, (float4*)S.d_dir.p, ranges, kb, NP, cpu_sem ? (double4*)S.d_dir64.p : nullptr);
-        if (cpu_sem)
-            k_score_cpu<<<(U + 127) / 128, 128, 0, st>>>(views, v, Mc, m_meta, m_dep, (const float2*)S.d_reg.p, (const double4*)S.d_dir64.p, ranges,
-                                                        two_sigA_sqr, min_similarity, m_os);
-        else
-            k_score<<<(U + 127) / 128, 128, 0, st>>>(views, v, Mc, m_meta, m_dep, (const float2*)S.d_reg.p, (const float4*)S.d_dir.p, ranges,
-                                                    two_sigA_sqr, min_similarity, q_thr, cos_thr, m_os);
-        k_post_score<<<nb, 256, 0, st>>>(Mc, m_meta, m_os, (float*)S.d_slot_score.p, vmax, cpu_sem ? (int*)S.d_slot_pos.p : nullptr);
-        k_filter<<<(nseg + 255) / 256, 256, 0, st>>>(segs, views, v, ranges, m_meta, m_dep, m_os, vmax, min_best_score, min_best_perc, kept,
-                                                    (int*)S.d_est_best.p, (double*)S.d_est_P.p);
-        c->launches += 5 + 8;   // + cub radix sort passes (histogram + 7 onesweep passes for 64-bit keys)
+    // ---- the chain: one launch per view, ascending camID
+    if (total > 0) {
+        SwScoreArgs<false> A;
+        A.segs = segs; A.cache = cache; A.rays = (const double*)S.d_rays.p; A.views = views; A.pairs = pairs; A.row_off = d_rowoff; A.num_pairs = NP; A.recs = recs; A.knn = knn; A.v = 0;
+        A.vt = d_vt; A.vp = (const SwChunk*)S.d_vp.p; A.pairc = d_pairc; A.cstart = (const long long*)S.d_cstart.p;
+        A.e_val = e_val; A.e_score = e_score; A.e_flag = e_flag; A.invpos = (const unsigned int*)S.d_invpos.p;
+        A.view_max_bits = (int*)S.d_vmax.p; A.M = (int*)S.d_M.p;
+        A.g_stage = (SwStage*)S.d_gstage.p; A.g_dir64 = cpu_sem ? (double4*)S.d_dir64.p : nullptr; A.g_pub = (int*)S.d_gpub.p;
+        A.angle_reg = two_sigA_sqr; A.sim_t = min_similarity; A.q_thr = q_thr; A.cos_thr = cos_thr;
+        SwScoreArgs<true> B;
+        std::memcpy(&B, &A, sizeof(A));
+        static_assert(sizeof(SwScoreArgs<true>) == sizeof(SwScoreArgs<false>), "same layout");
+        const size_t sm_gpu = (sizeof(SwStage) + sizeof(int)) * SW_WARPS * SW_CAP_GPU;
+        const size_t sm_cpu = (sizeof(SwStage) + sizeof(int) + sizeof(double4)) * SW_WARPS * SW_CAP_CPU;
+        for (int i = 0; i < V; ++i) {
+            const int v = S.order[i];
+            const int nseg = c->h_views[v].nseg;
+            if (nseg == 0 || S.region_off[i + 1] == S.region_off[i]) continue;
+            const unsigned int nb = (unsigned int)((nseg + SW_WARPS - 1) / SW_WARPS);
+            if (cpu_sem) { B.v = v; k_sw_score<true><<<nb, 32 * SW_WARPS, sm_cpu, st>>>(B); }
+            else { A.v = v; k_sw_score<false><<<nb, 32 * SW_WARPS, sm_gpu, st>>>(A); }
+            ++c->launches;
+        }
+        L3D_CUDA(c, cudaGetLastError(), "score sweep launch");
     }
-    L3D_CUDA(c, cudaGetLastError(), "score sweep launch");
-    // views without candidates never ran k_filter: no estimates there
-    for (int i = 0; i < V; ++i) {
-        const int v = S.order[i];
-        if ((S.U[v] == 0 || c->h_views[v].nseg == 0) && c->h_views[v].nseg > 0)
-            L3D_CUDA(c, cudaMemsetAsync((int*)S.d_est_best.p + c->h_views[v].seg_off, 0xFF, 4 * (size_t)c->h_views[v].nseg, st), "clear estimates");
-    }
-    S.h_M.resize(V);
-    L3D_CUDA(c, cudaMemcpyAsync(S.h_M.data(), S.d_M.p, 4 * (size_t)V, cudaMemcpyDeviceToHost, st), "download counts");
-    // compact the estimates on the device: flags -> exclusive scan -> gather (best match record + P1,P2)
+    // ---- filterMatches + best estimates for all views
     {
         const long long N = c->total_segs;
-        if ((rc = l3d_reserve(c, S.d_est_pos, 8 * (size_t)(N + 1), "estimate positions"))) return rc;
-        cub::TransformInputIterator<long long, HasEstimate, const int*> flags((const int*)S.d_est_best.p, HasEstimate());
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, (long long*)S.d_est_pos.p, N, st);
-        if ((rc = l3d_reserve(c, S.d_sort_tmp, tb, "scan temp"))) return rc;
-        tb = S.d_sort_tmp.cap;
-        L3D_CUDA(c, cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tb, flags, (long long*)S.d_est_pos.p, N, st), "estimate scan");
-        long long last_pos = 0; int last_best = -1;
-        L3D_CUDA(c, cudaMemcpyAsync(&last_pos, (long long*)S.d_est_pos.p + N - 1, 8, cudaMemcpyDeviceToHost, st), "estimate count");
-        L3D_CUDA(c, cudaMemcpyAsync(&last_best, (int*)S.d_est_best.p + N - 1, 4, cudaMemcpyDeviceToHost, st), "estimate count");
-        L3D_CUDA(c, cudaStreamSynchronize(st), "score sweep");
-        S.n_est = last_pos + (last_best >= 0 ? 1 : 0);
-        if ((rc = l3d_reserve(c, S.d_est_out_best, sizeof(l3d_match) * (size_t)std::max<long long>(S.n_est, 1), "estimate records"))) return rc;
-        if ((rc = l3d_reserve(c, S.d_est_out_P, 48 * (size_t)std::max<long long>(S.n_est, 1), "estimate points"))) return rc;
-        if (S.n_est > 0) {
-            k_collect_estimates<<<(unsigned int)((N + 255) / 256), 256, 0, st>>>(views, V, N, (const long long*)S.d_reg_of_view.p, (const int*)S.d_est_best.p,
-                                                                               (const long long*)S.d_est_pos.p, (const int4*)S.d_meta.p, (const float4*)S.d_dep.p,
-                                                                               (const float2*)S.d_os.p, (const double*)S.d_est_P.p,
-                                                                               (l3d_match*)S.d_est_out_best.p, (double*)S.d_est_out_P.p);
-            c->launches += 3;
-            L3D_CUDA(c, cudaGetLastError(), "k_collect_estimates");
+        if (N > 0) {
+            k_sw_filter<<<(unsigned int)((N + 255) / 256), 256, 0, st>>>(segs, views, V, N, d_vt, (const long long*)S.d_cstart.p, e_val, e_score, e_flag, recs,
+                                                                        (const int*)S.d_vmax.p, min_best_score, min_best_perc, (int2*)S.d_ranges.p,
+                                                                        (int*)S.d_est_best.p, (double*)S.d_est_P.p);
+            ++c->launches;
+            L3D_CUDA(c, cudaGetLastError(), "k_sw_filter");
+        }
+        std::vector<int> M(V);
+        L3D_CUDA(c, cudaMemcpyAsync(M.data(), S.d_M.p, 4 * (size_t)V, cudaMemcpyDeviceToHost, st), "download counts");
+        // compact the estimates on the device: flags -> exclusive scan -> gather (best match record + P1,P2)
+        S.n_est = 0;
+        if (N > 0) {
+            RES(S.d_est_pos, 8 * (size_t)(N + 1), "estimate positions");
+            cub::TransformInputIterator<long long, HasEstimate, const int*> flags((const int*)S.d_est_best.p, HasEstimate());
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, (long long*)S.d_est_pos.p, N, st);
+            RES(S.d_sort_tmp, tb, "scan temp");
+            tb = S.d_sort_tmp.cap;
+            L3D_CUDA(c, cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tb, flags, (long long*)S.d_est_pos.p, N, st), "estimate scan");
+            long long last_pos = 0; int last_best = -1;
+            L3D_CUDA(c, cudaMemcpyAsync(&last_pos, (long long*)S.d_est_pos.p + N - 1, 8, cudaMemcpyDeviceToHost, st), "estimate count");
+            L3D_CUDA(c, cudaMemcpyAsync(&last_best, (int*)S.d_est_best.p + N - 1, 4, cudaMemcpyDeviceToHost, st), "estimate count");
+            L3D_CUDA(c, cudaStreamSynchronize(st), "score sweep");
+            S.n_est = last_pos + (last_best >= 0 ? 1 : 0);
+            RES(S.d_est_out_best, sizeof(l3d_match) * (size_t)std::max<long long>(S.n_est, 1), "estimate records");
+            RES(S.d_est_out_P, 48 * (size_t)std::max<long long>(S.n_est, 1), "estimate points");
+            if (S.n_est > 0) {
+                k_collect_estimates<<<(unsigned int)((N + 255) / 256), 256, 0, st>>>(views, V, N, d_vt, (const int*)S.d_est_best.p, (const long long*)S.d_est_pos.p, pairs,
+                                                                                   d_rowoff, NP, knn, recs, e_val, e_score, (const double*)S.d_est_P.p,
+                                                                                   (l3d_match*)S.d_est_out_best.p, (double*)S.d_est_out_P.p);
+                c->launches += 3;
+                L3D_CUDA(c, cudaGetLastError(), "k_collect_estimates");
+            }
         }
         L3D_CUDA(c, cudaStreamSynchronize(st), "score sweep");
+        S.h_M.resize(V);
+        for (int i = 0; i < V; ++i) S.h_M[i] = M[S.order[i]];
     }
+#undef RES
     S.valid = true;
     return L3D_OK;
 }
 
-// matches of one view after scoring, in the reference's list order (segment, then tgt cam, tgt seg).
+// matches of one view after scoring, in the reference's list order (REF_GPU: segment, then tgt cam, tgt seg).
 // kept_only != 0: only the matches that survived filterMatches.  Returns the number of matches (even if > cap).
 long long l3d_get_view_matches(l3d_ctx* c, int view, int kept_only, l3d_match* out, long long cap)
 {
@@ -521,29 +723,28 @@ long long l3d_get_view_matches(l3d_ctx* c, int view, int kept_only, l3d_match* o
     if (view < 0 || view >= c->num_views) return l3d_fail(c, L3D_ERR_INVALID, "l3d_get_view_matches: view out of range");
     cudaSetDevice(c->device);
     SweepState& S = c->sweep;
-    int i = (int)(std::find(S.order.begin(), S.order.end(), view) - S.order.begin());
-    const int M = S.h_M[i];
-    if (M == 0) return 0;
+    const int i = (int)(std::find(S.order.begin(), S.order.end(), view) - S.order.begin());
     const long long ro = S.region_off[i];
-    std::vector<int4> meta(M); std::vector<float4> dep(M); std::vector<float2> os(M); std::vector<unsigned char> kept(M);
-    L3D_CUDA(c, cudaMemcpyAsync(meta.data(), (int4*)S.d_meta.p + ro, 16 * (size_t)M, cudaMemcpyDeviceToHost, c->stream), "download");
-    L3D_CUDA(c, cudaMemcpyAsync(dep.data(), (float4*)S.d_dep.p + ro, 16 * (size_t)M, cudaMemcpyDeviceToHost, c->stream), "download");
-    L3D_CUDA(c, cudaMemcpyAsync(os.data(), (float2*)S.d_os.p + ro, 8 * (size_t)M, cudaMemcpyDeviceToHost, c->stream), "download");
-    L3D_CUDA(c, cudaMemcpyAsync(kept.data(), (unsigned char*)S.d_kept.p + ro, (size_t)M, cudaMemcpyDeviceToHost, c->stream), "download");
+    const int n = (int)(S.region_off[i + 1] - ro);
+    if (n == 0) return 0;
+    int rc;
+    if ((rc = l3d_reserve(c, S.d_export, sizeof(l3d_match) * (size_t)n, "export records"))) return rc;
+    if ((rc = l3d_reserve(c, S.d_export_ok, (size_t)n, "export flags"))) return rc;
+    k_sw_export<<<(n + 255) / 256, 256, 0, c->stream>>>(c->views(), view, ro, n, (const L3DPairDev*)c->d_pairs.p, (const long long*)S.d_rowoff.p, c->num_pairs, c->knn,
+                                                     (const l3d_match_rec*)c->d_recs.p, (const unsigned int*)S.d_eval.p, (const float*)S.d_escore.p,
+                                                     (const unsigned char*)S.d_eflag.p, (unsigned char)(kept_only ? (SW_ACTIVE | SW_KEPT) : SW_ACTIVE),
+                                                     (l3d_match*)S.d_export.p, (unsigned char*)S.d_export_ok.p);
+    std::vector<l3d_match> m(n); std::vector<unsigned char> ok(n);
+    L3D_CUDA(c, cudaMemcpyAsync(m.data(), S.d_export.p, sizeof(l3d_match) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "download");
+    L3D_CUDA(c, cudaMemcpyAsync(ok.data(), S.d_export_ok.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "download");
     L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync");
-    long long n = 0;
-    for (int x = 0; x < M; ++x) {
-        if (kept_only && !kept[x]) continue;
-        if (out && n < cap) {
-            l3d_match& m = out[n];
-            m.src_cam = c->h_views[view].cam_id; m.src_seg = (uint32_t)meta[x].x;
-            m.tgt_cam = c->h_views[meta[x].y].cam_id; m.tgt_seg = (uint32_t)meta[x].z;
-            m.overlap = os[x].x; m.score3D = os[x].y;
-            m.d_p1 = dep[x].x; m.d_p2 = dep[x].y; m.d_q1 = dep[x].z; m.d_q2 = dep[x].w;
-        }
-        ++n;
+    long long cnt = 0;
+    for (int x = 0; x < n; ++x) {
+        if (!ok[x]) continue;
+        if (out && cnt < cap) out[cnt] = m[x];
+        ++cnt;
     }
-    return n;
+    return cnt;
 }
 
 // best-match 3D estimates (estimated_position3D_, line3D.cc:1635-1647), compacted on the device by k_collect_estimates

@@ -52,14 +52,16 @@
 #endif
 #include "clustering.cc"
 
-namespace {
-
+// flat C types of the ABI (outside the anonymous namespace: nvcc gives functions with internal-linkage parameter types internal linkage)
 struct rfl_match_t {                      // == orc_match_t / ref_match_t: flat L3DPP::Match (commons.h:186-203)
     uint32_t src_cam, src_seg, tgt_cam, tgt_seg;
     float overlap, score3D, d_p1, d_p2, d_q1, d_q2;
 };
 struct rfl_seg3d_t { int line; int pad; double p1[3], p2[3]; };
 struct rfl_residual_t { int line; uint32_t cam, seg; };
+
+namespace {
+
 struct Edge { int i, j; float w; };
 
 rfl_match_t flat(const L3DPP::Match& m)
