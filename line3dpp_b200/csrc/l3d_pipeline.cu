@@ -239,59 +239,74 @@ k_sw_chunksort(long long num_chunks, const long long* __restrict__ cstart, unsig
 }
 
 // ---------------------------------------------------------------------------------------------- the chain kernel
-#define SW_WARPS 4
-#define SW_CAP_GPU 160        // list entries of one segment staged in shared memory (longer lists: global scratch)
-#define SW_CAP_CPU 80
+// One CTA scores SW_SEGS consecutive segments of the view.  Their lists are contiguous in the match store, so the CTA stages
+// ONE entry range [x0, x1) in shared memory, thread by thread (what scoringGPU's host pass, line3D.cc:1311-1355, and
+// K_score_matches' prologue compute per match), compacts the indices of the active entries and then gives every active entry
+// a thread that walks its own segment's list - K_score_matches' loop (cudawrapper.cu:304-359) - out of shared memory.
+#ifndef SW_THREADS
+#define SW_THREADS 128
+#endif
+#ifndef SW_SEGS
+#define SW_SEGS 4
+#endif
+#ifndef SW_CAP_GPU
+#define SW_CAP_GPU 512        // list entries staged in shared memory per CTA (longer ranges: global scratch)
+#endif
+#define SW_CAP_CPU 256
 
-struct SwStage { float4 dir_cam; float4 dep_reg; };      // (dir.xyz, target view or -1 if inactive), (depth1, depth2, reg1, reg2)
+// staged entry: a = (depth1, depth2, target view or -1 if inactive, index of its segment in the CTA), b = (dir.xyz, view to announce a
+// positive score to or -1), r = (reg1, reg2) target regularisers; REF_CPU adds d64 = (double dir.xyz, length)
+struct SwPtrs { float4* a; float4* b; float2* r; double4* d64; int* act; };
 
 template <bool CPU>
 struct SwScoreArgs {
-    const float4* segs; const float4* cache; const double* rays; const L3DViewDev* views; const L3DPairDev* pairs; const long long* row_off; int num_pairs;
-    const l3d_match_rec* recs; int knn; int v;
+    const float4* cache; const double* rays; const L3DViewDev* views; const l3d_match_rec* recs; int v;
     const SwView* vt; const SwChunk* vp; const int2* pairc; const long long* cstart;
     const unsigned int* e_val; float* e_score; unsigned char* e_flag; const unsigned int* invpos;
     int* view_max_bits; int* M;
-    SwStage* g_stage; double4* g_dir64; int* g_pub;           // global scratch for lists longer than the shared-memory capacity
+    SwPtrs g;                       // global scratch (one view's region) for entry ranges longer than the shared-memory capacity
     float angle_reg, sim_t, q_thr, cos_thr;
 };
 
-// K_score_matches (cudawrapper.cu:256-367) for own entry `me` against the staged list of its segment
-__device__ __forceinline__ float sw_score_gpu(const SwStage* __restrict__ st, int n, int me, float k, float angle_reg, float sim_t, float q_thr,
-                                              float cos_thr)
+// K_score_matches (cudawrapper.cu:256-367) for own entry `me` against the staged list [lo, hi) of its segment.  The tests are
+// ordered cheapest first - the result is the same whichever of the three conditions rejects.
+__device__ __forceinline__ float sw_score_gpu(const float4* __restrict__ sa, const float4* __restrict__ sb, float2 rg, int lo, int hi, int me, float k,
+                                              float angle_reg, float sim_t, float q_thr, float cos_thr)
 {
-    const float4 mine = st[me].dir_cam, md = st[me].dep_reg;
-    const int tgt_cam_src = __float_as_int(mine.w);
-    const float d1_src = md.x, d2_src = md.y;
+    const float4 ma = sa[me], mb = sb[me];
+    const int tgt_cam_src = __float_as_int(ma.z);
+    const float d1_src = ma.x, d2_src = ma.y;
     const float sig1 = k * d1_src, sig2 = k * d2_src;
     float pos_reg1 = 2.0f * sig1 * sig1, pos_reg2 = 2.0f * sig2 * sig2;
-    const float pos_reg1_tgt = 2.0f * md.z * md.z, pos_reg2_tgt = 2.0f * md.w * md.w;
+    const float pos_reg1_tgt = 2.0f * rg.x * rg.x, pos_reg2_tgt = 2.0f * rg.y * rg.y;
     pos_reg1 = 0.5f * (pos_reg1 + pos_reg1_tgt);
     pos_reg2 = 0.5f * (pos_reg2 + pos_reg2_tgt);
+    const float thr1 = q_thr * pos_reg1, thr2 = q_thr * pos_reg2;
     float score3D = 0.0f, current_max_sim = 0.0f;
     int current_cam = -1;
-    for (int i = 0; i < n; ++i) {
-        const float4 dt = st[i].dir_cam;
-        const int tgt_cam_tgt = __float_as_int(dt.w);
+    for (int i = lo; i < hi; ++i) {
+        const float4 ta = sa[i];
+        const int tgt_cam_tgt = __float_as_int(ta.z);
         if (tgt_cam_tgt < 0 || tgt_cam_src == tgt_cam_tgt) continue;         // not (yet) in the list / same target camera
-        const float4 d2 = st[i].dep_reg;
-        const float dp = mine.x * dt.x + mine.y * dt.y + mine.z * dt.z;
-        const float e1 = d1_src - d2.x, e2 = d2_src - d2.y;
-        float sim;
+        const float e1 = d1_src - ta.x, e2 = d2_src - ta.y;
+        float sim = 0.0f;
         // Exact shortcut: sim = min(three terms), then truncated to 0 below sim_t.  If ONE term is certainly below
         // sim_t the result is 0 whatever the others are (fminf ignores NaN).  exp(-q) < sim_t is certain when
         // q > q_thr = 1.01 * -ln(sim_t) (1 % margin >> the rounding of the division and of expf), and the angular
         // term is certainly below sim_t when |cos| < cos_thr (same margin on the angle).  Everything inside the
         // margins takes the full, reference-order path.
-        if (e1 * e1 > q_thr * pos_reg1 || e2 * e2 > q_thr * pos_reg2 || fabsf(dp) < cos_thr) sim = 0.0f;
-        else {
-            // D_undirected_angle_3D_DEG (cudawrapper.cu:46-53): float acos, DOUBLE divide by pi, times 180, back to float
-            float angle = (float)((double)acosf(fmaxf(fminf(dp, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
-            if (angle > 90.0f) angle = 180.0f - angle;
-            const float sim_a = expf(-angle * angle / angle_reg);
-            const float sim_p1 = expf(-e1 * e1 / pos_reg1), sim_p2 = expf(-e2 * e2 / pos_reg2);
-            sim = fminf(sim_a, fminf(sim_p1, sim_p2));
-            if (sim < sim_t) sim = 0.0f;
+        if (!(e1 * e1 > thr1 || e2 * e2 > thr2)) {
+            const float4 tb = sb[i];
+            const float dp = mb.x * tb.x + mb.y * tb.y + mb.z * tb.z;
+            if (!(fabsf(dp) < cos_thr)) {
+                // D_undirected_angle_3D_DEG (cudawrapper.cu:46-53): float acos, DOUBLE divide by pi, times 180, back to float
+                float angle = (float)((double)acosf(fmaxf(fminf(dp, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
+                if (angle > 90.0f) angle = 180.0f - angle;
+                const float sim_a = expf(-angle * angle / angle_reg);
+                const float sim_p1 = expf(-e1 * e1 / pos_reg1), sim_p2 = expf(-e2 * e2 / pos_reg2);
+                sim = fminf(sim_a, fminf(sim_p1, sim_p2));
+                if (sim < sim_t) sim = 0.0f;
+            }
         }
         current_max_sim = fmaxf(current_max_sim, sim);
         if (current_cam != tgt_cam_tgt) { score3D += current_max_sim; current_max_sim = 0.0f; current_cam = tgt_cam_tgt; }
@@ -304,15 +319,15 @@ __device__ __forceinline__ float sw_score_gpu(const SwStage* __restrict__ st, in
 // over target cameras of the best similarity among that camera's matches, built with the reference's running update (add the
 // first value of a camera, replace it when a larger one arrives) in list order.
 #define SC_MAP 48
-__device__ __forceinline__ float sw_score_cpu(const SwStage* __restrict__ st, const double4* __restrict__ d64, int n, int me, float k,
+__device__ __forceinline__ float sw_score_cpu(const float4* __restrict__ sa, const double4* __restrict__ d64, float2 rg, int lo, int hi, int me, float k,
                                               float angle_reg, float sim_t)
 {
-    const float4 md = st[me].dep_reg;
-    const int my_cam = __float_as_int(st[me].dir_cam.w);
+    const float4 ma = sa[me];
+    const int my_cam = __float_as_int(ma.z);
     const double4 D1 = d64[me];
-    const float sig1 = md.x * k, sig2 = md.y * k;
+    const float sig1 = ma.x * k, sig2 = ma.y * k;
     float reg1 = 2.0f * sig1 * sig1, reg2 = 2.0f * sig2 * sig2;
-    reg1 = 0.5f * (reg1 + 2.0f * md.z * md.z); reg2 = 0.5f * (reg2 + 2.0f * md.w * md.w);
+    reg1 = 0.5f * (reg1 + 2.0f * rg.x * rg.x); reg2 = 0.5f * (reg2 + 2.0f * rg.y * rg.y);
     auto sim_of = [&](int i) -> float {
         const double4 D2 = d64[i];
         if ((float)D1.w < L3D_EPS_D || (float)D2.w < L3D_EPS_D) return 0.0f;
@@ -320,16 +335,16 @@ __device__ __forceinline__ float sw_score_cpu(const SwStage* __restrict__ st, co
         float angle = (float)((double)acosf(fmaxf(fminf(dot_p, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
         if (angle > 90.0f) angle = 180.0f - angle;
         const float sim_a = expf(-angle * angle / angle_reg);
-        const float4 d2 = st[i].dep_reg;
-        const float e1 = md.x - d2.x, e2 = md.y - d2.y;
+        const float4 d2 = sa[i];
+        const float e1 = ma.x - d2.x, e2 = ma.y - d2.y;
         const float sim_p = fminf(expf(-e1 * e1 / reg1), expf(-e2 * e2 / reg2));
         const float sm = fminf(sim_a, sim_p);
         return sm > sim_t ? sm : 0.0f;
     };
     int cams[SC_MAP]; float best[SC_MAP]; int ncam = 0;
     float score3D = 0.0f;
-    for (int i = 0; i < n; ++i) {
-        const int cam = __float_as_int(st[i].dir_cam.w);
+    for (int i = lo; i < hi; ++i) {
+        const int cam = __float_as_int(sa[i].z);
         if (cam < 0 || cam == my_cam) continue;
         const float sim = sim_of(i);
         int slot = -1;
@@ -338,7 +353,7 @@ __device__ __forceinline__ float sw_score_cpu(const SwStage* __restrict__ st, co
         else if (ncam < SC_MAP) { score3D += sim; cams[ncam] = cam; best[ncam] = sim; ++ncam; }
         else {      // more target cameras than map slots: recover this camera's running maximum from the earlier entries
             bool seen = false; float cur = 0.0f;
-            for (int j = 0; j < i; ++j) if (__float_as_int(st[j].dir_cam.w) == cam) { const float sj = sim_of(j); if (!seen) { cur = sj; seen = true; } else if (sj > cur) cur = sj; }
+            for (int j = lo; j < i; ++j) if (__float_as_int(sa[j].z) == cam) { const float sj = sim_of(j); if (!seen) { cur = sj; seen = true; } else if (sj > cur) cur = sj; }
             if (seen) { if (sim > cur) { score3D -= cur; score3D += sim; } } else score3D += sim;
         }
     }
@@ -346,97 +361,120 @@ __device__ __forceinline__ float sw_score_cpu(const SwStage* __restrict__ st, co
 }
 
 template <bool CPU>
-__global__ void __launch_bounds__(32 * SW_WARPS, CPU ? 4 : 6)
+__device__ __forceinline__ void sw_score_range(const SwScoreArgs<CPU>& A, const SwPtrs P, const int* __restrict__ segb, int* __restrict__ nact_smem,
+                                               int s0, int nsegs, long long x0, int n)
+{
+    const L3DViewDev* V = A.views + A.v;
+    const SwView me = A.vt[A.v];
+    const int lane = threadIdx.x & 31;
+    // ---- stage
+    for (int j0 = 0; j0 < n; j0 += SW_THREADS) {
+        const int j = j0 + threadIdx.x;
+        bool active = false;
+        if (j < n) {
+            const long long x = x0 + j;
+            int si = 0;
+            while (si + 1 < nsegs && segb[si + 1] <= j) ++si;
+            const int s = s0 + si;
+            const long long ch0 = me.chunk_base + (long long)s * me.np;
+            int lo = 0, hi = me.np - 1;             // chunk of x: last c with cstart[ch0 + c] <= x
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (A.cstart[ch0 + mid] <= x) lo = mid; else hi = mid - 1; }
+            const SwChunk ck = A.vp[me.vp_off + lo];
+            const unsigned int val = A.e_val[x];
+            const l3d_match_rec rec = A.recs[val & ~SW_INV];
+            const bool inv = (val & SW_INV) != 0u;
+            const float d1 = inv ? rec.d_q1 : rec.d_p1, d2 = inv ? rec.d_q2 : rec.d_p2;
+            active = inv ? (A.e_flag[x] & SW_ACTIVE) != 0 : true;
+            const long long gs = V->seg_off + s;
+            {   // D_unproject x2 + D_line_direction_3D (cudawrapper.cu:167-171, 40-43) with the cached float rays
+                const SegRays R = load_rays(A.cache, gs);
+                const float3 Cf = make_float3(V->C[0], V->C[1], V->C[2]);
+                const float3 P1 = make_float3(Cf.x + d1 * R.r1.x, Cf.y + d1 * R.r1.y, Cf.z + d1 * R.r1.z);
+                const float3 P2 = make_float3(Cf.x + d2 * R.r2.x, Cf.y + d2 * R.r2.y, Cf.z + d2 * R.r2.z);
+                const float3 dir = normalize3(make_float3(P2.x - P1.x, P2.y - P1.y, P2.z - P1.z));
+                // where a positive score has to be announced: the target view, if it is still to be processed (line3D.cc:1680)
+                P.b[j] = make_float4(dir.x, dir.y, dir.z, __int_as_float((!inv && A.pairc[ck.pair].y >= 0) ? ck.other : -1));
+            }
+            float2 reg = make_float2(0.f, 0.f);
+            if (active) {   // regularizers_tgt (line3D.cc:1350-1352) == View::regularizerFrom3Dpoint (view.cc:445-448): |P - C_tgt| * k_tgt in double, stored as float
+                const L3DViewDev* T = A.views + ck.other;
+                const SegRaysQ Q = sw_load_rays(A.rays, gs);
+                D3 P1, P2;
+                sw_unproject_pts(V, Q, d1, d2, &P1, &P2);
+                const D3 dd = dsub(P1, P2);
+                const double n2 = ddot(dd, dd);
+                const bool nondeg = sw_nondegenerate(n2);
+                if (!nondeg) P1 = P2 = d3(0, 0, 0);                                   // Segment3D ctor (segment3D.h:58-63)
+                const D3 Ct = d3(T->C_d[0], T->C_d[1], T->C_d[2]);
+                reg = make_float2((float)(dnorm(dsub(P1, Ct)) * (double)T->k), (float)(dnorm(dsub(P2, Ct)) * (double)T->k));
+                if (CPU) {      // scoringCPU works on the double 3D segment: direction and (float) length
+                    D3 dir = d3(0, 0, 0); float len = 0.0f;
+                    if (nondeg) { dir = dnormalized(dsub(P2, P1)); len = (float)sqrt(n2); }
+                    P.d64[j] = make_double4(dir.x, dir.y, dir.z, (double)len);
+                }
+            } else A.e_score[x] = 0.0f;
+            P.a[j] = make_float4(d1, d2, __int_as_float(active ? ck.other : -1), __int_as_float(si));
+            P.r[j] = reg;
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, active);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(nact_smem, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (active) P.act[base + __popc(bal & ((1u << lane) - 1u))] = j;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // ---- score the active entries, publish
+    const int nact = *nact_smem;
+    const float k = V->k;
+    float vmax = 0.0f;
+    for (int q = threadIdx.x; q < nact; q += SW_THREADS) {
+        const int j = P.act[q];
+        const float4 ma = P.a[j];
+        const int si = __float_as_int(ma.w);
+        const float sc = CPU ? sw_score_cpu(P.a, P.d64, P.r[j], segb[si], segb[si + 1], j, k, A.angle_reg, A.sim_t)
+                             : sw_score_gpu(P.a, P.b, P.r[j], segb[si], segb[si + 1], j, k, A.angle_reg, A.sim_t, A.q_thr, A.cos_thr);
+        const long long x = x0 + j;
+        const int T = __float_as_int(P.b[j].w);
+        if (T >= 0 && sc > 0.0f) {      // storeInverseMatches; an inverse match that fails T's orientation check has no entry there
+            const unsigned int ip = A.invpos[A.e_val[x]];
+            if (ip != 0xFFFFFFFFu) A.e_flag[A.vt[T].region_off + ip] = SW_ACTIVE;
+        }
+        vmax = fmaxf(vmax, sc);
+        A.e_score[x] = sc;
+    }
+    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > 0.0f) atomicMax(A.view_max_bits + A.v, __float_as_int(vmax));
+    if (threadIdx.x == 0 && nact) atomicAdd(A.M + A.v, nact);
+}
+
+template <bool CPU>
+__global__ void __launch_bounds__(SW_THREADS)
 k_sw_score(const SwScoreArgs<CPU> A)
 {
     constexpr int CAP = CPU ? SW_CAP_CPU : SW_CAP_GPU;
     extern __shared__ __align__(16) unsigned char sw_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int s = blockIdx.x * SW_WARPS + wid;
+    __shared__ int segb[SW_SEGS + 1];
+    __shared__ int nact_smem;
     const L3DViewDev* V = A.views + A.v;
-    if (s >= V->nseg) return;
+    const int s0 = blockIdx.x * SW_SEGS;
+    const int nsegs = min(SW_SEGS, V->nseg - s0);
     const SwView me = A.vt[A.v];
-    const long long ch0 = me.chunk_base + (long long)s * me.np;
-    const long long x0 = A.cstart[ch0], x1 = A.cstart[ch0 + me.np];
-    const int n = (int)(x1 - x0);
+    const long long x0 = A.cstart[me.chunk_base + (long long)s0 * me.np];
+    if (threadIdx.x <= nsegs) segb[threadIdx.x] = (int)(A.cstart[me.chunk_base + (long long)(s0 + threadIdx.x) * me.np] - x0);
+    if (threadIdx.x == 0) nact_smem = 0;
+    __syncthreads();
+    const int n = segb[nsegs];
     if (n == 0) return;
-    SwStage* st; double4* d64 = nullptr; int* pub;
+    SwPtrs P;
     if (n <= CAP) {
-        st = (SwStage*)sw_smem + wid * CAP;
-        pub = (int*)(sw_smem + sizeof(SwStage) * SW_WARPS * CAP) + wid * CAP;
-        if (CPU) d64 = (double4*)(sw_smem + (sizeof(SwStage) + sizeof(int)) * SW_WARPS * CAP) + wid * CAP;
+        P.a = (float4*)sw_smem; P.b = P.a + CAP; P.r = (float2*)(P.b + CAP); P.act = (int*)(P.r + CAP);
+        P.d64 = CPU ? (double4*)(sw_smem + (size_t)CAP * 48) : nullptr;           // 16 + 16 + 8 + 4 = 44 -> rounded up to 48 for the double4 alignment
     } else {
         const long long rel = x0 - me.region_off;
-        st = A.g_stage + rel; pub = A.g_pub + rel;
-        if (CPU) d64 = A.g_dir64 + rel;
+        P.a = A.g.a + rel; P.b = A.g.b + rel; P.r = A.g.r + rel; P.act = A.g.act + rel; P.d64 = CPU ? A.g.d64 + rel : nullptr;
     }
-    const SegRays R = load_rays(A.cache, V->seg_off + s);
-    const SegRaysQ Q = sw_load_rays(A.rays, V->seg_off + s);
-    const float3 Cf = make_float3(V->C[0], V->C[1], V->C[2]);
-    // ---- stage the segment's list: what scoringGPU's host pass (line3D.cc:1311-1355) and K_score_matches' prologue compute
-    for (int j = lane; j < n; j += 32) {
-        const long long x = x0 + j;
-        const unsigned int val = A.e_val[x];
-        int lo = 0, hi = me.np - 1;             // chunk of x: last c with cstart[ch0 + c] <= x
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (A.cstart[ch0 + mid] <= x) lo = mid; else hi = mid - 1; }
-        const SwChunk ck = A.vp[me.vp_off + lo];
-        const l3d_match_rec rec = A.recs[val & ~SW_INV];
-        const bool inv = (val & SW_INV) != 0u;
-        const float d1 = inv ? rec.d_q1 : rec.d_p1, d2 = inv ? rec.d_q2 : rec.d_p2;
-        const bool active = inv ? (A.e_flag[x] & SW_ACTIVE) != 0 : true;
-        SwStage e;
-        {   // D_unproject x2 + D_line_direction_3D (cudawrapper.cu:167-171, 40-43) with the cached float rays
-            const float3 P1 = make_float3(Cf.x + d1 * R.r1.x, Cf.y + d1 * R.r1.y, Cf.z + d1 * R.r1.z);
-            const float3 P2 = make_float3(Cf.x + d2 * R.r2.x, Cf.y + d2 * R.r2.y, Cf.z + d2 * R.r2.z);
-            const float3 dir = normalize3(make_float3(P2.x - P1.x, P2.y - P1.y, P2.z - P1.z));
-            e.dir_cam = make_float4(dir.x, dir.y, dir.z, __int_as_float(active ? ck.other : -1));
-        }
-        float2 reg = make_float2(0.f, 0.f);
-        if (active) {   // regularizers_tgt (line3D.cc:1350-1352) == View::regularizerFrom3Dpoint (view.cc:445-448): |P - C_tgt| * k_tgt in double, stored as float
-            const L3DViewDev* T = A.views + ck.other;
-            D3 P1, P2;
-            sw_unproject_pts(V, Q, d1, d2, &P1, &P2);
-            const D3 dd = dsub(P1, P2);
-            const double n2 = ddot(dd, dd);
-            const bool nondeg = sw_nondegenerate(n2);
-            if (!nondeg) P1 = P2 = d3(0, 0, 0);                                   // Segment3D ctor (segment3D.h:58-63)
-            const D3 Ct = d3(T->C_d[0], T->C_d[1], T->C_d[2]);
-            reg = make_float2((float)(dnorm(dsub(P1, Ct)) * (double)T->k), (float)(dnorm(dsub(P2, Ct)) * (double)T->k));
-            if (CPU) {      // scoringCPU works on the double 3D segment: direction and (float) length
-                D3 dir = d3(0, 0, 0); float len = 0.0f;
-                if (nondeg) { dir = dnormalized(dsub(P2, P1)); len = (float)sqrt(n2); }
-                d64[j] = make_double4(dir.x, dir.y, dir.z, (double)len);
-            }
-        }
-        e.dep_reg = make_float4(d1, d2, reg.x, reg.y);
-        st[j] = e;
-        // where a positive score has to be announced: the target view, if it is still to be processed (line3D.cc:1680)
-        pub[j] = (!inv && A.pairc[ck.pair].y >= 0) ? ck.other : -1;
-    }
-    __syncwarp();
-    // ---- score the active entries, publish
-    const float k = V->k;
-    float vmax = 0.0f; int cnt = 0;
-    for (int j = lane; j < n; j += 32) {
-        const long long x = x0 + j;
-        float sc = 0.0f;
-        if (__float_as_int(st[j].dir_cam.w) >= 0) {
-            ++cnt;
-            sc = CPU ? sw_score_cpu(st, d64, n, j, k, A.angle_reg, A.sim_t) : sw_score_gpu(st, n, j, k, A.angle_reg, A.sim_t, A.q_thr, A.cos_thr);
-            const int T = pub[j];
-            if (T >= 0 && sc > 0.0f) {      // storeInverseMatches; an inverse match that fails T's orientation check has no entry there
-                const unsigned int ip = A.invpos[A.e_val[x]];
-                if (ip != 0xFFFFFFFFu) A.e_flag[A.vt[T].region_off + ip] = SW_ACTIVE;
-            }
-            vmax = fmaxf(vmax, sc);
-        }
-        A.e_score[x] = sc;
-    }
-    for (int o = 16; o; o >>= 1) { vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-    if (lane == 0) {
-        if (vmax > 0.0f) atomicMax(A.view_max_bits + A.v, __float_as_int(vmax));
-        atomicAdd(A.M + A.v, cnt);
-    }
+    sw_score_range<CPU>(A, P, segb, &nact_smem, s0, nsegs, x0, n);
 }
 
 // ---------------------------------------------------------------------------------------------- after the chain
@@ -624,7 +662,7 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     for (int i = 0; i < V; ++i) Umax = std::max(Umax, S.region_off[i + 1] - S.region_off[i]);
     if (Umax >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: view with more than 2^31 matches");
     RES(S.d_eval, 4 * total, "entry records"); RES(S.d_escore, 4 * total, "entry scores"); RES(S.d_eflag, total, "entry flags");
-    RES(S.d_gstage, sizeof(SwStage) * Umax, "long-list scratch"); RES(S.d_gpub, 4 * Umax, "long-list scratch");
+    RES(S.d_gstage, 40 * Umax, "long-list scratch"); RES(S.d_gpub, 4 * Umax, "long-list scratch");
     if (cpu_sem) RES(S.d_dir64, 32 * Umax, "long-list scratch");
     unsigned int* e_val = (unsigned int*)S.d_eval.p; float* e_score = (float*)S.d_escore.p; unsigned char* e_flag = (unsigned char*)S.d_eflag.p;
     if (total > 0) {
@@ -646,24 +684,25 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     // ---- the chain: one launch per view, ascending camID
     if (total > 0) {
         SwScoreArgs<false> A;
-        A.segs = segs; A.cache = cache; A.rays = (const double*)S.d_rays.p; A.views = views; A.pairs = pairs; A.row_off = d_rowoff; A.num_pairs = NP; A.recs = recs; A.knn = knn; A.v = 0;
+        A.cache = cache; A.rays = (const double*)S.d_rays.p; A.views = views; A.recs = recs; A.v = 0;
         A.vt = d_vt; A.vp = (const SwChunk*)S.d_vp.p; A.pairc = d_pairc; A.cstart = (const long long*)S.d_cstart.p;
         A.e_val = e_val; A.e_score = e_score; A.e_flag = e_flag; A.invpos = (const unsigned int*)S.d_invpos.p;
         A.view_max_bits = (int*)S.d_vmax.p; A.M = (int*)S.d_M.p;
-        A.g_stage = (SwStage*)S.d_gstage.p; A.g_dir64 = cpu_sem ? (double4*)S.d_dir64.p : nullptr; A.g_pub = (int*)S.d_gpub.p;
+        A.g.a = (float4*)S.d_gstage.p; A.g.b = A.g.a + Umax; A.g.r = (float2*)(A.g.b + Umax); A.g.act = (int*)S.d_gpub.p;
+        A.g.d64 = cpu_sem ? (double4*)S.d_dir64.p : nullptr;
         A.angle_reg = two_sigA_sqr; A.sim_t = min_similarity; A.q_thr = q_thr; A.cos_thr = cos_thr;
         SwScoreArgs<true> B;
-        std::memcpy(&B, &A, sizeof(A));
         static_assert(sizeof(SwScoreArgs<true>) == sizeof(SwScoreArgs<false>), "same layout");
-        const size_t sm_gpu = (sizeof(SwStage) + sizeof(int)) * SW_WARPS * SW_CAP_GPU;
-        const size_t sm_cpu = (sizeof(SwStage) + sizeof(int) + sizeof(double4)) * SW_WARPS * SW_CAP_CPU;
+        std::memcpy((void*)&B, (const void*)&A, sizeof(A));
+        const size_t sm_gpu = (size_t)48 * SW_CAP_GPU;
+        const size_t sm_cpu = (size_t)(48 + 32) * SW_CAP_CPU;
         for (int i = 0; i < V; ++i) {
             const int v = S.order[i];
             const int nseg = c->h_views[v].nseg;
             if (nseg == 0 || S.region_off[i + 1] == S.region_off[i]) continue;
-            const unsigned int nb = (unsigned int)((nseg + SW_WARPS - 1) / SW_WARPS);
-            if (cpu_sem) { B.v = v; k_sw_score<true><<<nb, 32 * SW_WARPS, sm_cpu, st>>>(B); }
-            else { A.v = v; k_sw_score<false><<<nb, 32 * SW_WARPS, sm_gpu, st>>>(A); }
+            const unsigned int nb = (unsigned int)((nseg + SW_SEGS - 1) / SW_SEGS);
+            if (cpu_sem) { B.v = v; k_sw_score<true><<<nb, SW_THREADS, sm_cpu, st>>>(B); }
+            else { A.v = v; k_sw_score<false><<<nb, SW_THREADS, sm_gpu, st>>>(A); }
             ++c->launches;
         }
         L3D_CUDA(c, cudaGetLastError(), "score sweep launch");
