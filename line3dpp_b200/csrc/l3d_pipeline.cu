@@ -112,6 +112,17 @@ __device__ __forceinline__ bool sw_orientation_ok(const L3DViewDev* V, const Seg
 }
 
 // ---------------------------------------------------------------------------------------------- batched set-up kernels
+// pair of a record row for a thread block that covers consecutive slots: one binary search per block, then a short walk
+__device__ __forceinline__ int sw_pair_of_row_block(const long long* __restrict__ row_off, int num_pairs, long long row, long long first_row_of_block)
+{
+    __shared__ int p0;
+    if (threadIdx.x == 0) p0 = sw_pair_of_row(row_off, num_pairs, first_row_of_block);
+    __syncthreads();
+    int p = p0;
+    while (p + 1 < num_pairs && __ldg(row_off + p + 1) <= row) ++p;
+    return p;
+}
+
 // P1: one thread per record slot.  rflag bit 0: the record survives the orientation check as a direct match of its source
 // view, bit 1: as an inverse match of its target view (only asked for when the target is processed after the source).
 __global__ void __launch_bounds__(256)
@@ -121,11 +132,11 @@ k_sw_flags(const double* __restrict__ rays, const L3DViewDev* __restrict__ views
            int* __restrict__ csize)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = min(g, slots - 1) / knn;
+    const int p = sw_pair_of_row_block(row_off, num_pairs, row, ((long long)blockIdx.x * blockDim.x) / knn);
     if (g >= slots) return;
-    const long long row = g / knn;
     const int i = (int)(g - row * knn);
     if (i >= counts[row]) return;
-    const int p = sw_pair_of_row(row_off, num_pairs, row);
     const L3DPairDev* P = pairs + p;
     const int r = (int)(row - __ldg(row_off + p));
     const l3d_match_rec rec = recs[g];
@@ -174,11 +185,11 @@ k_sw_scatter(const L3DPairDev* __restrict__ pairs, const long long* __restrict__
              int cpu_sem)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = min(g, slots - 1) / knn;
+    const int p = sw_pair_of_row_block(row_off, num_pairs, row, ((long long)blockIdx.x * blockDim.x) / knn);
     if (g >= slots) return;
     const unsigned char f = rflag[g];
     if (!f) return;
-    const long long row = g / knn;
-    const int p = sw_pair_of_row(row_off, num_pairs, row);
     const L3DPairDev* P = pairs + p;
     const int r = (int)(row - __ldg(row_off + p));
     const unsigned int tseg = recs[g].tgt_seg;
@@ -244,7 +255,7 @@ k_sw_chunksort(long long num_chunks, const long long* __restrict__ cstart, unsig
 // K_score_matches' prologue compute per match), compacts the indices of the active entries and then gives every active entry
 // a thread that walks its own segment's list - K_score_matches' loop (cudawrapper.cu:304-359) - out of shared memory.
 #ifndef SW_THREADS
-#define SW_THREADS 128
+#define SW_THREADS 256
 #endif
 #ifndef SW_SEGS
 #define SW_SEGS 4
@@ -284,10 +295,11 @@ __device__ __forceinline__ float sw_score_gpu(const float4* __restrict__ sa, con
     const float thr1 = q_thr * pos_reg1, thr2 = q_thr * pos_reg2;
     float score3D = 0.0f, current_max_sim = 0.0f;
     int current_cam = -1;
+#pragma unroll 4
     for (int i = lo; i < hi; ++i) {
         const float4 ta = sa[i];
         const int tgt_cam_tgt = __float_as_int(ta.z);
-        if (tgt_cam_tgt < 0 || tgt_cam_src == tgt_cam_tgt) continue;         // not (yet) in the list / same target camera
+        const bool listed = !(tgt_cam_tgt < 0 || tgt_cam_src == tgt_cam_tgt);           // in the list (yet) and not the same target camera
         const float e1 = d1_src - ta.x, e2 = d2_src - ta.y;
         float sim = 0.0f;
         // Exact shortcut: sim = min(three terms), then truncated to 0 below sim_t.  If ONE term is certainly below
@@ -295,7 +307,7 @@ __device__ __forceinline__ float sw_score_gpu(const float4* __restrict__ sa, con
         // q > q_thr = 1.01 * -ln(sim_t) (1 % margin >> the rounding of the division and of expf), and the angular
         // term is certainly below sim_t when |cos| < cos_thr (same margin on the angle).  Everything inside the
         // margins takes the full, reference-order path.
-        if (!(e1 * e1 > thr1 || e2 * e2 > thr2)) {
+        if (listed && !(e1 * e1 > thr1 || e2 * e2 > thr2)) {
             const float4 tb = sb[i];
             const float dp = mb.x * tb.x + mb.y * tb.y + mb.z * tb.z;
             if (!(fabsf(dp) < cos_thr)) {
@@ -308,8 +320,10 @@ __device__ __forceinline__ float sw_score_gpu(const float4* __restrict__ sa, con
                 if (sim < sim_t) sim = 0.0f;
             }
         }
-        current_max_sim = fmaxf(current_max_sim, sim);
-        if (current_cam != tgt_cam_tgt) { score3D += current_max_sim; current_max_sim = 0.0f; current_cam = tgt_cam_tgt; }
+        if (listed) {
+            current_max_sim = fmaxf(current_max_sim, sim);
+            if (current_cam != tgt_cam_tgt) { score3D += current_max_sim; current_max_sim = 0.0f; current_cam = tgt_cam_tgt; }
+        }
     }
     score3D += current_max_sim;
     return score3D;
@@ -360,61 +374,91 @@ __device__ __forceinline__ float sw_score_cpu(const float4* __restrict__ sa, con
     return score3D;
 }
 
+// per-CTA tables in shared memory: chunk boundaries of the CTA's segments (relative to x0), what every chunk of the view points
+// at (other view, its double camera centre and k, whether a positive score has to be announced there), the rays of the segments
+#define SW_MAXCH 512          // chunk boundaries held in shared memory (SW_SEGS * np + 1); beyond that: global look-ups
+#define SW_MAXNP 64           // chunk descriptors held in shared memory
+struct SwChunkInfo { int other, pub; float k; float pad; double Cx, Cy, Cz; };
+struct SwSegInfo { float r1[3], r2[3]; double q1[3], q2[3]; };
+
 template <bool CPU>
-__device__ __forceinline__ void sw_score_range(const SwScoreArgs<CPU>& A, const SwPtrs P, const int* __restrict__ segb, int* __restrict__ nact_smem,
-                                               int s0, int nsegs, long long x0, int n)
+__device__ __forceinline__ void sw_score_range(const SwScoreArgs<CPU>& A, const SwPtrs P, const int* __restrict__ cb, bool cb_smem,
+                                               const SwChunkInfo* __restrict__ cinfo, bool cinfo_smem, const SwSegInfo* __restrict__ sinfo,
+                                               int* __restrict__ nact_smem, int s0, int nsegs, long long x0, int n)
 {
     const L3DViewDev* V = A.views + A.v;
     const SwView me = A.vt[A.v];
     const int lane = threadIdx.x & 31;
+    const int np = me.np;
+    const int nch = nsegs * np;
+    const long long chbase = me.chunk_base + (long long)s0 * np;
     // ---- stage
     for (int j0 = 0; j0 < n; j0 += SW_THREADS) {
         const int j = j0 + threadIdx.x;
         bool active = false;
         if (j < n) {
             const long long x = x0 + j;
-            int si = 0;
-            while (si + 1 < nsegs && segb[si + 1] <= j) ++si;
-            const int s = s0 + si;
-            const long long ch0 = me.chunk_base + (long long)s * me.np;
-            int lo = 0, hi = me.np - 1;             // chunk of x: last c with cstart[ch0 + c] <= x
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (A.cstart[ch0 + mid] <= x) lo = mid; else hi = mid - 1; }
-            const SwChunk ck = A.vp[me.vp_off + lo];
             const unsigned int val = A.e_val[x];
             const l3d_match_rec rec = A.recs[val & ~SW_INV];
+            int lo = 0, hi = nch - 1;               // chunk of entry j: last q with boundary[q] <= j
+            if (cb_smem) { while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cb[mid] <= j) lo = mid; else hi = mid - 1; } }
+            else { while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (A.cstart[chbase + mid] <= x) lo = mid; else hi = mid - 1; } }
+            const int si = lo / np, c = lo - si * np;
+            int other, pub; float kT; D3 Ct;
+            if (cinfo_smem) { const SwChunkInfo ci = cinfo[c]; other = ci.other; pub = ci.pub; kT = ci.k; Ct = d3(ci.Cx, ci.Cy, ci.Cz); }
+            else {
+                const SwChunk ck = A.vp[me.vp_off + c];
+                const L3DViewDev* T = A.views + ck.other;
+                other = ck.other; pub = (!ck.inv && A.pairc[ck.pair].y >= 0) ? ck.other : -1; kT = T->k; Ct = d3(T->C_d[0], T->C_d[1], T->C_d[2]);
+            }
             const bool inv = (val & SW_INV) != 0u;
             const float d1 = inv ? rec.d_q1 : rec.d_p1, d2 = inv ? rec.d_q2 : rec.d_p2;
-            active = inv ? (A.e_flag[x] & SW_ACTIVE) != 0 : true;
-            const long long gs = V->seg_off + s;
+            active = !inv;               // inverse entries learn after the grid-dependency wait whether their source scored them > 0
+            const SwSegInfo& sg = sinfo[si];
             {   // D_unproject x2 + D_line_direction_3D (cudawrapper.cu:167-171, 40-43) with the cached float rays
-                const SegRays R = load_rays(A.cache, gs);
                 const float3 Cf = make_float3(V->C[0], V->C[1], V->C[2]);
-                const float3 P1 = make_float3(Cf.x + d1 * R.r1.x, Cf.y + d1 * R.r1.y, Cf.z + d1 * R.r1.z);
-                const float3 P2 = make_float3(Cf.x + d2 * R.r2.x, Cf.y + d2 * R.r2.y, Cf.z + d2 * R.r2.z);
+                const float3 P1 = make_float3(Cf.x + d1 * sg.r1[0], Cf.y + d1 * sg.r1[1], Cf.z + d1 * sg.r1[2]);
+                const float3 P2 = make_float3(Cf.x + d2 * sg.r2[0], Cf.y + d2 * sg.r2[1], Cf.z + d2 * sg.r2[2]);
                 const float3 dir = normalize3(make_float3(P2.x - P1.x, P2.y - P1.y, P2.z - P1.z));
                 // where a positive score has to be announced: the target view, if it is still to be processed (line3D.cc:1680)
-                P.b[j] = make_float4(dir.x, dir.y, dir.z, __int_as_float((!inv && A.pairc[ck.pair].y >= 0) ? ck.other : -1));
+                P.b[j] = make_float4(dir.x, dir.y, dir.z, __int_as_float(inv ? -1 : pub));
             }
             float2 reg = make_float2(0.f, 0.f);
-            if (active) {   // regularizers_tgt (line3D.cc:1350-1352) == View::regularizerFrom3Dpoint (view.cc:445-448): |P - C_tgt| * k_tgt in double, stored as float
-                const L3DViewDev* T = A.views + ck.other;
-                const SegRaysQ Q = sw_load_rays(A.rays, gs);
+            {   // regularizers_tgt (line3D.cc:1350-1352) == View::regularizerFrom3Dpoint (view.cc:445-448): |P - C_tgt| * k_tgt in double, stored as float
+                SegRaysQ Q;
+                Q.r1 = d3(sg.q1[0], sg.q1[1], sg.q1[2]); Q.r2 = d3(sg.q2[0], sg.q2[1], sg.q2[2]); Q.rm = d3(0, 0, 0);
                 D3 P1, P2;
                 sw_unproject_pts(V, Q, d1, d2, &P1, &P2);
                 const D3 dd = dsub(P1, P2);
                 const double n2 = ddot(dd, dd);
                 const bool nondeg = sw_nondegenerate(n2);
                 if (!nondeg) P1 = P2 = d3(0, 0, 0);                                   // Segment3D ctor (segment3D.h:58-63)
-                const D3 Ct = d3(T->C_d[0], T->C_d[1], T->C_d[2]);
-                reg = make_float2((float)(dnorm(dsub(P1, Ct)) * (double)T->k), (float)(dnorm(dsub(P2, Ct)) * (double)T->k));
+                reg = make_float2((float)(dnorm(dsub(P1, Ct)) * (double)kT), (float)(dnorm(dsub(P2, Ct)) * (double)kT));
                 if (CPU) {      // scoringCPU works on the double 3D segment: direction and (float) length
                     D3 dir = d3(0, 0, 0); float len = 0.0f;
                     if (nondeg) { dir = dnormalized(dsub(P2, P1)); len = (float)sqrt(n2); }
                     P.d64[j] = make_double4(dir.x, dir.y, dir.z, (double)len);
                 }
-            } else A.e_score[x] = 0.0f;
-            P.a[j] = make_float4(d1, d2, __int_as_float(active ? ck.other : -1), __int_as_float(si));
+            }
+            // inverse entries carry their target view as -2 - view until they are known to be active
+            P.a[j] = make_float4(d1, d2, __int_as_float(active ? other : -2 - other), __int_as_float(si));
             P.r[j] = reg;
+        }
+    }
+    // ---- everything above only read what the set-up kernels wrote: it may overlap the previous view's kernel (programmatic
+    // dependent launch).  From here on the "active" bits that kernel publishes are needed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int j0 = 0; j0 < n; j0 += SW_THREADS) {
+        const int j = j0 + threadIdx.x;
+        bool active = false;
+        if (j < n) {
+            const int cam = __float_as_int(P.a[j].z);
+            active = cam >= 0;
+            if (!active) {
+                const long long x = x0 + j;
+                if (A.e_flag[x] & SW_ACTIVE) { active = true; P.a[j].z = __int_as_float(-2 - cam); }
+                else { P.a[j].z = __int_as_float(-1); A.e_score[x] = 0.0f; }
+            }
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, active);
         int base = 0;
@@ -432,8 +476,11 @@ __device__ __forceinline__ void sw_score_range(const SwScoreArgs<CPU>& A, const 
         const int j = P.act[q];
         const float4 ma = P.a[j];
         const int si = __float_as_int(ma.w);
-        const float sc = CPU ? sw_score_cpu(P.a, P.d64, P.r[j], segb[si], segb[si + 1], j, k, A.angle_reg, A.sim_t)
-                             : sw_score_gpu(P.a, P.b, P.r[j], segb[si], segb[si + 1], j, k, A.angle_reg, A.sim_t, A.q_thr, A.cos_thr);
+        int lo, hi;
+        if (cb_smem) { lo = cb[si * np]; hi = cb[(si + 1) * np]; }
+        else { lo = (int)(A.cstart[chbase + (long long)si * np] - x0); hi = (int)(A.cstart[chbase + (long long)(si + 1) * np] - x0); }
+        const float sc = CPU ? sw_score_cpu(P.a, P.d64, P.r[j], lo, hi, j, k, A.angle_reg, A.sim_t)
+                             : sw_score_gpu(P.a, P.b, P.r[j], lo, hi, j, k, A.angle_reg, A.sim_t, A.q_thr, A.cos_thr);
         const long long x = x0 + j;
         const int T = __float_as_int(P.b[j].w);
         if (T >= 0 && sc > 0.0f) {      // storeInverseMatches; an inverse match that fails T's orientation check has no entry there
@@ -449,32 +496,58 @@ __device__ __forceinline__ void sw_score_range(const SwScoreArgs<CPU>& A, const 
 }
 
 template <bool CPU>
-__global__ void __launch_bounds__(SW_THREADS)
+__global__ void __launch_bounds__(SW_THREADS, CPU ? 3 : 5)
 k_sw_score(const SwScoreArgs<CPU> A)
 {
     constexpr int CAP = CPU ? SW_CAP_CPU : SW_CAP_GPU;
+    asm volatile("griddepcontrol.launch_dependents;");       // the next view's kernel may start its independent part
     extern __shared__ __align__(16) unsigned char sw_smem[];
-    __shared__ int segb[SW_SEGS + 1];
+    __shared__ int cb[SW_MAXCH + 1];
+    __shared__ SwChunkInfo cinfo[SW_MAXNP];
+    __shared__ SwSegInfo sinfo[SW_SEGS];
     __shared__ int nact_smem;
     const L3DViewDev* V = A.views + A.v;
     const int s0 = blockIdx.x * SW_SEGS;
     const int nsegs = min(SW_SEGS, V->nseg - s0);
     const SwView me = A.vt[A.v];
-    const long long x0 = A.cstart[me.chunk_base + (long long)s0 * me.np];
-    if (threadIdx.x <= nsegs) segb[threadIdx.x] = (int)(A.cstart[me.chunk_base + (long long)(s0 + threadIdx.x) * me.np] - x0);
+    const int np = me.np, nch = nsegs * np;
+    const long long chbase = me.chunk_base + (long long)s0 * np;
+    const long long x0 = A.cstart[chbase];
+    const int n = (int)(A.cstart[chbase + nch] - x0);
+    if (n == 0) return;
+    const bool cb_smem = nch <= SW_MAXCH, cinfo_smem = np <= SW_MAXNP;
+    if (cb_smem) for (int q = threadIdx.x; q <= nch; q += SW_THREADS) cb[q] = (int)(A.cstart[chbase + q] - x0);
+    if (cinfo_smem)
+        for (int c = threadIdx.x; c < np; c += SW_THREADS) {
+            const SwChunk ck = A.vp[me.vp_off + c];
+            const L3DViewDev* T = A.views + ck.other;
+            SwChunkInfo ci;
+            ci.other = ck.other; ci.pub = (!ck.inv && A.pairc[ck.pair].y >= 0) ? ck.other : -1; ci.k = T->k; ci.pad = 0.f;
+            ci.Cx = T->C_d[0]; ci.Cy = T->C_d[1]; ci.Cz = T->C_d[2];
+            cinfo[c] = ci;
+        }
+    if (threadIdx.x < nsegs) {
+        const long long gs = V->seg_off + s0 + threadIdx.x;
+        const SegRays R = load_rays(A.cache, gs);
+        const SegRaysQ Q = sw_load_rays(A.rays, gs);
+        SwSegInfo si;
+        si.r1[0] = R.r1.x; si.r1[1] = R.r1.y; si.r1[2] = R.r1.z; si.r2[0] = R.r2.x; si.r2[1] = R.r2.y; si.r2[2] = R.r2.z;
+        si.q1[0] = Q.r1.x; si.q1[1] = Q.r1.y; si.q1[2] = Q.r1.z; si.q2[0] = Q.r2.x; si.q2[1] = Q.r2.y; si.q2[2] = Q.r2.z;
+        sinfo[threadIdx.x] = si;
+    }
     if (threadIdx.x == 0) nact_smem = 0;
     __syncthreads();
-    const int n = segb[nsegs];
-    if (n == 0) return;
     SwPtrs P;
     if (n <= CAP) {
         P.a = (float4*)sw_smem; P.b = P.a + CAP; P.r = (float2*)(P.b + CAP); P.act = (int*)(P.r + CAP);
         P.d64 = CPU ? (double4*)(sw_smem + (size_t)CAP * 48) : nullptr;           // 16 + 16 + 8 + 4 = 44 -> rounded up to 48 for the double4 alignment
     } else {
+        // the global scratch is shared with the kernels of the neighbouring views: only touch it once they are done
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         const long long rel = x0 - me.region_off;
         P.a = A.g.a + rel; P.b = A.g.b + rel; P.r = A.g.r + rel; P.act = A.g.act + rel; P.d64 = CPU ? A.g.d64 + rel : nullptr;
     }
-    sw_score_range<CPU>(A, P, segb, &nact_smem, s0, nsegs, x0, n);
+    sw_score_range<CPU>(A, P, cb, cb_smem, cinfo, cinfo_smem, sinfo, &nact_smem, s0, nsegs, x0, n);
 }
 
 // ---------------------------------------------------------------------------------------------- after the chain
@@ -662,8 +735,8 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     for (int i = 0; i < V; ++i) Umax = std::max(Umax, S.region_off[i + 1] - S.region_off[i]);
     if (Umax >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: view with more than 2^31 matches");
     RES(S.d_eval, 4 * total, "entry records"); RES(S.d_escore, 4 * total, "entry scores"); RES(S.d_eflag, total, "entry flags");
-    RES(S.d_gstage, 40 * Umax, "long-list scratch"); RES(S.d_gpub, 4 * Umax, "long-list scratch");
-    if (cpu_sem) RES(S.d_dir64, 32 * Umax, "long-list scratch");
+    RES(S.d_gstage, 2 * 48 * Umax, "long-list scratch"); RES(S.d_gpub, 2 * 4 * Umax, "long-list scratch");
+    if (cpu_sem) RES(S.d_dir64, 2 * 32 * Umax, "long-list scratch");
     unsigned int* e_val = (unsigned int*)S.d_eval.p; float* e_score = (float*)S.d_escore.p; unsigned char* e_flag = (unsigned char*)S.d_eflag.p;
     if (total > 0) {
         // the sort keys live in the score array until the chain starts
@@ -688,8 +761,15 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
         A.vt = d_vt; A.vp = (const SwChunk*)S.d_vp.p; A.pairc = d_pairc; A.cstart = (const long long*)S.d_cstart.p;
         A.e_val = e_val; A.e_score = e_score; A.e_flag = e_flag; A.invpos = (const unsigned int*)S.d_invpos.p;
         A.view_max_bits = (int*)S.d_vmax.p; A.M = (int*)S.d_M.p;
-        A.g.a = (float4*)S.d_gstage.p; A.g.b = A.g.a + Umax; A.g.r = (float2*)(A.g.b + Umax); A.g.act = (int*)S.d_gpub.p;
-        A.g.d64 = cpu_sem ? (double4*)S.d_dir64.p : nullptr;
+        SwPtrs gbuf[2];
+        for (int q = 0; q < 2; ++q) {
+            gbuf[q].a = (float4*)S.d_gstage.p + (size_t)q * Umax * 3;      // 40 B per entry = 2.5 float4: 3 keeps every part 16-byte aligned
+            gbuf[q].b = gbuf[q].a + Umax; gbuf[q].r = (float2*)(gbuf[q].b + Umax);
+            gbuf[q].act = (int*)S.d_gpub.p + (size_t)q * Umax;
+            gbuf[q].d64 = cpu_sem ? (double4*)S.d_dir64.p + (size_t)q * Umax : nullptr;
+        }
+        A.g = gbuf[0];
+        int launched = 0;
         A.angle_reg = two_sigA_sqr; A.sim_t = min_similarity; A.q_thr = q_thr; A.cos_thr = cos_thr;
         SwScoreArgs<true> B;
         static_assert(sizeof(SwScoreArgs<true>) == sizeof(SwScoreArgs<false>), "same layout");
@@ -701,8 +781,17 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
             const int nseg = c->h_views[v].nseg;
             if (nseg == 0 || S.region_off[i + 1] == S.region_off[i]) continue;
             const unsigned int nb = (unsigned int)((nseg + SW_SEGS - 1) / SW_SEGS);
-            if (cpu_sem) { B.v = v; k_sw_score<true><<<nb, SW_THREADS, sm_cpu, st>>>(B); }
-            else { A.v = v; k_sw_score<false><<<nb, SW_THREADS, sm_gpu, st>>>(A); }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(nb); cfg.blockDim = dim3(SW_THREADS); cfg.dynamicSmemBytes = cpu_sem ? sm_cpu : sm_gpu; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+            // programmatic dependent launch: this view's kernel may stage its lists while the previous view's kernel is still scoring
+            // (it waits before it reads the bits that kernel publishes).  The first one follows ordinary kernels: plain stream order.
+            cfg.attrs = attr; cfg.numAttrs = launched ? 1 : 0;
+            A.g = gbuf[launched & 1]; B.g = gbuf[launched & 1];       // long-list scratch: double-buffered, two kernels may be in flight
+            ++launched;
+            if (cpu_sem) { B.v = v; L3D_CUDA(c, cudaLaunchKernelEx(&cfg, k_sw_score<true>, B), "k_sw_score"); }
+            else { A.v = v; L3D_CUDA(c, cudaLaunchKernelEx(&cfg, k_sw_score<false>, A), "k_sw_score"); }
             ++c->launches;
         }
         L3D_CUDA(c, cudaGetLastError(), "score sweep launch");
