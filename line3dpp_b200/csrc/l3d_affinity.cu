@@ -13,6 +13,10 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
 #include <cstdlib>
@@ -88,14 +92,15 @@ __device__ __forceinline__ float4 sw_best_depths(const SwStore& M, int view, int
 
 __global__ void __launch_bounds__(256)
 k_affinity(const L3DViewDev* __restrict__ views, const long long* __restrict__ region_off, const int* __restrict__ order,
-           int V, long long total, const SwStore M, const int* __restrict__ est_best,
+           int V, long long K, const long long* __restrict__ kx, const SwStore M, const int* __restrict__ est_best,
            const double* __restrict__ est_P, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity,
            float* __restrict__ sim_out, int* __restrict__ flag_out, long long* __restrict__ gi_out, long long* __restrict__ gj_out)
 {
-    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= total) return;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= K) return;
+    const long long x = kx[q];                   // the q-th kept match in emission order
     int flag = 0; float sim = 0.0f; long long gi = -1, gj = -1;
-    if (M.e_flag[x] & SW_KEPT) {
+    {
         int lo = 0, hi = V - 1;                  // processing rank whose region contains x
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (region_off[mid] <= x) lo = mid; else hi = mid - 1; }
         const int v1i = order[lo];
@@ -110,7 +115,7 @@ k_affinity(const L3DViewDev* __restrict__ views, const long long* __restrict__ r
             flag = sim > min_affinity ? 1 : 0;
         }
     }
-    sim_out[x] = sim; flag_out[x] = flag; gi_out[x] = gi; gj_out[x] = gj;
+    sim_out[q] = sim; flag_out[q] = flag; gi_out[q] = gi; gj_out[q] = gj;
 }
 
 // ---- affinity candidates WITH collinearity links (line3D.cc:1904-1974), one thread per segment in estimate order ----
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(128)
 k_aff_events(const L3DViewDev* __restrict__ views, const long long* __restrict__ region_off, const int* __restrict__ order,
              const long long* __restrict__ segrank_off, int V, long long N, const SwStore M,
              const int2* __restrict__ ranges, const int* __restrict__ est_best, const double* __restrict__ est_P,
-             const float* __restrict__ sim_slot, const int* __restrict__ flag_slot, const long long* __restrict__ cptr,
+             long long K, const long long* __restrict__ kx, const float* __restrict__ sim_slot, const int* __restrict__ flag_slot, const long long* __restrict__ cptr,
              const int* __restrict__ cidx, float two_sigA_sqr, float med_scene_depth_lines, float min_affinity, int* __restrict__ evcnt,
              const long long* __restrict__ evptr, long long* __restrict__ out_i, long long* __restrict__ out_j, float* __restrict__ out_w,
              int* __restrict__ out_par)
@@ -146,14 +151,20 @@ k_aff_events(const L3DViewDev* __restrict__ views, const long long* __restrict__
         const double* P1 = est_P + 6 * g;
         const float4 m1 = sw_best_depths(M, v1i, b1);
         bool found = false;
-        for (int i = rng.x; i <= rng.y && rng.x >= 0; ++i) {
-            const long long x = ro + i;
-            if (!(M.e_flag[x] & SW_KEPT) || !flag_slot[x]) continue;
+        long long q = 0;
+        if (rng.x >= 0) {                        // first kept match of this segment in the compact list
+            long long a = 0, b = K;
+            while (a < b) { const long long mid = (a + b) >> 1; if (kx[mid] < ro + rng.x) a = mid + 1; else b = mid; }
+            q = a;
+        }
+        for (; rng.x >= 0 && q < K && kx[q] <= ro + rng.y; ++q) {
+            const long long x = kx[q];
+            if (!flag_slot[q]) continue;
             const SwEntry me = sw_decode(M.e_val[x], M.pairs, M.row_off, M.num_pairs, M.knn, M.recs);
             const L3DViewDev* v2 = views + me.tgt_view;
             const long long gj = v2->seg_off + me.tgt_seg;
             const long long parent = base + n;
-            if (FILL) { out_i[parent] = g; out_j[parent] = gj; out_w[parent] = sim_slot[x]; out_par[parent] = -1; }
+            if (FILL) { out_i[parent] = g; out_j[parent] = gj; out_w[parent] = sim_slot[q]; out_par[parent] = -1; }
             ++n; found = true;
             for (long long q = cptr[gj]; q < cptr[gj + 1]; ++q) {                  // collinear with the target (line3D.cc:1904-1937)
                 const long long g2 = v2->seg_off + cidx[q];
@@ -458,6 +469,8 @@ __global__ void __launch_bounds__(256) k_aff_emit(long long ne, const int* __res
     ei[o + 1] = b; ej[o + 1] = a; ew[o + 1] = w[e];
 }
 
+struct KeptFlag { const unsigned char* f; __host__ __device__ int operator()(long long x) const { return (f[x] & SW_KEPT) ? 1 : 0; } };
+
 extern "C" {
 
 // device part shared by l3d_affinity_edges / l3d_affinity_matrix: similarities of all kept matches, then the candidates with
@@ -470,30 +483,69 @@ static long long affinity_candidates(l3d_ctx* c, float two_sigA_sqr, float med_s
     const int V = c->num_views;
     int rc;
     DevBuf &d_sim = S.d_aff_sim, &d_flag = S.d_aff_flag, &d_gi = S.d_aff_gi, &d_gj = S.d_aff_gj, &d_pos = S.d_aff_pos;
-    if ((rc = l3d_reserve(c, d_sim, 4 * (size_t)total, "affinity sims"))) return rc;
-    if ((rc = l3d_reserve(c, d_flag, 4 * (size_t)total, "affinity flags"))) return rc;
-    if ((rc = l3d_reserve(c, d_gi, 8 * (size_t)total, "affinity gi"))) return rc;
-    if ((rc = l3d_reserve(c, d_gj, 8 * (size_t)total, "affinity gj"))) return rc;
-    if ((rc = l3d_reserve(c, d_pos, 8 * (size_t)(total + 1), "affinity pos"))) return rc;
+    cudaStream_t st = c->stream;
+    // the kept matches (filterMatches survivors), compacted in emission order: everything below works on this list, not on the
+    // whole match store (2.5e9 entries at BASELINE configs[4])
+    const long long BLK = 1ll << 30;
+    long long K = 0;
+    if ((rc = l3d_reserve(c, d_pos, 16, "kept count"))) return rc;
+    std::vector<long long> kept_in_block;
+    for (long long base = 0; base < total; base += BLK) {
+        const int nblk = (int)std::min(BLK, total - base);
+        cub::CountingInputIterator<long long> idx(base);
+        cub::TransformInputIterator<int, KeptFlag, cub::CountingInputIterator<long long> > flags(idx, KeptFlag{(const unsigned char*)S.d_eflag.p});
+        size_t tb = 0;
+        cub::DeviceReduce::Sum(nullptr, tb, flags, (int*)d_pos.p, nblk, st);
+        if ((rc = l3d_reserve(c, S.d_sort_tmp, tb, "reduce temp"))) return rc;
+        tb = S.d_sort_tmp.cap;
+        L3D_CUDA(c, cub::DeviceReduce::Sum(S.d_sort_tmp.p, tb, flags, (int*)d_pos.p, nblk, st), "kept count");
+        int cnt = 0;
+        L3D_CUDA(c, cudaMemcpyAsync(&cnt, d_pos.p, 4, cudaMemcpyDeviceToHost, st), "kept count");
+        L3D_CUDA(c, cudaStreamSynchronize(st), "kept count");
+        kept_in_block.push_back(cnt); K += cnt;
+    }
+    S.n_kept = K;
+    if (K == 0) return 0;
+    if ((rc = l3d_reserve(c, S.d_kx, 8 * (size_t)K, "kept list"))) return rc;
+    {
+        long long done = 0; size_t bi = 0;
+        for (long long base = 0; base < total; base += BLK, ++bi) {
+            const int nblk = (int)std::min(BLK, total - base);
+            if (kept_in_block[bi] == 0) continue;
+            cub::CountingInputIterator<long long> idx(base);
+            cub::TransformInputIterator<int, KeptFlag, cub::CountingInputIterator<long long> > flags(idx, KeptFlag{(const unsigned char*)S.d_eflag.p});
+            size_t tb = 0;
+            cub::DeviceSelect::Flagged(nullptr, tb, idx, flags, (long long*)S.d_kx.p + done, (int*)d_pos.p, nblk, st);
+            if ((rc = l3d_reserve(c, S.d_sort_tmp, tb, "select temp"))) return rc;
+            tb = S.d_sort_tmp.cap;
+            L3D_CUDA(c, cub::DeviceSelect::Flagged(S.d_sort_tmp.p, tb, idx, flags, (long long*)S.d_kx.p + done, (int*)d_pos.p, nblk, st), "kept list");
+            done += kept_in_block[bi];
+        }
+        c->launches += 2 * (long long)kept_in_block.size();
+    }
+    if ((rc = l3d_reserve(c, d_sim, 4 * (size_t)K, "affinity sims"))) return rc;
+    if ((rc = l3d_reserve(c, d_flag, 4 * (size_t)K, "affinity flags"))) return rc;
+    if ((rc = l3d_reserve(c, d_gi, 8 * (size_t)K, "affinity gi"))) return rc;
+    if ((rc = l3d_reserve(c, d_gj, 8 * (size_t)K, "affinity gj"))) return rc;
+    if ((rc = l3d_reserve(c, d_pos, 8 * (size_t)(K + 1), "affinity pos"))) return rc;
     std::vector<int> rank_of_view(V);
     for (int i = 0; i < V; ++i) rank_of_view[S.order[i]] = i;
     if ((rc = l3d_reserve(c, S.d_order, 4 * (size_t)V, "order"))) return rc;
     if ((rc = l3d_reserve(c, S.d_rankofview, 4 * (size_t)V, "rank of view"))) return rc;
     if ((rc = l3d_reserve(c, S.d_region_off, 8 * (size_t)(V + 1), "region offsets"))) return rc;
-    cudaStream_t st = c->stream;
     L3D_CUDA(c, cudaMemcpyAsync(S.d_order.p, S.order.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "order");
     L3D_CUDA(c, cudaMemcpyAsync(S.d_rankofview.p, rank_of_view.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "rank of view");
     L3D_CUDA(c, cudaMemcpyAsync(S.d_region_off.p, S.region_off.data(), 8 * (size_t)(V + 1), cudaMemcpyHostToDevice, st), "region offsets");
-    const unsigned int nb = (unsigned int)((total + 255) / 256);
+    const unsigned int nb = (unsigned int)((K + 255) / 256);
     SwStore M;
     M.vt = (const SwView*)S.d_vt.p; M.pairs = (const L3DPairDev*)c->d_pairs.p; M.row_off = (const long long*)S.d_rowoff.p; M.num_pairs = c->num_pairs; M.knn = c->knn;
     M.recs = (const l3d_match_rec*)c->d_recs.p; M.e_val = (const unsigned int*)S.d_eval.p; M.e_flag = (const unsigned char*)S.d_eflag.p;
-    k_affinity<<<nb, 256, 0, st>>>(c->views(), (const long long*)S.d_region_off.p, (const int*)S.d_order.p, V, total, M, (const int*)S.d_est_best.p,
+    k_affinity<<<nb, 256, 0, st>>>(c->views(), (const long long*)S.d_region_off.p, (const int*)S.d_order.p, V, K, (const long long*)S.d_kx.p, M, (const int*)S.d_est_best.p,
                                    (const double*)S.d_est_P.p, two_sigA_sqr, med_scene_depth_lines, min_affinity, (float*)d_sim.p, (int*)d_flag.p,
                                    (long long*)d_gi.p, (long long*)d_gj.p);
     if (c->collin.valid) {
         // collinearity links on: events per segment in estimate order (count, scan, fill), each with its parent
-        const CollinState& K = c->collin;
+        const CollinState& CL = c->collin;
         const long long N = c->total_segs;
         std::vector<long long> segrank_off((size_t)V + 1, 0);
         for (int i = 0; i < V; ++i) segrank_off[i + 1] = segrank_off[i] + c->h_views[S.order[i]].nseg;
@@ -505,7 +557,8 @@ static long long affinity_candidates(l3d_ctx* c, float two_sigA_sqr, float med_s
         const unsigned int nbs = (unsigned int)((N + 127) / 128);
 #define EV_ARGS c->views(), (const long long*)S.d_region_off.p, (const int*)S.d_order.p, (const long long*)S.d_segrank_off.p, V, N, M,                      \
                 (const int2*)S.d_ranges.p, (const int*)S.d_est_best.p,                                                                                        \
-                (const double*)S.d_est_P.p, (const float*)d_sim.p, (const int*)d_flag.p, (const long long*)K.d_ptr.p, (const int*)K.d_idx.p, two_sigA_sqr,          \
+                (const double*)S.d_est_P.p, K, (const long long*)S.d_kx.p, (const float*)d_sim.p, (const int*)d_flag.p, (const long long*)CL.d_ptr.p,             \
+                (const int*)CL.d_idx.p, two_sigA_sqr,                                                                                                         \
                 med_scene_depth_lines, min_affinity
         k_aff_events<false><<<nbs, 128, 0, st>>>(EV_ARGS, (int*)S.d_evcnt.p, nullptr, nullptr, nullptr, nullptr, nullptr);
         size_t tbe = 0;
@@ -533,13 +586,14 @@ static long long affinity_candidates(l3d_ctx* c, float two_sigA_sqr, float med_s
     }
     S.aff_has_parents = false;
     size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)d_flag.p, (long long*)d_pos.p, total, st);
+    if (K >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "affinity: more than 2^31 kept matches");
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)d_flag.p, (long long*)d_pos.p, (int)K, st);
     if ((rc = l3d_reserve(c, S.d_sort_tmp, tb, "scan temp"))) return rc;
-    tb = S.d_sort_tmp.cap;   // scan over `total` items; the edge count is pos[total-1] + flag[total-1]
-    L3D_CUDA(c, cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tb, (const int*)d_flag.p, (long long*)d_pos.p, total, st), "affinity scan");
+    tb = S.d_sort_tmp.cap;   // scan over the kept matches; the edge count is pos[K-1] + flag[K-1]
+    L3D_CUDA(c, cub::DeviceScan::ExclusiveSum(S.d_sort_tmp.p, tb, (const int*)d_flag.p, (long long*)d_pos.p, (int)K, st), "affinity scan");
     long long last_pos = 0; int last_flag = 0;
-    L3D_CUDA(c, cudaMemcpyAsync(&last_pos, (long long*)d_pos.p + total - 1, 8, cudaMemcpyDeviceToHost, st), "count");
-    L3D_CUDA(c, cudaMemcpyAsync(&last_flag, (int*)d_flag.p + total - 1, 4, cudaMemcpyDeviceToHost, st), "count");
+    L3D_CUDA(c, cudaMemcpyAsync(&last_pos, (long long*)d_pos.p + K - 1, 8, cudaMemcpyDeviceToHost, st), "count");
+    L3D_CUDA(c, cudaMemcpyAsync(&last_flag, (int*)d_flag.p + K - 1, 4, cudaMemcpyDeviceToHost, st), "count");
     L3D_CUDA(c, cudaStreamSynchronize(st), "affinity");
     const long long ne = last_pos + last_flag;
     c->launches += 3;
@@ -548,7 +602,7 @@ static long long affinity_candidates(l3d_ctx* c, float two_sigA_sqr, float med_s
     if ((rc = l3d_reserve(c, o_i, 8 * (size_t)ne, "edges i"))) return rc;
     if ((rc = l3d_reserve(c, o_j, 8 * (size_t)ne, "edges j"))) return rc;
     if ((rc = l3d_reserve(c, o_w, 4 * (size_t)ne, "edges w"))) return rc;
-    k_affinity_compact<<<nb, 256, 0, st>>>(total, (const int*)d_flag.p, (const long long*)d_pos.p, (const float*)d_sim.p, (const long long*)d_gi.p,
+    k_affinity_compact<<<nb, 256, 0, st>>>(K, (const int*)d_flag.p, (const long long*)d_pos.p, (const float*)d_sim.p, (const long long*)d_gi.p,
                                            (const long long*)d_gj.p, (long long*)o_i.p, (long long*)o_j.p, (float*)o_w.p);
     ++c->launches;
     L3D_CUDA(c, cudaGetLastError(), "k_affinity_compact");

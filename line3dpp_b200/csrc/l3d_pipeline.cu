@@ -112,15 +112,54 @@ __device__ __forceinline__ bool sw_orientation_ok(const L3DViewDev* V, const Seg
 }
 
 // ---------------------------------------------------------------------------------------------- batched set-up kernels
-// pair of a record row for a thread block that covers consecutive slots: one binary search per block, then a short walk
-__device__ __forceinline__ int sw_pair_of_row_block(const long long* __restrict__ row_off, int num_pairs, long long row, long long first_row_of_block)
+// What the record-parallel set-up kernels need to know about a pair, gathered once per thread block (a block of consecutive record
+// slots touches one pair, at most a few): without it every thread walks pairs[p] -> views[src] -> vt[src] ... as a chain of
+// dependent global loads.
+struct SwPairInfo {
+    long long row_off, row_end, src_seg_off, tgt_seg_off, src_chunk_base, tgt_chunk_base;
+    int src, tgt, src_np, tgt_np, cx, cy;
+};
+#define SW_PI 4
+__device__ __forceinline__ void sw_load_pair_info(SwPairInfo* __restrict__ pi, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
+                                                  const long long* __restrict__ row_off, int num_pairs, const SwView* __restrict__ vt,
+                                                  const int2* __restrict__ pairc, long long first_row)
 {
-    __shared__ int p0;
-    if (threadIdx.x == 0) p0 = sw_pair_of_row(row_off, num_pairs, first_row_of_block);
+    __shared__ int p0s;
+    if (threadIdx.x == 0) p0s = sw_pair_of_row(row_off, num_pairs, first_row);
     __syncthreads();
-    int p = p0;
-    while (p + 1 < num_pairs && __ldg(row_off + p + 1) <= row) ++p;
-    return p;
+    if (threadIdx.x < SW_PI) {
+        const int p = p0s + threadIdx.x;
+        SwPairInfo q;
+        if (p < num_pairs) {
+            const L3DPairDev* P = pairs + p;
+            q.row_off = row_off[p]; q.row_end = row_off[p + 1]; q.src = P->src; q.tgt = P->tgt;
+            q.src_seg_off = views[q.src].seg_off; q.tgt_seg_off = views[q.tgt].seg_off;
+            const SwView sv = vt[q.src], tv = vt[q.tgt];
+            q.src_chunk_base = sv.chunk_base; q.tgt_chunk_base = tv.chunk_base; q.src_np = sv.np; q.tgt_np = tv.np;
+            const int2 pc = pairc[p];
+            q.cx = pc.x; q.cy = pc.y;
+        } else { q.row_off = q.row_end = (1ll << 62); q.src = q.tgt = 0; q.src_seg_off = q.tgt_seg_off = q.src_chunk_base = q.tgt_chunk_base = 0; q.src_np = q.tgt_np = 0; q.cx = q.cy = -1; }
+        pi[threadIdx.x] = q;
+    }
+    __syncthreads();
+}
+// the info of the pair that holds `row` (in shared memory if it is one of the block's first SW_PI pairs)
+__device__ __forceinline__ SwPairInfo sw_pair_info(const SwPairInfo* __restrict__ pi, long long row, const L3DViewDev* __restrict__ views,
+                                                   const L3DPairDev* __restrict__ pairs, const long long* __restrict__ row_off, int num_pairs,
+                                                   const SwView* __restrict__ vt, const int2* __restrict__ pairc)
+{
+#pragma unroll
+    for (int k = 0; k < SW_PI; ++k) if (row < pi[k].row_end) return pi[k];
+    const int p = sw_pair_of_row(row_off, num_pairs, row);
+    const L3DPairDev* P = pairs + p;
+    SwPairInfo q;
+    q.row_off = row_off[p]; q.row_end = row_off[p + 1]; q.src = P->src; q.tgt = P->tgt;
+    q.src_seg_off = views[q.src].seg_off; q.tgt_seg_off = views[q.tgt].seg_off;
+    const SwView sv = vt[q.src], tv = vt[q.tgt];
+    q.src_chunk_base = sv.chunk_base; q.tgt_chunk_base = tv.chunk_base; q.src_np = sv.np; q.tgt_np = tv.np;
+    const int2 pc = pairc[p];
+    q.cx = pc.x; q.cy = pc.y;
+    return q;
 }
 
 // P1: one thread per record slot.  rflag bit 0: the record survives the orientation check as a direct match of its source
@@ -131,32 +170,24 @@ k_sw_flags(const double* __restrict__ rays, const L3DViewDev* __restrict__ views
            int knn, long long slots, const SwView* __restrict__ vt, const int2* __restrict__ pairc, unsigned char* __restrict__ rflag,
            int* __restrict__ csize)
 {
+    __shared__ SwPairInfo pi[SW_PI];
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long row = min(g, slots - 1) / knn;
-    const int p = sw_pair_of_row_block(row_off, num_pairs, row, ((long long)blockIdx.x * blockDim.x) / knn);
+    sw_load_pair_info(pi, views, pairs, row_off, num_pairs, vt, pairc, ((long long)blockIdx.x * blockDim.x) / knn);
     if (g >= slots) return;
+    const long long row = g / knn;
     const int i = (int)(g - row * knn);
     if (i >= counts[row]) return;
-    const L3DPairDev* P = pairs + p;
-    const int r = (int)(row - __ldg(row_off + p));
     const l3d_match_rec rec = recs[g];
-    const int2 pc = pairc[p];
+    const SwPairInfo q = sw_pair_info(pi, row, views, pairs, row_off, num_pairs, vt, pairc);
+    const int r = (int)(row - q.row_off);
     unsigned char f = 0;
-    {
-        const L3DViewDev* S = views + P->src;
-        if (sw_orientation_ok(S, sw_load_rays(rays, S->seg_off + r), rec.d_p1, rec.d_p2)) {
-            f |= 1;
-            const SwView sv = vt[P->src];
-            atomicAdd(csize + sv.chunk_base + (long long)r * sv.np + pc.x, 1);
-        }
+    if (sw_orientation_ok(views + q.src, sw_load_rays(rays, q.src_seg_off + r), rec.d_p1, rec.d_p2)) {
+        f |= 1;
+        atomicAdd(csize + q.src_chunk_base + (long long)r * q.src_np + q.cx, 1);
     }
-    if (pc.y >= 0) {
-        const L3DViewDev* T = views + P->tgt;
-        if (sw_orientation_ok(T, sw_load_rays(rays, T->seg_off + rec.tgt_seg), rec.d_q1, rec.d_q2)) {
-            f |= 2;
-            const SwView tv = vt[P->tgt];
-            atomicAdd(csize + tv.chunk_base + (long long)rec.tgt_seg * tv.np + pc.y, 1);
-        }
+    if (q.cy >= 0 && sw_orientation_ok(views + q.tgt, sw_load_rays(rays, q.tgt_seg_off + rec.tgt_seg), rec.d_q1, rec.d_q2)) {
+        f |= 2;
+        atomicAdd(csize + q.tgt_chunk_base + (long long)rec.tgt_seg * q.tgt_np + q.cy, 1);
     }
     rflag[g] = f;
 }
@@ -179,73 +210,91 @@ k_sw_regions(int V, SwView* __restrict__ vt, const long long* __restrict__ cstar
 // P4: records -> entries of their chunk(s), in arbitrary order inside the chunk; key = what the chunk is sorted by
 // (REF_GPU: the target segment of the list entry, sortMatchesByIDs commons.h:206-214; REF_CPU: the record index = append order)
 __global__ void __launch_bounds__(256)
-k_sw_scatter(const L3DPairDev* __restrict__ pairs, const long long* __restrict__ row_off, int num_pairs, const l3d_match_rec* __restrict__ recs,
-             int knn, long long slots, const SwView* __restrict__ vt, const int2* __restrict__ pairc, const unsigned char* __restrict__ rflag,
-             const long long* __restrict__ cstart, int* __restrict__ ccur, unsigned int* __restrict__ e_key, unsigned int* __restrict__ e_val,
-             int cpu_sem)
+k_sw_scatter(const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs, const long long* __restrict__ row_off, int num_pairs,
+             const l3d_match_rec* __restrict__ recs, int knn, long long slots, const SwView* __restrict__ vt, const int2* __restrict__ pairc,
+             const unsigned char* __restrict__ rflag, const long long* __restrict__ cstart, int* __restrict__ ccur, unsigned int* __restrict__ e_key,
+             unsigned int* __restrict__ e_val, int cpu_sem)
 {
+    __shared__ SwPairInfo pi[SW_PI];
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long row = min(g, slots - 1) / knn;
-    const int p = sw_pair_of_row_block(row_off, num_pairs, row, ((long long)blockIdx.x * blockDim.x) / knn);
+    sw_load_pair_info(pi, views, pairs, row_off, num_pairs, vt, pairc, ((long long)blockIdx.x * blockDim.x) / knn);
     if (g >= slots) return;
     const unsigned char f = rflag[g];
     if (!f) return;
-    const L3DPairDev* P = pairs + p;
-    const int r = (int)(row - __ldg(row_off + p));
     const unsigned int tseg = recs[g].tgt_seg;
-    const int2 pc = pairc[p];
+    const long long row = g / knn;
+    const SwPairInfo q = sw_pair_info(pi, row, views, pairs, row_off, num_pairs, vt, pairc);
+    const int r = (int)(row - q.row_off);
     if (f & 1) {
-        const SwView sv = vt[P->src];
-        const long long ch = sv.chunk_base + (long long)r * sv.np + pc.x;
+        const long long ch = q.src_chunk_base + (long long)r * q.src_np + q.cx;
         const long long x = cstart[ch] + atomicAdd(ccur + ch, 1);
         e_key[x] = cpu_sem ? (unsigned int)g : tseg;
         e_val[x] = (unsigned int)g;
     }
     if (f & 2) {
-        const SwView tv = vt[P->tgt];
-        const long long ch = tv.chunk_base + (long long)tseg * tv.np + pc.y;
+        const long long ch = q.tgt_chunk_base + (long long)tseg * q.tgt_np + q.cy;
         const long long x = cstart[ch] + atomicAdd(ccur + ch, 1);
         e_key[x] = cpu_sem ? (unsigned int)g : (unsigned int)r;
         e_val[x] = (unsigned int)g | SW_INV;
     }
 }
 
-// P5: one thread per chunk: insertion sort of its few entries by key (keys are unique inside a chunk), then the initial
-// flags (direct entries are active from the start) and, for inverse entries, where the source will find them
-__global__ void __launch_bounds__(256)
-k_sw_chunksort(long long num_chunks, const long long* __restrict__ cstart, unsigned int* __restrict__ e_key, unsigned int* __restrict__ e_val,
-               unsigned char* __restrict__ e_flag, unsigned int* __restrict__ invpos, int V, const long long* __restrict__ region_by_rank)
+// P5: one warp per segment: the segment's entries (all its chunks, contiguous) are read into shared memory, every entry finds its
+// place inside its chunk by counting the smaller keys (keys are unique inside a chunk), and is written back in list order together
+// with its initial flag (direct entries are active from the start) and, for inverse entries, the place its source will find it at.
+#define CS_WARPS 8
+#define CS_MAXN 192
+#define CS_MAXNP 64
+__global__ void __launch_bounds__(32 * CS_WARPS)
+k_sw_chunksort(const L3DViewDev* __restrict__ views, int V, long long N, const SwView* __restrict__ vt, const long long* __restrict__ cstart,
+               unsigned int* __restrict__ e_key, unsigned int* __restrict__ e_val, unsigned char* __restrict__ e_flag, unsigned int* __restrict__ invpos)
 {
-    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= num_chunks) return;
-    const long long a = cstart[ch], b = cstart[ch + 1];
-    if (a == b) return;
-    const int n = (int)(b - a);
-    if (n > 1 && n <= 32) {             // the usual case: sort in thread-local storage, one read and one write per entry
-        unsigned int k[32], v[32];
-        for (int i = 0; i < n; ++i) {
-            const unsigned int ki = e_key[a + i], vi = e_val[a + i];
-            int j = i - 1;
-            while (j >= 0 && k[j] > ki) { k[j + 1] = k[j]; v[j + 1] = v[j]; --j; }
-            k[j + 1] = ki; v[j + 1] = vi;
+    __shared__ unsigned int sk[CS_WARPS][CS_MAXN], sv[CS_WARPS][CS_MAXN];
+    __shared__ int scb[CS_WARPS][CS_MAXNP + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long gs = (long long)blockIdx.x * CS_WARPS + wid;
+    if (gs >= N) return;
+    int lo = 0, hi = V - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (views[mid].seg_off <= gs) lo = mid; else hi = mid - 1; }
+    const SwView me = vt[lo];
+    const int np = me.np;
+    if (np == 0) return;
+    const long long ch0 = me.chunk_base + (gs - views[lo].seg_off) * np;
+    const long long x0 = cstart[ch0], x1 = cstart[ch0 + np];
+    const int n = (int)(x1 - x0);
+    if (n == 0) return;
+    const long long ro = me.region_off;
+    if (n <= CS_MAXN && np <= CS_MAXNP) {
+        for (int c = lane; c <= np; c += 32) scb[wid][c] = (int)(cstart[ch0 + c] - x0);
+        for (int j = lane; j < n; j += 32) { sk[wid][j] = e_key[x0 + j]; sv[wid][j] = e_val[x0 + j]; }
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) {
+            int cl = 0, chh = np - 1;
+            while (cl < chh) { const int mid = (cl + chh + 1) >> 1; if (scb[wid][mid] <= j) cl = mid; else chh = mid - 1; }
+            const int a = scb[wid][cl], b = scb[wid][cl + 1];
+            const unsigned int key = sk[wid][j], val = sv[wid][j];
+            int rank = 0;
+            for (int i = a; i < b; ++i) rank += sk[wid][i] < key ? 1 : 0;
+            const long long pos = x0 + a + rank;
+            e_val[pos] = val;
+            if (val & SW_INV) { e_flag[pos] = 0; invpos[val & ~SW_INV] = (unsigned int)(pos - ro); }
+            else e_flag[pos] = SW_ACTIVE;
         }
-        for (int i = 0; i < n; ++i) e_val[a + i] = v[i];
-    } else if (n > 32) {
-        for (long long i = a + 1; i < b; ++i) {
-            const unsigned int k = e_key[i], v = e_val[i];
-            long long j = i - 1;
-            while (j >= a && e_key[j] > k) { e_key[j + 1] = e_key[j]; e_val[j + 1] = e_val[j]; --j; }
-            e_key[j + 1] = k; e_val[j + 1] = v;
+    } else {        // long lists / many neighbours: a lane per chunk, insertion sort in place
+        for (int c = lane; c < np; c += 32) {
+            const long long a = cstart[ch0 + c], b = cstart[ch0 + c + 1];
+            for (long long i = a + 1; i < b; ++i) {
+                const unsigned int k = e_key[i], v = e_val[i];
+                long long j = i - 1;
+                while (j >= a && e_key[j] > k) { e_key[j + 1] = e_key[j]; e_val[j + 1] = e_val[j]; --j; }
+                e_key[j + 1] = k; e_val[j + 1] = v;
+            }
+            for (long long i = a; i < b; ++i) {
+                const unsigned int v = e_val[i];
+                if (v & SW_INV) { e_flag[i] = 0; invpos[v & ~SW_INV] = (unsigned int)(i - ro); }
+                else e_flag[i] = SW_ACTIVE;
+            }
         }
-    }
-    int lo = 0, hi = V - 1;                 // region (processing rank) that holds this chunk's entries
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (region_by_rank[mid] <= a) lo = mid; else hi = mid - 1; }
-    // regions of views without entries share their offset with the next one: any of them gives the same relative position
-    const long long ro = region_by_rank[lo];
-    for (long long i = a; i < b; ++i) {
-        const unsigned int v = e_val[i];
-        if (v & SW_INV) { e_flag[i] = 0; invpos[v & ~SW_INV] = (unsigned int)(i - ro); }
-        else e_flag[i] = SW_ACTIVE;
     }
 }
 
@@ -551,7 +600,7 @@ k_sw_score(const SwScoreArgs<CPU> A)
 }
 
 // ---------------------------------------------------------------------------------------------- after the chain
-// filterMatches (line3D.cc:1586-1669) for every segment of every view: one thread per global segment
+// filterMatches (line3D.cc:1586-1669) for every segment of every view: one warp per global segment
 __global__ void __launch_bounds__(256)
 k_sw_filter(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int V, long long N, const SwView* __restrict__ vt,
             const long long* __restrict__ cstart, const unsigned int* __restrict__ e_val, const float* __restrict__ e_score,
@@ -559,7 +608,8 @@ k_sw_filter(const float4* __restrict__ segs, const L3DViewDev* __restrict__ view
             float perc, int2* __restrict__ ranges, int* __restrict__ est_best /*per global seg: index of best match in the view region or -1*/,
             double* __restrict__ est_P)
 {
-    const long long gs = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long gs = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gs >= N) return;
     int lo = 0, hi = V - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (views[mid].seg_off <= gs) lo = mid; else hi = mid - 1; }
@@ -571,26 +621,36 @@ k_sw_filter(const float4* __restrict__ segs, const L3DViewDev* __restrict__ view
     long long best = -1;
     if (x1 > x0) {
         const float score_lim = perc * __int_as_float(view_max_bits[lo]);
+        // the best kept match: the FIRST one in list order with the highest score (strict > in the reference's loop)
         float best_score = 0.0f;
-        for (long long x = x0; x < x1; ++x) {
-            const unsigned char f = e_flag[x];
-            if (!(f & SW_ACTIVE)) continue;
+        for (long long x = x0 + lane; x < x1; x += 32) {
+            if (!(e_flag[x] & SW_ACTIVE)) continue;
             const float sc = e_score[x];
-            const bool keep = sc > 0.0f && sc > score_lim;
-            if (keep) { e_flag[x] = f | SW_KEPT; if (sc > best_score) { best_score = sc; best = x; } }
+            if (sc > 0.0f && sc > score_lim && sc > best_score) { best_score = sc; best = x; }
         }
-        if (!(best_score > min_best)) {
-            best = -1;
-            for (long long x = x0; x < x1; ++x) e_flag[x] &= (unsigned char)~SW_KEPT;
+        for (int o = 16; o; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, best_score, o);
+            const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+            if (ob >= 0 && (os > best_score || (os == best_score && (best < 0 || ob < best)))) { best_score = os; best = ob; }
         }
-        ranges[gs] = make_int2((int)(x0 - me.region_off), (int)(x1 - 1 - me.region_off));
-    } else ranges[gs] = make_int2(-1, -1);
-    est_best[gs] = best >= 0 ? (int)(best - me.region_off) : -1;
-    if (best >= 0) {
-        const float4 dep = sw_depths(e_val[best], recs);
-        const DSeg S3 = dunproject(Vw, segs[gs], dep.x, dep.y);       // unprojectMatch(best_match, true)
-        double* o = est_P + 6 * gs;
-        o[0] = S3.P1.x; o[1] = S3.P1.y; o[2] = S3.P1.z; o[3] = S3.P2.x; o[4] = S3.P2.y; o[5] = S3.P2.z;
+        if (!(best_score > min_best)) best = -1;
+        if (best >= 0)
+            for (long long x = x0 + lane; x < x1; x += 32) {
+                const unsigned char f = e_flag[x];
+                if (!(f & SW_ACTIVE)) continue;
+                const float sc = e_score[x];
+                if (sc > 0.0f && sc > score_lim) e_flag[x] = f | SW_KEPT;
+            }
+        if (lane == 0) ranges[gs] = make_int2((int)(x0 - me.region_off), (int)(x1 - 1 - me.region_off));
+    } else if (lane == 0) ranges[gs] = make_int2(-1, -1);
+    if (lane == 0) {
+        est_best[gs] = best >= 0 ? (int)(best - me.region_off) : -1;
+        if (best >= 0) {
+            const float4 dep = sw_depths(e_val[best], recs);
+            const DSeg S3 = dunproject(Vw, segs[gs], dep.x, dep.y);       // unprojectMatch(best_match, true)
+            double* o = est_P + 6 * gs;
+            o[0] = S3.P1.x; o[1] = S3.P1.y; o[2] = S3.P1.z; o[3] = S3.P2.x; o[4] = S3.P2.y; o[5] = S3.P2.z;
+        }
     }
 }
 
@@ -740,10 +800,10 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     unsigned int* e_val = (unsigned int*)S.d_eval.p; float* e_score = (float*)S.d_escore.p; unsigned char* e_flag = (unsigned char*)S.d_eflag.p;
     if (total > 0) {
         // the sort keys live in the score array until the chain starts
-        k_sw_scatter<<<nbs, 256, 0, st>>>(pairs, d_rowoff, NP, recs, knn, slots, d_vt, d_pairc, (const unsigned char*)S.d_rflag.p, (const long long*)S.d_cstart.p,
+        k_sw_scatter<<<nbs, 256, 0, st>>>(views, pairs, d_rowoff, NP, recs, knn, slots, d_vt, d_pairc, (const unsigned char*)S.d_rflag.p, (const long long*)S.d_cstart.p,
                                           (int*)S.d_ccur.p, (unsigned int*)e_score, e_val, cpu_sem ? 1 : 0);
-        k_sw_chunksort<<<(unsigned int)((NC + 255) / 256), 256, 0, st>>>(NC, (const long long*)S.d_cstart.p, (unsigned int*)e_score, e_val, e_flag,
-                                                                         (unsigned int*)S.d_invpos.p, V, (const long long*)S.d_region_off.p);
+        k_sw_chunksort<<<(unsigned int)((c->total_segs + CS_WARPS - 1) / CS_WARPS), 32 * CS_WARPS, 0, st>>>(views, V, c->total_segs, d_vt, (const long long*)S.d_cstart.p,
+                                                                                                         (unsigned int*)e_score, e_val, e_flag, (unsigned int*)S.d_invpos.p);
         c->launches += 2;
     }
 
@@ -800,7 +860,7 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     {
         const long long N = c->total_segs;
         if (N > 0) {
-            k_sw_filter<<<(unsigned int)((N + 255) / 256), 256, 0, st>>>(segs, views, V, N, d_vt, (const long long*)S.d_cstart.p, e_val, e_score, e_flag, recs,
+            k_sw_filter<<<(unsigned int)((N * 32 + 255) / 256), 256, 0, st>>>(segs, views, V, N, d_vt, (const long long*)S.d_cstart.p, e_val, e_score, e_flag, recs,
                                                                         (const int*)S.d_vmax.p, min_best_score, min_best_perc, (int2*)S.d_ranges.p,
                                                                         (int*)S.d_est_best.p, (double*)S.d_est_P.p);
             ++c->launches;

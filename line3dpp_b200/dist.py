@@ -74,8 +74,11 @@ def attach(line3d, device: int, group=None):
             counts = device_bytes(counts_dev, 4 * rows, device)
             recs = device_bytes(recs_dev, REC_BYTES * knn * rows, device)
             torch.cuda.synchronize(device)                     # the match kernel ran on the context's own stream
+            import time
+            t0 = time.perf_counter()
             exchange_rows(counts, recs, rb, knn, group)
             torch.cuda.synchronize(device)
+            state["exchange_ms"] = (time.perf_counter() - t0) * 1e3     # includes waiting for the slowest rank's matching
             return 0
         except Exception as e:  # noqa: BLE001 — must not unwind through the C frame
             state["error"] = e
