@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the Line3D++ matching hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Metric: matched line-pairs/sec = (source segment, target segment) pair evaluations per second of the epipolar matching
@@ -10,6 +10,9 @@ Workload (BASELINE.json configs[3]): synthetic 1000 views x 3000 segments/view p
 (5000 view pairs, 4.5e10 pair evaluations per GPU).  Weak scaling: N GPUs match a ring of N*1000 views; every rank
 owns 1000 views, one NCCL all-gather of the per-view segment lists makes all views resident, then each rank matches
 the view pairs whose source view it owns (no other collective on the data path).
+
+`--scaling strong` keeps the ring at 1000 views for every N (BASELINE.json configs[3] "sharded 1/2/4/8"): every rank owns
+1000/N views and matches the pairs whose source view it owns.
 
 One step = all-gather (N>1) + per-segment pre-pass + one fused match/top-k launch over this rank's pairs.
   value : device-timed, inputs already in HBM.
@@ -34,7 +37,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-VIEWS_PER_GPU, SEGS_PER_VIEW, RING, KNN, EPI = 1000, 3000, 5, 10, 0.25
+VIEWS_PER_GPU, SEGS_PER_VIEW, RING, KNN, EPI = 1000, 3000, 5, 10, 0.25      # VIEWS_PER_GPU becomes 1000 / N with --scaling strong
+SCALING = "weak"
 FLOP_PER_PAIR_EVAL = 100.0     # algorithmic FP32 flop per pair evaluation (DESIGN.md "Roofline")
 DENSE_BYTES_PER_CELL = 20.0    # float4 depths + float overlap per cell (cudawrapper.cu:226-251)
 RDD_BYTES_PER_NNZ = 20.0       # P val + col idx + W val + transpose slot + P' store
@@ -117,23 +121,14 @@ def cpu_matching_sample(seconds_target: float = 12.0, threads: int | None = None
     RtKinv, C = synth.camera_blocks(sc)
     pairs = synth.view_pairs(sc.neighbors)
     fn = po.lib().orc_match_lines_f64
-    ncpu = os.cpu_count() or 1
-    if threads:
-        cores = threads
-    else:
-        # "all the host threads it can use": SMT siblings / cgroup quotas can make cpu_count() threads slower than
-        # half of them, so take whichever of {all, half} matches faster on a short calibration (untimed)
-        cores, best = ncpu, None
-        for cand in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
-            po.set_threads(cand)
-            s, t = pairs[0]
-            F0 = synth.fundamental(sc.K[s], sc.R[s], sc.t[s], sc.K[t], sc.R[t], sc.t[t])
-            ms = min(po.match_lines(fn, sc.segs[s], sc.segs[t], F0, RtKinv[s], RtKinv[t], C[s], C[t], int(s), int(t), EPI, KNN, f64=True)[3]
-                     for _ in range(3))
-            if best is None or ms < best:
-                cores, best = cand, ms
+    # all the host threads the box reports (nproc), pinned: no calibration, the same thread count in every leg
+    cores = threads or len(os.sched_getaffinity(0)) or (os.cpu_count() or 1)
     po.set_threads(cores)
+    s, t = pairs[0]                       # one untimed pair: thread pool start-up, page faults
+    F0 = synth.fundamental(sc.K[s], sc.R[s], sc.t[s], sc.K[t], sc.R[t], sc.t[t])
+    po.match_lines(fn, sc.segs[s], sc.segs[t], F0, RtKinv[s], RtKinv[t], C[s], C[t], int(s), int(t), EPI, KNN, f64=True)
     done, t_used, n = 0, 0.0, 0
+    rates = []
     wall0 = time.perf_counter()
     while t_used < seconds_target and time.perf_counter() - wall0 < 3.0 * seconds_target:
         for (s, t) in pairs:
@@ -141,9 +136,12 @@ def cpu_matching_sample(seconds_target: float = 12.0, threads: int | None = None
             ms = po.match_lines(fn, sc.segs[s], sc.segs[t], F, RtKinv[s], RtKinv[t], C[s], C[t], int(s), int(t), EPI, KNN, f64=True)[3]
             t_used += ms * 1e-3      # the port's own steady_clock around matching (LSD / I/O / Python glue excluded)
             done += len(sc.segs[s]) * len(sc.segs[t]); n += 1
+            rates.append(len(sc.segs[s]) * len(sc.segs[t]) / (ms * 1e-3))
             if t_used >= seconds_target:
                 break
-    return done / t_used, cores, f"{n} view pairs of {SEGS_PER_VIEW}x{SEGS_PER_VIEW} segments ({done:.3g} pair evaluations, {t_used:.1f} s), matchingCPU double path, OpenMP over source segments"
+    spread = float(np.std(rates) / np.mean(rates)) if rates else 0.0
+    return done / t_used, cores, (f"{n} view pairs of {SEGS_PER_VIEW}x{SEGS_PER_VIEW} segments ({done:.3g} pair evaluations, {t_used:.1f} s, per-pair rate spread "
+                                  f"{100 * spread:.1f} % rsd), matchingCPU double path, OpenMP over source segments, {cores} threads")
 
 
 def ref_cuda_sample(scene, npairs: int = 6):
@@ -183,15 +181,16 @@ def run_reference(args):
     sample = ""
     cores = os.cpu_count() or 1
     for i in range(args.warmup + args.steps):
-        budget = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
+        budget = max(2.0, min(30.0, 150.0 / max(args.steps + args.warmup, 1)))
         v, cores, sample = cpu_matching_sample(budget)
         if i >= args.warmup:
             per_step.append(v)
     value = float(np.mean(per_step))
-    pe_step = 4.5e10 * max(world, 1)
+    pe_step = 4.5e10 * (max(world, 1) if SCALING == "weak" else 1)
     line = {"impl": "reference", "metric": "matched_line_pairs_per_sec", "value": value, "unit": "pair-evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": pe_step / value * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "value_rsd_over_steps": float(np.std(per_step) / value) if len(per_step) > 1 else None,
             "config": workload_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -202,9 +201,11 @@ def run_reference(args):
 
 
 def workload_config(n):
-    return {"workload": f"BASELINE.json configs[3]: synthetic {VIEWS_PER_GPU} views x {SEGS_PER_VIEW} segments per GPU, ring +-{RING} neighbours, "
-                        f"kNN={KNN}, epi_overlap={EPI}; {n} GPU(s) -> ring of {n * VIEWS_PER_GPU} views, {n * 5000} view pairs",
-            "views": n * VIEWS_PER_GPU, "segments_per_view": SEGS_PER_VIEW, "view_pairs": n * 5000, "knn": KNN,
+    V = n * VIEWS_PER_GPU
+    how = f"{VIEWS_PER_GPU} views x {SEGS_PER_VIEW} segments per GPU" if SCALING == "weak" else f"1000 views x {SEGS_PER_VIEW} segments in total, {VIEWS_PER_GPU} views per GPU"
+    return {"workload": f"BASELINE.json configs[3]: synthetic {how}, ring +-{RING} neighbours, "
+                        f"kNN={KNN}, epi_overlap={EPI}; {n} GPU(s) -> ring of {V} views, {V * RING} view pairs",
+            "views": V, "segments_per_view": SEGS_PER_VIEW, "view_pairs": V * RING, "knn": KNN,
             "epi_overlap": EPI, "sharding": f"views sharded over {n} GPU(s), one NCCL all-gather of segment lists" if n > 1 else "single GPU",
             "l2": "flushed between timed steps (256 MiB write); outputs (3.6 GB/step) exceed L2"}
 
@@ -311,6 +312,21 @@ def run_ours(args):
     extra = {}
     if rank == 0:
         extra = roofline_legs(ctx, st, scene, torch)
+        try:    # REF_CPU semantics on the GPU (matchingCPU's double arithmetic, k_match_topk_f64): the f64-vs-f64 figure next to the CPU arm
+            npf = min(len(pairs), 500)
+            Fd = F[:npf].astype(np.float64)
+            with torch.cuda.stream(st):
+                ctx.match_pairs_f64(pairs[:npf], Fd, EPI, KNN)
+            ctx.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            with torch.cuda.stream(st):
+                ctx.match_pairs_f64(pairs[:npf], Fd, EPI, KNN)
+            e1.record(st); ctx.sync()
+            extra.setdefault("extras", {})["match_f64"] = {"kernel": "k_match_topk_f64 (REF_CPU semantics: matchingCPU's double arithmetic)", "view_pairs": npf,
+                                                           "pair_evals_per_sec": npf * SEGS_PER_VIEW * SEGS_PER_VIEW / (e0.elapsed_time(e1) * 1e-3), "ms": e0.elapsed_time(e1)}
+        except Exception as e:   # noqa
+            extra.setdefault("extras", {})["match_f64"] = {"error": str(e)[:200]}
 
     dev_total = sum(m[0] for m in dev_ms)
     e2e_total = sum(max(m) for m in e2e_ms)          # e2e includes host-side waits: take max(device, wall) per step
@@ -332,7 +348,7 @@ def run_ours(args):
         peaks = load_peaks()
         line = {
             "metric": "matched_line_pairs_per_sec", "value": value, "unit": "pair-evals/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
             "emitted_matches_per_sec": matches_all / (ms_step * 1e-3),
             "e2e": {"value": pe_all / (e2e_step * 1e-3), "unit": "pair-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -351,7 +367,7 @@ def run_ours(args):
             "extras": extra.get("extras"),
             "peaks": peaks,
         }
-        cpu_v, cores, sample = cpu_matching_sample(12.0)
+        cpu_v, cores, sample = cpu_matching_sample(20.0)
         line["cpu_baseline"] = {"value": cpu_v, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample}
         line["ref_cuda_baseline"] = ref_cuda_sample(scene)
         print(json.dumps(line))
@@ -472,7 +488,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
+    global VIEWS_PER_GPU, SCALING
+    SCALING = args.scaling
+    if SCALING == "strong":
+        if 1000 % max(args.gpus, 1):
+            print(json.dumps({"error": "--scaling strong needs a GPU count that divides 1000"}))
+            return 2
+        VIEWS_PER_GPU = 1000 // max(args.gpus, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

@@ -32,6 +32,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -58,7 +60,7 @@ __device__ __forceinline__ DSeg dunproject(const L3DViewDev* v, float4 s, float 
 // mid point (segmentQualityAngle, view.cc:466-484) - the same values dunproject / the orientation check would recompute per match
 struct SegRaysQ { D3 r1, r2, rm; };
 __global__ void __launch_bounds__(256)
-k_sw_rays(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int V, long long N, double* __restrict__ rays)
+k_sw_rays(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int V, long long N, double* __restrict__ rays, float4* __restrict__ rmf)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
@@ -70,6 +72,7 @@ k_sw_rays(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views,
     const D3 rm = dray(Vw->RtKinv_d, 0.5 * ((double)s.x + (double)s.z), 0.5 * ((double)s.y + (double)s.w));
     double* o = rays + 9 * g;
     o[0] = r1.x; o[1] = r1.y; o[2] = r1.z; o[3] = r2.x; o[4] = r2.y; o[5] = r2.z; o[6] = rm.x; o[7] = rm.y; o[8] = rm.z;
+    rmf[g] = make_float4((float)rm.x, (float)rm.y, (float)rm.z, 0.f);
 }
 __device__ __forceinline__ SegRaysQ sw_load_rays(const double* __restrict__ rays, long long g)
 {
@@ -162,10 +165,24 @@ __device__ __forceinline__ SwPairInfo sw_pair_info(const SwPairInfo* __restrict_
     return q;
 }
 
+// Orientation check decided in FLOAT where that is safe: the angle between the mid-point ray and the 3D direction does not
+// depend on the camera centre (d = r2*d2 - r1*d1), the float rays differ from the double ones by ~1e-7, and for |d| > 1 % of the
+// depths the cosine is good to ~1e-5 - two orders below the 1e-4 margin kept around cos(pi/32).  Returns 1 keep, 0 drop, -1 undecided.
+__device__ __forceinline__ int sw_orientation_fast(float3 r1, float3 r2, float3 rm, float d1, float d2)
+{
+    const float3 d = make_float3(r2.x * d2 - r1.x * d1, r2.y * d2 - r1.y * d1, r2.z * d2 - r1.z * d1);
+    const float n2 = d.x * d.x + d.y * d.y + d.z * d.z;
+    if (!(n2 > 1e-4f * (d1 * d1 + d2 * d2))) return -1;
+    const float c = fabsf((rm.x * d.x + rm.y * d.y + rm.z * d.z) * rsqrtf(n2));
+    if (c < 0.99518473f - 1e-4f) return 1;
+    if (c > 0.99518473f + 1e-4f) return 0;
+    return -1;
+}
+
 // P1: one thread per record slot.  rflag bit 0: the record survives the orientation check as a direct match of its source
 // view, bit 1: as an inverse match of its target view (only asked for when the target is processed after the source).
 __global__ void __launch_bounds__(256)
-k_sw_flags(const double* __restrict__ rays, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
+k_sw_flags(const double* __restrict__ rays, const float4* __restrict__ cache, const float4* __restrict__ rmf, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
            const long long* __restrict__ row_off, int num_pairs, const int* __restrict__ counts, const l3d_match_rec* __restrict__ recs,
            int knn, long long slots, const SwView* __restrict__ vt, const int2* __restrict__ pairc, unsigned char* __restrict__ rflag,
            int* __restrict__ csize)
@@ -181,13 +198,21 @@ k_sw_flags(const double* __restrict__ rays, const L3DViewDev* __restrict__ views
     const SwPairInfo q = sw_pair_info(pi, row, views, pairs, row_off, num_pairs, vt, pairc);
     const int r = (int)(row - q.row_off);
     unsigned char f = 0;
-    if (sw_orientation_ok(views + q.src, sw_load_rays(rays, q.src_seg_off + r), rec.d_p1, rec.d_p2)) {
-        f |= 1;
-        atomicAdd(csize + q.src_chunk_base + (long long)r * q.src_np + q.cx, 1);
+    {
+        const long long gs = q.src_seg_off + r;
+        const SegRays R = load_rays(cache, gs);
+        const float4 m = __ldg(rmf + gs);
+        int ok = sw_orientation_fast(R.r1, R.r2, make_float3(m.x, m.y, m.z), rec.d_p1, rec.d_p2);
+        if (ok < 0) ok = sw_orientation_ok(views + q.src, sw_load_rays(rays, gs), rec.d_p1, rec.d_p2) ? 1 : 0;
+        if (ok) { f |= 1; atomicAdd(csize + q.src_chunk_base + (long long)r * q.src_np + q.cx, 1); }
     }
-    if (q.cy >= 0 && sw_orientation_ok(views + q.tgt, sw_load_rays(rays, q.tgt_seg_off + rec.tgt_seg), rec.d_q1, rec.d_q2)) {
-        f |= 2;
-        atomicAdd(csize + q.tgt_chunk_base + (long long)rec.tgt_seg * q.tgt_np + q.cy, 1);
+    if (q.cy >= 0) {
+        const long long gs = q.tgt_seg_off + rec.tgt_seg;
+        const SegRays R = load_rays(cache, gs);
+        const float4 m = __ldg(rmf + gs);
+        int ok = sw_orientation_fast(R.r1, R.r2, make_float3(m.x, m.y, m.z), rec.d_q1, rec.d_q2);
+        if (ok < 0) ok = sw_orientation_ok(views + q.tgt, sw_load_rays(rays, gs), rec.d_q1, rec.d_q2) ? 1 : 0;
+        if (ok) { f |= 2; atomicAdd(csize + q.tgt_chunk_base + (long long)rec.tgt_seg * q.tgt_np + q.cy, 1); }
     }
     rflag[g] = f;
 }
@@ -600,7 +625,7 @@ k_sw_score(const SwScoreArgs<CPU> A)
 }
 
 // ---------------------------------------------------------------------------------------------- after the chain
-// filterMatches (line3D.cc:1586-1669) for every segment of every view: one warp per global segment
+// filterMatches (line3D.cc:1586-1669) for every segment of every view: one thread per global segment
 __global__ void __launch_bounds__(256)
 k_sw_filter(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int V, long long N, const SwView* __restrict__ vt,
             const long long* __restrict__ cstart, const unsigned int* __restrict__ e_val, const float* __restrict__ e_score,
@@ -608,8 +633,7 @@ k_sw_filter(const float4* __restrict__ segs, const L3DViewDev* __restrict__ view
             float perc, int2* __restrict__ ranges, int* __restrict__ est_best /*per global seg: index of best match in the view region or -1*/,
             double* __restrict__ est_P)
 {
-    const int lane = threadIdx.x & 31;
-    const long long gs = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long gs = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gs >= N) return;
     int lo = 0, hi = V - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (views[mid].seg_off <= gs) lo = mid; else hi = mid - 1; }
@@ -621,36 +645,26 @@ k_sw_filter(const float4* __restrict__ segs, const L3DViewDev* __restrict__ view
     long long best = -1;
     if (x1 > x0) {
         const float score_lim = perc * __int_as_float(view_max_bits[lo]);
-        // the best kept match: the FIRST one in list order with the highest score (strict > in the reference's loop)
         float best_score = 0.0f;
-        for (long long x = x0 + lane; x < x1; x += 32) {
-            if (!(e_flag[x] & SW_ACTIVE)) continue;
+        for (long long x = x0; x < x1; ++x) {
+            const unsigned char f = e_flag[x];
+            if (!(f & SW_ACTIVE)) continue;
             const float sc = e_score[x];
-            if (sc > 0.0f && sc > score_lim && sc > best_score) { best_score = sc; best = x; }
+            const bool keep = sc > 0.0f && sc > score_lim;
+            if (keep) { e_flag[x] = f | SW_KEPT; if (sc > best_score) { best_score = sc; best = x; } }
         }
-        for (int o = 16; o; o >>= 1) {
-            const float os = __shfl_xor_sync(0xffffffffu, best_score, o);
-            const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
-            if (ob >= 0 && (os > best_score || (os == best_score && (best < 0 || ob < best)))) { best_score = os; best = ob; }
+        if (!(best_score > min_best)) {
+            best = -1;
+            for (long long x = x0; x < x1; ++x) e_flag[x] &= (unsigned char)~SW_KEPT;
         }
-        if (!(best_score > min_best)) best = -1;
-        if (best >= 0)
-            for (long long x = x0 + lane; x < x1; x += 32) {
-                const unsigned char f = e_flag[x];
-                if (!(f & SW_ACTIVE)) continue;
-                const float sc = e_score[x];
-                if (sc > 0.0f && sc > score_lim) e_flag[x] = f | SW_KEPT;
-            }
-        if (lane == 0) ranges[gs] = make_int2((int)(x0 - me.region_off), (int)(x1 - 1 - me.region_off));
-    } else if (lane == 0) ranges[gs] = make_int2(-1, -1);
-    if (lane == 0) {
-        est_best[gs] = best >= 0 ? (int)(best - me.region_off) : -1;
-        if (best >= 0) {
-            const float4 dep = sw_depths(e_val[best], recs);
-            const DSeg S3 = dunproject(Vw, segs[gs], dep.x, dep.y);       // unprojectMatch(best_match, true)
-            double* o = est_P + 6 * gs;
-            o[0] = S3.P1.x; o[1] = S3.P1.y; o[2] = S3.P1.z; o[3] = S3.P2.x; o[4] = S3.P2.y; o[5] = S3.P2.z;
-        }
+        ranges[gs] = make_int2((int)(x0 - me.region_off), (int)(x1 - 1 - me.region_off));
+    } else ranges[gs] = make_int2(-1, -1);
+    est_best[gs] = best >= 0 ? (int)(best - me.region_off) : -1;
+    if (best >= 0) {
+        const float4 dep = sw_depths(e_val[best], recs);
+        const DSeg S3 = dunproject(Vw, segs[gs], dep.x, dep.y);       // unprojectMatch(best_match, true)
+        double* o = est_P + 6 * gs;
+        o[0] = S3.P1.x; o[1] = S3.P1.y; o[2] = S3.P1.z; o[3] = S3.P2.x; o[4] = S3.P2.y; o[5] = S3.P2.z;
     }
 }
 
@@ -751,7 +765,7 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
 #define RES(buf, bytes, what) if ((rc = l3d_reserve(c, buf, (size_t)std::max<long long>((long long)(bytes), 16), what))) return rc
     RES(S.d_vt, sizeof(SwView) * (size_t)V, "view table"); RES(S.d_vp, sizeof(SwChunk) * vp.size(), "chunk descriptors"); RES(S.d_pairc, 8 * (size_t)NP, "pair chunks");
     RES(S.d_rowoff, 8 * (size_t)(NP + 1), "pair row offsets"); RES(S.d_order, 4 * (size_t)V, "order"); RES(S.d_region_off, 8 * (size_t)(V + 1), "region offsets");
-    RES(S.d_rays, 72 * c->total_segs, "segment rays"); RES(S.d_rflag, slots, "record flags"); RES(S.d_invpos, 4 * slots, "inverse positions");
+    RES(S.d_rays, 72 * c->total_segs, "segment rays"); RES(S.d_rmf, 16 * c->total_segs, "mid-point rays"); RES(S.d_rflag, slots, "record flags"); RES(S.d_invpos, 4 * slots, "inverse positions");
     RES(S.d_csize, 4 * (NC + 1), "chunk sizes"); RES(S.d_ccur, 4 * (NC + 1), "chunk cursors"); RES(S.d_cstart, 8 * (NC + 1), "chunk offsets");
     RES(S.d_ranges, 8 * c->total_segs, "ranges"); RES(S.d_est_best, 4 * c->total_segs, "estimates"); RES(S.d_est_P, 48 * c->total_segs, "estimate points");
     RES(S.d_M, 4 * (size_t)V, "match counts"); RES(S.d_vmax, 4 * (size_t)V, "view max");
@@ -767,6 +781,9 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     L3D_CUDA(c, cudaMemsetAsync(S.d_M.p, 0, 4 * (size_t)V, st), "init counts");
     L3D_CUDA(c, cudaMemsetAsync(S.d_vmax.p, 0, 4 * (size_t)V, st), "init maxima");
 
+    cudaEvent_t ev[4];
+    for (int q = 0; q < 4; ++q) cudaEventCreate(&ev[q]);
+    cudaEventRecord(ev[0], st);
     const float4* segs = c->segs(); const float4* cache = (const float4*)c->d_cache.p;
     const L3DViewDev* views = c->views(); const L3DPairDev* pairs = (const L3DPairDev*)c->d_pairs.p;
     const int* counts = (const int*)c->d_counts.p; const l3d_match_rec* recs = (const l3d_match_rec*)c->d_recs.p;
@@ -774,8 +791,8 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     const unsigned int nbs = (unsigned int)((slots + 255) / 256);
     S.region_off.assign(V + 1, 0); S.total = 0;
     if (NP > 0 && slots > 0) {
-        k_sw_rays<<<(unsigned int)((c->total_segs + 255) / 256), 256, 0, st>>>(segs, views, V, c->total_segs, (double*)S.d_rays.p);
-        k_sw_flags<<<nbs, 256, 0, st>>>((const double*)S.d_rays.p, views, pairs, d_rowoff, NP, counts, recs, knn, slots, d_vt, d_pairc, (unsigned char*)S.d_rflag.p, (int*)S.d_csize.p);
+        k_sw_rays<<<(unsigned int)((c->total_segs + 255) / 256), 256, 0, st>>>(segs, views, V, c->total_segs, (double*)S.d_rays.p, (float4*)S.d_rmf.p);
+        k_sw_flags<<<nbs, 256, 0, st>>>((const double*)S.d_rays.p, cache, (const float4*)S.d_rmf.p, views, pairs, d_rowoff, NP, counts, recs, knn, slots, d_vt, d_pairc, (unsigned char*)S.d_rflag.p, (int*)S.d_csize.p);
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)S.d_csize.p, (long long*)S.d_cstart.p, NC + 1, st);
         RES(S.d_sort_tmp, tb, "scan temp");
@@ -814,6 +831,7 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
         const double ang = std::sqrt((double)q_thr * (double)two_sigA_sqr);           // degrees
         cos_thr = ang < 89.0 ? (float)(std::cos(ang * L3D_PI_D / 180.0) * (1.0 - 1e-4)) : -1.0f;
     }
+    cudaEventRecord(ev[1], st);
     // ---- the chain: one launch per view, ascending camID
     if (total > 0) {
         SwScoreArgs<false> A;
@@ -856,11 +874,12 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
         }
         L3D_CUDA(c, cudaGetLastError(), "score sweep launch");
     }
+    cudaEventRecord(ev[2], st);
     // ---- filterMatches + best estimates for all views
     {
         const long long N = c->total_segs;
         if (N > 0) {
-            k_sw_filter<<<(unsigned int)((N * 32 + 255) / 256), 256, 0, st>>>(segs, views, V, N, d_vt, (const long long*)S.d_cstart.p, e_val, e_score, e_flag, recs,
+            k_sw_filter<<<(unsigned int)((N + 255) / 256), 256, 0, st>>>(segs, views, V, N, d_vt, (const long long*)S.d_cstart.p, e_val, e_score, e_flag, recs,
                                                                         (const int*)S.d_vmax.p, min_best_score, min_best_perc, (int2*)S.d_ranges.p,
                                                                         (int*)S.d_est_best.p, (double*)S.d_est_P.p);
             ++c->launches;
@@ -893,7 +912,11 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
                 L3D_CUDA(c, cudaGetLastError(), "k_collect_estimates");
             }
         }
+        cudaEventRecord(ev[3], st);
         L3D_CUDA(c, cudaStreamSynchronize(st), "score sweep");
+        cudaEventElapsedTime(&S.ms_setup, ev[0], ev[1]); cudaEventElapsedTime(&S.ms_chain, ev[1], ev[2]); cudaEventElapsedTime(&S.ms_filter, ev[2], ev[3]);
+        for (int q = 0; q < 4; ++q) cudaEventDestroy(ev[q]);
+        if (getenv("L3D_SWEEP_TIMING")) fprintf(stderr, "[l3d] score sweep: set-up %.3f ms, chain %.3f ms (%d views), filter+estimates %.3f ms\n", S.ms_setup, S.ms_chain, V, S.ms_filter);
         S.h_M.resize(V);
         for (int i = 0; i < V; ++i) S.h_M[i] = M[S.order[i]];
     }
