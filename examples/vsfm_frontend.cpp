@@ -51,8 +51,8 @@ int main(int argc, char** argv)
             std::vector<L3DPP::Vec4f> segs;
             if (!read_segments(segdir + "/" + name + ".txt", w, h, segs)) { std::fprintf(stderr, "no segments for %s, skipped\n", name.c_str()); continue; }
             if (c.distortion != 0.0f) std::fprintf(stderr, "note: %s has radial distortion %g; segments are expected in the undistorted image\n", name.c_str(), c.distortion);
-            line3D.addImage((unsigned int)i, w, h, L3DPP::intrinsicsFromFocal(c.focal, w, h), c.R, c.t, c.median_depth, c.worldpoints, segs);
-            if (line3D.lastError()[0]) std::fprintf(stderr, "addImage(%zu): %s\n", i, line3D.lastError());
+            if (!line3D.addImage((unsigned int)i, w, h, L3DPP::intrinsicsFromFocal(c.focal, w, h), c.R, c.t, c.median_depth, c.worldpoints, segs))
+                std::fprintf(stderr, "addImage(%zu): %s\n", i, line3D.lastError());
         }
         if (line3D.numImages() < 3) { std::fprintf(stderr, "fewer than three usable images\n"); return 1; }
         line3D.matchImages();                                                                           // main_vsfm.cpp:313-315, defaults

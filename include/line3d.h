@@ -6,7 +6,11 @@
  * include/l3d_capi.h; this class only does what line3D.cc does on the host around the accelerator calls.
  *
  * Differences forced by this image (no Eigen / OpenCV / Boost headers):
- *   - Matrix3d / Vector3d / Vec4f are small PODs; Eigen / cv overloads are compiled in when those headers exist.
+ *   - Matrix3d / Vector3d / Vec4f are small PODs.  When <eigen3/Eigen/Eigen> and <opencv2/core.hpp> are on the include path
+ *     (or L3DPP_WITH_EIGEN_OPENCV is defined) the reference's own addImage signature (line3D.h:104-108: cv::Mat&,
+ *     Eigen::Matrix3d, Eigen::Vector3d, std::vector<cv::Vec4f>) is available as an inline overload that converts and
+ *     forwards; tests/test_cpu.py compiles it against the header stand-ins of oracle/ref_shim.  get3Dlines() returns the POD
+ *     types (P1().x is a member, not Eigen's x()): a frontend that reads the result lines needs that one-character change.
  *   - addImage takes the image SIZE and explicit 2D segments (the reference's own line_segments argument,
  *     line3D.h:102-108); LSD detection inside addImage (line3D.cc:249-372) is outside the hot path.
  *   - save3DLinesAsBIN (boost archive) is not provided; TXT / OBJ / STL are.
@@ -19,6 +23,16 @@
 #include <list>
 #include <string>
 #include <vector>
+
+#if !defined(L3DPP_WITH_EIGEN_OPENCV) && defined(__has_include)
+#if __has_include(<eigen3/Eigen/Eigen>) && __has_include(<opencv2/core.hpp>)
+#define L3DPP_WITH_EIGEN_OPENCV 1
+#endif
+#endif
+#ifdef L3DPP_WITH_EIGEN_OPENCV
+#include <eigen3/Eigen/Eigen>
+#include <opencv2/core.hpp>
+#endif
 
 namespace L3DPP {
 
@@ -113,9 +127,25 @@ public:
     Line3D& operator=(const Line3D&) = delete;
 
     /* line3D.h:104-108 with (image_width, image_height) instead of cv::Mat& image; line_segments must be non-empty */
-    void addImage(const unsigned int camID, const int image_width, const int image_height, const Matrix3d& K, const Matrix3d& R,
+    /* Returns false (and sets lastError(), which a later successful addImage does not clear) if the view was rejected. */
+    bool addImage(const unsigned int camID, const int image_width, const int image_height, const Matrix3d& K, const Matrix3d& R,
                   const Vector3d& t, const float median_depth, const std::list<unsigned int>& wps_or_neighbors,
                   const std::vector<Vec4f>& line_segments);
+
+#ifdef L3DPP_WITH_EIGEN_OPENCV
+    /* The reference's exact signature (line3D.h:104-108).  The image only contributes its size; line_segments must be given
+     * (line detection is outside this library): with an empty list the call fails like any other rejected view. */
+    bool addImage(const unsigned int camID, cv::Mat& image, const Eigen::Matrix3d& K, const Eigen::Matrix3d& R, const Eigen::Vector3d& t,
+                  const float median_depth, const std::list<unsigned int>& wps_or_neighbors,
+                  const std::vector<cv::Vec4f>& line_segments = std::vector<cv::Vec4f>())
+    {
+        Matrix3d Kp, Rp;
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { Kp(r, c) = K(r, c); Rp(r, c) = R(r, c); }
+        std::vector<Vec4f> segs(line_segments.size());
+        for (size_t i = 0; i < line_segments.size(); ++i) for (int k = 0; k < 4; ++k) segs[i].v[k] = line_segments[i](k);
+        return addImage(camID, image.cols, image.rows, Kp, Rp, Vector3d(t(0), t(1), t(2)), median_depth, wps_or_neighbors, segs);
+    }
+#endif
 
     /* line3D.h:140-145 */
     void matchImages(const float sigma_position = L3D_DEF_SCORING_POS_REGULARIZER, const float sigma_angle = L3D_DEF_SCORING_ANG_REGULARIZER,

@@ -211,8 +211,11 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
     if (!c->have_views) return l3d_fail(c, L3D_ERR_STATE, "l3d_match_pairs: call l3d_set_views first");
     if (num_pairs < 0 || (num_pairs && (!pairs || (!F && !Fd)))) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs: bad arguments");
     if (first_pair < 0 || last_pair < first_pair || last_pair > num_pairs) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs_range: bad pair range");
-    const bool keep_all = knn <= 0;
-    if (knn > 32) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: kNN > 32 not implemented");
+    // kNN > 32 exceeds the fused kernel's per-row key list: the keep-all passes run instead and every row is cut to its kNN best
+    // afterwards (same matches as the reference's priority queue, line3D.cc:999-1006 / cudawrapper.cu:637-645)
+    const int big_k = knn > 32 ? knn : 0;
+    const bool keep_all = knn <= 0 || big_k > 0;
+    if (big_k && host) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs_host: kNN > 32 has no fixed row stride; use l3d_match_pairs + l3d_get_pair_matches");
     cudaSetDevice(c->device);
     L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync before pair staging");   // h_pairs/h_tiles may still be in flight
     c->h_pairs.resize(num_pairs);
@@ -286,7 +289,7 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
             L3D_CUDA(c, cudaGetLastError(), "k_match_all (store)");
             L3D_CUDA(c, cudaFuncSetAttribute(k_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)), "k_sort_rows smem");
             const long long blocks = std::min<long long>((rows + wpb - 1) / wpb, (long long)c->num_sms * 16);
-            k_sort_rows<<<(unsigned int)blocks, wpb * 32, per_warp * wpb, c->stream>>>((const int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, stride, rows);
+            k_sort_rows<<<(unsigned int)blocks, wpb * 32, per_warp * wpb, c->stream>>>((int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, stride, rows, big_k);
             L3D_CUDA(c, cudaGetLastError(), "k_sort_rows");
             c->launches += 2;
         }

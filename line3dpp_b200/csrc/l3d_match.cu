@@ -387,7 +387,9 @@ k_match_all(const float4* __restrict__ segs, const float4* __restrict__ cache, c
 
 // keep-all rows arrive in queue order; the reference appends them in ascending target order.  One warp per row, the row
 // staged in shared memory (stride * 24 B per warp), rank = number of smaller target indices (unique per row).
-__global__ void __launch_bounds__(128) k_sort_rows(const int* __restrict__ counts, l3d_match_rec* __restrict__ recs, int stride, long long rows)
+// topk > 0 (kNN beyond the fused kernel's 32 keys per row): the rows keep their `topk` best matches instead, in the order the
+// reference pops its priority queue (descending overlap, cudawrapper.cu:637-645; equal overlaps by target index), counts clipped.
+__global__ void __launch_bounds__(128) k_sort_rows(int* __restrict__ counts, l3d_match_rec* __restrict__ recs, int stride, long long rows, int topk)
 {
     extern __shared__ __align__(16) unsigned char sort_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -400,11 +402,13 @@ __global__ void __launch_bounds__(128) k_sort_rows(const int* __restrict__ count
             __syncwarp();
             for (int i = lane; i < n; i += 32) {
                 const unsigned int t = buf[i].tgt_seg;
+                const float ov = buf[i].overlap;
                 int r = 0;
-                for (int j = 0; j < n; ++j) r += buf[j].tgt_seg < t;
-                g[r] = buf[i];
+                if (topk > 0) { for (int j = 0; j < n; ++j) r += (buf[j].overlap > ov || (buf[j].overlap == ov && buf[j].tgt_seg < t)) ? 1 : 0; if (r < topk) g[r] = buf[i]; }
+                else { for (int j = 0; j < n; ++j) r += buf[j].tgt_seg < t; g[r] = buf[i]; }
             }
         }
+        if (topk > 0 && lane == 0 && n > topk) counts[row] = topk;
         __syncwarp();
     }
 }

@@ -57,7 +57,7 @@ __global__ void k_match_all(const float4* __restrict__ segs, const float4* __res
                             const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
                             const int2* __restrict__ tiles, int stride, float epi, int* __restrict__ counts_out,
                             l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d);
-__global__ void k_sort_rows(const int* __restrict__ counts, l3d_match_rec* __restrict__ recs, int stride, long long rows);
+__global__ void k_sort_rows(int* __restrict__ counts, l3d_match_rec* __restrict__ recs, int stride, long long rows, int topk);
 __global__ void k_prep_segments_f64(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int num_views,
                                     long long total, double* __restrict__ cache);
 __global__ void k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,

@@ -353,62 +353,105 @@ struct SwScoreArgs {
     float angle_reg, sim_t, q_thr, cos_thr;
 };
 
-// K_score_matches (cudawrapper.cu:256-367) for own entry `me` against the staged list [lo, hi) of its segment.  The tests are
-// ordered cheapest first - the result is the same whichever of the three conditions rejects.
-__device__ __forceinline__ float sw_score_gpu(const float4* __restrict__ sa, const float4* __restrict__ sb, float2 rg, int lo, int hi, int me, float k,
-                                              float angle_reg, float sim_t, float q_thr, float cos_thr)
+// similarity of K_score_matches' inner loop (cudawrapper.cu:318-347) between the own entry and staged entry i, tests ordered
+// cheapest first - the result is the same whichever of the three conditions rejects.
+// Exact shortcut: sim = min(three terms), then truncated to 0 below sim_t.  If ONE term is certainly below sim_t the result is 0
+// whatever the others are (fminf ignores NaN).  exp(-q) < sim_t is certain when q > q_thr = 1.01 * -ln(sim_t) (1 % margin >> the
+// rounding of the division and of expf), and the angular term is certainly below sim_t when |cos| < cos_thr (same margin on the
+// angle).  Everything inside the margins takes the full, reference-order path.
+struct SwOwn { float d1, d2, pos_reg1, pos_reg2, thr1, thr2; float3 dir; };
+__device__ __forceinline__ SwOwn sw_own(float4 ma, float4 mb, float2 rg, float k, float q_thr)
 {
-    const float4 ma = sa[me], mb = sb[me];
-    const int tgt_cam_src = __float_as_int(ma.z);
-    const float d1_src = ma.x, d2_src = ma.y;
-    const float sig1 = k * d1_src, sig2 = k * d2_src;
+    SwOwn o;
+    o.d1 = ma.x; o.d2 = ma.y;
+    const float sig1 = k * o.d1, sig2 = k * o.d2;
     float pos_reg1 = 2.0f * sig1 * sig1, pos_reg2 = 2.0f * sig2 * sig2;
     const float pos_reg1_tgt = 2.0f * rg.x * rg.x, pos_reg2_tgt = 2.0f * rg.y * rg.y;
-    pos_reg1 = 0.5f * (pos_reg1 + pos_reg1_tgt);
-    pos_reg2 = 0.5f * (pos_reg2 + pos_reg2_tgt);
-    const float thr1 = q_thr * pos_reg1, thr2 = q_thr * pos_reg2;
+    o.pos_reg1 = 0.5f * (pos_reg1 + pos_reg1_tgt);
+    o.pos_reg2 = 0.5f * (pos_reg2 + pos_reg2_tgt);
+    o.thr1 = q_thr * o.pos_reg1; o.thr2 = q_thr * o.pos_reg2;
+    o.dir = make_float3(mb.x, mb.y, mb.z);
+    return o;
+}
+__device__ __forceinline__ float sw_sim(const SwOwn& o, const float4* __restrict__ sa, const float4* __restrict__ sb, int i, float angle_reg, float sim_t,
+                                        float cos_thr)
+{
+    const float4 ta = sa[i];
+    const float e1 = o.d1 - ta.x, e2 = o.d2 - ta.y;
+    if (e1 * e1 > o.thr1 || e2 * e2 > o.thr2) return 0.0f;
+    const float4 tb = sb[i];
+    const float dp = o.dir.x * tb.x + o.dir.y * tb.y + o.dir.z * tb.z;
+    if (fabsf(dp) < cos_thr) return 0.0f;
+    // D_undirected_angle_3D_DEG (cudawrapper.cu:46-53): float acos, DOUBLE divide by pi, times 180, back to float
+    float angle = (float)((double)acosf(fmaxf(fminf(dp, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
+    if (angle > 90.0f) angle = 180.0f - angle;
+    const float sim_a = expf(-angle * angle / angle_reg);
+    const float sim_p1 = expf(-e1 * e1 / o.pos_reg1), sim_p2 = expf(-e2 * e2 / o.pos_reg2);
+    float sim = fminf(sim_a, fminf(sim_p1, sim_p2));
+    if (sim < sim_t) sim = 0.0f;
+    return sim;
+}
+
+// K_score_matches' accumulation (cudawrapper.cu:304-359) over the staged list [lo, hi) in list order: inactive entries (target
+// view < 0) and entries of the own target camera are not in the reference's loop.  Used when the chunk tables are not in shared memory.
+__device__ __forceinline__ float sw_score_gpu_list(const float4* __restrict__ sa, const float4* __restrict__ sb, float2 rg, int lo, int hi, int me, float k,
+                                                   float angle_reg, float sim_t, float q_thr, float cos_thr)
+{
+    const SwOwn o = sw_own(sa[me], sb[me], rg, k, q_thr);
+    const int tgt_cam_src = __float_as_int(sa[me].z);
     float score3D = 0.0f, current_max_sim = 0.0f;
     int current_cam = -1;
-#pragma unroll 4
     for (int i = lo; i < hi; ++i) {
-        const float4 ta = sa[i];
-        const int tgt_cam_tgt = __float_as_int(ta.z);
-        const bool listed = !(tgt_cam_tgt < 0 || tgt_cam_src == tgt_cam_tgt);           // in the list (yet) and not the same target camera
-        const float e1 = d1_src - ta.x, e2 = d2_src - ta.y;
-        float sim = 0.0f;
-        // Exact shortcut: sim = min(three terms), then truncated to 0 below sim_t.  If ONE term is certainly below
-        // sim_t the result is 0 whatever the others are (fminf ignores NaN).  exp(-q) < sim_t is certain when
-        // q > q_thr = 1.01 * -ln(sim_t) (1 % margin >> the rounding of the division and of expf), and the angular
-        // term is certainly below sim_t when |cos| < cos_thr (same margin on the angle).  Everything inside the
-        // margins takes the full, reference-order path.
-        if (listed && !(e1 * e1 > thr1 || e2 * e2 > thr2)) {
-            const float4 tb = sb[i];
-            const float dp = mb.x * tb.x + mb.y * tb.y + mb.z * tb.z;
-            if (!(fabsf(dp) < cos_thr)) {
-                // D_undirected_angle_3D_DEG (cudawrapper.cu:46-53): float acos, DOUBLE divide by pi, times 180, back to float
-                float angle = (float)((double)acosf(fmaxf(fminf(dp, 1.0f), -1.0f)) / L3D_PI_D * (double)180.0f);
-                if (angle > 90.0f) angle = 180.0f - angle;
-                const float sim_a = expf(-angle * angle / angle_reg);
-                const float sim_p1 = expf(-e1 * e1 / pos_reg1), sim_p2 = expf(-e2 * e2 / pos_reg2);
-                sim = fminf(sim_a, fminf(sim_p1, sim_p2));
-                if (sim < sim_t) sim = 0.0f;
-            }
-        }
-        if (listed) {
-            current_max_sim = fmaxf(current_max_sim, sim);
-            if (current_cam != tgt_cam_tgt) { score3D += current_max_sim; current_max_sim = 0.0f; current_cam = tgt_cam_tgt; }
-        }
+        const int tgt_cam_tgt = __float_as_int(sa[i].z);
+        if (tgt_cam_tgt < 0 || tgt_cam_src == tgt_cam_tgt) continue;
+        const float sim = sw_sim(o, sa, sb, i, angle_reg, sim_t, cos_thr);
+        current_max_sim = fmaxf(current_max_sim, sim);
+        if (current_cam != tgt_cam_tgt) { score3D += current_max_sim; current_max_sim = 0.0f; current_cam = tgt_cam_tgt; }
     }
     score3D += current_max_sim;
     return score3D;
 }
 
+// The same accumulation, chunk by chunk over the ACTIVE entries only (ord = their indices in list order, cbA = chunk boundaries
+// in that list).  A chunk is a run of entries with one target camera: its first entry flushes what the previous camera left
+// pending (score += max(pending, sim); pending = 0), the others raise pending - exactly the reference's sequence of float
+// additions, because the entries it skips contribute nothing (x + 0 == x) and a camera without active entries does not appear
+// in the reference's list at all.
+__device__ __forceinline__ float sw_score_gpu_chunks(const float4* __restrict__ sa, const float4* __restrict__ sb, float2 rg, const int* __restrict__ ord,
+                                                     const int* __restrict__ cbA, const int* __restrict__ chunk_cam, int c0, int np, int my_chunk, int me,
+                                                     float k, float angle_reg, float sim_t, float q_thr, float cos_thr)
+{
+    const SwOwn o = sw_own(sa[me], sb[me], rg, k, q_thr);
+    const int my_cam = __float_as_int(sa[me].z);
+    float score3D = 0.0f, pending = 0.0f;
+    int current_cam = -1;
+    for (int c = 0; c < np; ++c) {
+        const int cc = c0 + c;
+        int t = cbA[cc];
+        const int te = cbA[cc + 1];
+        if (t == te || cc == my_chunk) continue;
+        const int cam = chunk_cam[c];
+        if (cam == my_cam) continue;
+        if (cam != current_cam) {
+            const float sim = sw_sim(o, sa, sb, ord[t], angle_reg, sim_t, cos_thr);
+            pending = fmaxf(pending, sim);
+            score3D += pending; pending = 0.0f; current_cam = cam;
+            ++t;
+        }
+#pragma unroll 2
+        for (; t < te; ++t) pending = fmaxf(pending, sw_sim(o, sa, sb, ord[t], angle_reg, sim_t, cos_thr));
+    }
+    score3D += pending;
+    return score3D;
+}
+
 // scoringCPU (line3D.cc:1208-1294) + similarityForScoring (1417-1446) + angleBetweenSeg3D (1571-1583): the score is the sum
 // over target cameras of the best similarity among that camera's matches, built with the reference's running update (add the
-// first value of a camera, replace it when a larger one arrives) in list order.
+// first value of a camera, replace it when a larger one arrives) in list order.  ord != nullptr: [lo, hi) indexes the ordered
+// list of active entries, else the staged list itself (inactive entries carry a negative camera).
 #define SC_MAP 48
-__device__ __forceinline__ float sw_score_cpu(const float4* __restrict__ sa, const double4* __restrict__ d64, float2 rg, int lo, int hi, int me, float k,
-                                              float angle_reg, float sim_t)
+__device__ __forceinline__ float sw_score_cpu(const float4* __restrict__ sa, const double4* __restrict__ d64, float2 rg, const int* __restrict__ ord, int lo,
+                                              int hi, int me, float k, float angle_reg, float sim_t)
 {
     const float4 ma = sa[me];
     const int my_cam = __float_as_int(ma.z);
@@ -431,7 +474,8 @@ __device__ __forceinline__ float sw_score_cpu(const float4* __restrict__ sa, con
     };
     int cams[SC_MAP]; float best[SC_MAP]; int ncam = 0;
     float score3D = 0.0f;
-    for (int i = lo; i < hi; ++i) {
+    for (int t = lo; t < hi; ++t) {
+        const int i = ord ? ord[t] : t;
         const int cam = __float_as_int(sa[i].z);
         if (cam < 0 || cam == my_cam) continue;
         const float sim = sim_of(i);
@@ -441,7 +485,10 @@ __device__ __forceinline__ float sw_score_cpu(const float4* __restrict__ sa, con
         else if (ncam < SC_MAP) { score3D += sim; cams[ncam] = cam; best[ncam] = sim; ++ncam; }
         else {      // more target cameras than map slots: recover this camera's running maximum from the earlier entries
             bool seen = false; float cur = 0.0f;
-            for (int j = lo; j < i; ++j) if (__float_as_int(sa[j].z) == cam) { const float sj = sim_of(j); if (!seen) { cur = sj; seen = true; } else if (sj > cur) cur = sj; }
+            for (int u = lo; u < t; ++u) {
+                const int j = ord ? ord[u] : u;
+                if (__float_as_int(sa[j].z) == cam) { const float sj = sim_of(j); if (!seen) { cur = sj; seen = true; } else if (sj > cur) cur = sj; }
+            }
             if (seen) { if (sim > cur) { score3D -= cur; score3D += sim; } } else score3D += sim;
         }
     }
@@ -455,21 +502,49 @@ __device__ __forceinline__ float sw_score_cpu(const float4* __restrict__ sa, con
 struct SwChunkInfo { int other, pub; float k; float pad; double Cx, Cy, Cz; };
 struct SwSegInfo { float r1[3], r2[3]; double q1[3], q2[3]; };
 
+// regularizers_tgt (line3D.cc:1350-1352) == View::regularizerFrom3Dpoint (view.cc:445-448): |P - C_tgt| * k_tgt in double, stored as
+// float; REF_CPU also needs the double 3D segment (direction, float length) scoringCPU works on
 template <bool CPU>
-__device__ __forceinline__ void sw_score_range(const SwScoreArgs<CPU>& A, const SwPtrs P, const int* __restrict__ cb, bool cb_smem,
-                                               const SwChunkInfo* __restrict__ cinfo, bool cinfo_smem, const SwSegInfo* __restrict__ sinfo,
-                                               int* __restrict__ nact_smem, int s0, int nsegs, long long x0, int n)
+__device__ __forceinline__ float2 sw_target_reg(const L3DViewDev* V, const SwSegInfo& sg, float d1, float d2, D3 Ct, float kT, double4* d64_out)
+{
+    SegRaysQ Q;
+    Q.r1 = d3(sg.q1[0], sg.q1[1], sg.q1[2]); Q.r2 = d3(sg.q2[0], sg.q2[1], sg.q2[2]); Q.rm = d3(0, 0, 0);
+    D3 P1, P2;
+    sw_unproject_pts(V, Q, d1, d2, &P1, &P2);
+    const D3 dd = dsub(P1, P2);
+    const double n2 = ddot(dd, dd);
+    const bool nondeg = sw_nondegenerate(n2);
+    if (!nondeg) P1 = P2 = d3(0, 0, 0);                                   // Segment3D ctor (segment3D.h:58-63)
+    if (CPU) {
+        D3 dir = d3(0, 0, 0); float len = 0.0f;
+        if (nondeg) { dir = dnormalized(dsub(P2, P1)); len = (float)sqrt(n2); }
+        *d64_out = make_double4(dir.x, dir.y, dir.z, (double)len);
+    }
+    return make_float2((float)(dnorm(dsub(P1, Ct)) * (double)kT), (float)(dnorm(dsub(P2, Ct)) * (double)kT));
+}
+
+template <bool CPU>
+__device__ __forceinline__ void sw_score_range(const SwScoreArgs<CPU>& A, const SwPtrs P, const int* __restrict__ cb, int* __restrict__ cbA, bool cb_smem,
+                                               const SwChunkInfo* __restrict__ cinfo, const int* __restrict__ ccam, bool cinfo_smem,
+                                               const SwSegInfo* __restrict__ sinfo, int* __restrict__ wcnt, int s0, int nsegs, long long x0, int n)
 {
     const L3DViewDev* V = A.views + A.v;
     const SwView me = A.vt[A.v];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int np = me.np;
     const int nch = nsegs * np;
     const long long chbase = me.chunk_base + (long long)s0 * np;
-    // ---- stage
+    auto chunk_info = [&](int c, int* other, int* pub, float* kT, D3* Ct) {
+        if (cinfo_smem) { const SwChunkInfo ci = cinfo[c]; *other = ci.other; *pub = ci.pub; *kT = ci.k; *Ct = d3(ci.Cx, ci.Cy, ci.Cz); }
+        else {
+            const SwChunk ck = A.vp[me.vp_off + c];
+            const L3DViewDev* T = A.views + ck.other;
+            *other = ck.other; *pub = (!ck.inv && A.pairc[ck.pair].y >= 0) ? ck.other : -1; *kT = T->k; *Ct = d3(T->C_d[0], T->C_d[1], T->C_d[2]);
+        }
+    };
+    // ---- stage: a = (depth1, depth2, target view [inverse entries: -2 - view until they are known to be active], chunk index in the CTA)
     for (int j0 = 0; j0 < n; j0 += SW_THREADS) {
         const int j = j0 + threadIdx.x;
-        bool active = false;
         if (j < n) {
             const long long x = x0 + j;
             const unsigned int val = A.e_val[x];
@@ -477,17 +552,11 @@ __device__ __forceinline__ void sw_score_range(const SwScoreArgs<CPU>& A, const 
             int lo = 0, hi = nch - 1;               // chunk of entry j: last q with boundary[q] <= j
             if (cb_smem) { while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cb[mid] <= j) lo = mid; else hi = mid - 1; } }
             else { while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (A.cstart[chbase + mid] <= x) lo = mid; else hi = mid - 1; } }
-            const int si = lo / np, c = lo - si * np;
+            const int si = lo / np;
             int other, pub; float kT; D3 Ct;
-            if (cinfo_smem) { const SwChunkInfo ci = cinfo[c]; other = ci.other; pub = ci.pub; kT = ci.k; Ct = d3(ci.Cx, ci.Cy, ci.Cz); }
-            else {
-                const SwChunk ck = A.vp[me.vp_off + c];
-                const L3DViewDev* T = A.views + ck.other;
-                other = ck.other; pub = (!ck.inv && A.pairc[ck.pair].y >= 0) ? ck.other : -1; kT = T->k; Ct = d3(T->C_d[0], T->C_d[1], T->C_d[2]);
-            }
+            chunk_info(lo - si * np, &other, &pub, &kT, &Ct);
             const bool inv = (val & SW_INV) != 0u;
             const float d1 = inv ? rec.d_q1 : rec.d_p1, d2 = inv ? rec.d_q2 : rec.d_p2;
-            active = !inv;               // inverse entries learn after the grid-dependency wait whether their source scored them > 0
             const SwSegInfo& sg = sinfo[si];
             {   // D_unproject x2 + D_line_direction_3D (cudawrapper.cu:167-171, 40-43) with the cached float rays
                 const float3 Cf = make_float3(V->C[0], V->C[1], V->C[2]);
@@ -497,64 +566,73 @@ __device__ __forceinline__ void sw_score_range(const SwScoreArgs<CPU>& A, const 
                 // where a positive score has to be announced: the target view, if it is still to be processed (line3D.cc:1680)
                 P.b[j] = make_float4(dir.x, dir.y, dir.z, __int_as_float(inv ? -1 : pub));
             }
-            float2 reg = make_float2(0.f, 0.f);
-            {   // regularizers_tgt (line3D.cc:1350-1352) == View::regularizerFrom3Dpoint (view.cc:445-448): |P - C_tgt| * k_tgt in double, stored as float
-                SegRaysQ Q;
-                Q.r1 = d3(sg.q1[0], sg.q1[1], sg.q1[2]); Q.r2 = d3(sg.q2[0], sg.q2[1], sg.q2[2]); Q.rm = d3(0, 0, 0);
-                D3 P1, P2;
-                sw_unproject_pts(V, Q, d1, d2, &P1, &P2);
-                const D3 dd = dsub(P1, P2);
-                const double n2 = ddot(dd, dd);
-                const bool nondeg = sw_nondegenerate(n2);
-                if (!nondeg) P1 = P2 = d3(0, 0, 0);                                   // Segment3D ctor (segment3D.h:58-63)
-                reg = make_float2((float)(dnorm(dsub(P1, Ct)) * (double)kT), (float)(dnorm(dsub(P2, Ct)) * (double)kT));
-                if (CPU) {      // scoringCPU works on the double 3D segment: direction and (float) length
-                    D3 dir = d3(0, 0, 0); float len = 0.0f;
-                    if (nondeg) { dir = dnormalized(dsub(P2, P1)); len = (float)sqrt(n2); }
-                    P.d64[j] = make_double4(dir.x, dir.y, dir.z, (double)len);
-                }
-            }
-            // inverse entries carry their target view as -2 - view until they are known to be active
-            P.a[j] = make_float4(d1, d2, __int_as_float(active ? other : -2 - other), __int_as_float(si));
-            P.r[j] = reg;
+            if (!inv) P.r[j] = sw_target_reg<CPU>(V, sg, d1, d2, Ct, kT, CPU ? P.d64 + j : nullptr);      // inverse entries: only if they turn out active
+            P.a[j] = make_float4(d1, d2, __int_as_float(inv ? -2 - other : other), __int_as_float(lo));
         }
     }
     // ---- everything above only read what the set-up kernels wrote: it may overlap the previous view's kernel (programmatic
     // dependent launch).  From here on the "active" bits that kernel publishes are needed.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // active flags of the inverse entries + the ordered list of active entries (ord = P.act)
+    int nact = 0;
     for (int j0 = 0; j0 < n; j0 += SW_THREADS) {
         const int j = j0 + threadIdx.x;
         bool active = false;
         if (j < n) {
-            const int cam = __float_as_int(P.a[j].z);
+            const float4 ma = P.a[j];
+            const int cam = __float_as_int(ma.z);
             active = cam >= 0;
             if (!active) {
                 const long long x = x0 + j;
-                if (A.e_flag[x] & SW_ACTIVE) { active = true; P.a[j].z = __int_as_float(-2 - cam); }
-                else { P.a[j].z = __int_as_float(-1); A.e_score[x] = 0.0f; }
+                if (A.e_flag[x] & SW_ACTIVE) {
+                    active = true;
+                    const int lo = __float_as_int(ma.w), si = lo / np;
+                    int other, pub; float kT; D3 Ct;
+                    chunk_info(lo - si * np, &other, &pub, &kT, &Ct);
+                    P.a[j].z = __int_as_float(other);
+                    P.r[j] = sw_target_reg<CPU>(V, sinfo[si], ma.x, ma.y, Ct, kT, CPU ? P.d64 + j : nullptr);
+                } else { P.a[j].z = __int_as_float(-1); A.e_score[x] = 0.0f; }
             }
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, active);
-        int base = 0;
-        if (lane == 0 && bal) base = atomicAdd(nact_smem, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (active) P.act[base + __popc(bal & ((1u << lane) - 1u))] = j;
+        if (lane == 0) wcnt[wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < SW_THREADS / 32; ++w) { const int cw = wcnt[w]; if (w < wid) woff += cw; tot += cw; }
+        if (active) P.act[nact + woff + __popc(bal & ((1u << lane) - 1u))] = j;
+        nact += tot;
+        __syncthreads();
     }
-    __threadfence_block();
-    __syncthreads();
+    // chunk boundaries in the list of active entries
+    const bool chunked = !CPU && cb_smem && cinfo_smem;
+    if (cb_smem) {
+        for (int q = threadIdx.x; q <= nch; q += SW_THREADS) {
+            const int bound = cb[q];
+            int lo = 0, hi = nact;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.act[mid] < bound) lo = mid + 1; else hi = mid; }
+            cbA[q] = lo;
+        }
+        __syncthreads();
+    }
     // ---- score the active entries, publish
-    const int nact = *nact_smem;
     const float k = V->k;
     float vmax = 0.0f;
     for (int q = threadIdx.x; q < nact; q += SW_THREADS) {
         const int j = P.act[q];
-        const float4 ma = P.a[j];
-        const int si = __float_as_int(ma.w);
-        int lo, hi;
-        if (cb_smem) { lo = cb[si * np]; hi = cb[(si + 1) * np]; }
-        else { lo = (int)(A.cstart[chbase + (long long)si * np] - x0); hi = (int)(A.cstart[chbase + (long long)(si + 1) * np] - x0); }
-        const float sc = CPU ? sw_score_cpu(P.a, P.d64, P.r[j], lo, hi, j, k, A.angle_reg, A.sim_t)
-                             : sw_score_gpu(P.a, P.b, P.r[j], lo, hi, j, k, A.angle_reg, A.sim_t, A.q_thr, A.cos_thr);
+        const int my_chunk = __float_as_int(P.a[j].w);
+        const int si = my_chunk / np;
+        float sc;
+        if (chunked) {
+            sc = sw_score_gpu_chunks(P.a, P.b, P.r[j], P.act, cbA, ccam, si * np, np, my_chunk, j, k, A.angle_reg, A.sim_t, A.q_thr, A.cos_thr);
+        } else if (cb_smem) {
+            sc = CPU ? sw_score_cpu(P.a, P.d64, P.r[j], P.act, cbA[si * np], cbA[(si + 1) * np], j, k, A.angle_reg, A.sim_t)
+                     : sw_score_gpu_list(P.a, P.b, P.r[j], cb[si * np], cb[(si + 1) * np], j, k, A.angle_reg, A.sim_t, A.q_thr, A.cos_thr);
+        } else {
+            const int lo = (int)(A.cstart[chbase + (long long)si * np] - x0), hi = (int)(A.cstart[chbase + (long long)(si + 1) * np] - x0);
+            sc = CPU ? sw_score_cpu(P.a, P.d64, P.r[j], nullptr, lo, hi, j, k, A.angle_reg, A.sim_t)
+                     : sw_score_gpu_list(P.a, P.b, P.r[j], lo, hi, j, k, A.angle_reg, A.sim_t, A.q_thr, A.cos_thr);
+        }
         const long long x = x0 + j;
         const int T = __float_as_int(P.b[j].w);
         if (T >= 0 && sc > 0.0f) {      // storeInverseMatches; an inverse match that fails T's orientation check has no entry there
@@ -576,10 +654,11 @@ k_sw_score(const SwScoreArgs<CPU> A)
     constexpr int CAP = CPU ? SW_CAP_CPU : SW_CAP_GPU;
     asm volatile("griddepcontrol.launch_dependents;");       // the next view's kernel may start its independent part
     extern __shared__ __align__(16) unsigned char sw_smem[];
-    __shared__ int cb[SW_MAXCH + 1];
+    __shared__ int cb[SW_MAXCH + 1], cbA[SW_MAXCH + 1];
     __shared__ SwChunkInfo cinfo[SW_MAXNP];
+    __shared__ int ccam[SW_MAXNP];
     __shared__ SwSegInfo sinfo[SW_SEGS];
-    __shared__ int nact_smem;
+    __shared__ int wcnt[SW_THREADS / 32];
     const L3DViewDev* V = A.views + A.v;
     const int s0 = blockIdx.x * SW_SEGS;
     const int nsegs = min(SW_SEGS, V->nseg - s0);
@@ -598,7 +677,7 @@ k_sw_score(const SwScoreArgs<CPU> A)
             SwChunkInfo ci;
             ci.other = ck.other; ci.pub = (!ck.inv && A.pairc[ck.pair].y >= 0) ? ck.other : -1; ci.k = T->k; ci.pad = 0.f;
             ci.Cx = T->C_d[0]; ci.Cy = T->C_d[1]; ci.Cz = T->C_d[2];
-            cinfo[c] = ci;
+            cinfo[c] = ci; ccam[c] = ck.other;
         }
     if (threadIdx.x < nsegs) {
         const long long gs = V->seg_off + s0 + threadIdx.x;
@@ -609,7 +688,6 @@ k_sw_score(const SwScoreArgs<CPU> A)
         si.q1[0] = Q.r1.x; si.q1[1] = Q.r1.y; si.q1[2] = Q.r1.z; si.q2[0] = Q.r2.x; si.q2[1] = Q.r2.y; si.q2[2] = Q.r2.z;
         sinfo[threadIdx.x] = si;
     }
-    if (threadIdx.x == 0) nact_smem = 0;
     __syncthreads();
     SwPtrs P;
     if (n <= CAP) {
@@ -621,7 +699,7 @@ k_sw_score(const SwScoreArgs<CPU> A)
         const long long rel = x0 - me.region_off;
         P.a = A.g.a + rel; P.b = A.g.b + rel; P.r = A.g.r + rel; P.act = A.g.act + rel; P.d64 = CPU ? A.g.d64 + rel : nullptr;
     }
-    sw_score_range<CPU>(A, P, cb, cb_smem, cinfo, cinfo_smem, sinfo, &nact_smem, s0, nsegs, x0, n);
+    sw_score_range<CPU>(A, P, cb, cbA, cb_smem, cinfo, ccam, cinfo_smem, sinfo, wcnt, s0, nsegs, x0, n);
 }
 
 // ---------------------------------------------------------------------------------------------- after the chain

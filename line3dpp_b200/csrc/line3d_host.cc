@@ -333,14 +333,11 @@ void Line3D::setShard(int rank, int world, MatchExchangeFn fn, void* user)
 }
 size_t Line3D::numImages() { std::lock_guard<std::mutex> g(p_->mtx); return p_->views.size(); }
 
-void Line3D::addImage(const unsigned int camID, const int w, const int h, const Matrix3d& K, const Matrix3d& R, const Vector3d& t,
+bool Line3D::addImage(const unsigned int camID, const int w, const int h, const Matrix3d& K, const Matrix3d& R, const Vector3d& t,
                       const float median_depth, const std::list<unsigned int>& wps_or_neighbors, const std::vector<Vec4f>& line_segments)
 {
     Impl& P = *p_;
-    P.err.clear();
-    if (std::max(w, h) < 800) { P.fail("image is too small for reliable results (larger side should be >= 800px)"); return; }   // line3D.cc:119
-    if (wps_or_neighbors.empty()) { P.fail(P.by_wps ? "view has no worldpoints" : "view has no visual neighbors"); return; }    // line3D.cc:154
-    if (line_segments.empty()) { P.fail("no line segments given (LSD detection is outside this library's scope)"); return; }
+    // everything that needs no shared state first (the reference's frontends call addImage from an OpenMP loop) ...
     HostView v;
     v.id = camID; v.width = w; v.height = h; v.K = K; v.R = R; v.t = t; v.lines = line_segments; v.wps_or_neighbors = wps_or_neighbors;
     v.min_line_length = std::sqrt(float((unsigned)w * (unsigned)w + (unsigned)h * (unsigned)h)) * 0.005f;                           // view.cc:17-18
@@ -350,12 +347,19 @@ void Line3D::addImage(const unsigned int camID, const int w, const int h, const 
     v.C = matvec(Rt, t * -1.0);
     v.C_f3[0] = (float)v.C.x; v.C_f3[1] = (float)v.C.y; v.C_f3[2] = (float)v.C.z;
     for (int i = 0; i < 9; ++i) v.RtKinv_f[i] = (float)v.RtKinv.m[i];
+    // ... then one critical section for the checks, the insertion and the error string.  A failure is reported through the return
+    // value AND stays in lastError() (a later successful addImage does not clear it) until the next non-addImage call.
     std::lock_guard<std::mutex> g(P.mtx);
-    if (P.views.count(camID)) { P.fail("camera ID already in use"); return; }                                                     // line3D.cc:130
+    auto failed = [&](const std::string& what) { P.fail("addImage [" + std::to_string(camID) + "]: " + what); return false; };
+    if (std::max(w, h) < 800) return failed("image is too small for reliable results (larger side should be >= 800px)");   // line3D.cc:119
+    if (wps_or_neighbors.empty()) return failed(P.by_wps ? "view has no worldpoints" : "view has no visual neighbors");    // line3D.cc:154
+    if (line_segments.empty()) return failed("no line segments given (LSD detection is outside this library's scope)");
+    if (P.views.count(camID)) return failed("camera ID already in use");                                                     // line3D.cc:130
     if (P.by_wps) for (unsigned int wp : wps_or_neighbors) P.wps2views[wp].push_back(camID);
     P.views[camID] = v;
     P.visual_neighbors[camID];
     P.views_avg_depths.push_back((float)std::fmax((double)median_depth, EPS));
+    return true;
 }
 
 void Line3D::matchImages(const float sigma_position, const float sigma_angle, const unsigned int num_neighbors, const float epipolar_overlap,
@@ -419,7 +423,7 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
         return P.use_gpu ? P.chk(l3d_match_pairs_range(P.ctx, npairs, P.pairs.data(), F.data(), P.epi, P.kNN, first, last), "l3d_match_pairs_range")
                          : P.chk(l3d_match_pairs_f64(P.ctx, npairs, P.pairs.data(), Fdbl.data(), P.epi, P.kNN, first, last), "l3d_match_pairs_f64");
     };
-    if (ok && P.shard_world > 1 && P.kNN <= 0) { P.fail("matchImages: kNN <= 0 (keep all matches) cannot be sharded: the row stride is only known after matching"); ok = false; }
+    if (ok && P.shard_world > 1 && (P.kNN <= 0 || P.kNN > 32)) { P.fail("matchImages: kNN <= 0 (keep all matches) or kNN > 32 cannot be sharded: the row stride is only known after matching"); ok = false; }
     if (ok && P.shard_world > 1) {
         // this rank's contiguous share of the pair list, balanced by Ns*Nt; the same split on every rank
         std::vector<long long> cost((size_t)npairs), row_off((size_t)npairs + 1), row_bounds((size_t)P.shard_world + 1);
@@ -727,7 +731,9 @@ void Line3D::save3DLinesAsTXT(const std::string& folder)   // line3D.cc:2631-268
 {
     std::lock_guard<std::mutex> g(p_->mtx);
     if (p_->lines3D.empty()) { p_->fail("no 3D lines to save!"); return; }
-    std::ofstream f((folder + "/" + createOutputFilename() + ".txt").c_str());
+    const std::string path = folder + "/" + createOutputFilename() + ".txt";
+    std::ofstream f(path.c_str());
+    if (!f) { p_->fail("cannot open " + path + " for writing"); return; }
     for (const FinalLine3D& L : p_->lines3D) {
         if (L.collinear3Dsegments_.empty()) continue;
         f << L.collinear3Dsegments_.size() << " ";
@@ -747,7 +753,9 @@ void Line3D::saveResultAsOBJ(const std::string& folder)
 {
     std::lock_guard<std::mutex> g(p_->mtx);
     if (p_->lines3D.empty()) { p_->fail("no 3D lines to save!"); return; }
-    std::ofstream f((folder + "/" + createOutputFilename() + ".obj").c_str());
+    const std::string path = folder + "/" + createOutputFilename() + ".obj";
+    std::ofstream f(path.c_str());
+    if (!f) { p_->fail("cannot open " + path + " for writing"); return; }
     size_t nseg = 0;
     for (const FinalLine3D& L : p_->lines3D)
         for (const Segment3D& s : L.collinear3Dsegments_) {
@@ -764,7 +772,9 @@ void Line3D::saveResultAsSTL(const std::string& folder)
 {
     std::lock_guard<std::mutex> g(p_->mtx);
     if (p_->lines3D.empty()) { p_->fail("no 3D lines to save!"); return; }
-    std::ofstream f((folder + "/" + createOutputFilename() + ".stl").c_str());
+    const std::string path = folder + "/" + createOutputFilename() + ".stl";
+    std::ofstream f(path.c_str());
+    if (!f) { p_->fail("cannot open " + path + " for writing"); return; }
     auto vertex = [&f](const Vector3d& v) { char b[200]; snprintf(b, sizeof(b), "   vertex %e %e %e", v.x, v.y, v.z); f << b << std::endl; };
     f << "solid lineModel" << std::endl;
     for (const FinalLine3D& L : p_->lines3D)
@@ -805,8 +815,7 @@ int l3dpp_add_image(void* h, unsigned int cam, int w, int hgt, const double* K, 
     Matrix3d Km, Rm; memcpy(Km.m, K, 72); memcpy(Rm.m, R, 72);
     std::vector<Vec4f> s(nseg); if (nseg) memcpy(s.data(), segs, 16 * (size_t)nseg);
     Line3D* L = (Line3D*)h;
-    L->addImage(cam, w, hgt, Km, Rm, Vector3d(t[0], t[1], t[2]), median_depth, std::list<unsigned int>(list, list + nlist), s);
-    return L->lastError()[0] ? -1 : 0;
+    return L->addImage(cam, w, hgt, Km, Rm, Vector3d(t[0], t[1], t[2]), median_depth, std::list<unsigned int>(list, list + nlist), s) ? 0 : -1;
 }
 int l3dpp_match_images(void* h, float sp, float sa, unsigned int nn, float epi, int knn, float crd)
 { Line3D* L = (Line3D*)h; L->matchImages(sp, sa, nn, epi, knn, crd); return L->lastError()[0] ? -1 : 0; }

@@ -25,11 +25,15 @@ bool readNVM(const std::string& path, std::vector<NVMCamera>& cams, std::string*
     if (num_cams == 0) { if (error) *error = "No aligned cameras in NVM file!"; return false; }     // main_vsfm.cpp:157-161
     cams.resize(num_cams);
     for (unsigned int i = 0; i < num_cams; ++i) {
-        std::getline(f, line);
-        std::stringstream s(line);
         double focal = 0, qw = 1, qx = 0, qy = 0, qz = 0, Cx = 0, Cy = 0, Cz = 0, dist = 0;
         NVMCamera& c = cams[i];
-        s >> c.image >> focal >> qw >> qx >> qy >> qz >> Cx >> Cy >> Cz >> dist;
+        // a truncated or malformed camera line must not become a default camera (the reference has the same hole, main_vsfm.cpp:168-190)
+        if (!std::getline(f, line)) { if (error) *error = "unexpected end of file in the camera list of " + path + " (camera " + std::to_string(i) + ")"; return false; }
+        std::stringstream s(line);
+        if (!(s >> c.image >> focal >> qw >> qx >> qy >> qz >> Cx >> Cy >> Cz >> dist)) {
+            if (error) *error = "malformed camera line " + std::to_string(i) + " in " + path;
+            return false;
+        }
         c.focal = (float)focal; c.distortion = (float)dist;
         Matrix3d& R = c.R;                        // main_vsfm.cpp:193-203 (the quaternion is used as stored, not re-normalised)
         R(0, 0) = 1.0 - 2.0 * qy * qy - 2.0 * qz * qz; R(0, 1) = 2.0 * qx * qy - 2.0 * qz * qw; R(0, 2) = 2.0 * qx * qz + 2.0 * qy * qw;
@@ -89,14 +93,15 @@ bool readBundler(const std::string& bundle_file, const std::string& image_list_f
         SfMCamera& c = cams[i];
         c.id = i; c.has_K = false; std::memset(c.K.m, 0, sizeof(c.K.m)); c.median_depth = 0.0f;
         double focal = 0, d1 = 0, d2 = 0;
-        std::getline(f, line);
-        { std::stringstream s(line); s >> focal >> d1 >> d2; }
+        bool good = (bool)std::getline(f, line);
+        if (good) { std::stringstream s(line); good = (bool)(s >> focal >> d1 >> d2); }
         c.focal = (float)focal;
         c.radial[0] = (float)d1; c.radial[1] = (float)d2; c.radial[2] = 0.0; c.tangential[0] = c.tangential[1] = 0.0;   // float pair, main_bundler.cpp:170, 183
-        for (int j = 0; j < 3; ++j) { std::getline(f, line); std::stringstream s(line); s >> c.R(j, 0) >> c.R(j, 1) >> c.R(j, 2); }
+        for (int j = 0; j < 3 && good; ++j) { good = (bool)std::getline(f, line); std::stringstream s(line); good = good && (bool)(s >> c.R(j, 0) >> c.R(j, 1) >> c.R(j, 2)); }
         for (int k = 0; k < 3; ++k) { c.R(1, k) *= -1.0; c.R(2, k) *= -1.0; }                                           // main_bundler.cpp:196-198
-        std::getline(f, line);
-        { std::stringstream s(line); s >> c.t.x >> c.t.y >> c.t.z; }
+        good = good && (bool)std::getline(f, line);
+        if (good) { std::stringstream s(line); good = (bool)(s >> c.t.x >> c.t.y >> c.t.z); }
+        if (!good) { if (error) *error = "truncated or malformed camera " + std::to_string(i) + " in " + bundle_file; return false; }
         c.t.y *= -1.0; c.t.z *= -1.0;                                                                                    // main_bundler.cpp:210-212
         c.C = center_of(c.R, c.t);
     }

@@ -446,6 +446,17 @@ def test_capi_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, n)
 
 
+def test_nvm_reader_rejects_truncated_camera_list(tmp_path):
+    """a truncated camera section must be an error, not a default camera"""
+    f = tmp_path / "t.nvm"
+    f.write_text("NVM_V3\n\n3\nimg0.jpg 1000 1 0 0 0 0 0 0 0 0\nimg1.jpg 1000 1 0 0 0\n")
+    cams, err = _read_nvm_product(f)
+    assert cams is None and "camera" in err
+    f.write_text("NVM_V3\n\n2\nimg0.jpg 1000 1 0 0 0 0 0 0 0 0\n")
+    cams, err = _read_nvm_product(f)
+    assert cams is None and "end of file" in err
+
+
 def _read_sfm_product(kind, path, aux=""):
     from line3dpp_b200 import build
     L = ctypes.CDLL(build.build())
@@ -580,6 +591,45 @@ def test_cpp_frontend_compiles_against_the_public_headers(tmp_path):
     else:
         assert r.returncode == 3 and "no usable CUDA device" in r.stderr, (r.returncode, r.stderr)
 
+
+
+def test_reference_addimage_signature_compiles_against_eigen_opencv_headers(tmp_path):
+    """include/line3d.h offers the reference's own addImage signature (line3D.h:104-108) when Eigen and OpenCV headers are on the
+    include path.  Neither is installed here: compile against the stand-ins of oracle/ref_shim (the headers the verbatim reference
+    build uses), link against the in-tree library and check that a view without segments is rejected, not detected on the CPU."""
+    from line3dpp_b200 import build
+    so = build.build()
+    src = tmp_path / "facade.cpp"
+    src.write_text(r"""
+#include "line3d.h"
+#ifndef L3DPP_WITH_EIGEN_OPENCV
+#error "the Eigen / OpenCV overloads were not enabled"
+#endif
+#include <cstdio>
+int main() {
+    try {
+        L3DPP::Line3D L("/tmp", true, -1, 3000, false, true);
+        cv::Mat img(2304, 3072, CV_8U);
+        Eigen::Matrix3d K = Eigen::Matrix3d::Identity(), R = Eigen::Matrix3d::Identity();
+        Eigen::Vector3d t(0, 0, 1);
+        std::list<unsigned int> nb; nb.push_back(1);
+        std::vector<cv::Vec4f> segs(1, cv::Vec4f(1.f, 2.f, 300.f, 400.f));
+        bool a = L.addImage(0u, img, K, R, t, 4.0f, nb, segs);
+        bool b = L.addImage(1u, img, K, R, t, 4.0f, nb);          // no segments: rejected (no LSD here)
+        std::printf("%d %d %zu\n", int(a), int(b), L.numImages());
+        return (a && !b && L.numImages() == 1) ? 0 : 1;
+    } catch (const std::exception& e) { std::printf("no GPU: %s\n", e.what()); return 3; }
+}
+""")
+    exe = tmp_path / "facade"
+    shim = os.path.join(ROOT, "oracle", "ref_shim")
+    cmd = ["g++", "-std=c++17", "-Wall", "-Werror", str(src), "-I" + os.path.join(ROOT, "include"), "-I" + shim, "-L" + os.path.dirname(so), "-ll3d_b200",
+           "-Wl,-rpath," + os.path.dirname(so), "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    import torch
+    assert r.returncode == (0 if torch.cuda.is_available() else 3), (r.returncode, r.stdout, r.stderr)
 
 
 def test_no_cpu_fallback_without_gpu():

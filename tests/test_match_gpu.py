@@ -298,3 +298,26 @@ def test_capi_error_behaviour(gpu_ctx):
     assert L.l3d_get_pair_matches(fresh.h, 3, p(counts), p(counts)) == -1
     assert L.l3d_rdd(fresh.h, 0, C.c_longlong(0), None, None, None, 10, None, None, None, None) == -1
     fresh.close()
+
+
+def test_knn_above_32_vs_reference_wrapper(loaded, scene, oracle, ref_nofma):
+    """kNN > 32 (beyond the fused kernel's per-row key list; the reference accepts any kNN, cudawrapper.cu:637-645): the keep-all
+    passes + per-row cut must give the reference wrapper's matches, in its pop order (overlap descending)."""
+    knn = 40
+    pairs = np.array(PAIRS[:2], np.int32)
+    loaded.match_pairs(pairs, util.pair_F(scene, pairs), 0.05, knn)       # low threshold: rows longer than 32 exist
+    nlong = 0
+    for p, (src, tgt) in enumerate(PAIRS[:2]):
+        pi = util.pair_inputs(scene, src, tgt)
+        rcounts, rout, rtotal, _ = oracle.match_lines(ref_nofma.ref_match_lines, pi["ls"], pi["lt"], pi["F"], pi["Rs"], pi["Rt"], pi["Cs"], pi["Ct"], src, tgt, 0.05, knn)
+        counts, recs = loaded.pair_matches(p, len(pi["ls"]))
+        assert np.array_equal(counts, rcounts) and counts.max() <= knn
+        nlong += int((counts > 32).sum())
+        mine, ref = util.rows_as_sets(counts, recs), util.rows_as_sets(rcounts, rout)
+        for r in range(len(counts)):
+            if mine[r] != ref[r]:
+                kth = min(e[1] for e in ref[r])
+                assert {e for e in mine[r] if e[1] != kth} == {e for e in ref[r] if e[1] != kth}, (src, tgt, r)
+            ov = recs[r, :counts[r]]["overlap"]
+            assert np.all(ov[:-1] >= ov[1:])
+    assert nlong > 0, "the test scene must have rows with more than 32 matches"

@@ -277,3 +277,28 @@ def test_writers_reproduce_the_reference_result_files_byte_for_byte(tmp_path):
     assert written(segs3d, L.L.l3dpp_save_obj, "obj") == str(gold["sha_obj"])
     assert written(gold["stl_segs"], L.L.l3dpp_save_stl, "stl") == str(gold["sha_stl"])
     L.close()
+
+
+def test_add_image_and_writer_errors_are_reported(tmp_path):
+    """addImage failures are attributable (status + sticky lastError), writers report unwritable folders"""
+    sc = synth.make_scene(6, 200, 3, "ring2")
+    L = line3d.Line3D(neighbors_by_worldpoints=False, use_gpu=True)
+    L.add_scene(sc)
+    import ctypes as C
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    K, R, t = np.ascontiguousarray(sc.K[0]), np.ascontiguousarray(sc.R[0]), np.ascontiguousarray(sc.t[0])
+    nb, sg = np.ascontiguousarray(sc.neighbors[0], np.uint32), np.ascontiguousarray(sc.segs[0], np.float32)
+    add = lambda cam, w: L.L.l3dpp_add_image(L.h, C.c_uint(cam), w, 2304, p(K), p(R), p(t), C.c_float(4.0), p(nb), len(nb), p(sg), len(sg))
+    assert add(0, 3072) < 0 and b"already in use" in L.L.l3dpp_last_error(L.h)          # duplicate camera id
+    assert add(77, 100) < 0 and b"too small" in L.L.l3dpp_last_error(L.h)
+    assert add(78, 3072) == 0                                                          # a success ...
+    assert b"too small" in L.L.l3dpp_last_error(L.h)                                   # ... does not wipe the earlier failure
+    L.match_images()
+    L.reconstruct_3d_lines(3, False)
+    assert L.stats()["lines3D"] > 20
+    with pytest.raises(Exception) as e:
+        L.save_txt(str(tmp_path / "does" / "not" / "exist"))
+    assert "cannot open" in str(e.value)
+    L.save_txt(str(tmp_path))
+    assert any(f.name.endswith(".txt") for f in tmp_path.iterdir())
+    L.close()
