@@ -15,14 +15,14 @@ struct SweepState {
     std::vector<long long> region_off;      // per processing rank (+1): first entry of the view's region
     long long total = 0;
     // match store (l3d_sweep.cuh): view table, chunk descriptors, chunk offsets, entries
-    DevBuf d_vt, d_vp, d_pairc, d_rowoff, d_rays, d_rmf, d_rflag, d_invpos, d_csize, d_ccur, d_cstart, d_eval, d_escore, d_eflag, d_gstage, d_gpub, d_dir64, d_export, d_export_ok,
+    DevBuf d_vt, d_vp, d_pairc, d_rowoff, d_pinfo, d_bpair, d_ekv, d_rays, d_rmf, d_rflag, d_invpos, d_csize, d_ccur, d_cstart, d_eval, d_escore, d_eflag, d_gstage, d_gpub, d_dir64, d_export, d_export_ok,
         d_ranges, d_est_best, d_est_P, d_M, d_vmax, d_sort_tmp, d_aff_sim, d_aff_flag, d_aff_gi, d_aff_gj, d_aff_pos, d_aff_oi, d_aff_oj,
         d_aff_ow, d_kx, d_order, d_rankofview, d_region_off, d_est_pos, d_est_out_best, d_est_out_P, d_segrank_off, d_evcnt, d_evptr, d_aff_par;
     long long n_est = 0, n_kept = 0;
     float ms_setup = 0.f, ms_chain = 0.f, ms_filter = 0.f;   // device time of the last sweep's three phases
     bool aff_has_parents = false;           // d_aff_par valid: candidates carry parents (collinearity links)
     std::vector<DevBuf*> bufs()
-    { return {&d_vt, &d_vp, &d_pairc, &d_rowoff, &d_rays, &d_rmf, &d_rflag, &d_invpos, &d_csize, &d_ccur, &d_cstart, &d_eval, &d_escore, &d_eflag, &d_gstage, &d_gpub, &d_dir64,
+    { return {&d_vt, &d_vp, &d_pairc, &d_rowoff, &d_pinfo, &d_bpair, &d_ekv, &d_rays, &d_rmf, &d_rflag, &d_invpos, &d_csize, &d_ccur, &d_cstart, &d_eval, &d_escore, &d_eflag, &d_gstage, &d_gpub, &d_dir64,
               &d_export, &d_export_ok, &d_ranges, &d_est_best, &d_est_P, &d_M, &d_vmax, &d_sort_tmp, &d_aff_sim, &d_aff_flag, &d_aff_gi, &d_aff_gj,
               &d_aff_pos, &d_aff_oi, &d_aff_oj, &d_aff_ow, &d_kx, &d_order, &d_rankofview, &d_region_off, &d_est_pos,
               &d_est_out_best, &d_est_out_P, &d_segrank_off, &d_evcnt, &d_evptr, &d_aff_par}; }

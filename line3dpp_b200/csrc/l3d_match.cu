@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) k_prep_segments_f64(const float4* __restr
 // ------------------------------------------------------------------------------------------------ fused match + top-k
 struct MatchSmem {
     float4 stage[MK_STAGES][MK_TT];                  // TMA-staged target segments (x1,y1,x2,y2)
-    unsigned long long lists[MK_ROWS][MK_CAP];       // per-row survivor keys
+    unsigned long long lists[MK_ROWS][MK_CAP + 1];   // per-row survivor keys (+1: rows start on different banks, lanes that push keys of different rows do not collide)
     float4 rowA[MK_ROWS];                            // (e1.x, e1.y, e1.z, e2.x)
     float4 rowB[MK_ROWS];                            // (e2.y, e2.z, g, 0.95 * score-to-beat)
     float row_thr[MK_ROWS];                          // overlap of the current k-th best survivor (0 until k are known)

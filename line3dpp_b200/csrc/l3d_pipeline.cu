@@ -115,54 +115,19 @@ __device__ __forceinline__ bool sw_orientation_ok(const L3DViewDev* V, const Seg
 }
 
 // ---------------------------------------------------------------------------------------------- batched set-up kernels
-// What the record-parallel set-up kernels need to know about a pair, gathered once per thread block (a block of consecutive record
-// slots touches one pair, at most a few): without it every thread walks pairs[p] -> views[src] -> vt[src] ... as a chain of
-// dependent global loads.
+// What the record-parallel set-up kernels need to know about a pair.  The table (one entry per pair) and the first pair of every
+// thread block are built on the HOST once per sweep: with them a thread reaches its pair without walking
+// pairs[p] -> views[src] -> vt[src] ... as a chain of dependent global loads and without any block-level synchronisation.
 struct SwPairInfo {
     long long row_off, row_end, src_seg_off, tgt_seg_off, src_chunk_base, tgt_chunk_base;
     int src, tgt, src_np, tgt_np, cx, cy;
 };
-#define SW_PI 4
-__device__ __forceinline__ void sw_load_pair_info(SwPairInfo* __restrict__ pi, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
-                                                  const long long* __restrict__ row_off, int num_pairs, const SwView* __restrict__ vt,
-                                                  const int2* __restrict__ pairc, long long first_row)
+#define SW_SETUP_THREADS 256
+__device__ __forceinline__ SwPairInfo sw_pair_info(const SwPairInfo* __restrict__ pinfo, const int* __restrict__ block_pair0, long long row)
 {
-    __shared__ int p0s;
-    if (threadIdx.x == 0) p0s = sw_pair_of_row(row_off, num_pairs, first_row);
-    __syncthreads();
-    if (threadIdx.x < SW_PI) {
-        const int p = p0s + threadIdx.x;
-        SwPairInfo q;
-        if (p < num_pairs) {
-            const L3DPairDev* P = pairs + p;
-            q.row_off = row_off[p]; q.row_end = row_off[p + 1]; q.src = P->src; q.tgt = P->tgt;
-            q.src_seg_off = views[q.src].seg_off; q.tgt_seg_off = views[q.tgt].seg_off;
-            const SwView sv = vt[q.src], tv = vt[q.tgt];
-            q.src_chunk_base = sv.chunk_base; q.tgt_chunk_base = tv.chunk_base; q.src_np = sv.np; q.tgt_np = tv.np;
-            const int2 pc = pairc[p];
-            q.cx = pc.x; q.cy = pc.y;
-        } else { q.row_off = q.row_end = (1ll << 62); q.src = q.tgt = 0; q.src_seg_off = q.tgt_seg_off = q.src_chunk_base = q.tgt_chunk_base = 0; q.src_np = q.tgt_np = 0; q.cx = q.cy = -1; }
-        pi[threadIdx.x] = q;
-    }
-    __syncthreads();
-}
-// the info of the pair that holds `row` (in shared memory if it is one of the block's first SW_PI pairs)
-__device__ __forceinline__ SwPairInfo sw_pair_info(const SwPairInfo* __restrict__ pi, long long row, const L3DViewDev* __restrict__ views,
-                                                   const L3DPairDev* __restrict__ pairs, const long long* __restrict__ row_off, int num_pairs,
-                                                   const SwView* __restrict__ vt, const int2* __restrict__ pairc)
-{
-#pragma unroll
-    for (int k = 0; k < SW_PI; ++k) if (row < pi[k].row_end) return pi[k];
-    const int p = sw_pair_of_row(row_off, num_pairs, row);
-    const L3DPairDev* P = pairs + p;
-    SwPairInfo q;
-    q.row_off = row_off[p]; q.row_end = row_off[p + 1]; q.src = P->src; q.tgt = P->tgt;
-    q.src_seg_off = views[q.src].seg_off; q.tgt_seg_off = views[q.tgt].seg_off;
-    const SwView sv = vt[q.src], tv = vt[q.tgt];
-    q.src_chunk_base = sv.chunk_base; q.tgt_chunk_base = tv.chunk_base; q.src_np = sv.np; q.tgt_np = tv.np;
-    const int2 pc = pairc[p];
-    q.cx = pc.x; q.cy = pc.y;
-    return q;
+    int p = __ldg(block_pair0 + blockIdx.x);
+    while (row >= pinfo[p].row_end) ++p;            // a block of consecutive record slots touches one pair, rarely two
+    return pinfo[p];
 }
 
 // Orientation check decided in FLOAT where that is safe: the angle between the mid-point ray and the 3D direction does not
@@ -182,20 +147,17 @@ __device__ __forceinline__ int sw_orientation_fast(float3 r1, float3 r2, float3 
 // P1: one thread per record slot.  rflag bit 0: the record survives the orientation check as a direct match of its source
 // view, bit 1: as an inverse match of its target view (only asked for when the target is processed after the source).
 __global__ void __launch_bounds__(256)
-k_sw_flags(const double* __restrict__ rays, const float4* __restrict__ cache, const float4* __restrict__ rmf, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
-           const long long* __restrict__ row_off, int num_pairs, const int* __restrict__ counts, const l3d_match_rec* __restrict__ recs,
-           int knn, long long slots, const SwView* __restrict__ vt, const int2* __restrict__ pairc, unsigned char* __restrict__ rflag,
-           int* __restrict__ csize)
+k_sw_flags(const double* __restrict__ rays, const float4* __restrict__ cache, const float4* __restrict__ rmf, const L3DViewDev* __restrict__ views,
+           const SwPairInfo* __restrict__ pinfo, const int* __restrict__ block_pair0, const int* __restrict__ counts, const l3d_match_rec* __restrict__ recs,
+           int knn, long long slots, unsigned char* __restrict__ rflag, int* __restrict__ csize)
 {
-    __shared__ SwPairInfo pi[SW_PI];
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    sw_load_pair_info(pi, views, pairs, row_off, num_pairs, vt, pairc, ((long long)blockIdx.x * blockDim.x) / knn);
     if (g >= slots) return;
     const long long row = g / knn;
     const int i = (int)(g - row * knn);
     if (i >= counts[row]) return;
     const l3d_match_rec rec = recs[g];
-    const SwPairInfo q = sw_pair_info(pi, row, views, pairs, row_off, num_pairs, vt, pairc);
+    const SwPairInfo q = sw_pair_info(pinfo, block_pair0, row);
     const int r = (int)(row - q.row_off);
     unsigned char f = 0;
     {
@@ -235,32 +197,26 @@ k_sw_regions(int V, SwView* __restrict__ vt, const long long* __restrict__ cstar
 // P4: records -> entries of their chunk(s), in arbitrary order inside the chunk; key = what the chunk is sorted by
 // (REF_GPU: the target segment of the list entry, sortMatchesByIDs commons.h:206-214; REF_CPU: the record index = append order)
 __global__ void __launch_bounds__(256)
-k_sw_scatter(const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs, const long long* __restrict__ row_off, int num_pairs,
-             const l3d_match_rec* __restrict__ recs, int knn, long long slots, const SwView* __restrict__ vt, const int2* __restrict__ pairc,
-             const unsigned char* __restrict__ rflag, const long long* __restrict__ cstart, int* __restrict__ ccur, unsigned int* __restrict__ e_key,
-             unsigned int* __restrict__ e_val, int cpu_sem)
+k_sw_scatter(const SwPairInfo* __restrict__ pinfo, const int* __restrict__ block_pair0, const l3d_match_rec* __restrict__ recs, int knn, long long slots,
+             const unsigned char* __restrict__ rflag, const long long* __restrict__ cstart, int* __restrict__ ccur, uint2* __restrict__ e_kv, int cpu_sem)
 {
-    __shared__ SwPairInfo pi[SW_PI];
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    sw_load_pair_info(pi, views, pairs, row_off, num_pairs, vt, pairc, ((long long)blockIdx.x * blockDim.x) / knn);
     if (g >= slots) return;
     const unsigned char f = rflag[g];
     if (!f) return;
     const unsigned int tseg = recs[g].tgt_seg;
     const long long row = g / knn;
-    const SwPairInfo q = sw_pair_info(pi, row, views, pairs, row_off, num_pairs, vt, pairc);
+    const SwPairInfo q = sw_pair_info(pinfo, block_pair0, row);
     const int r = (int)(row - q.row_off);
     if (f & 1) {
         const long long ch = q.src_chunk_base + (long long)r * q.src_np + q.cx;
         const long long x = cstart[ch] + atomicAdd(ccur + ch, 1);
-        e_key[x] = cpu_sem ? (unsigned int)g : tseg;
-        e_val[x] = (unsigned int)g;
+        e_kv[x] = make_uint2(cpu_sem ? (unsigned int)g : tseg, (unsigned int)g);               // (sort key, record) in one 8-byte store
     }
     if (f & 2) {
         const long long ch = q.tgt_chunk_base + (long long)tseg * q.tgt_np + q.cy;
         const long long x = cstart[ch] + atomicAdd(ccur + ch, 1);
-        e_key[x] = cpu_sem ? (unsigned int)g : (unsigned int)r;
-        e_val[x] = (unsigned int)g | SW_INV;
+        e_kv[x] = make_uint2(cpu_sem ? (unsigned int)g : (unsigned int)r, (unsigned int)g | SW_INV);
     }
 }
 
@@ -272,7 +228,7 @@ k_sw_scatter(const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict_
 #define CS_MAXNP 64
 __global__ void __launch_bounds__(32 * CS_WARPS)
 k_sw_chunksort(const L3DViewDev* __restrict__ views, int V, long long N, const SwView* __restrict__ vt, const long long* __restrict__ cstart,
-               unsigned int* __restrict__ e_key, unsigned int* __restrict__ e_val, unsigned char* __restrict__ e_flag, unsigned int* __restrict__ invpos)
+               uint2* __restrict__ e_kv, unsigned int* __restrict__ e_val, unsigned char* __restrict__ e_flag, unsigned int* __restrict__ invpos)
 {
     __shared__ unsigned int sk[CS_WARPS][CS_MAXN], sv[CS_WARPS][CS_MAXN];
     __shared__ int scb[CS_WARPS][CS_MAXNP + 1];
@@ -291,7 +247,7 @@ k_sw_chunksort(const L3DViewDev* __restrict__ views, int V, long long N, const S
     const long long ro = me.region_off;
     if (n <= CS_MAXN && np <= CS_MAXNP) {
         for (int c = lane; c <= np; c += 32) scb[wid][c] = (int)(cstart[ch0 + c] - x0);
-        for (int j = lane; j < n; j += 32) { sk[wid][j] = e_key[x0 + j]; sv[wid][j] = e_val[x0 + j]; }
+        for (int j = lane; j < n; j += 32) { const uint2 kv = e_kv[x0 + j]; sk[wid][j] = kv.x; sv[wid][j] = kv.y; }
         __syncwarp();
         for (int j = lane; j < n; j += 32) {
             int cl = 0, chh = np - 1;
@@ -309,13 +265,14 @@ k_sw_chunksort(const L3DViewDev* __restrict__ views, int V, long long N, const S
         for (int c = lane; c < np; c += 32) {
             const long long a = cstart[ch0 + c], b = cstart[ch0 + c + 1];
             for (long long i = a + 1; i < b; ++i) {
-                const unsigned int k = e_key[i], v = e_val[i];
+                const uint2 kv = e_kv[i];
                 long long j = i - 1;
-                while (j >= a && e_key[j] > k) { e_key[j + 1] = e_key[j]; e_val[j + 1] = e_val[j]; --j; }
-                e_key[j + 1] = k; e_val[j + 1] = v;
+                while (j >= a && e_kv[j].x > kv.x) { e_kv[j + 1] = e_kv[j]; --j; }
+                e_kv[j + 1] = kv;
             }
             for (long long i = a; i < b; ++i) {
-                const unsigned int v = e_val[i];
+                const unsigned int v = e_kv[i].y;
+                e_val[i] = v;
                 if (v & SW_INV) { e_flag[i] = 0; invpos[v & ~SW_INV] = (unsigned int)(i - ro); }
                 else e_flag[i] = SW_ACTIVE;
             }
@@ -843,6 +800,8 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
 #define RES(buf, bytes, what) if ((rc = l3d_reserve(c, buf, (size_t)std::max<long long>((long long)(bytes), 16), what))) return rc
     RES(S.d_vt, sizeof(SwView) * (size_t)V, "view table"); RES(S.d_vp, sizeof(SwChunk) * vp.size(), "chunk descriptors"); RES(S.d_pairc, 8 * (size_t)NP, "pair chunks");
     RES(S.d_rowoff, 8 * (size_t)(NP + 1), "pair row offsets"); RES(S.d_order, 4 * (size_t)V, "order"); RES(S.d_region_off, 8 * (size_t)(V + 1), "region offsets");
+    const long long nblocks = (slots + SW_SETUP_THREADS - 1) / SW_SETUP_THREADS;
+    RES(S.d_pinfo, sizeof(SwPairInfo) * (size_t)(NP + 1), "pair table"); RES(S.d_bpair, 4 * std::max<long long>(nblocks, 1), "first pair of every block");
     RES(S.d_rays, 72 * c->total_segs, "segment rays"); RES(S.d_rmf, 16 * c->total_segs, "mid-point rays"); RES(S.d_rflag, slots, "record flags"); RES(S.d_invpos, 4 * slots, "inverse positions");
     RES(S.d_csize, 4 * (NC + 1), "chunk sizes"); RES(S.d_ccur, 4 * (NC + 1), "chunk cursors"); RES(S.d_cstart, 8 * (NC + 1), "chunk offsets");
     RES(S.d_ranges, 8 * c->total_segs, "ranges"); RES(S.d_est_best, 4 * c->total_segs, "estimates"); RES(S.d_est_P, 48 * c->total_segs, "estimate points");
@@ -852,6 +811,28 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     if (NP) L3D_CUDA(c, cudaMemcpyAsync(S.d_pairc.p, pairc.data(), 8 * (size_t)NP, cudaMemcpyHostToDevice, st), "pair chunks");
     L3D_CUDA(c, cudaMemcpyAsync(S.d_rowoff.p, row_off.data(), 8 * (size_t)(NP + 1), cudaMemcpyHostToDevice, st), "pair row offsets");
     L3D_CUDA(c, cudaMemcpyAsync(S.d_order.p, S.order.data(), 4 * (size_t)V, cudaMemcpyHostToDevice, st), "order");
+    std::vector<SwPairInfo> pinfo((size_t)NP + 1);
+    for (int p = 0; p < NP; ++p) {
+        const L3DPairDev& P = c->h_pairs[p];
+        SwPairInfo& q = pinfo[p];
+        q.row_off = row_off[p]; q.row_end = row_off[p + 1]; q.src = P.src; q.tgt = P.tgt;
+        q.src_seg_off = c->h_views[P.src].seg_off; q.tgt_seg_off = c->h_views[P.tgt].seg_off;
+        q.src_chunk_base = vt[P.src].chunk_base; q.tgt_chunk_base = vt[P.tgt].chunk_base; q.src_np = vt[P.src].np; q.tgt_np = vt[P.tgt].np;
+        q.cx = pairc[p].x; q.cy = pairc[p].y;
+    }
+    { SwPairInfo& q = pinfo[NP]; std::memset(&q, 0, sizeof(q)); q.row_off = c->total_rows; q.row_end = (1ll << 62); q.cx = q.cy = -1; }   // sentinel
+    std::vector<int> bpair((size_t)std::max<long long>(nblocks, 1), 0);
+    {
+        int p = 0;
+        for (long long b = 0; b < nblocks; ++b) {
+            const long long row = (b * SW_SETUP_THREADS) / knn;
+            while (p < NP && row >= row_off[p + 1]) ++p;          // pairs without rows are skipped
+            bpair[b] = p;
+        }
+    }
+    L3D_CUDA(c, cudaMemcpyAsync(S.d_pinfo.p, pinfo.data(), sizeof(SwPairInfo) * (size_t)(NP + 1), cudaMemcpyHostToDevice, st), "pair table");
+    L3D_CUDA(c, cudaMemcpyAsync(S.d_bpair.p, bpair.data(), 4 * bpair.size(), cudaMemcpyHostToDevice, st), "first pair of every block");
+    L3D_CUDA(c, cudaStreamSynchronize(st), "score sweep tables");      // pinfo / bpair are locals
     L3D_CUDA(c, cudaMemsetAsync(S.d_csize.p, 0, 4 * (size_t)(NC + 1), st), "init chunk sizes");
     L3D_CUDA(c, cudaMemsetAsync(S.d_ccur.p, 0, 4 * (size_t)(NC + 1), st), "init chunk cursors");
     L3D_CUDA(c, cudaMemsetAsync(S.d_rflag.p, 0, (size_t)slots, st), "init record flags");
@@ -866,11 +847,12 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     const L3DViewDev* views = c->views(); const L3DPairDev* pairs = (const L3DPairDev*)c->d_pairs.p;
     const int* counts = (const int*)c->d_counts.p; const l3d_match_rec* recs = (const l3d_match_rec*)c->d_recs.p;
     const SwView* d_vt = (const SwView*)S.d_vt.p; const int2* d_pairc = (const int2*)S.d_pairc.p; const long long* d_rowoff = (const long long*)S.d_rowoff.p;
-    const unsigned int nbs = (unsigned int)((slots + 255) / 256);
+    const unsigned int nbs = (unsigned int)nblocks;
     S.region_off.assign(V + 1, 0); S.total = 0;
     if (NP > 0 && slots > 0) {
         k_sw_rays<<<(unsigned int)((c->total_segs + 255) / 256), 256, 0, st>>>(segs, views, V, c->total_segs, (double*)S.d_rays.p, (float4*)S.d_rmf.p);
-        k_sw_flags<<<nbs, 256, 0, st>>>((const double*)S.d_rays.p, cache, (const float4*)S.d_rmf.p, views, pairs, d_rowoff, NP, counts, recs, knn, slots, d_vt, d_pairc, (unsigned char*)S.d_rflag.p, (int*)S.d_csize.p);
+        k_sw_flags<<<nbs, SW_SETUP_THREADS, 0, st>>>((const double*)S.d_rays.p, cache, (const float4*)S.d_rmf.p, views, (const SwPairInfo*)S.d_pinfo.p, (const int*)S.d_bpair.p,
+                                                     counts, recs, knn, slots, (unsigned char*)S.d_rflag.p, (int*)S.d_csize.p);
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)S.d_csize.p, (long long*)S.d_cstart.p, NC + 1, st);
         RES(S.d_sort_tmp, tb, "scan temp");
@@ -890,15 +872,15 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
     for (int i = 0; i < V; ++i) Umax = std::max(Umax, S.region_off[i + 1] - S.region_off[i]);
     if (Umax >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_score_sweep: view with more than 2^31 matches");
     RES(S.d_eval, 4 * total, "entry records"); RES(S.d_escore, 4 * total, "entry scores"); RES(S.d_eflag, total, "entry flags");
+    RES(S.d_ekv, 8 * total, "unsorted entries");
     RES(S.d_gstage, 2 * 48 * Umax, "long-list scratch"); RES(S.d_gpub, 2 * 4 * Umax, "long-list scratch");
     if (cpu_sem) RES(S.d_dir64, 2 * 32 * Umax, "long-list scratch");
     unsigned int* e_val = (unsigned int*)S.d_eval.p; float* e_score = (float*)S.d_escore.p; unsigned char* e_flag = (unsigned char*)S.d_eflag.p;
     if (total > 0) {
-        // the sort keys live in the score array until the chain starts
-        k_sw_scatter<<<nbs, 256, 0, st>>>(views, pairs, d_rowoff, NP, recs, knn, slots, d_vt, d_pairc, (const unsigned char*)S.d_rflag.p, (const long long*)S.d_cstart.p,
-                                          (int*)S.d_ccur.p, (unsigned int*)e_score, e_val, cpu_sem ? 1 : 0);
+        k_sw_scatter<<<nbs, SW_SETUP_THREADS, 0, st>>>((const SwPairInfo*)S.d_pinfo.p, (const int*)S.d_bpair.p, recs, knn, slots, (const unsigned char*)S.d_rflag.p,
+                                                       (const long long*)S.d_cstart.p, (int*)S.d_ccur.p, (uint2*)S.d_ekv.p, cpu_sem ? 1 : 0);
         k_sw_chunksort<<<(unsigned int)((c->total_segs + CS_WARPS - 1) / CS_WARPS), 32 * CS_WARPS, 0, st>>>(views, V, c->total_segs, d_vt, (const long long*)S.d_cstart.p,
-                                                                                                         (unsigned int*)e_score, e_val, e_flag, (unsigned int*)S.d_invpos.p);
+                                                                                                         (uint2*)S.d_ekv.p, e_val, e_flag, (unsigned int*)S.d_invpos.p);
         c->launches += 2;
     }
 

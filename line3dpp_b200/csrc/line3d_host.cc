@@ -730,6 +730,7 @@ std::string Line3D::createOutputFilename()   // line3D.cc:2855-2894
 void Line3D::save3DLinesAsTXT(const std::string& folder)   // line3D.cc:2631-2687; format README.md:272-277
 {
     std::lock_guard<std::mutex> g(p_->mtx);
+    p_->err.clear();
     if (p_->lines3D.empty()) { p_->fail("no 3D lines to save!"); return; }
     const std::string path = folder + "/" + createOutputFilename() + ".txt";
     std::ofstream f(path.c_str());
@@ -752,6 +753,7 @@ void Line3D::save3DLinesAsTXT(const std::string& folder)   // line3D.cc:2631-268
 void Line3D::saveResultAsOBJ(const std::string& folder)
 {
     std::lock_guard<std::mutex> g(p_->mtx);
+    p_->err.clear();
     if (p_->lines3D.empty()) { p_->fail("no 3D lines to save!"); return; }
     const std::string path = folder + "/" + createOutputFilename() + ".obj";
     std::ofstream f(path.c_str());
@@ -771,6 +773,7 @@ void Line3D::saveResultAsOBJ(const std::string& folder)
 void Line3D::saveResultAsSTL(const std::string& folder)
 {
     std::lock_guard<std::mutex> g(p_->mtx);
+    p_->err.clear();
     if (p_->lines3D.empty()) { p_->fail("no 3D lines to save!"); return; }
     const std::string path = folder + "/" + createOutputFilename() + ".stl";
     std::ofstream f(path.c_str());

@@ -291,7 +291,7 @@ def test_capi_error_behaviour(gpu_ctx):
     pairs[0, 1] = 1
     assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 0) == 0           # kNN <= 0: keep all (here: none)
     assert L.l3d_match_stride(fresh.h) == 1
-    assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 33) == -4
+    assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 33) == 0           # kNN > 32: keep-all passes + per-row cut (round 2)
     assert L.l3d_match_pairs(fresh.h, 1, p(pairs), p(F), C.c_float(0.25), 5) == 0           # F = 0: valid call, no matches
     counts, total = fresh.match_counts()
     assert total == 0
@@ -305,6 +305,7 @@ def test_knn_above_32_vs_reference_wrapper(loaded, scene, oracle, ref_nofma):
     passes + per-row cut must give the reference wrapper's matches, in its pop order (overlap descending)."""
     knn = 40
     pairs = np.array(PAIRS[:2], np.int32)
+    loaded.set_views(util.scene_descs(scene), scene.segs)        # earlier tests put other scenes into the shared context
     loaded.match_pairs(pairs, util.pair_F(scene, pairs), 0.05, knn)       # low threshold: rows longer than 32 exist
     nlong = 0
     for p, (src, tgt) in enumerate(PAIRS[:2]):

@@ -288,7 +288,7 @@ def test_add_image_and_writer_errors_are_reported(tmp_path):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     K, R, t = np.ascontiguousarray(sc.K[0]), np.ascontiguousarray(sc.R[0]), np.ascontiguousarray(sc.t[0])
     nb, sg = np.ascontiguousarray(sc.neighbors[0], np.uint32), np.ascontiguousarray(sc.segs[0], np.float32)
-    add = lambda cam, w: L.L.l3dpp_add_image(L.h, C.c_uint(cam), w, 2304, p(K), p(R), p(t), C.c_float(4.0), p(nb), len(nb), p(sg), len(sg))
+    add = lambda cam, w: L.L.l3dpp_add_image(L.h, C.c_uint(cam), w, w * 3 // 4, p(K), p(R), p(t), C.c_float(4.0), p(nb), len(nb), p(sg), len(sg))
     assert add(0, 3072) < 0 and b"already in use" in L.L.l3dpp_last_error(L.h)          # duplicate camera id
     assert add(77, 100) < 0 and b"too small" in L.L.l3dpp_last_error(L.h)
     assert add(78, 3072) == 0                                                          # a success ...
