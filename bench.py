@@ -310,7 +310,8 @@ def run_ours(args):
 
     # ---- roofline legs measured live (rank 0): FP32 peak probe + HBM-bound dense kernel
     extra = {}
-    if rank == 0:
+    LEAN = bool(os.environ.get("L3D_BENCH_LEAN"))       # scaling sweeps: only the step itself (no roofline legs / baselines, which belong to the N=1 line)
+    if rank == 0 and not LEAN:
         extra = roofline_legs(ctx, st, scene, torch)
         try:    # REF_CPU semantics on the GPU (matchingCPU's double arithmetic, k_match_topk_f64): the f64-vs-f64 figure next to the CPU arm
             npf = min(len(pairs), 500)
@@ -367,9 +368,10 @@ def run_ours(args):
             "extras": extra.get("extras"),
             "peaks": peaks,
         }
-        cpu_v, cores, sample = cpu_matching_sample(20.0)
-        line["cpu_baseline"] = {"value": cpu_v, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample}
-        line["ref_cuda_baseline"] = ref_cuda_sample(scene)
+        if not LEAN:
+            cpu_v, cores, sample = cpu_matching_sample(20.0)
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample}
+            line["ref_cuda_baseline"] = ref_cuda_sample(scene)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

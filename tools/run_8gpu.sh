@@ -18,11 +18,13 @@ for n in 1 2 4 8; do
   timeout 600 $TR --nproc-per-node $n --master-port $((p++)) tools/run_dist_pipeline.py --views 1000 --segs 3000 --ring 5 --diffusion 1 --reps 3 \
       > $O/r02_strong_pipeline_$n.json 2> $O/r02_strong_pipeline_$n.err
 done
-# 2b. strong scaling of the matching step (bench contract, one JSON line each)
+# 2b. strong scaling of the matching step (bench contract, one JSON line each; lean: no roofline legs / baselines)
+export L3D_BENCH_LEAN=1
 for n in 1 2 4 8; do
   if [ $n = 1 ]; then timeout 900 python bench.py --gpus 1 --scaling strong --steps 5 --warmup 3 > $O/r02_strong_$n.json 2> $O/r02_strong_$n.err
   else timeout 900 $TR --nproc-per-node $n --master-port $((p++)) bench.py --gpus $n --scaling strong --steps 5 --warmup 3 > $O/r02_strong_$n.json 2> $O/r02_strong_$n.err; fi
 done
+unset L3D_BENCH_LEAN
 # 3. two processes over NCCL: sharded == single GPU, bit for bit
 timeout 600 python -m pytest tests/test_dist_gpu.py -q -m gpu > $O/r02_pytest_dist_8gpubox.log 2>&1
 tail -c 400 $O/r02_cfg5_8gpu.json; tail -n 3 $O/r02_cfg5_8gpu.err
