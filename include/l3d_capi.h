@@ -123,6 +123,7 @@ int l3d_pair_row_offsets(l3d_ctx* ctx, long long* row_off_out);
 int l3d_balanced_split(const long long* cost, int n, int parts, int32_t* bounds_out);
 /* sizes of the last l3d_match_pairs result */
 long long l3d_match_total_rows(const l3d_ctx* ctx);      /* sum of Ns over pairs */
+long long l3d_match_total_matches(l3d_ctx* ctx);         /* matches of the last result (sum of the row counts), reduced on the device */
 long long l3d_match_pair_evals(const l3d_ctx* ctx);      /* sum of Ns*Nt over pairs */
 /* counts_out[row_off(pair)+r] for all pairs (row_off = prefix sum of Ns in pair order); returns total matches */
 long long l3d_get_match_counts(l3d_ctx* ctx, int32_t* counts_out);

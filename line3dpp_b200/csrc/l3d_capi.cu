@@ -399,6 +399,33 @@ long long l3d_get_match_counts(l3d_ctx* c, int32_t* counts_out)
     return total;
 }
 
+// number of matches of the last match result (sum of the per-row counts), reduced on the device: no download of the count array
+long long l3d_match_total_matches(l3d_ctx* c)
+{
+    if (!c) return L3D_ERR_INVALID;
+    if (!c->have_matches) return l3d_fail(c, L3D_ERR_STATE, "l3d_match_total_matches: no match result");
+    if (c->total_rows == 0) return 0;
+    cudaSetDevice(c->device);
+    int rc;
+    long long total = 0;
+    const long long BLK = 1ll << 30;
+    if ((rc = l3d_reserve(c, c->d_rowptr, 16, "match total"))) return rc;
+    for (long long base = 0; base < c->total_rows; base += BLK) {
+        const int n = (int)std::min(BLK, c->total_rows - base);
+        size_t tb = 0;
+        cub::DeviceReduce::Sum(nullptr, tb, (const int*)c->d_counts.p + base, (long long*)c->d_rowptr.p, n, c->stream);
+        if ((rc = l3d_reserve(c, c->d_scan_tmp, tb, "reduce temp"))) return rc;
+        tb = c->d_scan_tmp.cap;
+        long long part = 0;
+        L3D_CUDA(c, cub::DeviceReduce::Sum(c->d_scan_tmp.p, tb, (const int*)c->d_counts.p + base, (long long*)c->d_rowptr.p, n, c->stream), "match total");
+        L3D_CUDA(c, cudaMemcpyAsync(&part, c->d_rowptr.p, 8, cudaMemcpyDeviceToHost, c->stream), "match total");
+        L3D_CUDA(c, cudaStreamSynchronize(c->stream), "match total");
+        total += part;
+        ++c->launches;
+    }
+    return total;
+}
+
 int l3d_get_pair_matches(l3d_ctx* c, int pair, int32_t* counts_out, l3d_match_rec* recs_out)
 {
     if (!c || !counts_out || !recs_out) return L3D_ERR_INVALID;

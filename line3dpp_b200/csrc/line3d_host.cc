@@ -7,6 +7,7 @@
 // (2036-2071), graph clustering (clustering.cc:6-48) and the cluster -> 3D segment tail (2079-2452) + writers.
 // All matching / scoring / affinity / diffusion arithmetic runs on the GPU; without a GPU the constructor fails.
 #include "../../include/line3d.h"
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges show up in nsys / ncu timelines
 #include "../../include/l3d_capi.h"
 
 #include <algorithm>
@@ -416,6 +417,7 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
     std::vector<const float*> segp(P.vlist.size());
     for (size_t i = 0; i < P.vlist.size(); ++i) segp[i] = &P.vlist[i]->lines[0].v[0];
     auto t0 = std::chrono::steady_clock::now();
+    nvtxRangePushA("l3d:set_views+match");
     bool ok = P.chk(l3d_set_views(P.ctx, (int)d.size(), d.data(), segp.data()), "l3d_set_views");
     // use_GPU selects the reference's semantics, not the processor (line3D.cc:708-757): true = K_match_lines / K_score_matches
     // float arithmetic, false = matchingCPU / scoringCPU double arithmetic.  Both run on the B200.
@@ -441,7 +443,9 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
     } else
         ok = ok && match_range(0, npairs) && P.chk(l3d_sync(P.ctx), "l3d_sync");
     auto t1 = std::chrono::steady_clock::now();
+    nvtxRangePop(); nvtxRangePushA("l3d:score_sweep");
     ok = ok && P.chk(l3d_score_sweep(P.ctx, P.two_sigA_sqr, MIN_SIMILARITY_3D, MIN_BEST_SCORE_3D, MIN_BEST_SCORE_PERC), "l3d_score_sweep");
+    nvtxRangePop();
     auto t2 = std::chrono::steady_clock::now();
     if (ok) {
         const long long ne = l3d_get_estimates(P.ctx, nullptr, nullptr, 0);
@@ -469,8 +473,7 @@ void Line3D::matchImages(const float sigma_position, const float sigma_angle, co
             if (P.fixed3Dreg) kv.second.k = P.sigma_p / P.med_scene_depth;
         }
         P.st.view_pairs = npairs; P.st.pair_evaluations = l3d_match_pair_evals(P.ctx); P.st.estimates = (long long)P.est_best.size();
-        std::vector<int32_t> cnt((size_t)std::max<long long>(l3d_match_total_rows(P.ctx), 1));
-        P.st.matches_after_knn = l3d_get_match_counts(P.ctx, cnt.data());
+        P.st.matches_after_knn = l3d_match_total_matches(P.ctx);      // reduced on the device (was: download of the whole count array)
         P.st.ms_match = std::chrono::duration<double, std::milli>(t1 - t0).count();
         P.st.ms_score = std::chrono::duration<double, std::milli>(t2 - t1).count();
         P.matched = true;
