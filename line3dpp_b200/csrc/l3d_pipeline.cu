@@ -288,13 +288,9 @@ k_sw_chunksort(const L3DViewDev* __restrict__ views, int V, long long N, const S
 #ifndef SW_THREADS
 #define SW_THREADS 256
 #endif
-#ifndef SW_SEGS
-#define SW_SEGS 4
-#endif
-#ifndef SW_CAP_GPU
-#define SW_CAP_GPU 512        // list entries staged in shared memory per CTA (longer ranges: global scratch)
-#endif
-#define SW_CAP_CPU 256
+#define SW_SEGS_MAX 16        // segments per CTA: chosen per view at launch time so that the view's CTAs are ONE resident wave
+                              // (tools/sweep_score.py: 750 CTAs on 740 slots cost 20.7 ms per 1000 views, 600 CTAs 14.7 ms)
+#define SW_CAP_MAX 4096       // list entries staged in shared memory per CTA, upper bound (longer ranges: global scratch)
 
 // staged entry: a = (depth1, depth2, target view or -1 if inactive, index of its segment in the CTA), b = (dir.xyz, view to announce a
 // positive score to or -1), r = (reg1, reg2) target regularisers; REF_CPU adds d64 = (double dir.xyz, length)
@@ -308,6 +304,7 @@ struct SwScoreArgs {
     int* view_max_bits; int* M;
     SwPtrs g;                       // global scratch (one view's region) for entry ranges longer than the shared-memory capacity
     float angle_reg, sim_t, q_thr, cos_thr;
+    int segs, cap;                  // this launch: segments per CTA, staged entries per CTA (dynamic shared memory = 48 (+32 REF_CPU) bytes x cap)
 };
 
 // similarity of K_score_matches' inner loop (cudawrapper.cu:318-347) between the own entry and staged entry i, tests ordered
@@ -605,20 +602,20 @@ __device__ __forceinline__ void sw_score_range(const SwScoreArgs<CPU>& A, const 
 }
 
 template <bool CPU>
-__global__ void __launch_bounds__(SW_THREADS, CPU ? 3 : 5)
+__global__ void __launch_bounds__(SW_THREADS, CPU ? (SW_THREADS <= 256 ? 3 : 2) : (SW_THREADS <= 256 ? 5 : SW_THREADS <= 320 ? 4 : SW_THREADS <= 384 ? 3 : 2))
 k_sw_score(const SwScoreArgs<CPU> A)
 {
-    constexpr int CAP = CPU ? SW_CAP_CPU : SW_CAP_GPU;
+    const int CAP = A.cap;
     asm volatile("griddepcontrol.launch_dependents;");       // the next view's kernel may start its independent part
     extern __shared__ __align__(16) unsigned char sw_smem[];
     __shared__ int cb[SW_MAXCH + 1], cbA[SW_MAXCH + 1];
     __shared__ SwChunkInfo cinfo[SW_MAXNP];
     __shared__ int ccam[SW_MAXNP];
-    __shared__ SwSegInfo sinfo[SW_SEGS];
+    __shared__ SwSegInfo sinfo[SW_SEGS_MAX];
     __shared__ int wcnt[SW_THREADS / 32];
     const L3DViewDev* V = A.views + A.v;
-    const int s0 = blockIdx.x * SW_SEGS;
-    const int nsegs = min(SW_SEGS, V->nseg - s0);
+    const int s0 = blockIdx.x * A.segs;
+    const int nsegs = min(A.segs, V->nseg - s0);
     const SwView me = A.vt[A.v];
     const int np = me.np, nch = nsegs * np;
     const long long chbase = me.chunk_base + (long long)s0 * np;
@@ -912,15 +909,33 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
         SwScoreArgs<true> B;
         static_assert(sizeof(SwScoreArgs<true>) == sizeof(SwScoreArgs<false>), "same layout");
         std::memcpy((void*)&B, (const void*)&A, sizeof(A));
-        const size_t sm_gpu = (size_t)48 * SW_CAP_GPU;
-        const size_t sm_cpu = (size_t)(48 + 32) * SW_CAP_CPU;
+        const size_t per_entry = cpu_sem ? 48 + 32 : 48;
+        L3D_CUDA(c, cudaFuncSetAttribute(k_sw_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(48 * SW_CAP_MAX)), "k_sw_score shared memory");
+        L3D_CUDA(c, cudaFuncSetAttribute(k_sw_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(80 * 2048)), "k_sw_score shared memory");
+        const int cap_max = cpu_sem ? 2048 : SW_CAP_MAX;
+        const int occ_regs = cpu_sem ? 3 : 5;               // resident CTAs per SM the register budget allows (launch bounds)
+        const int force_segs = getenv("L3D_SW_SEGS") ? atoi(getenv("L3D_SW_SEGS")) : 0;      // tools/sweep_score.py: override the geometry choice
         for (int i = 0; i < V; ++i) {
             const int v = S.order[i];
             const int nseg = c->h_views[v].nseg;
             if (nseg == 0 || S.region_off[i + 1] == S.region_off[i]) continue;
-            const unsigned int nb = (unsigned int)((nseg + SW_SEGS - 1) / SW_SEGS);
+            // geometry of this view's launch: the fewest segments per CTA for which all CTAs are resident at once (one wave)
+            const double avg = (double)(S.region_off[i + 1] - S.region_off[i]) / nseg;
+            int segs = 1, cap = 64; double best = 1e300;
+            for (int sgs = 1; sgs <= SW_SEGS_MAX; ++sgs) {
+                const int cp = std::min(cap_max, (int)((sgs * avg * 1.3 + 127) / 64) * 64);
+                const int occ = std::max(1, std::min(occ_regs, (int)((220 * 1024) / (per_entry * cp + 8 * 1024))));
+                const long long ctas = (nseg + sgs - 1) / sgs;
+                const double waves = std::ceil((double)ctas / ((double)c->num_sms * occ));
+                const double cost = waves * (1.0 + sgs * avg / SW_THREADS);      // waves x rounds of work per thread
+                if (cost < best - 1e-9) { best = cost; segs = sgs; cap = cp; }
+            }
+            if (force_segs > 0) { segs = std::min(force_segs, SW_SEGS_MAX); cap = std::min(cap_max, (int)((segs * avg * 1.3 + 127) / 64) * 64); }
+            const size_t smem = per_entry * (size_t)cap;
+            A.segs = B.segs = segs; A.cap = B.cap = cap;
+            const unsigned int nb = (unsigned int)((nseg + segs - 1) / segs);
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(nb); cfg.blockDim = dim3(SW_THREADS); cfg.dynamicSmemBytes = cpu_sem ? sm_cpu : sm_gpu; cfg.stream = st;
+            cfg.gridDim = dim3(nb); cfg.blockDim = dim3(SW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
             // programmatic dependent launch: this view's kernel may stage its lists while the previous view's kernel is still scoring
