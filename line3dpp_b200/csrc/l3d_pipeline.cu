@@ -923,14 +923,15 @@ int l3d_score_sweep(l3d_ctx* c, float two_sigA_sqr, float min_similarity, float 
             const double avg = (double)(S.region_off[i + 1] - S.region_off[i]) / nseg;
             int segs = 1, cap = 64; double best = 1e300;
             for (int sgs = 1; sgs <= SW_SEGS_MAX; ++sgs) {
-                const int cp = std::min(cap_max, (int)((sgs * avg * 1.3 + 127) / 64) * 64);
-                const int occ = std::max(1, std::min(occ_regs, (int)((220 * 1024) / (per_entry * cp + 8 * 1024))));
+                // staged entries: 45 % + 160 above the mean (a CTA whose range is longer falls back to the slow global-scratch path)
+                const int cp = std::min(cap_max, (int)((sgs * avg * 1.45 + 160 + 63) / 64) * 64);
+                const int occ = std::max(1, std::min(occ_regs, (int)((227 * 1024) / (per_entry * cp + 8500))));
                 const long long ctas = (nseg + sgs - 1) / sgs;
                 const double waves = std::ceil((double)ctas / ((double)c->num_sms * occ));
                 const double cost = waves * (1.0 + sgs * avg / SW_THREADS);      // waves x rounds of work per thread
                 if (cost < best - 1e-9) { best = cost; segs = sgs; cap = cp; }
             }
-            if (force_segs > 0) { segs = std::min(force_segs, SW_SEGS_MAX); cap = std::min(cap_max, (int)((segs * avg * 1.3 + 127) / 64) * 64); }
+            if (force_segs > 0) { segs = std::min(force_segs, SW_SEGS_MAX); cap = std::min(cap_max, (int)((segs * avg * 1.45 + 160 + 63) / 64) * 64); }
             const size_t smem = per_entry * (size_t)cap;
             A.segs = B.segs = segs; A.cap = B.cap = cap;
             const unsigned int nb = (unsigned int)((nseg + segs - 1) / segs);

@@ -23,10 +23,26 @@
 #include <set>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 
 namespace L3DPP {
+
+// Independent per-cluster host work (the reference runs the same loops under `#pragma omp parallel for`, line3D.cc:2125, 2283):
+// static partition over a few std::threads, results stored by index, so the output order does not depend on timing.
+template <class F> static void parallel_for(size_t n, F&& body)
+{
+    unsigned int nt = std::min<unsigned int>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    if (const char* e = getenv("L3D_HOST_THREADS")) nt = (unsigned int)std::max(1, atoi(e));
+    if (n < 256 || nt <= 1) { for (size_t i = 0; i < n; ++i) body(i); return; }
+    nt = (unsigned int)std::min<size_t>(nt, n / 64);
+    std::vector<std::thread> th;
+    for (unsigned int t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() { for (size_t i = n * t / nt; i < n * (t + 1) / nt; ++i) body(i); });
+    for (auto& x : th) x.join();
+}
+
 
 namespace {
 const double EPS = 1e-12;                    // L3D_EPS commons.h:92
@@ -637,8 +653,11 @@ void Line3D::reconstruct3Dlines(const unsigned int visibility_t, const bool perf
             members[cl].push_back(s); cams[cl].insert(s.camID());
         }
         P.st.clusters_total = (long long)order.size();
-        for (int cl : order)
-            if (cams[cl].size() >= P.visibility_t) { LineCluster3D LC; if (P.line_from_cluster(members[cl], LC)) clusters.push_back(LC); }
+        std::vector<const std::list<Segment2D>*> todo;
+        for (int cl : order) if (cams[cl].size() >= P.visibility_t) todo.push_back(&members[cl]);
+        std::vector<LineCluster3D> fitted(todo.size()); std::vector<unsigned char> good(todo.size(), 0);
+        parallel_for(todo.size(), [&](size_t i) { good[i] = P.line_from_cluster(*todo[i], fitted[i]) ? 1 : 0; });
+        for (size_t i = 0; i < todo.size(); ++i) if (good[i]) clusters.push_back(fitted[i]);
     }
     P.st.clusters_valid = (long long)clusters.size();
     // optimizeClusters (line3D.cc:1800-1805, 2269-2275): bundle the cluster lines against their 2D residuals.  The reference
@@ -682,17 +701,20 @@ void Line3D::reconstruct3Dlines(const unsigned int visibility_t, const bool perf
     }
     P.use_ceres = use_CERES;
     // computeFinal3Dsegments + filterTinySegments (line3D.cc:2278-2339)
-    for (const LineCluster3D& cl : clusters) {
+    std::vector<std::list<Segment3D> > kept_segs(clusters.size());
+    parallel_for(clusters.size(), [&](size_t i) {
+        const LineCluster3D& cl = clusters[i];
         std::list<Segment3D> col = P.collinear_segments(cl);
-        if (col.empty()) continue;
+        if (col.empty()) return;
         const HostView& rv = *P.vlist[P.index_of.at(cl.reference_view())];
-        std::list<Segment3D> keep;
         for (const Segment3D& s : col) {
             double u1, v1, u2, v2; rv.project(s.P1(), u1, v1); rv.project(s.P2(), u2, v2);
-            if (std::sqrt((u1 - u2) * (u1 - u2) + (v1 - v2) * (v1 - v2)) > rv.min_line_length) keep.push_back(s);          // projectedLongEnough view.cc:423-428
+            if (std::sqrt((u1 - u2) * (u1 - u2) + (v1 - v2) * (v1 - v2)) > rv.min_line_length) kept_segs[i].push_back(s);  // projectedLongEnough view.cc:423-428
         }
-        if (keep.empty()) continue;
-        FinalLine3D f; f.collinear3Dsegments_ = keep; f.underlyingCluster_ = cl;
+    });
+    for (size_t i = 0; i < clusters.size(); ++i) {
+        if (kept_segs[i].empty()) continue;
+        FinalLine3D f; f.collinear3Dsegments_ = kept_segs[i]; f.underlyingCluster_ = clusters[i];
         P.lines3D.push_back(f);
     }
     auto t3 = std::chrono::steady_clock::now();
