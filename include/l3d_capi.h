@@ -139,6 +139,11 @@ long long l3d_get_matches_csr(l3d_ctx* ctx, int64_t* row_ptr_out, l3d_match_rec*
 int l3d_match_dense(l3d_ctx* ctx, int src_view, int tgt_view, const float* F, float epi_overlap, float* depths,
                     float* overlaps, int out_on_device);
 
+/* the same contract for many view pairs in ONE launch (tiles of all pairs in one grid).  pairs: (src, tgt) view indices, F: 9 floats per
+ * pair, depths_dev[i] / overlaps_dev[i]: DEVICE pointers to pair i's Ns*Nt float4 / float outputs.  Asynchronous on the context's stream. */
+int l3d_match_dense_pairs(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, float* const* depths_dev,
+                          float* const* overlaps_dev);
+
 /* test hook: same contract with the conservative pre-filter disabled (every cell through the exact path) */
 int l3d_match_dense_nofilter(l3d_ctx* ctx, int src_view, int tgt_view, const float* F, float epi_overlap, float* depths,
                              float* overlaps, int out_on_device);

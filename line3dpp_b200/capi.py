@@ -241,6 +241,14 @@ class Context:
         self._chk(self.L.l3d_fp32_peak_probe(self.h, C.byref(v)), "l3d_fp32_peak_probe")
         return v.value
 
+    def match_dense_pairs(self, pairs, F, epi_overlap, depth_ptrs, overlap_ptrs):
+        """dense contract for many view pairs in one launch; depth_ptrs / overlap_ptrs: device addresses per pair"""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        F = np.ascontiguousarray(F, np.float32).reshape(-1, 9)
+        dp = (C.c_void_p * len(pairs))(*[int(x) for x in depth_ptrs])
+        op = (C.c_void_p * len(pairs))(*[int(x) for x in overlap_ptrs])
+        self._chk(self.L.l3d_match_dense_pairs(self.h, len(pairs), _p(pairs), _p(F), C.c_float(epi_overlap), dp, op), "l3d_match_dense_pairs")
+
     def match_dense(self, src_view, tgt_view, F, epi_overlap, ns, nt, nofilter=False, dev_ptrs=None):
         F = np.ascontiguousarray(F, np.float32).reshape(9)
         fn = self.L.l3d_match_dense_nofilter if nofilter else self.L.l3d_match_dense

@@ -542,6 +542,45 @@ int l3d_fp32_peak_probe(l3d_ctx* c, double* tflops_out)
 
 int l3d_match_dense(l3d_ctx* c, int sv, int tv, const float* F, float epi, float* depths, float* overlaps, int on_dev)
 { return match_dense_impl(c, sv, tv, F, epi, depths, overlaps, on_dev, true); }
+
+// K_match_lines' dense device contract for MANY view pairs in ONE launch; outputs are device pointers, one pair of arrays per view pair
+int l3d_match_dense_pairs(l3d_ctx* c, int npairs, const int32_t* pairs, const float* F, float epi, float* const* depths_dev, float* const* overlaps_dev)
+{
+    if (!c) return L3D_ERR_INVALID;
+    if (!c->have_views) return l3d_fail(c, L3D_ERR_STATE, "l3d_match_dense_pairs: call l3d_set_views first");
+    if (npairs < 0 || (npairs && (!pairs || !F || !depths_dev || !overlaps_dev))) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_dense_pairs: bad arguments");
+    if (npairs == 0) return L3D_OK;
+    cudaSetDevice(c->device);
+    std::vector<L3DDenseJob> jobs;
+    const float4* cache = (const float4*)c->d_cache.p;
+    long long tiles = 0;
+    for (int i = 0; i < npairs; ++i) {
+        const int sv = pairs[2 * i], tv = pairs[2 * i + 1];
+        if (sv < 0 || tv < 0 || sv >= c->num_views || tv >= c->num_views || !depths_dev[i] || !overlaps_dev[i]) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_dense_pairs: bad pair");
+        const L3DViewDev& vs = c->h_views[sv]; const L3DViewDev& vt = c->h_views[tv];
+        if (vs.nseg == 0 || vt.nseg == 0) continue;
+        L3DDenseJob J;
+        J.ssegs = c->segs() + vs.seg_off; J.tsegs = c->segs() + vt.seg_off; J.scache = cache + 3 * vs.seg_off; J.tcache = cache + 3 * vt.seg_off;
+        J.depths = (float4*)depths_dev[i]; J.overlaps = overlaps_dev[i];
+        memcpy(J.F.m, F + 9 * (size_t)i, sizeof(J.F.m));
+        J.Cs = make_float3(vs.C[0], vs.C[1], vs.C[2]); J.Ct = make_float3(vt.C[0], vt.C[1], vt.C[2]);
+        J.Ns = vs.nseg; J.Nt = vt.nseg; J.rows_per_cta = DK_ROWS;       // whole waves do not matter inside a batch: the tallest tile amortises the per-tile set-up best
+        J.colb = (vt.nseg + DK_WARPS * DK_T * 32 - 1) / (DK_WARPS * DK_T * 32);
+        J.tile0 = tiles;
+        tiles += (long long)J.colb * ((vs.nseg + DK_ROWS - 1) / DK_ROWS);
+        jobs.push_back(J);
+    }
+    if (jobs.empty()) return L3D_OK;
+    if (tiles >= (1ll << 31)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_dense_pairs: more than 2^31 tiles");
+    int rc;
+    if ((rc = l3d_reserve(c, c->d_dense_jobs, sizeof(L3DDenseJob) * jobs.size(), "dense jobs"))) return rc;
+    L3D_CUDA(c, cudaMemcpyAsync(c->d_dense_jobs.p, jobs.data(), sizeof(L3DDenseJob) * jobs.size(), cudaMemcpyHostToDevice, c->stream), "dense jobs");
+    L3D_CUDA(c, cudaStreamSynchronize(c->stream), "dense jobs");       // `jobs` is a local
+    k_match_dense_batch<<<(unsigned int)tiles, DK_THREADS, l3d_dense_smem_bytes(), c->stream>>>((const L3DDenseJob*)c->d_dense_jobs.p, (int)jobs.size(), epi);
+    ++c->launches;
+    L3D_CUDA(c, cudaGetLastError(), "k_match_dense_batch");
+    return L3D_OK;
+}
 int l3d_match_dense_nofilter(l3d_ctx* c, int sv, int tv, const float* F, float epi, float* depths, float* overlaps, int on_dev)
 { return match_dense_impl(c, sv, tv, F, epi, depths, overlaps, on_dev, false); }
 

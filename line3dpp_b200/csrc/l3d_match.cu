@@ -474,15 +474,15 @@ __device__ __noinline__ void dense_exact_batch(DenseSmem& S, unsigned int entry,
     __stcs(S.overlaps + o, ov);
 }
 
-__global__ void __launch_bounds__(DK_THREADS, DK_MINB)
-k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
-              const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F, float3 Cs, float3 Ct,
-              float epi, float4* __restrict__ depths, float* __restrict__ overlaps, int rows_per_cta)
+// one tile (rows_per_cta source rows x DK_WARPS * DK_T * 32 target columns) of one view pair; (bx, by) = the tile's column / row block
+__device__ __forceinline__ void dense_tile(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
+                                           const float4* __restrict__ scache, const float4* __restrict__ tcache, const L3DMat3& F, float3 Cs, float3 Ct,
+                                           float epi, float4* __restrict__ depths, float* __restrict__ overlaps, int rows_per_cta, int bx, int by)
 {
     extern __shared__ __align__(128) unsigned char dense_smem_raw[];
     DenseSmem& S = *reinterpret_cast<DenseSmem*>(dense_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row0 = blockIdx.y * rows_per_cta;
+    const int row0 = by * rows_per_cta;
     const int nrows = min(rows_per_cta, Ns - row0);
     if (tid == 0) { S.depths = depths; S.overlaps = overlaps; S.tcache = tcache; S.Cs = Cs; S.Ct = Ct; S.epi = epi; S.Nt = Nt; S.row0 = row0; }
     if (tid < nrows) {
@@ -493,7 +493,7 @@ k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict
         S.rowB[tid] = make_float4(e2.y, e2.z, g, 0.f);      // threshold 0: reject only provably empty cells
     }
     if (tid < 3 * nrows) S.sray[tid / 3][tid % 3] = __ldg(scache + 3 * (size_t)row0 + tid);
-    const int x0 = (blockIdx.x * DK_WARPS + warp) * (32 * DK_T);
+    const int x0 = (bx * DK_WARPS + warp) * (32 * DK_T);
     float4 q[DK_T];
     bool ok[DK_T];
 #pragma unroll
@@ -528,6 +528,29 @@ k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict
         }
     }
     if (qn > 0) dense_exact_batch(S, lane < qn ? S.queue[warp][lane] : 0u, lane < qn, warp, x0);
+}
+
+__global__ void __launch_bounds__(DK_THREADS, DK_MINB)
+k_match_dense(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
+              const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F, float3 Cs, float3 Ct,
+              float epi, float4* __restrict__ depths, float* __restrict__ overlaps, int rows_per_cta)
+{ dense_tile(ssegs, Ns, tsegs, Nt, scache, tcache, F, Cs, Ct, epi, depths, overlaps, rows_per_cta, blockIdx.x, blockIdx.y); }
+
+// The same contract for MANY view pairs in one launch (l3d_match_dense_pairs): a 1-D grid over the tiles of all jobs, so the tail of
+// one pair's tiles overlaps the head of the next pair's instead of leaving SMs idle at the end of every 88 us launch.
+__global__ void __launch_bounds__(DK_THREADS, DK_MINB)
+k_match_dense_batch(const L3DDenseJob* __restrict__ jobs, int njobs, float epi)
+{
+    __shared__ int job_s;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = njobs - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (jobs[mid].tile0 <= (long long)blockIdx.x) lo = mid; else hi = mid - 1; }
+        job_s = lo;
+    }
+    __syncthreads();
+    const L3DDenseJob& J = jobs[job_s];
+    const int t = (int)((long long)blockIdx.x - J.tile0);
+    dense_tile(J.ssegs, J.Ns, J.tsegs, J.Nt, J.scache, J.tcache, J.F, J.Cs, J.Ct, epi, J.depths, J.overlaps, J.rows_per_cta, t % J.colb, t / J.colb);
 }
 
 // same contract, NO pre-filter: every cell goes through the exact path.  Test-only cross-check of the filter.

@@ -64,6 +64,11 @@ __global__ void k_match_dense(const float4* __restrict__ ssegs, int Ns, const fl
                               const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F, float3 Cs,
                               float3 Ct, float epi, float4* __restrict__ depths, float* __restrict__ overlaps, int rows_per_cta);
 int l3d_dense_rows_per_cta(int Ns, int Nt, int num_sms);
+struct L3DDenseJob {            // one view pair of a batched dense launch
+    const float4* ssegs; const float4* tsegs; const float4* scache; const float4* tcache; float4* depths; float* overlaps;
+    L3DMat3 F; float3 Cs, Ct; int Ns, Nt, rows_per_cta, colb; long long tile0;
+};
+__global__ void k_match_dense_batch(const L3DDenseJob* __restrict__ jobs, int njobs, float epi);
 __global__ void k_match_dense_nofilter(const float4* __restrict__ ssegs, int Ns, const float4* __restrict__ tsegs, int Nt,
                                        const float4* __restrict__ scache, const float4* __restrict__ tcache, L3DMat3 F,
                                        float3 Cs, float3 Ct, float epi, float4* __restrict__ depths,

@@ -3,12 +3,14 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * liboracle.so.  The product library (line3dpp_b200/csrc) never includes, links or calls anything here.
  *
- * Parity status (see DESIGN.md "Oracle pinning"):
- *   - kernel-level functions (orc_match_*_f32, orc_score_matches_f32, orc_rdd_f32, orc_cluster) are PINNED against
- *     the reference's own cudawrapper.cu / sparsematrix.cc / clustering.cc compiled in place (oracle/_ref) and against
- *     golden vectors those produced on a B200 (tests/golden/).
- *   - the restatement of line3D.cc / view.cc host logic (Eigen/OpenCV/Boost needed -> unbuildable here) is pinned only
- *     statistically, against testdata/Line3D++_ref (README.md:214-221).  "parity unpinned" at index level for that part.
+ * Parity status (see DESIGN.md "Oracle pinning"): PINNED.
+ *   - kernel-level functions (orc_match_*_f32, orc_score_matches_f32, orc_rdd_f32, orc_cluster) against the reference's own
+ *     cudawrapper.cu / sparsematrix.cc / clustering.cc compiled in place (oracle/_ref) and against golden vectors those produced
+ *     on a B200 (tests/golden/ref_kernels_v1.npz, ref_collinear_v1.npz).
+ *   - the restatement of the line3D.cc / view.cc host logic (the orc_ctx pipeline) against the reference's WHOLE pipeline compiled
+ *     verbatim (oracle/ref_full_harness.cu -> oracle/_ref/libl3dref_full_{cpu,gpu}.so, Eigen/OpenCV/Boost replaced by the header
+ *     stand-ins of oracle/ref_shim): index-exact at every stage on synthetic scenes (live) and on the vsfm_result.nvm inputs
+ *     (tests/golden/ref_full_nvm_cpu_v1.npz), tests/test_ref_full_cpu.py.
  */
 #ifndef L3D_ORACLE_H_
 #define L3D_ORACLE_H_

@@ -322,3 +322,23 @@ def test_knn_above_32_vs_reference_wrapper(loaded, scene, oracle, ref_nofma):
             ov = recs[r, :counts[r]]["overlap"]
             assert np.all(ov[:-1] >= ov[1:])
     assert nlong > 0, "the test scene must have rows with more than 32 matches"
+
+
+def test_dense_batch_equals_single_launches(loaded, scene):
+    """l3d_match_dense_pairs (all view pairs in one launch) writes exactly what l3d_match_dense writes pair by pair"""
+    import torch
+    loaded.set_views(util.scene_descs(scene), scene.segs)
+    pairs = np.array(PAIRS, np.int32)
+    F = util.pair_F(scene, pairs)
+    deps, ovs = [], []
+    for (s, t) in PAIRS:
+        ns, nt = len(scene.segs[s]), len(scene.segs[t])
+        deps.append(torch.full((ns * nt * 4,), 7.0, dtype=torch.float32, device="cuda"))
+        ovs.append(torch.full((ns * nt,), 7.0, dtype=torch.float32, device="cuda"))
+    loaded.match_dense_pairs(pairs, F, 0.25, [d.data_ptr() for d in deps], [o.data_ptr() for o in ovs])
+    loaded.sync()
+    for i, (s, t) in enumerate(PAIRS):
+        ns, nt = len(scene.segs[s]), len(scene.segs[t])
+        d1, o1 = loaded.match_dense(s, t, F[i], 0.25, ns, nt)
+        assert np.array_equal(util.bits(deps[i].cpu().numpy()), util.bits(d1.reshape(-1)))
+        assert np.array_equal(util.bits(ovs[i].cpu().numpy()), util.bits(o1.reshape(-1)))
