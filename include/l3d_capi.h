@@ -207,6 +207,9 @@ long long l3d_affinity_matrix(l3d_ctx* ctx, float two_sigA_sqr, float med_scene_
  * with nnz entries (what the reference downloads from W, line3D.cc:2036-2044).  No ownership transfer. */
 int l3d_rdd(l3d_ctx* ctx, int n, long long nnz, const int* ei, const int* ej, const float* ew, int iters, int* out_i,
             int* out_j, float* out_w, float* kernel_ms);
+/* performRDD (line3D.cc:2026-2076) on the affinity matrix that l3d_affinity_matrix left on the device: diffusion + the
+ * min(w12, w21) symmetrisation without a host round trip; out_*: 2*K entries in (i, j) order.  Returns the entry count. */
+long long l3d_rdd_affinity(l3d_ctx* ctx, int iters, int32_t* out_i, int32_t* out_j, float* out_w, long long cap);
 
 /* ---- line bundling (optional, reconstruct3Dlines' use_CERES): replaces LineOptimizer::optimize (optimization.h:174-190,
  * optimization.cc:8-303; called from Line3D::optimizeClusters line3D.cc:2269-2275), i.e. the Ceres problem the reference

@@ -735,17 +735,23 @@ long long l3d_affinity_matrix(l3d_ctx* c, float two_sigA_sqr, float med_scene_de
 // replicator_dynamics_diffusion_GPU (cudawrapper.h:80) on a COO edge list (the CLEdge list A_ of line3D.cc:2030).
 // out_*: row-sorted COO of the diffused matrix, nnz entries (same order as the reference's downloaded W).
 // kernel_ms (optional): device time of the `iters` diffusion iterations only (CUDA events on the context's stream).
-int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, const float* ew, int iters, int* out_i, int* out_j,
-            float* out_w, float* kernel_ms)
+// min(w12, w21) of performRDD (line3D.cc:2039-2071): every entry takes the smaller of itself and its transposed entry
+__global__ void __launch_bounds__(256) k_rdd_symmetrise(long long nnz, const float* __restrict__ P, const int* __restrict__ tslot, float* __restrict__ out)
 {
-    if (!c || n <= 0 || nnz < 0 || (nnz && (!ei || !ej || !ew || !out_i || !out_j || !out_w))) return l3d_fail(c, L3D_ERR_INVALID, "l3d_rdd: bad arguments");
-    if (nnz == 0) return L3D_OK;
-    if (nnz >= (1ll << 31) - 2) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_rdd: more than 2^31 entries");
-    cudaSetDevice(c->device);
+    const long long y = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= nnz) return;
+    const int t = tslot[y];
+    out[y] = t >= 0 ? fminf(P[y], P[t]) : P[y];
+}
+
+// the diffusion proper on DEVICE edge arrays d_ei/d_ej/d_ew (in_rdd_bufs: they already are R.d_ei/ej/ew); symmetrise: performRDD's
+// min(w12, w21) applied before the download.  Output in row-sorted (i, j) order - the order std::map iterates in (line3D.cc:2063-2071).
+static int rdd_core(l3d_ctx* c, int n, long long nnz, const int* d_ei, const int* d_ej, const float* d_ew, int iters, bool symmetrise,
+                    int* out_i, int* out_j, float* out_w, float* kernel_ms)
+{
     RddState& R = c->rdd;
     int rc;
 #define RES(buf, bytes, what) if ((rc = l3d_reserve(c, buf, (size_t)(bytes), what))) return rc
-    RES(R.d_ei, 4 * nnz, "rdd i"); RES(R.d_ej, 4 * nnz, "rdd j"); RES(R.d_ew, 4 * nnz, "rdd w");
     RES(R.d_krow, 8 * nnz, "rdd keys"); RES(R.d_kcol, 8 * nnz, "rdd keys"); RES(R.d_k2, 8 * nnz, "rdd keys"); RES(R.d_idx, 4 * nnz, "rdd idx"); RES(R.d_idx2, 4 * nnz, "rdd idx");
     RES(R.d_P, 4 * nnz, "rdd P"); RES(R.d_Pn, 4 * nnz, "rdd P'"); RES(R.d_W, 4 * nnz, "rdd W");
     RES(R.d_prow, 4 * nnz, "rdd rows"); RES(R.d_pcol, 4 * nnz, "rdd cols"); RES(R.d_wmaj, 4 * nnz, "rdd cols"); RES(R.d_wmin, 4 * nnz, "rdd rows");
@@ -755,19 +761,16 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     RES(R.d_tmp, sb, "rdd sort temp");
 #undef RES
     cudaStream_t st = c->stream;
-    L3D_CUDA(c, cudaMemcpyAsync(R.d_ei.p, ei, 4 * nnz, cudaMemcpyHostToDevice, st), "rdd upload");
-    L3D_CUDA(c, cudaMemcpyAsync(R.d_ej.p, ej, 4 * nnz, cudaMemcpyHostToDevice, st), "rdd upload");
-    L3D_CUDA(c, cudaMemcpyAsync(R.d_ew.p, ew, 4 * nnz, cudaMemcpyHostToDevice, st), "rdd upload");
     const unsigned int nb = (unsigned int)((nnz + 255) / 256);
-    k_rdd_keys<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_ei.p, (const int*)R.d_ej.p, (unsigned long long*)R.d_krow.p, (unsigned long long*)R.d_kcol.p, (unsigned int*)R.d_idx.p);
+    k_rdd_keys<<<nb, 256, 0, st>>>(nnz, d_ei, d_ej, (unsigned long long*)R.d_krow.p, (unsigned long long*)R.d_kcol.p, (unsigned int*)R.d_idx.p);
     size_t tb = R.d_tmp.cap;
     // P: row-sorted (stable, like std::list::sort with sortCLEdgesByRow, sparsematrix.cc:22-25 / 104-107)
     cub::DeviceRadixSort::SortPairs(R.d_tmp.p, tb, (const unsigned long long*)R.d_krow.p, (unsigned long long*)R.d_k2.p, (const unsigned int*)R.d_idx.p, (unsigned int*)R.d_idx2.p, (int)nnz, 0, 64, st);
-    k_rdd_gather<<<nb, 256, 0, st>>>(nnz, (const unsigned long long*)R.d_k2.p, (const unsigned int*)R.d_idx2.p, (const float*)R.d_ew.p, (float*)R.d_P.p, (int*)R.d_prow.p, (int*)R.d_pcol.p);
+    k_rdd_gather<<<nb, 256, 0, st>>>(nnz, (const unsigned long long*)R.d_k2.p, (const unsigned int*)R.d_idx2.p, d_ew, (float*)R.d_P.p, (int*)R.d_prow.p, (int*)R.d_pcol.p);
     // W: col-sorted
     tb = R.d_tmp.cap;
     cub::DeviceRadixSort::SortPairs(R.d_tmp.p, tb, (const unsigned long long*)R.d_kcol.p, (unsigned long long*)R.d_k2.p, (const unsigned int*)R.d_idx.p, (unsigned int*)R.d_idx2.p, (int)nnz, 0, 64, st);
-    k_rdd_gather<<<nb, 256, 0, st>>>(nnz, (const unsigned long long*)R.d_k2.p, (const unsigned int*)R.d_idx2.p, (const float*)R.d_ew.p, (float*)R.d_W.p, (int*)R.d_wmaj.p, (int*)R.d_wmin.p);
+    k_rdd_gather<<<nb, 256, 0, st>>>(nnz, (const unsigned long long*)R.d_k2.p, (const unsigned int*)R.d_idx2.p, d_ew, (float*)R.d_W.p, (int*)R.d_wmaj.p, (int*)R.d_wmin.p);
     k_rdd_ptr<<<(n + 256) / 256, 256, 0, st>>>(n, (int)nnz, (const int*)R.d_prow.p, (int*)R.d_rowptr.p);
     k_rdd_ptr<<<(n + 256) / 256, 256, 0, st>>>(n, (int)nnz, (const int*)R.d_wmaj.p, (int*)R.d_colptr.p);
     k_rdd_tslot<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_pcol.p, (const int*)R.d_rowptr.p, (int*)R.d_tslot.p);
@@ -816,14 +819,52 @@ int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, cons
     }
     if (kernel_ms) cudaEventRecord(e1, st);
     k_rdd_unpad<<<nb, 256, 0, st>>>(nnz, (const int*)R.d_prow.p, (const int*)R.d_rowptr.p, (const int*)R.d_rp4.p, P, (float*)R.d_P.p);
+    const float* result = (const float*)R.d_P.p;
+    if (symmetrise) {
+        k_rdd_symmetrise<<<nb, 256, 0, st>>>(nnz, (const float*)R.d_P.p, (const int*)R.d_tslot.p, (float*)R.d_Pn.p);
+        result = (const float*)R.d_Pn.p;
+        ++c->launches;
+    }
     c->launches += 9 + 16 + 10 + 2 * iters;
     L3D_CUDA(c, cudaGetLastError(), "rdd kernels");
-    L3D_CUDA(c, cudaMemcpyAsync(out_w, R.d_P.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
+    L3D_CUDA(c, cudaMemcpyAsync(out_w, result, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
     L3D_CUDA(c, cudaMemcpyAsync(out_i, R.d_prow.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
     L3D_CUDA(c, cudaMemcpyAsync(out_j, R.d_pcol.p, 4 * nnz, cudaMemcpyDeviceToHost, st), "rdd download");
     L3D_CUDA(c, cudaStreamSynchronize(st), "rdd");
     if (kernel_ms) { cudaEventElapsedTime(kernel_ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
     return L3D_OK;
+}
+
+int l3d_rdd(l3d_ctx* c, int n, long long nnz, const int* ei, const int* ej, const float* ew, int iters, int* out_i, int* out_j,
+            float* out_w, float* kernel_ms)
+{
+    if (!c || n <= 0 || nnz < 0 || (nnz && (!ei || !ej || !ew || !out_i || !out_j || !out_w))) return l3d_fail(c, L3D_ERR_INVALID, "l3d_rdd: bad arguments");
+    if (nnz == 0) return L3D_OK;
+    if (nnz >= (1ll << 31) - 2) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_rdd: more than 2^31 entries");
+    cudaSetDevice(c->device);
+    RddState& R = c->rdd;
+    int rc;
+    if ((rc = l3d_reserve(c, R.d_ei, 4 * (size_t)nnz, "rdd i")) || (rc = l3d_reserve(c, R.d_ej, 4 * (size_t)nnz, "rdd j")) || (rc = l3d_reserve(c, R.d_ew, 4 * (size_t)nnz, "rdd w"))) return rc;
+    L3D_CUDA(c, cudaMemcpyAsync(R.d_ei.p, ei, 4 * nnz, cudaMemcpyHostToDevice, c->stream), "rdd upload");
+    L3D_CUDA(c, cudaMemcpyAsync(R.d_ej.p, ej, 4 * nnz, cudaMemcpyHostToDevice, c->stream), "rdd upload");
+    L3D_CUDA(c, cudaMemcpyAsync(R.d_ew.p, ew, 4 * nnz, cudaMemcpyHostToDevice, c->stream), "rdd upload");
+    return rdd_core(c, n, nnz, (const int*)R.d_ei.p, (const int*)R.d_ej.p, (const float*)R.d_ew.p, iters, false, out_i, out_j, out_w, kernel_ms);
+}
+
+// performRDD (line3D.cc:2026-2076) on the affinity matrix l3d_affinity_matrix left on the device: no download / re-upload of A_, the
+// min(w12, w21) symmetrisation on the device, the result in the (i, j) order the reference rebuilds A_ in.  out arrays: 2 * K entries
+// (the count l3d_affinity_matrix returned).
+long long l3d_rdd_affinity(l3d_ctx* c, int iters, int* out_i, int* out_j, float* out_w, long long cap)
+{
+    if (!c || !out_i || !out_j || !out_w) return L3D_ERR_INVALID;
+    AffinityState& A = c->aff;
+    if (!A.valid) return l3d_fail(c, L3D_ERR_STATE, "l3d_rdd_affinity: call l3d_affinity_matrix first");
+    const long long nnz = 2 * A.K;
+    if (nnz == 0 || nnz > cap) return nnz;
+    if (nnz >= (1ll << 31) - 2) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_rdd_affinity: more than 2^31 entries");
+    cudaSetDevice(c->device);
+    const int rc = rdd_core(c, (int)A.n_ids, nnz, (const int*)A.d_ei.p, (const int*)A.d_ej.p, (const float*)A.d_ew.p, iters, true, out_i, out_j, out_w, nullptr);
+    return rc < 0 ? rc : nnz;
 }
 
 // Stable ascending argsort of float keys on the device (the edge-weight sort of performClustering, clustering.cc:13-14:

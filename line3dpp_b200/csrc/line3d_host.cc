@@ -616,21 +616,12 @@ void Line3D::reconstruct3Dlines(const unsigned int visibility_t, const bool perf
     P.st.affinity_entries = (long long)P.A.size(); P.st.affinity_rows = n;
     // diffusion (performRDD line3D.cc:2026-2076)
     if (P.perform_RDD && !P.A.empty()) {
+        // the matrix is still on the device (l3d_affinity_matrix): diffusion + min(w12, w21) there, one download of the result in the
+        // (i, j) order the reference's std::map rebuilds A_ in (line3D.cc:2039-2071)
         const long long nnz = (long long)P.A.size();
-        std::vector<int> ei(nnz), ej(nnz), oi(nnz), oj(nnz); std::vector<float> ew(nnz), ow(nnz);
-        for (long long e = 0; e < nnz; ++e) { ei[e] = P.A[e].i; ej[e] = P.A[e].j; ew[e] = P.A[e].w; }
-        if (!P.chk(l3d_rdd(P.ctx, n, nnz, ei.data(), ej.data(), ew.data(), RDD_MAX_ITER, oi.data(), oj.data(), ow.data(), nullptr), "l3d_rdd")) { P.untranslate(); return; }
-        // symmetrise w = min(w12, w21) in download order, then rebuild A_ in (i,j) order (line3D.cc:2039-2071)
-        std::map<std::pair<int, int>, float> ent;
-        for (long long e = 0; e < nnz; ++e) {
-            float w21 = ow[e];
-            auto it = ent.find(std::make_pair(oj[e], oi[e]));
-            if (it != ent.end()) w21 = it->second;
-            const float w = std::fmin(ow[e], w21);
-            ent[std::make_pair(oi[e], oj[e])] = w; ent[std::make_pair(oj[e], oi[e])] = w;
-        }
-        P.A.clear();
-        for (auto& kv : ent) { Edge e = {kv.first.first, kv.first.second, kv.second}; P.A.push_back(e); }
+        std::vector<int> oi(nnz), oj(nnz); std::vector<float> ow(nnz);
+        if (!P.chk(l3d_rdd_affinity(P.ctx, RDD_MAX_ITER, oi.data(), oj.data(), ow.data(), nnz), "l3d_rdd_affinity")) { P.untranslate(); return; }
+        for (long long e = 0; e < nnz; ++e) { P.A[e].i = oi[e]; P.A[e].j = oj[e]; P.A[e].w = ow[e]; }
     }
     auto t2 = std::chrono::steady_clock::now();
     // clustering (clusterSegments line3D.cc:2079-2152)
