@@ -220,7 +220,7 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
     L3D_CUDA(c, cudaStreamSynchronize(c->stream), "sync before pair staging");   // h_pairs/h_tiles may still be in flight
     c->h_pairs.resize(num_pairs);
     c->h_tiles.clear();
-    long long rows = 0, evals = 0;
+    long long rows = 0, evals = 0, narcs = 0;
     for (int i = 0; i < num_pairs; ++i) {
         int s = pairs[2 * i], t = pairs[2 * i + 1];
         if (s < 0 || t < 0 || s >= c->num_views || t >= c->num_views) return l3d_fail(c, L3D_ERR_INVALID, "l3d_match_pairs: view index out of range");
@@ -232,6 +232,8 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
         } else { memcpy(p.F, F + 9 * (size_t)i, sizeof(p.F)); memset(p.Fd, 0, sizeof(p.Fd)); }
         int Ns = c->h_views[s].nseg, Nt = c->h_views[t].nseg;
         if (Nt >= (1 << 24)) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: more than 2^24 segments in one view");
+        p.arc_off = narcs;
+        if (i >= first_pair && i < last_pair) narcs += Nt;
         if (Nt > 0 && i >= first_pair && i < last_pair)
             for (int r0 = 0; r0 < Ns; r0 += MK_ROWS) c->h_tiles.push_back(make_int2(i, r0));
         rows += Ns;
@@ -241,11 +243,24 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
     int rc;
     if ((rc = l3d_reserve(c, c->d_pairs, sizeof(L3DPairDev) * (size_t)std::max(num_pairs, 1), "pairs"))) return rc;
     if ((rc = l3d_reserve(c, c->d_tiles, sizeof(int2) * std::max<size_t>(c->h_tiles.size(), 1), "tiles"))) return rc;
+    if ((rc = l3d_reserve(c, c->d_arcs, sizeof(uint4) * (size_t)std::max<long long>(narcs, 1), "target arcs"))) return rc;
+    if ((rc = l3d_reserve(c, c->d_basis, sizeof(L3DPairBasis) * (size_t)std::max(num_pairs, 1), "pair bases"))) return rc;
     if ((rc = l3d_reserve(c, c->d_counts, sizeof(int) * (size_t)std::max<long long>(rows, 1), "match counts"))) return rc;
     if (!keep_all && (rc = l3d_reserve(c, c->d_recs, sizeof(l3d_match_rec) * (size_t)std::max<long long>(rows, 1) * knn, "match records"))) return rc;
     if (num_pairs) L3D_CUDA(c, cudaMemcpyAsync(c->d_pairs.p, c->h_pairs.data(), sizeof(L3DPairDev) * num_pairs, cudaMemcpyHostToDevice, c->stream), "upload pairs");
     if (!c->h_tiles.empty()) L3D_CUDA(c, cudaMemcpyAsync(c->d_tiles.p, c->h_tiles.data(), sizeof(int2) * c->h_tiles.size(), cudaMemcpyHostToDevice, c->stream), "upload tiles");
     if (rows) L3D_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(int) * rows, c->stream), "clear counts");   // rows of pairs with Nt == 0
+    const uint4* arcs = (const uint4*)c->d_arcs.p;
+    const L3DPairBasis* basis = (const L3DPairBasis*)c->d_basis.p;
+    if (last_pair > first_pair) {
+        // level-1 pre-filter tables of the pairs matched here (l3d_device.cuh "pencil parameter"); below epi_overlap 1e-3 a far
+        // intersection could still count as a match, so the tables then pass everything on to the float filter
+        const bool no_l1 = getenv("L3D_NO_LEVEL1") != nullptr;
+        k_pair_arcs<<<(unsigned int)(last_pair - first_pair), 256, 0, c->stream>>>(c->segs(), c->views(), (const L3DPairDev*)c->d_pairs.p, first_pair,
+                                                                                   (epi_overlap >= 1e-3f && !no_l1) ? 1 : 0, (uint4*)c->d_arcs.p, (L3DPairBasis*)c->d_basis.p);
+        ++c->launches;
+        L3D_CUDA(c, cudaGetLastError(), "k_pair_arcs");
+    }
     const double* cache_d = nullptr;
     if (Fd && c->total_segs > 0) {      // matchingCPU's rays / plane normals in double; camera blocks may have been updated since set_views
         if ((rc = l3d_reserve(c, c->d_cache_d, sizeof(double) * 9 * (size_t)c->total_segs, "double segment cache"))) return rc;
@@ -261,7 +276,7 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
         if (!c->h_tiles.empty()) {
             k_match_all<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
                 c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, 0,
-                epi_overlap, (int*)c->d_counts.p, nullptr, cache_d);
+                epi_overlap, (int*)c->d_counts.p, nullptr, cache_d, arcs, basis);
             ++c->launches;
             L3D_CUDA(c, cudaGetLastError(), "k_match_all (count)");
             size_t tb = 0;
@@ -285,7 +300,7 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
             if (per_warp * wpb > 200 * 1024) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: a row with more than 8500 matches (kNN <= 0)");
             k_match_all<<<(unsigned int)c->h_tiles.size(), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
                 c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p, stride,
-                epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, cache_d);
+                epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, cache_d, arcs, basis);
             L3D_CUDA(c, cudaGetLastError(), "k_match_all (store)");
             L3D_CUDA(c, cudaFuncSetAttribute(k_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)), "k_sort_rows smem");
             const long long blocks = std::min<long long>((rows + wpb - 1) / wpb, (long long)c->num_sms * 16);
@@ -313,11 +328,11 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
                 if (cache_d)
                     k_match_topk_f64<<<(unsigned int)(t1 - t0), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
                         c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p + t0, knn,
-                        epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, cache_d);
+                        epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, cache_d, arcs, basis);
                 else
                     k_match_topk<<<(unsigned int)(t1 - t0), MK_THREADS, l3d_match_smem_bytes(), c->stream>>>(
                         c->segs(), (const float4*)c->d_cache.p, c->views(), (const L3DPairDev*)c->d_pairs.p, (const int2*)c->d_tiles.p + t0, knn,
-                        epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p);
+                        epi_overlap, (int*)c->d_counts.p, (l3d_match_rec*)c->d_recs.p, arcs, basis);
                 ++c->launches;
                 L3D_CUDA(c, cudaGetLastError(), "k_match_topk");
             }

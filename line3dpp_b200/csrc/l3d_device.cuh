@@ -31,7 +31,31 @@ struct L3DPairDev {
     float F[9];             // row-major float fundamental matrix
     long long row_off;      // first output row of this pair (prefix sum of Ns)
     double Fd[9];           // the double matrix (REF_CPU semantics, l3d_match_pairs_f64); unused otherwise
+    long long arc_off;      // first entry of this pair in the array of target arcs (level-1 pre-filter, k_pair_arcs)
 };
+
+// ---- level-1 pre-filter: the pencil parameter -----------------------------------------------------------------------
+// All epipolar lines F*p of one view pair pass through the epipole E of the target image, i.e. they live in the 2-D subspace
+// {e : e . E = 0} of R^3.  With image coordinates divided by L3D_ARC_SCALE (so that points are ~unit vectors and the subspace is
+// well conditioned whether E lies inside the image or at infinity) and (u, v) an orthonormal basis of that subspace, the angle
+//     kappa(e) = atan2(e.v, e.u)   (mod pi)
+// is a 1-D coordinate of the pencil; the pencil line through an image point x has kappa(x) = atan2(x.u, -x.v).  Along a target
+// line l the map kappa -> intersection point is monotone on the circle cut at kappa_l (the pencil line parallel to l), so the
+// projections of the two epipolar lines of a source segment both fall outside the target segment on the SAME side - the case in
+// which the reference's overlap (cudawrapper.cu:89-136) is 0 - exactly when, in cut coordinates, both kappa values lie below or
+// both above the target's arc.  Angles are stored in units of pi / 2^32: unsigned subtraction wraps mod pi for free.
+#define L3D_ARC_SCALE 2048.0
+struct L3DPairBasis { double u[3], v[3]; };
+__device__ __forceinline__ unsigned int arc_units(double kappa)
+{ return (unsigned int)(long long)llrint(kappa * (4294967296.0 / 3.14159265358979323846)); }
+// kappa of an epipolar line (float, exactly as the kernels form it)
+__device__ __forceinline__ unsigned int line_kappa(const L3DPairBasis& B, float3 e)
+{
+    const double x = L3D_ARC_SCALE * (double)e.x, y = L3D_ARC_SCALE * (double)e.y, z = (double)e.z;
+    const double cu = x * B.u[0] + y * B.u[1] + z * B.u[2], cv = x * B.v[0] + y * B.v[1] + z * B.v[2];
+    const double k = atan2(cv, cu);
+    return isfinite(k) ? arc_units(k) : 0u;      // a pair without a usable basis has pass-all arcs: any value will do
+}
 
 // per-segment cache written by k_prep_segments: 3 float4 per segment
 //   c0 = (ray1.x, ray1.y, ray1.z, ray2.x)  c1 = (ray2.y, ray2.z, n.x, n.y)  c2 = (n.z, 0, 0, 0)

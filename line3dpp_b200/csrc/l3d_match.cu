@@ -58,13 +58,15 @@ __global__ void __launch_bounds__(256) k_prep_segments_f64(const float4* __restr
 
 // ------------------------------------------------------------------------------------------------ fused match + top-k
 struct MatchSmem {
-    float4 stage[MK_STAGES][MK_TT];                  // TMA-staged target segments (x1,y1,x2,y2)
+    uint4 stage[MK_STAGES][MK_TT];                   // TMA-staged target ARCS of the level-1 pre-filter (kappa_l, lo, hi, -), k_pair_arcs
+    uint2 rowK[MK_ROWS];                             // pencil parameters of the row's two epipolar lines (l3d_device.cuh)
     unsigned long long lists[MK_ROWS][MK_CAP + 1];   // per-row survivor keys (+1: rows start on different banks, lanes that push keys of different rows do not collide)
     float4 rowA[MK_ROWS];                            // (e1.x, e1.y, e1.z, e2.x)
     float4 rowB[MK_ROWS];                            // (e2.y, e2.z, g, 0.95 * score-to-beat)
     float row_thr[MK_ROWS];                          // overlap of the current k-th best survivor (0 until k are known)
     int list_cnt[MK_ROWS];
-    unsigned int queue[MK_WARPS][32 * MK_T + 32];    // candidate queue per warp: (row_local << 24) | tgt
+    unsigned int queue[MK_WARPS][32 * MK_T + 32];    // level-1 survivors per warp: (row_local << 24) | tgt
+    unsigned int queue2[MK_WARPS][64];               // level-2 survivors (filter_may_survive), evaluated exactly 32 at a time
     unsigned long long bars[MK_STAGES];
     // per-CTA constants of the (rarely executed, deliberately out-of-line) exact path
     const float4* tsegs; const float4* cache;
@@ -235,10 +237,107 @@ __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int
     }
 }
 
+// ---- level-1 tables ------------------------------------------------------------------------------------------------
+// orthonormal basis (u, v) of the pencil's subspace in scaled coordinates; NaN when F has no usable null vector
+__device__ void pair_basis(const float* F, L3DPairBasis* B)
+{
+    double c[3][3];
+    for (int k = 0; k < 3; ++k) {                         // columns of F: the epipolar lines of (1,0,0), (0,1,0), (0,0,1)
+        const double x = F[k], y = F[3 + k], z = F[6 + k], n = sqrt(x * x + y * y + z * z);
+        c[k][0] = n > 0.0 ? x / n : 0.0; c[k][1] = n > 0.0 ? y / n : 0.0; c[k][2] = n > 0.0 ? z / n : 0.0;
+    }
+    double E[3] = {0.0, 0.0, 0.0}, best = 0.0;
+    for (int a = 0; a < 3; ++a)
+        for (int b = a + 1; b < 3; ++b) {                 // E is orthogonal to every column: the best-conditioned cross product
+            const double x = c[a][1] * c[b][2] - c[a][2] * c[b][1], y = c[a][2] * c[b][0] - c[a][0] * c[b][2], z = c[a][0] * c[b][1] - c[a][1] * c[b][0];
+            const double n = x * x + y * y + z * z;
+            if (n > best) { best = n; E[0] = x; E[1] = y; E[2] = z; }
+        }
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    double n[3] = {E[0] / L3D_ARC_SCALE, E[1] / L3D_ARC_SCALE, E[2]};       // the epipole in scaled coordinates
+    const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (!(best > 1e-20) || !(len > 0.0) || !isfinite(len)) { for (int i = 0; i < 3; ++i) B->u[i] = B->v[i] = nan; return; }
+    for (int i = 0; i < 3; ++i) n[i] /= len;
+    int ax = 0;
+    if (fabs(n[1]) < fabs(n[ax])) ax = 1;
+    if (fabs(n[2]) < fabs(n[ax])) ax = 2;
+    double a[3] = {0.0, 0.0, 0.0}; a[ax] = 1.0;
+    double u[3] = {n[1] * a[2] - n[2] * a[1], n[2] * a[0] - n[0] * a[2], n[0] * a[1] - n[1] * a[0]};
+    const double ul = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    for (int i = 0; i < 3; ++i) u[i] /= ul;
+    const double v[3] = {n[1] * u[2] - n[2] * u[1], n[2] * u[0] - n[0] * u[2], n[0] * u[1] - n[1] * u[0]};     // u x v = n
+    for (int i = 0; i < 3; ++i) { B->u[i] = u[i]; B->v[i] = v[i]; }
+}
+
+// arc of one target segment: (kappa of the cut, lower end, upper end) in cut coordinates, margins included.  A source row is
+// rejected by level 1 iff both its kappa values, minus the cut, are < lo or both are > hi.  Margin: a displacement of
+//     delta = 0.05 px + 0.4 % of the segment length
+// of the pencil line at either end point (200 x the rounding error of the reference's float intersection, 2.4e-4 px / sin(phi),
+// and above the level-2 filter's own margins), plus 4e-6 rad for the rounding of the angles themselves.  Everything uncertain
+// (epipole within the margin of the segment or of its line, degenerate segment, non-finite values) gets the pass-all arc.
+__device__ uint4 target_arc(const L3DPairBasis& B, float4 q, bool enabled)
+{
+    const uint4 pass_all = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+    if (!enabled) return pass_all;
+    const double x1 = (double)q.x / L3D_ARC_SCALE, y1 = (double)q.y / L3D_ARC_SCALE, x2 = (double)q.z / L3D_ARC_SCALE, y2 = (double)q.w / L3D_ARC_SCALE;
+    const double a1 = x1 * B.u[0] + y1 * B.u[1] + B.u[2], b1 = x1 * B.v[0] + y1 * B.v[1] + B.v[2];
+    const double a2 = x2 * B.u[0] + y2 * B.u[1] + B.u[2], b2 = x2 * B.v[0] + y2 * B.v[1] + B.v[2];
+    const double dx = x2 - x1, dy = y2 - y1, ac = dx * B.u[0] + dy * B.u[1], bc = dx * B.v[0] + dy * B.v[1];
+    const double len = sqrt(dx * dx + dy * dy), rho1 = sqrt(a1 * a1 + b1 * b1), rho2 = sqrt(a2 * a2 + b2 * b2), rhoc = sqrt(ac * ac + bc * bc);
+    const double delta = (0.05 + 4e-3 * len * L3D_ARC_SCALE) / L3D_ARC_SCALE;
+    if (!(len > 1e-9) || !isfinite(rho1 + rho2 + rhoc) || !(delta < 0.25 * rho1) || !(delta < 0.25 * rho2) || !(rhoc > 1e-3 * len)) return pass_all;
+    // the target line through the epipole: (x1 x x2) . n ~ 0, n = u x v
+    {
+        const double lx = y1 - y2, ly = x2 - x1, lz = x1 * y2 - y1 * x2;
+        const double nx = B.u[1] * B.v[2] - B.u[2] * B.v[1], ny = B.u[2] * B.v[0] - B.u[0] * B.v[2], nz = B.u[0] * B.v[1] - B.u[1] * B.v[0];
+        if (!(fabs(lx * nx + ly * ny + lz * nz) > 1e-4 * sqrt(lx * lx + ly * ly + lz * lz))) return pass_all;
+    }
+    const unsigned int kc = arc_units(atan2(ac, -bc));
+    const unsigned int al1 = arc_units(atan2(a1, -b1)) - kc, al2 = arc_units(atan2(a2, -b2)) - kc;
+    const double to_units = 4294967296.0 / 3.14159265358979323846;
+    const double m1 = (1.2 * delta / rho1 + 4e-6) * to_units, m2 = (1.2 * delta / rho2 + 4e-6) * to_units;
+    const double lo = al1 < al2 ? (double)al1 - m1 : (double)al2 - m2, hi = al1 < al2 ? (double)al2 + m2 : (double)al1 + m1;
+    return make_uint4(kc, lo > 0.0 ? (unsigned int)lo : 0u, hi < 4294967295.0 ? (unsigned int)hi : 0xFFFFFFFFu, 0u);
+}
+
+__global__ void __launch_bounds__(256)
+k_pair_arcs(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs, int first_pair,
+            int enabled, uint4* __restrict__ arcs, L3DPairBasis* __restrict__ basis)
+{
+    __shared__ L3DPairBasis B;
+    const L3DPairDev* P = pairs + first_pair + blockIdx.x;
+    if (threadIdx.x == 0) { pair_basis(P->F, &B); basis[first_pair + blockIdx.x] = B; }
+    __syncthreads();
+    const L3DViewDev* vt = views + P->tgt;
+    const float4* t = segs + vt->seg_off;
+    uint4* out = arcs + P->arc_off;
+    for (int j = threadIdx.x; j < vt->nseg; j += 256) out[j] = target_arc(B, t[j], enabled != 0);
+}
+
+// level 2: the float filter on up to 32 level-1 survivors (one per lane); its survivors are queued for the exact path
+template <int MODE, int KEEP>
+__device__ __forceinline__ void filter_batch(MatchSmem& S, unsigned int entry, bool has, int warp, int lane, unsigned int lt_mask, int& qn2)
+{
+    bool pass = false;
+    if (has) {
+        const int rl = (int)(entry >> 24);
+        const unsigned int j = entry & 0xFFFFFFu;
+        if (j < (unsigned int)S.Nt) pass = filter_may_survive(__ldg(S.tsegs + j), S.rowA[rl], S.rowB[rl]);      // j >= Nt: padding of a partial stage
+    }
+    const unsigned int b = __ballot_sync(0xffffffffu, pass);
+    if (b) {
+        if (pass) S.queue2[warp][qn2 + __popc(b & lt_mask)] = entry;
+        qn2 += __popc(b);
+        __syncwarp();
+        if (qn2 >= 32) { qn2 -= 32; exact_batch<MODE, KEEP>(S, S.queue2[warp][qn2 + lane], true, lane); }
+    }
+}
+
 template <int MODE, int KEEP>
 __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
              const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
-             int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d)
+             int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d,
+             const uint4* __restrict__ arcs, const L3DPairBasis* __restrict__ basis)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MatchSmem& S = *reinterpret_cast<MatchSmem*>(smem_raw);
@@ -252,6 +351,7 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
     const int Ns = vs->nseg, Nt = vt->nseg;
     const int nrows = min(MK_ROWS, Ns - row0);
     const float4* tsegs = segs + toff;
+    const uint4* tarcs = arcs + P->arc_off;
     const int nchunks = (Nt + MK_TT - 1) / MK_TT;
 
     if (tid == 0) {
@@ -267,17 +367,17 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
         for (int i = 0; i < MK_STAGES && i < nchunks; ++i) {           // whole ring in flight while the rows are set up
             const unsigned int bytes = (unsigned int)min(MK_TT, Nt - i * MK_TT) * 16u;
             mbar_expect_tx(&S.bars[i], bytes);
-            tma_load_1d(S.stage[i], tsegs + (size_t)i * MK_TT, bytes, &S.bars[i]);
+            tma_load_1d(S.stage[i], tarcs + (size_t)i * MK_TT, bytes, &S.bars[i]);
         }
     }
-    // The last stage is usually partial: pad it to a multiple of the warp step with a segment 3e7 px away that the filter
-    // rejects (should an epipolar line ever pass through it, exact_batch drops indices >= Nt), so the hot loop needs no
+    // The last stage is usually partial: pad it to a multiple of the warp step with an arc no row can meet (lo = hi = 2^32 - 1;
+    // should a kappa ever hit that value, filter_batch drops indices >= Nt), so the hot loop needs no
     // per-lane bounds predicate.  When the ring is not reused (Nt <= MK_STAGES*MK_TT, the common case) the padding is
     // written now - TMA only fills the first n entries of that stage - and the chunk loop runs without any CTA barrier.
     const int n_last = Nt - (nchunks - 1) * MK_TT;
     const int pad_last = ((n_last + 32 * MK_T - 1) & ~(32 * MK_T - 1)) - n_last;
     const bool ring_reused = nchunks > MK_STAGES;
-    if (!ring_reused && nchunks > 0 && tid < pad_last) S.stage[(nchunks - 1) % MK_STAGES][n_last + tid] = make_float4(3.0e7f, 3.0e7f, 3.0e7f + 100.0f, 3.0e7f);
+    if (!ring_reused && nchunks > 0 && tid < pad_last) S.stage[(nchunks - 1) % MK_STAGES][n_last + tid] = make_uint4(0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
     if (tid < MK_ROWS) {
         S.list_cnt[tid] = 0;
         S.row_thr[tid] = 0.0f;
@@ -287,12 +387,14 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
             float g = L3D_FILTER_C1 * fmaxf(sqrtf(e1.x * e1.x + e1.y * e1.y), sqrtf(e2.x * e2.x + e2.y * e2.y));
             S.rowA[tid] = make_float4(e1.x, e1.y, e1.z, e2.x);
             S.rowB[tid] = make_float4(e2.y, e2.z, g, 0.95f * epi);
+            const L3DPairBasis B = basis[tile.x];
+            S.rowK[tid] = make_uint2(line_kappa(B, e1), line_kappa(B, e2));
         }
     }
     __syncthreads();
 
     const unsigned int lt_mask = (1u << lane) - 1u;
-    int qn = 0;   // warp-uniform number of queued candidates
+    int qn = 0, qn2 = 0;   // warp-uniform fill of the two candidate queues
 
     for (int c = 0; c < nchunks; ++c) {
         const int sg = c % MK_STAGES;
@@ -300,22 +402,25 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
         const int base = c * MK_TT;
         const int n = min(MK_TT, Nt - base);
         if (ring_reused && c == nchunks - 1 && pad_last) {
-            if (tid < pad_last) S.stage[sg][n + tid] = make_float4(3.0e7f, 3.0e7f, 3.0e7f + 100.0f, 3.0e7f);
+            if (tid < pad_last) S.stage[sg][n + tid] = make_uint4(0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
             __syncthreads();
         }
-        const float4* st = S.stage[sg];
+        const uint4* st = S.stage[sg];
         const int my_rows = min(MK_RPW, nrows - warp * MK_RPW);
         if (my_rows > 0) {
             for (int j0 = 0; j0 < n; j0 += 32 * MK_T) {
-                float4 q[MK_T];
+                uint4 a[MK_T];
 #pragma unroll
-                for (int t = 0; t < MK_T; ++t) q[t] = st[j0 + t * 32 + lane];
+                for (int t = 0; t < MK_T; ++t) a[t] = st[j0 + t * 32 + lane];
                 for (int r = 0; r < my_rows; ++r) {
                     const int rl = warp * MK_RPW + r;
-                    const float4 rA = S.rowA[rl], rB = S.rowB[rl];
+                    const uint2 kr = S.rowK[rl];
                     bool pass[MK_T];
 #pragma unroll
-                    for (int t = 0; t < MK_T; ++t) pass[t] = filter_may_survive(q[t], rA, rB);   // MK_T independent chains
+                    for (int t = 0; t < MK_T; ++t) {     // level 1: both epipolar lines on the same side of the target's arc -> overlap 0
+                        const unsigned int u1 = kr.x - a[t].x, u2 = kr.y - a[t].x;
+                        pass[t] = !(max(u1, u2) < a[t].y || min(u1, u2) > a[t].z);
+                    }
                     unsigned int b[MK_T], any = 0u;
 #pragma unroll
                     for (int t = 0; t < MK_T; ++t) { b[t] = __ballot_sync(0xffffffffu, pass[t]); any |= b[t]; }
@@ -331,7 +436,7 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
                         __syncwarp();
                         while (qn >= 32) {
                             qn -= 32;
-                            exact_batch<MODE, KEEP>(S, S.queue[warp][qn + lane], true, lane);
+                            filter_batch<MODE, KEEP>(S, S.queue[warp][qn + lane], true, warp, lane, lt_mask, qn2);
                         }
                     }
                 }
@@ -343,13 +448,18 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
                 const int base1 = (c + MK_STAGES) * MK_TT;
                 const unsigned int bytes = (unsigned int)min(MK_TT, Nt - base1) * 16u;
                 mbar_expect_tx(&S.bars[sg], bytes);
-                tma_load_1d(S.stage[sg], tsegs + base1, bytes, &S.bars[sg]);
+                tma_load_1d(S.stage[sg], tarcs + base1, bytes, &S.bars[sg]);
             }
         }
     }
     if (qn > 0) {
-        bool has = lane < qn;
-        exact_batch<MODE, KEEP>(S, has ? S.queue[warp][lane] : 0u, has, lane);
+        const bool has = lane < qn;
+        filter_batch<MODE, KEEP>(S, has ? S.queue[warp][lane] : 0u, has, warp, lane, lt_mask, qn2);
+    }
+    __syncwarp();
+    if (qn2 > 0) {
+        const bool has = lane < qn2;
+        exact_batch<MODE, KEEP>(S, has ? S.queue2[warp][lane] : 0u, has, lane);
     }
     __syncwarp();
 
@@ -359,29 +469,31 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
 __global__ void __launch_bounds__(MK_THREADS, MK_MINB)
 k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
              const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
-             int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out)
-{ match_topk_body<0, 0>(segs, cache, views, pairs, tiles, knn, epi, counts_out, recs_out, nullptr); }
+             int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const uint4* __restrict__ arcs, const L3DPairBasis* __restrict__ basis)
+{ match_topk_body<0, 0>(segs, cache, views, pairs, tiles, knn, epi, counts_out, recs_out, nullptr, arcs, basis); }
 
 // REF_CPU semantics: same tiling, staging and filter; the exact path is matchingCPU's double arithmetic
 __global__ void __launch_bounds__(MK_THREADS, MK_MINB)
 k_match_topk_f64(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
                  const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
-                 int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d)
-{ match_topk_body<1, 0>(segs, cache, views, pairs, tiles, knn, epi, counts_out, recs_out, cache_d); }
+                 int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d,
+                 const uint4* __restrict__ arcs, const L3DPairBasis* __restrict__ basis)
+{ match_topk_body<1, 0>(segs, cache, views, pairs, tiles, knn, epi, counts_out, recs_out, cache_d, arcs, basis); }
 
 // kNN <= 0 ("keep all matches", cudawrapper.cu:628-636 / line3D.cc:988-996): pass 1 counts the survivors of every row
 // (stride == 0), pass 2 stores them with the row stride found by pass 1.  cache_d != nullptr selects REF_CPU arithmetic.
 __global__ void __launch_bounds__(MK_THREADS, MK_MINB)
 k_match_all(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
             const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int stride, float epi,
-            int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d)
+            int* __restrict__ counts_out, l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d,
+            const uint4* __restrict__ arcs, const L3DPairBasis* __restrict__ basis)
 {
     if (cache_d) {
-        if (stride == 0) match_topk_body<1, 1>(segs, cache, views, pairs, tiles, 0, epi, counts_out, recs_out, cache_d);
-        else match_topk_body<1, 2>(segs, cache, views, pairs, tiles, stride, epi, counts_out, recs_out, cache_d);
+        if (stride == 0) match_topk_body<1, 1>(segs, cache, views, pairs, tiles, 0, epi, counts_out, recs_out, cache_d, arcs, basis);
+        else match_topk_body<1, 2>(segs, cache, views, pairs, tiles, stride, epi, counts_out, recs_out, cache_d, arcs, basis);
     } else {
-        if (stride == 0) match_topk_body<0, 1>(segs, cache, views, pairs, tiles, 0, epi, counts_out, recs_out, nullptr);
-        else match_topk_body<0, 2>(segs, cache, views, pairs, tiles, stride, epi, counts_out, recs_out, nullptr);
+        if (stride == 0) match_topk_body<0, 1>(segs, cache, views, pairs, tiles, 0, epi, counts_out, recs_out, nullptr, arcs, basis);
+        else match_topk_body<0, 2>(segs, cache, views, pairs, tiles, stride, epi, counts_out, recs_out, nullptr, arcs, basis);
     }
 }
 

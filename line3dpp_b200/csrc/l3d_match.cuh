@@ -48,15 +48,20 @@ __global__ void k_prep_segments(const float4* __restrict__ segs, const L3DViewDe
 __global__ void k_match_topk(const float4* __restrict__ segs, const float4* __restrict__ cache,
                              const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
                              const int2* __restrict__ tiles, int knn, float epi, int* __restrict__ counts_out,
-                             l3d_match_rec* __restrict__ recs_out);
+                             l3d_match_rec* __restrict__ recs_out, const uint4* __restrict__ arcs, const L3DPairBasis* __restrict__ basis);
 __global__ void k_match_topk_f64(const float4* __restrict__ segs, const float4* __restrict__ cache,
                                  const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
                                  const int2* __restrict__ tiles, int knn, float epi, int* __restrict__ counts_out,
-                                 l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d);
+                                 l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d, const uint4* __restrict__ arcs,
+                                 const L3DPairBasis* __restrict__ basis);
 __global__ void k_match_all(const float4* __restrict__ segs, const float4* __restrict__ cache,
                             const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
                             const int2* __restrict__ tiles, int stride, float epi, int* __restrict__ counts_out,
-                            l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d);
+                            l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d, const uint4* __restrict__ arcs,
+                            const L3DPairBasis* __restrict__ basis);
+// level-1 pre-filter tables: one CTA per view pair of [first_pair, first_pair + gridDim.x)
+__global__ void k_pair_arcs(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
+                            int first_pair, int enabled, uint4* __restrict__ arcs, L3DPairBasis* __restrict__ basis);
 __global__ void k_sort_rows(int* __restrict__ counts, l3d_match_rec* __restrict__ recs, int stride, long long rows, int topk);
 __global__ void k_prep_segments_f64(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int num_views,
                                     long long total, double* __restrict__ cache);
