@@ -3,6 +3,7 @@
 // l3d_pipeline.cu.  There is no CPU fallback: every entry needs a live CUDA context and fails loudly otherwise.
 #include "l3d_ctx.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -252,14 +253,29 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
     if (rows) L3D_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(int) * rows, c->stream), "clear counts");   // rows of pairs with Nt == 0
     const uint4* arcs = (const uint4*)c->d_arcs.p;
     const L3DPairBasis* basis = (const L3DPairBasis*)c->d_basis.p;
-    if (last_pair > first_pair) {
-        // level-1 pre-filter tables of the pairs matched here (l3d_device.cuh "pencil parameter"); below epi_overlap 1e-3 a far
-        // intersection could still count as a match, so the tables then pass everything on to the float filter
-        const bool no_l1 = getenv("L3D_NO_LEVEL1") != nullptr;
-        k_pair_arcs<<<(unsigned int)(last_pair - first_pair), 256, 0, c->stream>>>(c->segs(), c->views(), (const L3DPairDev*)c->d_pairs.p, first_pair,
-                                                                                   (epi_overlap >= 1e-3f && !no_l1) ? 1 : 0, (uint4*)c->d_arcs.p, (L3DPairBasis*)c->d_basis.p);
-        ++c->launches;
+    if (last_pair > first_pair && narcs > 0) {
+        // level-1 tables of the pairs matched here (l3d_device.cuh "pencil parameter"): raw arcs + keys, one sort, packed entries in window
+        // order.  Below epi_overlap 0.01 the extended arcs would span the whole line: everything is then handed to the float filter.
+        if (narcs >= (1ll << 31) - 2) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: more than 2^31 (pair, target segment) combinations in one call");
+        const int npr = last_pair - first_pair;
+        const bool on = epi_overlap >= 0.01f && getenv("L3D_NO_LEVEL1") == nullptr;
+        int end_bit = 33;
+        while (end_bit < 64 && (1ll << (end_bit - 33)) < npr) ++end_bit;
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const unsigned int*)nullptr, (unsigned int*)nullptr, (int)narcs, 0, end_bit, c->stream);
+        if ((rc = l3d_reserve(c, c->d_arcraw, 16 * (size_t)narcs, "raw arcs")) || (rc = l3d_reserve(c, c->d_arckeys, 8 * (size_t)narcs, "arc keys")) ||
+            (rc = l3d_reserve(c, c->d_arckeys2, 8 * (size_t)narcs, "arc keys")) || (rc = l3d_reserve(c, c->d_arcvals, 4 * (size_t)narcs, "arc order")) ||
+            (rc = l3d_reserve(c, c->d_arcvals2, 4 * (size_t)narcs, "arc order")) || (rc = l3d_reserve(c, c->d_arctmp, tb, "arc sort temp"))) return rc;
+        k_pair_arcs<<<(unsigned int)npr, 256, 0, c->stream>>>(c->segs(), c->views(), (const L3DPairDev*)c->d_pairs.p, first_pair, on ? 1 : 0,
+                                                             1.0 / (double)std::max(epi_overlap, 0.01f) + 0.5, (uint4*)c->d_arcraw.p,
+                                                             (unsigned long long*)c->d_arckeys.p, (unsigned int*)c->d_arcvals.p, (L3DPairBasis*)c->d_basis.p);
         L3D_CUDA(c, cudaGetLastError(), "k_pair_arcs");
+        L3D_CUDA(c, cub::DeviceRadixSort::SortPairs(c->d_arctmp.p, tb, (const unsigned long long*)c->d_arckeys.p, (unsigned long long*)c->d_arckeys2.p,
+                                                    (const unsigned int*)c->d_arcvals.p, (unsigned int*)c->d_arcvals2.p, (int)narcs, 0, end_bit, c->stream), "arc sort");
+        k_arcs_gather<<<(unsigned int)((narcs + 255) / 256), 256, 0, c->stream>>>(narcs, (const unsigned long long*)c->d_arckeys2.p, (const unsigned int*)c->d_arcvals2.p,
+                                                                                 (const uint4*)c->d_arcraw.p, (const L3DPairDev*)c->d_pairs.p, first_pair, (uint4*)c->d_arcs.p);
+        L3D_CUDA(c, cudaGetLastError(), "k_arcs_gather");
+        c->launches += 2 + 8;
     }
     const double* cache_d = nullptr;
     if (Fd && c->total_segs > 0) {      // matchingCPU's rays / plane normals in double; camera blocks may have been updated since set_views

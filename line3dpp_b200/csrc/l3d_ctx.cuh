@@ -84,7 +84,7 @@ struct l3d_ctx {
     long long total_rows = 0, pair_evals = 0;
     std::vector<L3DPairDev> h_pairs;
     std::vector<int2> h_tiles;
-    DevBuf d_pairs, d_tiles, d_counts, d_recs, d_rowptr, d_csr, d_scan_tmp, d_dense_dep, d_dense_ov, d_dense_jobs, d_arcs, d_basis;
+    DevBuf d_pairs, d_tiles, d_counts, d_recs, d_rowptr, d_csr, d_scan_tmp, d_dense_dep, d_dense_ov, d_dense_jobs, d_arcs, d_basis, d_arcraw, d_arckeys, d_arckeys2, d_arcvals, d_arcvals2, d_arctmp;
 
     SweepState sweep;
     RddState rdd;
@@ -96,7 +96,7 @@ struct l3d_ctx {
     const L3DViewDev* views() const { return (const L3DViewDev*)d_views.p; }
     std::vector<DevBuf*> all_bufs()
     {
-        std::vector<DevBuf*> b = {&d_segs, &d_cache, &d_cache_d, &d_views, &d_pairs, &d_tiles, &d_counts, &d_recs, &d_rowptr, &d_csr, &d_scan_tmp, &d_dense_dep, &d_dense_ov, &d_dense_jobs, &d_arcs, &d_basis};
+        std::vector<DevBuf*> b = {&d_segs, &d_cache, &d_cache_d, &d_views, &d_pairs, &d_tiles, &d_counts, &d_recs, &d_rowptr, &d_csr, &d_scan_tmp, &d_dense_dep, &d_dense_ov, &d_dense_jobs, &d_arcs, &d_basis, &d_arcraw, &d_arckeys, &d_arckeys2, &d_arcvals, &d_arcvals2, &d_arctmp};
         for (DevBuf* x : sweep.bufs()) b.push_back(x);
         for (DevBuf* x : rdd.bufs()) b.push_back(x);
         for (DevBuf* x : aff.bufs()) b.push_back(x);

@@ -40,21 +40,41 @@ struct L3DPairDev {
 // well conditioned whether E lies inside the image or at infinity) and (u, v) an orthonormal basis of that subspace, the angle
 //     kappa(e) = atan2(e.v, e.u)   (mod pi)
 // is a 1-D coordinate of the pencil; the pencil line through an image point x has kappa(x) = atan2(x.u, -x.v).  Along a target
-// line l the map kappa -> intersection point is monotone on the circle cut at kappa_l (the pencil line parallel to l), so the
-// projections of the two epipolar lines of a source segment both fall outside the target segment on the SAME side - the case in
-// which the reference's overlap (cudawrapper.cu:89-136) is 0 - exactly when, in cut coordinates, both kappa values lie below or
-// both above the target's arc.  Angles are stored in units of pi / 2^32: unsigned subtraction wraps mod pi for free.
+// line l the map kappa -> intersection point is monotone on the circle cut at kappa_l (the pencil line parallel to l), so a target
+// segment [q1, q2] is an ARC T of the circle, and so is the stretch T_ext of its line between t = -X and t = 1 + X (t = 0 at q1,
+// 1 at q2, X = 1/epi_overlap + 0.5).  The reference's overlap (cudawrapper.cu:89-136) is inner / outer length of two collinear
+// intervals, hence
+//   * 0 when the projections of both epipolar lines of a source segment fall outside [q1, q2] on the SAME side (both kappa below T
+//     or both above T),
+//   * below epi_overlap when either projection is farther than X segment lengths away (outer > X, inner <= 1): a kappa outside T_ext.
+// A row can therefore only match targets with both kappa inside T_ext and not on the same side of T - which implies that T meets the
+// short arc between the two kappa values: with the targets of a view pair sorted by the start of T, a row's candidates are a WINDOW of
+// that order (k_match_topk).  Angles are stored in units of pi / 2^32: unsigned subtraction wraps mod pi for free.
 #define L3D_ARC_SCALE 2048.0
-struct L3DPairBasis { double u[3], v[3]; };
+struct L3DPairBasis { double u[3], v[3]; int n_narrow; unsigned int wmax; };    // + the pair's window data (k_pair_arcs)
+#define L3D_ARC_WIDE 0x80000000u      /* entry.z flag: no usable arc (epipole too close, degenerate segment, arc too long): always a candidate */
+// sorted entry: x = start A of T (absolute), y = e1 | w << 16, z = ehi | flag, w = target index; e1 / w / ehi = length of T_ext below T,
+// of T, of T_ext above T in units of 2^16 (rounded up).  Both kappa inside T_ext, not both below T, not both above T.
+__device__ __forceinline__ bool arc_may_match(uint4 e, unsigned int k1, unsigned int k2)
+{
+    const unsigned int E1 = e.y << 16, E2 = E1 + (e.y & 0xFFFF0000u), E3 = E2 + (e.z << 16);
+    const unsigned int base = e.x - E1, d1 = k1 - base, d2 = k2 - base, mx = max(d1, d2), mn = min(d1, d2);
+    return (mx <= E3 && mx >= E1 && mn <= E2) || (e.z & L3D_ARC_WIDE);
+}
 __device__ __forceinline__ unsigned int arc_units(double kappa)
 { return (unsigned int)(long long)llrint(kappa * (4294967296.0 / 3.14159265358979323846)); }
-// kappa of an epipolar line (float, exactly as the kernels form it)
-__device__ __forceinline__ unsigned int line_kappa(const L3DPairBasis& B, float3 e)
+// kappa of an epipolar line (float, exactly as the kernels form it).  *off: the line misses the pencil by more than 0.02 px inside
+// the image (its component along n = u x v, i.e. a source point so close to the epipole that F*p is rounding noise): the 1-D model
+// does not describe it and the row must skip level 1.
+__device__ __forceinline__ unsigned int line_kappa(const L3DPairBasis& B, float3 e, bool* off)
 {
     const double x = L3D_ARC_SCALE * (double)e.x, y = L3D_ARC_SCALE * (double)e.y, z = (double)e.z;
     const double cu = x * B.u[0] + y * B.u[1] + z * B.u[2], cv = x * B.v[0] + y * B.v[1] + z * B.v[2];
+    const double nx = B.u[1] * B.v[2] - B.u[2] * B.v[1], ny = B.u[2] * B.v[0] - B.u[0] * B.v[2], nz = B.u[0] * B.v[1] - B.u[1] * B.v[0];
+    const double cn = x * nx + y * ny + z * nz, exy = sqrt((double)e.x * (double)e.x + (double)e.y * (double)e.y);
     const double k = atan2(cv, cu);
-    return isfinite(k) ? arc_units(k) : 0u;      // a pair without a usable basis has pass-all arcs: any value will do
+    *off = !(4.0 * fabs(cn) <= 0.02 * exy) || !isfinite(k);     // |n . x| <= ~3 for scaled image points
+    return isfinite(k) ? arc_units(k) : 0u;
 }
 
 // per-segment cache written by k_prep_segments: 3 float4 per segment
@@ -114,22 +134,27 @@ __device__ __forceinline__ float exact_overlap(float4 q, float3 e1, float3 e2, b
     if (len_src < 1.0f || len_tgt < 1.0f) return 0.0f;
     bool A = on_seg(q.x, q.y, q.z, q.w, ax, ay);   // proj1 inside tgt segment
     bool B = on_seg(q.x, q.y, q.z, q.w, bx, by);   // proj2 inside tgt segment
-    if (A && B) return len_tgt / len_src;
     bool Cc = on_seg(ax, ay, bx, by, q.x, q.y);    // tgt p1 inside projected interval
     bool D = on_seg(ax, ay, bx, by, q.z, q.w);     // tgt p2 inside projected interval
-    if (Cc && D) return len_src / len_tgt;
-    if (A) {
-        float len1 = len2d(q.z, q.w, bx, by);
-        float len2 = len2d(q.x, q.y, bx, by);
-        if (Cc && len1 > 1.0f) return len2d(ax, ay, q.x, q.y) / len1;
-        else if (len2 > 1.0f) return len2d(ax, ay, q.z, q.w) / len2;
-    } else if (B) {
-        float len1 = len2d(q.x, q.y, ax, ay);
-        float len2 = len2d(q.z, q.w, ax, ay);
-        if (D && len1 > 1.0f) return len2d(bx, by, q.z, q.w) / len1;
-        else if (len2 > 1.0f) return len2d(bx, by, q.x, q.y) / len2;
-    }
-    return 0.0f;
+    // The reference's case analysis (cudawrapper.cu:99-131) returns a ratio of two lengths in every case.  Written without branches -
+    // operands selected first, then the same sqrtf / division on the same values - so that the 32 candidates of a batch do not
+    // serialise over five different paths:
+    //   A && B        : len_tgt / len_src                    Cc && D       : len_src / len_tgt
+    //   A (b outside) : len1 = |q2 - b|, len2 = |q1 - b|;    Cc && len1 > 1 ? |a - q1| / len1 : len2 > 1 ? |a - q2| / len2 : 0
+    //   B (a outside) : len1 = |q1 - a|, len2 = |q2 - a|;    D  && len1 > 1 ? |b - q2| / len1 : len2 > 1 ? |b - q1| / len2 : 0
+    const bool cAB = A && B, cCD = !cAB && Cc && D, cA = !cAB && !cCD && A, cB = !cAB && !cCD && !A && B;
+    const float fx = cA ? bx : ax, fy = cA ? by : ay;            // the projection outside the tgt segment
+    const float ix = cA ? ax : bx, iy = cA ? ay : by;            // the projection inside it
+    const float u1x = cA ? q.z : q.x, u1y = cA ? q.w : q.y;      // tgt end point of len1
+    const float u2x = cA ? q.x : q.z, u2y = cA ? q.y : q.w;      // tgt end point of len2
+    const float len1 = len2d(u1x, u1y, fx, fy), len2 = len2d(u2x, u2y, fx, fy);
+    const bool first = (cA ? Cc : D) && len1 > 1.0f, second = !first && len2 > 1.0f;
+    const float num1 = len2d(ix, iy, first ? u2x : u1x, first ? u2y : u1y);
+    const float num = cAB ? len_tgt : cCD ? len_src : num1;
+    const float den = cAB ? len_src : cCD ? len_tgt : first ? len1 : len2;
+    const bool any = cAB || cCD || ((cA || cB) && (first || second));
+    const float r = num / den;
+    return any ? r : 0.0f;
 }
 
 // The two D_triangulate_depth calls of K_match_lines (cudawrapper.cu:139-164, 237-242) from cached rays / normals.

@@ -58,21 +58,23 @@ __global__ void __launch_bounds__(256) k_prep_segments_f64(const float4* __restr
 
 // ------------------------------------------------------------------------------------------------ fused match + top-k
 struct MatchSmem {
-    uint4 stage[MK_STAGES][MK_TT];                   // TMA-staged target ARCS of the level-1 pre-filter (kappa_l, lo, hi, -), k_pair_arcs
+    uint4 stage[MK_STAGES][MK_TT];                   // TMA-staged target arcs in window order (arc_may_match, l3d_device.cuh)
     uint2 rowK[MK_ROWS];                             // pencil parameters of the row's two epipolar lines (l3d_device.cuh)
+    unsigned char rowall[MK_ROWS];                   // 1: an epipolar line of this row is not a pencil member to within the margins (source point at the epipole): no level 1
     unsigned long long lists[MK_ROWS][MK_CAP + 1];   // per-row survivor keys (+1: rows start on different banks, lanes that push keys of different rows do not collide)
     float4 rowA[MK_ROWS];                            // (e1.x, e1.y, e1.z, e2.x)
     float4 rowB[MK_ROWS];                            // (e2.y, e2.z, g, 0.95 * score-to-beat)
     float row_thr[MK_ROWS];                          // overlap of the current k-th best survivor (0 until k are known)
     int list_cnt[MK_ROWS];
-    unsigned int queue[MK_WARPS][32 * MK_T + 32];    // level-1 survivors per warp: (row_local << 24) | tgt
-    unsigned int queue2[MK_WARPS][64];               // level-2 survivors (filter_may_survive), evaluated exactly 32 at a time
+    unsigned int queue[MK_WARPS][96];                // level-1 survivors per warp: (row_local << 24) | tgt, filtered 64 at a time
+    unsigned int queue2[MK_WARPS][96];               // level-2 survivors (filter_may_survive), evaluated exactly 32 at a time
     unsigned long long bars[MK_STAGES];
     // per-CTA constants of the (rarely executed, deliberately out-of-line) exact path
     const float4* tsegs; const float4* cache;
     long long src_base, toff;
     float3 Cs, Ct;
     float epi; int knn, Nt;
+    int cap;                                         // keys a row list collects before it is cut to its k best (and the score-to-beat rises); 16 instead of 32 was measured 7 % slower
     // REF_CPU semantics (k_match_topk_f64): the exact path is matchingCPU's double arithmetic; the float filter stays the same
     const double* cache_d; const float4* ssegs;
     double Fd[9]; D3 Csd, Ctd;
@@ -94,7 +96,7 @@ __device__ __noinline__ void prune_row(MatchSmem& S, int row, int lane)
 {
     const int knn = S.knn; const float epi = S.epi;
     __syncwarp();
-    const int n = min(S.list_cnt[row], MK_CAP);
+    const int n = min(S.list_cnt[row], S.cap);
     const unsigned long long k = lane < n ? S.lists[row][lane] : 0ull;
     const int r = rank_in_row(S.lists[row], n, k);
     __syncwarp();
@@ -175,7 +177,7 @@ __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool 
     while (KEEP == 0) {
         if (pending) {
             int slot = atomicAdd(&S.list_cnt[rl], 1);
-            if (slot < MK_CAP) { S.lists[rl][slot] = key; pending = false; }
+            if (slot < S.cap) { S.lists[rl][slot] = key; pending = false; }
         }
         unsigned int pm = __ballot_sync(0xffffffffu, pending);
         if (!pm) break;
@@ -186,12 +188,12 @@ __device__ __noinline__ void exact_batch(MatchSmem& S, unsigned int entry, bool 
             prune_row(S, row, lane);
             unsigned int mine = __ballot_sync(0xffffffffu, pending && rl == row);
             todo &= ~mine;
-            if (knn >= MK_CAP) {                      // list stays full (k == capacity): fold the pending keys in one by one
+            if (knn >= S.cap) {                       // list stays full (k == capacity): fold the pending keys in one by one
                 while (mine) {
                     int l = __ffs(mine) - 1;
                     mine &= mine - 1;
                     unsigned long long k = __shfl_sync(0xffffffffu, key, l);
-                    if (lane == 0 && k > S.lists[row][MK_CAP - 1]) S.lists[row][MK_CAP - 1] = k;
+                    if (lane == 0 && k > S.lists[row][S.cap - 1]) S.lists[row][S.cap - 1] = k;
                     if (lane == l) pending = false;
                     prune_row(S, row, lane);   // re-sort; also refreshes the score-to-beat
                 }
@@ -212,7 +214,7 @@ __device__ __noinline__ void finalize_rows(MatchSmem& S, int warp, int lane, int
         if (rl >= nrows) break;
         const long long R = R0 + rl;
         if (KEEP != 0) { if (lane == 0) counts_out[R] = S.list_cnt[rl]; continue; }
-        const int n = min(S.list_cnt[rl], MK_CAP);
+        const int n = min(S.list_cnt[rl], S.cap);
         if (lane == 0) counts_out[R] = min(n, knn);
         if (n == 0) continue;
         const unsigned long long key = lane < n ? S.lists[rl][lane] : 0ull;
@@ -269,68 +271,146 @@ __device__ void pair_basis(const float* F, L3DPairBasis* B)
     for (int i = 0; i < 3; ++i) { B->u[i] = u[i]; B->v[i] = v[i]; }
 }
 
-// arc of one target segment: (kappa of the cut, lower end, upper end) in cut coordinates, margins included.  A source row is
-// rejected by level 1 iff both its kappa values, minus the cut, are < lo or both are > hi.  Margin: a displacement of
-//     delta = 0.05 px + 0.4 % of the segment length
-// of the pencil line at either end point (200 x the rounding error of the reference's float intersection, 2.4e-4 px / sin(phi),
-// and above the level-2 filter's own margins), plus 4e-6 rad for the rounding of the angles themselves.  Everything uncertain
-// (epipole within the margin of the segment or of its line, degenerate segment, non-finite values) gets the pass-all arc.
-__device__ uint4 target_arc(const L3DPairBasis& B, float4 q, bool enabled)
+// raw arc of one target segment: x = start A of T (absolute units), y = length of T, z / w = length of T_ext below / above T; y ==
+// 0xFFFFFFFF: no usable arc.  Margins: a displacement of delta = 0.05 px + 0.4 % of the segment length of the pencil line at the point
+// in question (200 x the rounding error of the reference's float intersection, 2.4e-4 px / sin(phi), and above the float filter's own
+// margins), plus 4e-6 rad for the rounding of the angles themselves.  Everything uncertain (epipole within the margin of the extended
+// segment or of its line, degenerate segment, non-monotone or non-finite values, T_ext longer than pi/2) has no arc.
+__device__ uint4 target_arc(const L3DPairBasis& B, float4 q, double ext, bool enabled)
 {
-    const uint4 pass_all = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
-    if (!enabled) return pass_all;
+    const uint4 none = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
+    if (!enabled) return none;
     const double x1 = (double)q.x / L3D_ARC_SCALE, y1 = (double)q.y / L3D_ARC_SCALE, x2 = (double)q.z / L3D_ARC_SCALE, y2 = (double)q.w / L3D_ARC_SCALE;
     const double a1 = x1 * B.u[0] + y1 * B.u[1] + B.u[2], b1 = x1 * B.v[0] + y1 * B.v[1] + B.v[2];
-    const double a2 = x2 * B.u[0] + y2 * B.u[1] + B.u[2], b2 = x2 * B.v[0] + y2 * B.v[1] + B.v[2];
     const double dx = x2 - x1, dy = y2 - y1, ac = dx * B.u[0] + dy * B.u[1], bc = dx * B.v[0] + dy * B.v[1];
-    const double len = sqrt(dx * dx + dy * dy), rho1 = sqrt(a1 * a1 + b1 * b1), rho2 = sqrt(a2 * a2 + b2 * b2), rhoc = sqrt(ac * ac + bc * bc);
+    const double len = sqrt(dx * dx + dy * dy), rhoc = sqrt(ac * ac + bc * bc);
     const double delta = (0.05 + 4e-3 * len * L3D_ARC_SCALE) / L3D_ARC_SCALE;
-    if (!(len > 1e-9) || !isfinite(rho1 + rho2 + rhoc) || !(delta < 0.25 * rho1) || !(delta < 0.25 * rho2) || !(rhoc > 1e-3 * len)) return pass_all;
-    // the target line through the epipole: (x1 x x2) . n ~ 0, n = u x v
-    {
+    if (!(len > 1e-9) || !isfinite(rhoc) || !(rhoc > 1e-3 * len) || !(ext >= 0.0)) return none;
+    {   // the target line through the epipole: (x1 x x2) . n ~ 0, n = u x v
         const double lx = y1 - y2, ly = x2 - x1, lz = x1 * y2 - y1 * x2;
         const double nx = B.u[1] * B.v[2] - B.u[2] * B.v[1], ny = B.u[2] * B.v[0] - B.u[0] * B.v[2], nz = B.u[0] * B.v[1] - B.u[1] * B.v[0];
-        if (!(fabs(lx * nx + ly * ny + lz * nz) > 1e-4 * sqrt(lx * lx + ly * ly + lz * lz))) return pass_all;
+        if (!(fabs(lx * nx + ly * ny + lz * nz) > 1e-4 * sqrt(lx * lx + ly * ly + lz * lz))) return none;
     }
-    const unsigned int kc = arc_units(atan2(ac, -bc));
-    const unsigned int al1 = arc_units(atan2(a1, -b1)) - kc, al2 = arc_units(atan2(a2, -b2)) - kc;
     const double to_units = 4294967296.0 / 3.14159265358979323846;
-    const double m1 = (1.2 * delta / rho1 + 4e-6) * to_units, m2 = (1.2 * delta / rho2 + 4e-6) * to_units;
-    const double lo = al1 < al2 ? (double)al1 - m1 : (double)al2 - m2, hi = al1 < al2 ? (double)al2 + m2 : (double)al1 + m1;
-    return make_uint4(kc, lo > 0.0 ? (unsigned int)lo : 0u, hi < 4294967295.0 ? (unsigned int)hi : 0xFFFFFFFFu, 0u);
+    const unsigned int kc = arc_units(atan2(ac, -bc));
+    const double ts[4] = {-ext, 0.0, 1.0, 1.0 + ext};
+    double al[4], mg[4];
+    for (int i = 0; i < 4; ++i) {          // (x.u, x.v) is linear along the line
+        const double a = a1 + ts[i] * ac, b = b1 + ts[i] * bc, rho = sqrt(a * a + b * b);
+        if (!isfinite(rho) || !(delta < 0.25 * rho)) return none;
+        al[i] = (double)(unsigned int)(arc_units(atan2(a, -b)) - kc);
+        mg[i] = (1.2 * delta / rho + 4e-6) * to_units;
+    }
+    const bool up = al[0] <= al[1] && al[1] <= al[2] && al[2] <= al[3], down = al[0] >= al[1] && al[1] >= al[2] && al[2] >= al[3];
+    if (!up && !down) return none;
+    const int i0 = up ? 0 : 3, i1 = up ? 1 : 2, i2 = up ? 2 : 1, i3 = up ? 3 : 0;      // ascending in cut coordinates
+    const double top = 4294967295.0;
+    double lo = fmax(al[i1] - mg[i1], 0.0), hi = fmin(al[i2] + mg[i2], top);
+    double lox = fmin(fmax(al[i0] - mg[i0], 0.0), lo), hix = fmax(fmin(al[i3] + mg[i3], top), hi);
+    lo = floor(lo); lox = floor(lox); hi = ceil(hi); hix = ceil(hix);
+    if (!(hix - lox < 2147483648.0 - 524288.0)) return none;
+    return make_uint4(kc + (unsigned int)lo, (unsigned int)(hi - lo), (unsigned int)(lo - lox), (unsigned int)(hix - hi));
 }
 
+// one CTA per view pair: basis, raw arcs, the window width of the pair (so that at most ~3 % of the targets are wider) and the sort keys
 __global__ void __launch_bounds__(256)
 k_pair_arcs(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs, int first_pair,
-            int enabled, uint4* __restrict__ arcs, L3DPairBasis* __restrict__ basis)
+            int enabled, double ext, uint4* __restrict__ raw, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals,
+            L3DPairBasis* __restrict__ basis)
 {
     __shared__ L3DPairBasis B;
+    __shared__ int hist[33];
+    __shared__ int narrow;
     const L3DPairDev* P = pairs + first_pair + blockIdx.x;
-    if (threadIdx.x == 0) { pair_basis(P->F, &B); basis[first_pair + blockIdx.x] = B; }
+    if (threadIdx.x == 0) { pair_basis(P->F, &B); narrow = 0; }
+    if (threadIdx.x < 33) hist[threadIdx.x] = 0;
     __syncthreads();
     const L3DViewDev* vt = views + P->tgt;
     const float4* t = segs + vt->seg_off;
-    uint4* out = arcs + P->arc_off;
-    for (int j = threadIdx.x; j < vt->nseg; j += 256) out[j] = target_arc(B, t[j], enabled != 0);
+    const int Nt = vt->nseg;
+    uint4* out = raw + P->arc_off;
+    for (int j = threadIdx.x; j < Nt; j += 256) {
+        const uint4 r = target_arc(B, t[j], ext, enabled != 0);
+        out[j] = r;
+        if (r.y != 0xFFFFFFFFu) atomicAdd(&hist[r.y <= 65536u ? 16 : 32 - __clz(r.y - 1u)], 1);      // ceil(log2(length of T))
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+        for (int b = 16; b <= 32; ++b) total += hist[b];
+        const int allowed = max(8, (3 * Nt) / 100);
+        int b = 16, cum = hist[16];
+        while (b < 28 && total - cum > allowed) cum += hist[++b];
+        B.wmax = 1u << b;
+    }
+    __syncthreads();
+    const unsigned int wmax = B.wmax;
+    int mine = 0;
+    for (int j = threadIdx.x; j < Nt; j += 256) {
+        const uint4 r = out[j];
+        const bool wide = r.y == 0xFFFFFFFFu || r.y > wmax;
+        keys[P->arc_off + j] = ((unsigned long long)blockIdx.x << 33) | (wide ? (1ull << 32) | (unsigned long long)j : (unsigned long long)r.x);
+        vals[P->arc_off + j] = (unsigned int)(P->arc_off + j);
+        mine += wide ? 0 : 1;
+    }
+    if (mine) atomicAdd(&narrow, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) { B.n_narrow = narrow; basis[first_pair + blockIdx.x] = B; }
 }
 
-// level 2: the float filter on up to 32 level-1 survivors (one per lane); its survivors are queued for the exact path
-template <int MODE, int KEEP>
-__device__ __forceinline__ void filter_batch(MatchSmem& S, unsigned int entry, bool has, int warp, int lane, unsigned int lt_mask, int& qn2)
+// packed entries in sorted order (arc_may_match, l3d_device.cuh)
+__global__ void __launch_bounds__(256)
+k_arcs_gather(long long n, const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals, const uint4* __restrict__ raw,
+              const L3DPairDev* __restrict__ pairs, int first_pair, uint4* __restrict__ out)
 {
-    bool pass = false;
-    if (has) {
-        const int rl = (int)(entry >> 24);
-        const unsigned int j = entry & 0xFFFFFFu;
-        if (j < (unsigned int)S.Nt) pass = filter_may_survive(__ldg(S.tsegs + j), S.rowA[rl], S.rowB[rl]);      // j >= Nt: padding of a partial stage
-    }
-    const unsigned int b = __ballot_sync(0xffffffffu, pass);
-    if (b) {
-        if (pass) S.queue2[warp][qn2 + __popc(b & lt_mask)] = entry;
-        qn2 += __popc(b);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    const unsigned int src = vals[i];
+    const uint4 r = raw[src];
+    const bool wide = (k >> 32) & 1ull;
+    const unsigned int j = src - (unsigned int)pairs[first_pair + (int)(k >> 33)].arc_off;
+    const unsigned int w16 = (r.y + 65535u) >> 16, e1 = (r.z + 65535u) >> 16, eh = (r.w + 65535u) >> 16;
+    out[i] = wide ? make_uint4(0u, 0u, L3D_ARC_WIDE, j) : make_uint4(r.x, e1 | (w16 << 16), eh, j);
+}
+
+// level 2: the float filter on up to 64 level-1 survivors (two per lane: both gathers of the target segment in flight together);
+// its survivors are queued for the exact path
+template <int MODE, int KEEP>
+__device__ __forceinline__ void filter_batch(MatchSmem& S, unsigned int e0, bool has0, unsigned int e1, bool has1, int warp, int lane,
+                                             unsigned int lt_mask, int& qn2)
+{
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+    if (has0) q0 = __ldg(S.tsegs + (e0 & 0xFFFFFFu));
+    if (has1) q1 = __ldg(S.tsegs + (e1 & 0xFFFFFFu));
+    bool p0 = false, p1 = false;
+    if (has0) { const int rl = (int)(e0 >> 24); p0 = filter_may_survive(q0, S.rowA[rl], S.rowB[rl]); }
+    if (has1) { const int rl = (int)(e1 >> 24); p1 = filter_may_survive(q1, S.rowA[rl], S.rowB[rl]); }
+    const unsigned int b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+    if (b0 | b1) {
+        if (p0) S.queue2[warp][qn2 + __popc(b0 & lt_mask)] = e0;
+        qn2 += __popc(b0);
+        if (p1) S.queue2[warp][qn2 + __popc(b1 & lt_mask)] = e1;
+        qn2 += __popc(b1);
         __syncwarp();
-        if (qn2 >= 32) { qn2 -= 32; exact_batch<MODE, KEEP>(S, S.queue2[warp][qn2 + lane], true, lane); }
+        while (qn2 >= 32) { qn2 -= 32; exact_batch<MODE, KEEP>(S, S.queue2[warp][qn2 + lane], true, lane); }
     }
+}
+
+// first index in [0, n) of the sorted keys whose start is >= key (n if none): 32-ary search, one probe per lane and round
+__device__ __forceinline__ int arc_lower_bound(const uint4* __restrict__ ent, int n, unsigned int key, int lane)
+{
+    int lo = 0, hi = n;
+    while (hi > lo) {
+        const int step = (hi - lo + 31) >> 5, idx = lo + lane * step;
+        const bool below = idx < hi && ent[idx].x < key;
+        const int c = __popc(__ballot_sync(0xffffffffu, below));       // probes 0..c-1 are below the key (sorted: a prefix of the lanes)
+        if (c == 0) { hi = lo; break; }
+        const int nlo = lo + (c - 1) * step + 1;
+        hi = min(hi, lo + c * step);
+        lo = nlo;
+    }
+    return lo;
 }
 
 template <int MODE, int KEEP>
@@ -352,10 +432,13 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
     const int nrows = min(MK_ROWS, Ns - row0);
     const float4* tsegs = segs + toff;
     const uint4* tarcs = arcs + P->arc_off;
-    const int nchunks = (Nt + MK_TT - 1) / MK_TT;
+    const int RES = MK_STAGES * MK_TT;                     // entries resident at a time; larger target views take several passes
+    const int npass = (Nt + RES - 1) / RES;
+    const int n_narrow = basis[tile.x].n_narrow;
+    const unsigned int wmax = basis[tile.x].wmax;
 
     if (tid == 0) {
-        S.tsegs = tsegs; S.cache = cache; S.src_base = soff + row0; S.toff = toff; S.epi = epi; S.knn = knn; S.Nt = Nt;
+        S.tsegs = tsegs; S.cache = cache; S.src_base = soff + row0; S.toff = toff; S.epi = epi; S.knn = knn; S.Nt = Nt; S.cap = MK_CAP;
         S.Cs = make_float3(vs->C[0], vs->C[1], vs->C[2]); S.Ct = make_float3(vt->C[0], vt->C[1], vt->C[2]);
         S.cache_d = cache_d; S.ssegs = segs + soff + row0; S.R0 = P->row_off + row0; S.recs_out = recs_out;
         if (MODE) {
@@ -364,20 +447,12 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
         }
         for (int i = 0; i < MK_STAGES; ++i) mbar_init(&S.bars[i], 1);
         mbar_fence_init();
-        for (int i = 0; i < MK_STAGES && i < nchunks; ++i) {           // whole ring in flight while the rows are set up
+        for (int i = 0; i < MK_STAGES && i * MK_TT < Nt; ++i) {        // the first pass is in flight while the rows are set up
             const unsigned int bytes = (unsigned int)min(MK_TT, Nt - i * MK_TT) * 16u;
             mbar_expect_tx(&S.bars[i], bytes);
             tma_load_1d(S.stage[i], tarcs + (size_t)i * MK_TT, bytes, &S.bars[i]);
         }
     }
-    // The last stage is usually partial: pad it to a multiple of the warp step with an arc no row can meet (lo = hi = 2^32 - 1;
-    // should a kappa ever hit that value, filter_batch drops indices >= Nt), so the hot loop needs no
-    // per-lane bounds predicate.  When the ring is not reused (Nt <= MK_STAGES*MK_TT, the common case) the padding is
-    // written now - TMA only fills the first n entries of that stage - and the chunk loop runs without any CTA barrier.
-    const int n_last = Nt - (nchunks - 1) * MK_TT;
-    const int pad_last = ((n_last + 32 * MK_T - 1) & ~(32 * MK_T - 1)) - n_last;
-    const bool ring_reused = nchunks > MK_STAGES;
-    if (!ring_reused && nchunks > 0 && tid < pad_last) S.stage[(nchunks - 1) % MK_STAGES][n_last + tid] = make_uint4(0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
     if (tid < MK_ROWS) {
         S.list_cnt[tid] = 0;
         S.row_thr[tid] = 0.0f;
@@ -388,73 +463,73 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
             S.rowA[tid] = make_float4(e1.x, e1.y, e1.z, e2.x);
             S.rowB[tid] = make_float4(e2.y, e2.z, g, 0.95f * epi);
             const L3DPairBasis B = basis[tile.x];
-            S.rowK[tid] = make_uint2(line_kappa(B, e1), line_kappa(B, e2));
+            bool off1, off2;
+            S.rowK[tid] = make_uint2(line_kappa(B, e1, &off1), line_kappa(B, e2, &off2));
+            S.rowall[tid] = (off1 || off2) ? 1 : 0;
         }
     }
     __syncthreads();
 
     const unsigned int lt_mask = (1u << lane) - 1u;
+    const uint4* ent = &S.stage[0][0];
+    const int my_rows = min(MK_RPW, nrows - warp * MK_RPW);
     int qn = 0, qn2 = 0;   // warp-uniform fill of the two candidate queues
 
-    for (int c = 0; c < nchunks; ++c) {
-        const int sg = c % MK_STAGES;
-        mbar_wait(&S.bars[sg], (unsigned int)((c / MK_STAGES) & 1));
-        const int base = c * MK_TT;
-        const int n = min(MK_TT, Nt - base);
-        if (ring_reused && c == nchunks - 1 && pad_last) {
-            if (tid < pad_last) S.stage[sg][n + tid] = make_uint4(0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+    for (int pass = 0; pass < npass; ++pass) {
+        const int base = pass * RES, cnt = min(RES, Nt - base);
+        if (pass > 0) {                                // everybody is done with the resident entries: refill
             __syncthreads();
+            if (tid == 0)
+                for (int i = 0; i < MK_STAGES && i * MK_TT < cnt; ++i) {
+                    const unsigned int bytes = (unsigned int)min(MK_TT, cnt - i * MK_TT) * 16u;
+                    mbar_expect_tx(&S.bars[i], bytes);
+                    tma_load_1d(S.stage[i], tarcs + (size_t)base + (size_t)i * MK_TT, bytes, &S.bars[i]);
+                }
         }
-        const uint4* st = S.stage[sg];
-        const int my_rows = min(MK_RPW, nrows - warp * MK_RPW);
-        if (my_rows > 0) {
-            for (int j0 = 0; j0 < n; j0 += 32 * MK_T) {
-                uint4 a[MK_T];
-#pragma unroll
-                for (int t = 0; t < MK_T; ++t) a[t] = st[j0 + t * 32 + lane];
-                for (int r = 0; r < my_rows; ++r) {
-                    const int rl = warp * MK_RPW + r;
-                    const uint2 kr = S.rowK[rl];
-                    bool pass[MK_T];
-#pragma unroll
-                    for (int t = 0; t < MK_T; ++t) {     // level 1: both epipolar lines on the same side of the target's arc -> overlap 0
-                        const unsigned int u1 = kr.x - a[t].x, u2 = kr.y - a[t].x;
-                        pass[t] = !(max(u1, u2) < a[t].y || min(u1, u2) > a[t].z);
-                    }
-                    unsigned int b[MK_T], any = 0u;
-#pragma unroll
-                    for (int t = 0; t < MK_T; ++t) { b[t] = __ballot_sync(0xffffffffu, pass[t]); any |= b[t]; }
-                    if (any) {
-                        const unsigned int e0 = ((unsigned int)rl << 24) | (unsigned int)(base + j0 + lane);
-                        int off = qn;
-#pragma unroll
-                        for (int t = 0; t < MK_T; ++t) {
-                            if (pass[t]) S.queue[warp][off + __popc(b[t] & lt_mask)] = e0 + 32u * t;
-                            off += __popc(b[t]);
-                        }
-                        qn = off;
+        for (int i = 0; i < MK_STAGES && i * MK_TT < cnt; ++i) mbar_wait(&S.bars[i], (unsigned int)(pass & 1));
+        // resident part of the sorted narrow arcs [0, nn) and of the always-candidates behind them [nn, cnt)
+        const int nn = max(0, min(n_narrow - base, cnt));
+        for (int r = 0; r < my_rows; ++r) {
+            const int rl = warp * MK_RPW + r;
+            const uint2 kr = S.rowK[rl];
+            const bool rall = S.rowall[rl] != 0;
+            // short arc [ka, kb] between the two kappa values; a narrow target can only match if its arc starts in [ka - wmax, kb]
+            const bool fwd = (kr.y - kr.x) < 0x80000000u;
+            const unsigned int ka = fwd ? kr.x : kr.y, kb = fwd ? kr.y : kr.x, ws = ka - wmax;
+            int i0 = 0, i1 = nn;
+            if (nn > 0 && !rall) {
+                i0 = arc_lower_bound(ent, nn, ws, lane);
+                i1 = kb == 0xFFFFFFFFu ? nn : arc_lower_bound(ent, nn, kb + 1u, lane);
+            }
+            // up to three index ranges: the window (two pieces when it wraps around 2^32) and the always-candidates
+            const bool wrap = ws > kb && !rall;
+            for (int piece = 0; piece < 3; ++piece) {
+                int lo, hi;
+                if (piece == 0) { lo = wrap ? 0 : i0; hi = i1; }
+                else if (piece == 1) { lo = wrap ? i0 : 0; hi = wrap ? nn : 0; }
+                else { lo = nn; hi = cnt; }
+                for (int j0 = lo; j0 < hi; j0 += 32) {
+                    const int idx = j0 + lane;
+                    bool pass1 = false;
+                    unsigned int tj = 0u;
+                    if (idx < hi) { const uint4 e = ent[idx]; pass1 = arc_may_match(e, kr.x, kr.y) || rall; tj = e.w; }
+                    const unsigned int b = __ballot_sync(0xffffffffu, pass1);
+                    if (b) {
+                        if (pass1) S.queue[warp][qn + __popc(b & lt_mask)] = ((unsigned int)rl << 24) | tj;
+                        qn += __popc(b);
                         __syncwarp();
-                        while (qn >= 32) {
-                            qn -= 32;
-                            filter_batch<MODE, KEEP>(S, S.queue[warp][qn + lane], true, warp, lane, lt_mask, qn2);
+                        if (qn >= 64) {
+                            qn -= 64;
+                            filter_batch<MODE, KEEP>(S, S.queue[warp][qn + lane], true, S.queue[warp][qn + 32 + lane], true, warp, lane, lt_mask, qn2);
                         }
                     }
                 }
             }
         }
-        if (c + MK_STAGES < nchunks) {              // this stage buffer will be refilled: everybody must be done with it
-            __syncthreads();
-            if (tid == 0) {
-                const int base1 = (c + MK_STAGES) * MK_TT;
-                const unsigned int bytes = (unsigned int)min(MK_TT, Nt - base1) * 16u;
-                mbar_expect_tx(&S.bars[sg], bytes);
-                tma_load_1d(S.stage[sg], tarcs + base1, bytes, &S.bars[sg]);
-            }
-        }
     }
     if (qn > 0) {
-        const bool has = lane < qn;
-        filter_batch<MODE, KEEP>(S, has ? S.queue[warp][lane] : 0u, has, warp, lane, lt_mask, qn2);
+        const bool h0 = lane < qn, h1 = lane + 32 < qn;
+        filter_batch<MODE, KEEP>(S, h0 ? S.queue[warp][lane] : 0u, h0, h1 ? S.queue[warp][lane + 32] : 0u, h1, warp, lane, lt_mask, qn2);
     }
     __syncwarp();
     if (qn2 > 0) {

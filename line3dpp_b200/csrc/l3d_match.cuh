@@ -59,9 +59,13 @@ __global__ void k_match_all(const float4* __restrict__ segs, const float4* __res
                             const int2* __restrict__ tiles, int stride, float epi, int* __restrict__ counts_out,
                             l3d_match_rec* __restrict__ recs_out, const double* __restrict__ cache_d, const uint4* __restrict__ arcs,
                             const L3DPairBasis* __restrict__ basis);
-// level-1 pre-filter tables: one CTA per view pair of [first_pair, first_pair + gridDim.x)
+// level-1 pre-filter tables: one CTA per view pair of [first_pair, first_pair + gridDim.x): raw arcs + sort keys; after the sort
+// k_arcs_gather writes the packed entries in window order
 __global__ void k_pair_arcs(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs,
-                            int first_pair, int enabled, uint4* __restrict__ arcs, L3DPairBasis* __restrict__ basis);
+                            int first_pair, int enabled, double ext, uint4* __restrict__ raw, unsigned long long* __restrict__ keys,
+                            unsigned int* __restrict__ vals, L3DPairBasis* __restrict__ basis);
+__global__ void k_arcs_gather(long long n, const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals,
+                              const uint4* __restrict__ raw, const L3DPairDev* __restrict__ pairs, int first_pair, uint4* __restrict__ out);
 __global__ void k_sort_rows(int* __restrict__ counts, l3d_match_rec* __restrict__ recs, int stride, long long rows, int topk);
 __global__ void k_prep_segments_f64(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, int num_views,
                                     long long total, double* __restrict__ cache);

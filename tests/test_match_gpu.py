@@ -374,10 +374,10 @@ def _two_view_scene(kind, n, seed):
 
 
 @pytest.mark.parametrize("kind", ["sideways", "forward", "edge", "rolled"])
-def test_level1_prefilter_never_drops(gpu_ctx, oracle, kind):
+def test_level1_prefilter_never_drops(gpu_ctx, oracle, ref_nofma, kind):
     """the pencil-parameter pre-filter (k_pair_arcs, l3d_device.cuh) with the epipole at infinity, inside the image, near its border
-    and with a rolled camera: same matches as the exhaustive CPU oracle, both directions; horizontal / vertical / tiny segments and
-    segments through the epipole added on purpose"""
+    and with a rolled camera: same matches as the unmodified reference kernel + host kNN pass (which evaluate every cell), both
+    directions; horizontal / vertical / tiny segments and segments through the epipole added on purpose"""
     sc = _two_view_scene(kind, 1500, 31)
     rng = np.random.default_rng(5)
     for v in range(2):
@@ -398,10 +398,10 @@ def test_level1_prefilter_never_drops(gpu_ctx, oracle, kind):
         tot = 0
         for p, (s, t) in enumerate(pairs):
             pi = util.pair_inputs(sc, s, t)
-            oc, oo, _, _ = oracle.match_lines(oracle.lib().orc_match_lines_f32, pi["ls"], pi["lt"], pi["F"], pi["Rs"], pi["Rt"], pi["Cs"], pi["Ct"], s, t, epi, knn)
+            oc, oo, _, _ = oracle.match_lines(ref_nofma.ref_match_lines, pi["ls"], pi["lt"], pi["F"], pi["Rs"], pi["Rt"], pi["Cs"], pi["Ct"], s, t, epi, knn)
             counts, recs = gpu_ctx.pair_matches(p, len(pi["ls"]))
-            assert np.array_equal(counts, oc), (kind, s, t, epi)
-            f = ("tgt_seg", "overlap")
+            assert np.array_equal(counts, oc), (kind, s, t, epi, np.flatnonzero(counts != oc)[:10])
+            f = ("tgt_seg", "overlap", "d_p1", "d_p2", "d_q1", "d_q2")
             ours, theirs = util.rows_as_sets(counts, recs, f), util.rows_as_sets(oc, oo, f)
             for row, (a, b) in enumerate(zip(ours, theirs)):
                 if a != b:      # only an exact tie in the k-th place may differ (the reference pops an unordered heap)
