@@ -1,0 +1,44 @@
+"""The level-1 pre-filter of k_match_topk never rejects a match of the exhaustive CPU oracle: checked on the numpy restatement of its
+arithmetic (tests/level1_model.py) for the epipole at infinity, inside the image, near its border and with a rolled camera.  The GPU
+suite (test_match_gpu.py::test_level1_prefilter_never_drops) runs the same geometries through the real kernels."""
+import numpy as np
+import pytest
+
+from tests import level1_model as m
+from tests import util
+
+
+@pytest.mark.parametrize("kind", ["sideways", "forward", "edge", "rolled"])
+@pytest.mark.parametrize("epi", [0.25, 0.05])
+def test_arc_model_keeps_every_oracle_match(oracle, kind, epi):
+    sc = util.two_view_scene(kind, 400, 31)
+    checked = narrow_checked = 0
+    for s, t in ((0, 1), (1, 0)):
+        pi = util.pair_inputs(sc, s, t)
+        oc, oo, _, _ = oracle.match_lines(oracle.lib().orc_match_lines_f32, pi["ls"], pi["lt"], pi["F"], pi["Rs"], pi["Rt"], pi["Cs"], pi["Ct"], s, t, epi, 10)
+        u, v, _ = m.basis(pi["F"])
+        arcs = [m.target_arc(u, v, q, 1.0 / epi + 0.5) for q in pi["lt"]]
+        wmax = 1 << m.window_bits(arcs)
+        for r in range(len(oc)):
+            p = pi["ls"][r]
+            k1, off1 = m.line_kappa(u, v, m.epipolar_line(pi["F"], p[0], p[1]))
+            k2, off2 = m.line_kappa(u, v, m.epipolar_line(pi["F"], p[2], p[3]))
+            for i in range(oc[r]):
+                a = arcs[int(oo[r, i]["tgt_seg"])]
+                checked += 1
+                if a is None or off1 or off2:
+                    continue                      # always a candidate
+                assert m.arc_may_match(a, k1, k2), (kind, s, t, r, int(oo[r, i]["tgt_seg"]))
+                if a[1] <= wmax:
+                    assert m.in_window(a[0], k1, k2, wmax), (kind, s, t, r, int(oo[r, i]["tgt_seg"]))
+                    narrow_checked += 1
+        if kind == "sideways" and epi == 0.25:    # ... and it is a filter: most cells of a row are rejected
+            passed = total = 0
+            for r in range(0, len(oc), 20):
+                p = pi["ls"][r]
+                k1, _ = m.line_kappa(u, v, m.epipolar_line(pi["F"], p[0], p[1]))
+                k2, _ = m.line_kappa(u, v, m.epipolar_line(pi["F"], p[2], p[3]))
+                passed += sum(1 for a in arcs if a is None or m.arc_may_match(a, k1, k2))
+                total += len(arcs)
+            assert passed < 0.3 * total
+    assert checked > 1000 and (narrow_checked > 500 or kind == "forward")

@@ -344,41 +344,12 @@ def test_dense_batch_equals_single_launches(loaded, scene):
         assert np.array_equal(util.bits(ovs[i].cpu().numpy()), util.bits(o1.reshape(-1)))
 
 
-def _two_view_scene(kind, n, seed):
-    """two views of the same random 3D lines with an epipolar geometry the ring scenes do not have"""
-    import dataclasses
-    base = synth.make_scene(2, n, seed, "dense")
-    rng = np.random.default_rng(seed)
-    K = base.K[0]
-    I = np.eye(3)
-    rz = lambda a: np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
-    ry = lambda a: np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
-    cams = {"sideways": [(I, (-0.3, 0.0, -4.0)), (I, (0.3, 0.0, -4.0))],            # epipole at infinity (E.z == 0), horizontal epipolar lines
-            "forward": [(I, (0.0, 0.0, -4.6)), (I, (0.04, -0.03, -3.7))],            # epipole inside the image
-            "edge": [(I, (0.0, 0.0, -4.2)), (ry(0.05), (0.9, 0.1, -3.6))],           # epipole a little outside the image border
-            "rolled": [(I, (-0.4, 0.1, -4.0)), (rz(1.45) @ ry(-0.08), (0.5, -0.2, -4.1))]}[kind]
-    P1, P2 = base.lines3d[:, :3], base.lines3d[:, 3:]
-    Rs, ts, segs = [], [], []
-    for R, C in cams:
-        C = np.array(C)
-        t = -R @ C
-        X1, X2 = (R @ P1.T).T + t, (R @ P2.T).T + t
-        u1 = X1[:, :2] / X1[:, 2:3] * synth.FOCAL + K[:2, 2] + rng.normal(scale=0.5, size=(len(P1), 2))
-        u2 = X2[:, :2] / X2[:, 2:3] * synth.FOCAL + K[:2, 2] + rng.normal(scale=0.5, size=(len(P1), 2))
-        ok = (X1[:, 2] > 0.1) & (X2[:, 2] > 0.1) & (np.linalg.norm(u1 - u2, axis=1) >= synth.MIN_LEN_PX)
-        for u in (u1, u2):
-            ok &= (u[:, 0] >= 0) & (u[:, 0] <= synth.WIDTH - 1) & (u[:, 1] >= 0) & (u[:, 1] <= synth.HEIGHT - 1)
-        segs.append(np.ascontiguousarray(np.concatenate([u1, u2], axis=1)[ok][:n].astype(np.float32)))
-        Rs.append(R); ts.append(t)
-    return dataclasses.replace(base, R=np.array(Rs), t=np.array(ts), segs=segs)
-
-
 @pytest.mark.parametrize("kind", ["sideways", "forward", "edge", "rolled"])
 def test_level1_prefilter_never_drops(gpu_ctx, oracle, ref_nofma, kind):
     """the pencil-parameter pre-filter (k_pair_arcs, l3d_device.cuh) with the epipole at infinity, inside the image, near its border
     and with a rolled camera: same matches as the unmodified reference kernel + host kNN pass (which evaluate every cell), both
     directions; horizontal / vertical / tiny segments and segments through the epipole added on purpose"""
-    sc = _two_view_scene(kind, 1500, 31)
+    sc = util.two_view_scene(kind, 1500, 31)
     rng = np.random.default_rng(5)
     for v in range(2):
         s = sc.segs[v]

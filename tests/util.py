@@ -45,3 +45,32 @@ def rows_as_sets(counts, recs, fields=("tgt_seg", "overlap", "d_p1", "d_p2", "d_
             row.append(tuple(int(np.float32(e[f]).view(np.uint32)) if recs.dtype[f].kind == "f" else int(e[f]) for f in fields))
         out.append(sorted(row))
     return out
+
+
+def two_view_scene(kind, n, seed):
+    """two views of the same random 3D lines with an epipolar geometry the ring scenes do not have"""
+    import dataclasses
+    base = synth.make_scene(2, n, seed, "dense")
+    rng = np.random.default_rng(seed)
+    K = base.K[0]
+    I = np.eye(3)
+    rz = lambda a: np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    ry = lambda a: np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    cams = {"sideways": [(I, (-0.3, 0.0, -4.0)), (I, (0.3, 0.0, -4.0))],            # epipole at infinity (E.z == 0), horizontal epipolar lines
+            "forward": [(I, (0.0, 0.0, -4.6)), (I, (0.04, -0.03, -3.7))],            # epipole inside the image
+            "edge": [(I, (0.0, 0.0, -4.2)), (ry(0.05), (0.9, 0.1, -3.6))],           # epipole a little outside the image border
+            "rolled": [(I, (-0.4, 0.1, -4.0)), (rz(1.45) @ ry(-0.08), (0.5, -0.2, -4.1))]}[kind]
+    P1, P2 = base.lines3d[:, :3], base.lines3d[:, 3:]
+    Rs, ts, segs = [], [], []
+    for R, C in cams:
+        C = np.array(C)
+        t = -R @ C
+        X1, X2 = (R @ P1.T).T + t, (R @ P2.T).T + t
+        u1 = X1[:, :2] / X1[:, 2:3] * synth.FOCAL + K[:2, 2] + rng.normal(scale=0.5, size=(len(P1), 2))
+        u2 = X2[:, :2] / X2[:, 2:3] * synth.FOCAL + K[:2, 2] + rng.normal(scale=0.5, size=(len(P1), 2))
+        ok = (X1[:, 2] > 0.1) & (X2[:, 2] > 0.1) & (np.linalg.norm(u1 - u2, axis=1) >= synth.MIN_LEN_PX)
+        for u in (u1, u2):
+            ok &= (u[:, 0] >= 0) & (u[:, 0] <= synth.WIDTH - 1) & (u[:, 1] >= 0) & (u[:, 1] <= synth.HEIGHT - 1)
+        segs.append(np.ascontiguousarray(np.concatenate([u1, u2], axis=1)[ok][:n].astype(np.float32)))
+        Rs.append(R); ts.append(t)
+    return dataclasses.replace(base, R=np.array(Rs), t=np.array(ts), segs=segs)
