@@ -368,6 +368,10 @@ def run_ours(args):
                          "peak_source": "FFMA probe kernel run live in this process (MEASURED_PEAKS.json has no FP32 non-tensor figure)",
                          "algorithmic_flop_per_pair_eval": FLOP_PER_PAIR_EVAL,
                          "hbm_frac": (pe_all / world * 0.1 / (ms_step * 1e-3) / 1e9) / peaks["hbm_gbs"],
+                         "accounting": "achieved = pair evaluations x 100 flop (SURVEY 8d: what a kernel that evaluates every cell spends) / step time; "
+                                       "since round 2 k_match_topk only visits the cells inside a row's arc windows (~11 % of them), so the figure is "
+                                       "throughput in brute-force-equivalent flops, not executed flops - `executed` is what the SMs issued",
+                         "executed": committed_capture("k_match_topk"),
                          "traffic": committed_traffic("k_match_topk"),
                          "traffic_note": "DRAM read+write bytes per launch from the committed ncu --set full capture of this command (profiles/traffic.json); "
                                          "algorithmic output is 24 B per emitted match + 4 B per (pair,row) count"},
@@ -391,6 +395,15 @@ def run_ours(args):
     ctx.close()
     sys.stdout.flush()
     return 0
+
+
+def committed_capture(kernel: str):
+    """warp instructions / issue utilisation per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        return {k: d[k] for k in ("warp_instructions", "issue_active_pct", "capture") if k in d}
+    except Exception:   # noqa
+        return None
 
 
 def committed_traffic(kernel: str):

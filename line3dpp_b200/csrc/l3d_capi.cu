@@ -259,8 +259,8 @@ static int match_impl(l3d_ctx* c, int num_pairs, const int32_t* pairs, const flo
         if (narcs >= (1ll << 31) - 2) return l3d_fail(c, L3D_ERR_UNSUPPORTED, "l3d_match_pairs: more than 2^31 (pair, target segment) combinations in one call");
         const int npr = last_pair - first_pair;
         const bool on = epi_overlap >= 0.01f && getenv("L3D_NO_LEVEL1") == nullptr;
-        int end_bit = 33;
-        while (end_bit < 64 && (1ll << (end_bit - 33)) < npr) ++end_bit;
+        int end_bit = 36;                       // key = pair << 36 | class << 32 | start of the arc
+        while (end_bit < 64 && (1ll << (end_bit - 36)) < npr) ++end_bit;
         size_t tb = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const unsigned int*)nullptr, (unsigned int*)nullptr, (int)narcs, 0, end_bit, c->stream);
         if ((rc = l3d_reserve(c, c->d_arcraw, 16 * (size_t)narcs, "raw arcs")) || (rc = l3d_reserve(c, c->d_arckeys, 8 * (size_t)narcs, "arc keys")) ||

@@ -48,10 +48,20 @@ struct L3DPairDev {
 //     or both above T),
 //   * below epi_overlap when either projection is farther than X segment lengths away (outer > X, inner <= 1): a kappa outside T_ext.
 // A row can therefore only match targets with both kappa inside T_ext and not on the same side of T - which implies that T meets the
-// short arc between the two kappa values: with the targets of a view pair sorted by the start of T, a row's candidates are a WINDOW of
-// that order (k_match_topk).  Angles are stored in units of pi / 2^32: unsigned subtraction wraps mod pi for free.
+// short arc [ka, kb] between the two kappa values, i.e. that T starts in [ka - |T|, kb].  The targets of a view pair are therefore grouped
+// into L3D_ARC_NCLS classes by the length of T (class c: |T| <= 2^(L3D_ARC_CLS0 + c)) and sorted by the start of T inside a class: a
+// row's candidates are one WINDOW [ka - 2^(L3D_ARC_CLS0 + c), kb] per class (k_match_topk); targets without a usable arc form a last
+// class that every row looks at.  Angles are stored in units of pi / 2^32: unsigned subtraction wraps mod pi for free.
 #define L3D_ARC_SCALE 2048.0
-struct L3DPairBasis { double u[3], v[3]; int n_narrow; unsigned int wmax; };    // + the pair's window data (k_pair_arcs)
+#define L3D_ARC_NCLS 8
+#define L3D_ARC_CLS0 21
+struct L3DPairBasis { double u[3], v[3]; int cls_off[L3D_ARC_NCLS + 2]; };    // + first sorted entry of every class of the pair, and the end
+__device__ __forceinline__ int arc_class(unsigned int len)      // L3D_ARC_NCLS = no usable arc / longer than the last class
+{
+    if (len == 0xFFFFFFFFu) return L3D_ARC_NCLS;
+    const int b = len <= 1u ? 0 : 32 - __clz(len - 1u);          // ceil(log2(len))
+    return b <= L3D_ARC_CLS0 ? 0 : min(b - L3D_ARC_CLS0, L3D_ARC_NCLS);
+}
 #define L3D_ARC_WIDE 0x80000000u      /* entry.z flag: no usable arc (epipole too close, degenerate segment, arc too long): always a candidate */
 // sorted entry: x = start A of T (absolute), y = e1 | w << 16, z = ehi | flag, w = target index; e1 / w / ehi = length of T_ext below T,
 // of T, of T_ext above T in units of 2^16 (rounded up).  Both kappa inside T_ext, not both below T, not both above T.

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) k_prep_segments_f64(const float4* __restr
 struct MatchSmem {
     uint4 stage[MK_STAGES][MK_TT];                   // TMA-staged target arcs in window order (arc_may_match, l3d_device.cuh)
     uint2 rowK[MK_ROWS];                             // pencil parameters of the row's two epipolar lines (l3d_device.cuh)
+    int cls_off[L3D_ARC_NCLS + 2];                   // first sorted entry of every arc class of this view pair, and the end (k_pair_arcs)
     unsigned char rowall[MK_ROWS];                   // 1: an epipolar line of this row is not a pencil member to within the margins (source point at the epipole): no level 1
     unsigned long long lists[MK_ROWS][MK_CAP + 1];   // per-row survivor keys (+1: rows start on different banks, lanes that push keys of different rows do not collide)
     float4 rowA[MK_ROWS];                            // (e1.x, e1.y, e1.z, e2.x)
@@ -312,50 +313,36 @@ __device__ uint4 target_arc(const L3DPairBasis& B, float4 q, double ext, bool en
     return make_uint4(kc + (unsigned int)lo, (unsigned int)(hi - lo), (unsigned int)(lo - lox), (unsigned int)(hix - hi));
 }
 
-// one CTA per view pair: basis, raw arcs, the window width of the pair (so that at most ~3 % of the targets are wider) and the sort keys
+// one CTA per view pair: basis, raw arcs, class sizes and the sort keys (pair, class, start of T)
 __global__ void __launch_bounds__(256)
 k_pair_arcs(const float4* __restrict__ segs, const L3DViewDev* __restrict__ views, const L3DPairDev* __restrict__ pairs, int first_pair,
             int enabled, double ext, uint4* __restrict__ raw, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals,
             L3DPairBasis* __restrict__ basis)
 {
     __shared__ L3DPairBasis B;
-    __shared__ int hist[33];
-    __shared__ int narrow;
+    __shared__ int cnt[L3D_ARC_NCLS + 1];
     const L3DPairDev* P = pairs + first_pair + blockIdx.x;
-    if (threadIdx.x == 0) { pair_basis(P->F, &B); narrow = 0; }
-    if (threadIdx.x < 33) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) pair_basis(P->F, &B);
+    if (threadIdx.x <= L3D_ARC_NCLS) cnt[threadIdx.x] = 0;
     __syncthreads();
     const L3DViewDev* vt = views + P->tgt;
     const float4* t = segs + vt->seg_off;
     const int Nt = vt->nseg;
-    uint4* out = raw + P->arc_off;
     for (int j = threadIdx.x; j < Nt; j += 256) {
         const uint4 r = target_arc(B, t[j], ext, enabled != 0);
-        out[j] = r;
-        if (r.y != 0xFFFFFFFFu) atomicAdd(&hist[r.y <= 65536u ? 16 : 32 - __clz(r.y - 1u)], 1);      // ceil(log2(length of T))
+        const int c = arc_class(r.y);
+        raw[P->arc_off + j] = r;
+        keys[P->arc_off + j] = ((unsigned long long)blockIdx.x << 36) | ((unsigned long long)c << 32) | (c == L3D_ARC_NCLS ? (unsigned long long)j : (unsigned long long)r.x);
+        vals[P->arc_off + j] = (unsigned int)(P->arc_off + j);
+        atomicAdd(&cnt[c], 1);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int total = 0;
-        for (int b = 16; b <= 32; ++b) total += hist[b];
-        const int allowed = max(8, (3 * Nt) / 100);
-        int b = 16, cum = hist[16];
-        while (b < 28 && total - cum > allowed) cum += hist[++b];
-        B.wmax = 1u << b;
+        int off = 0;
+        for (int c = 0; c <= L3D_ARC_NCLS; ++c) { B.cls_off[c] = off; off += cnt[c]; }
+        B.cls_off[L3D_ARC_NCLS + 1] = off;
+        basis[first_pair + blockIdx.x] = B;
     }
-    __syncthreads();
-    const unsigned int wmax = B.wmax;
-    int mine = 0;
-    for (int j = threadIdx.x; j < Nt; j += 256) {
-        const uint4 r = out[j];
-        const bool wide = r.y == 0xFFFFFFFFu || r.y > wmax;
-        keys[P->arc_off + j] = ((unsigned long long)blockIdx.x << 33) | (wide ? (1ull << 32) | (unsigned long long)j : (unsigned long long)r.x);
-        vals[P->arc_off + j] = (unsigned int)(P->arc_off + j);
-        mine += wide ? 0 : 1;
-    }
-    if (mine) atomicAdd(&narrow, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) { B.n_narrow = narrow; basis[first_pair + blockIdx.x] = B; }
 }
 
 // packed entries in sorted order (arc_may_match, l3d_device.cuh)
@@ -368,8 +355,8 @@ k_arcs_gather(long long n, const unsigned long long* __restrict__ keys, const un
     const unsigned long long k = keys[i];
     const unsigned int src = vals[i];
     const uint4 r = raw[src];
-    const bool wide = (k >> 32) & 1ull;
-    const unsigned int j = src - (unsigned int)pairs[first_pair + (int)(k >> 33)].arc_off;
+    const bool wide = ((k >> 32) & 0xFull) == (unsigned long long)L3D_ARC_NCLS;
+    const unsigned int j = src - (unsigned int)pairs[first_pair + (int)(k >> 36)].arc_off;
     const unsigned int w16 = (r.y + 65535u) >> 16, e1 = (r.z + 65535u) >> 16, eh = (r.w + 65535u) >> 16;
     out[i] = wide ? make_uint4(0u, 0u, L3D_ARC_WIDE, j) : make_uint4(r.x, e1 | (w16 << 16), eh, j);
 }
@@ -397,22 +384,6 @@ __device__ __forceinline__ void filter_batch(MatchSmem& S, unsigned int e0, bool
     }
 }
 
-// first index in [0, n) of the sorted keys whose start is >= key (n if none): 32-ary search, one probe per lane and round
-__device__ __forceinline__ int arc_lower_bound(const uint4* __restrict__ ent, int n, unsigned int key, int lane)
-{
-    int lo = 0, hi = n;
-    while (hi > lo) {
-        const int step = (hi - lo + 31) >> 5, idx = lo + lane * step;
-        const bool below = idx < hi && ent[idx].x < key;
-        const int c = __popc(__ballot_sync(0xffffffffu, below));       // probes 0..c-1 are below the key (sorted: a prefix of the lanes)
-        if (c == 0) { hi = lo; break; }
-        const int nlo = lo + (c - 1) * step + 1;
-        hi = min(hi, lo + c * step);
-        lo = nlo;
-    }
-    return lo;
-}
-
 template <int MODE, int KEEP>
 __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs, const float4* __restrict__ cache, const L3DViewDev* __restrict__ views,
              const L3DPairDev* __restrict__ pairs, const int2* __restrict__ tiles, int knn, float epi,
@@ -434,9 +405,6 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
     const uint4* tarcs = arcs + P->arc_off;
     const int RES = MK_STAGES * MK_TT;                     // entries resident at a time; larger target views take several passes
     const int npass = (Nt + RES - 1) / RES;
-    const int n_narrow = basis[tile.x].n_narrow;
-    const unsigned int wmax = basis[tile.x].wmax;
-
     if (tid == 0) {
         S.tsegs = tsegs; S.cache = cache; S.src_base = soff + row0; S.toff = toff; S.epi = epi; S.knn = knn; S.Nt = Nt; S.cap = MK_CAP;
         S.Cs = make_float3(vs->C[0], vs->C[1], vs->C[2]); S.Ct = make_float3(vt->C[0], vt->C[1], vt->C[2]);
@@ -453,6 +421,7 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
             tma_load_1d(S.stage[i], tarcs + (size_t)i * MK_TT, bytes, &S.bars[i]);
         }
     }
+    if (tid >= MK_THREADS - (L3D_ARC_NCLS + 2)) S.cls_off[MK_THREADS - 1 - tid] = basis[tile.x].cls_off[MK_THREADS - 1 - tid];
     if (tid < MK_ROWS) {
         S.list_cnt[tid] = 0;
         S.row_thr[tid] = 0.0f;
@@ -487,27 +456,47 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
                 }
         }
         for (int i = 0; i < MK_STAGES && i * MK_TT < cnt; ++i) mbar_wait(&S.bars[i], (unsigned int)(pass & 1));
-        // resident part of the sorted narrow arcs [0, nn) and of the always-candidates behind them [nn, cnt)
-        const int nn = max(0, min(n_narrow - base, cnt));
         for (int r = 0; r < my_rows; ++r) {
             const int rl = warp * MK_RPW + r;
             const uint2 kr = S.rowK[rl];
             const bool rall = S.rowall[rl] != 0;
-            // short arc [ka, kb] between the two kappa values; a narrow target can only match if its arc starts in [ka - wmax, kb]
+            // short arc [ka, kb] between the two kappa values: a target of class c can only match if its arc starts in [ka - 2^(CLS0 + c), kb]
             const bool fwd = (kr.y - kr.x) < 0x80000000u;
-            const unsigned int ka = fwd ? kr.x : kr.y, kb = fwd ? kr.y : kr.x, ws = ka - wmax;
-            int i0 = 0, i1 = nn;
-            if (nn > 0 && !rall) {
-                i0 = arc_lower_bound(ent, nn, ws, lane);
-                i1 = kb == 0xFFFFFFFFu ? nn : arc_lower_bound(ent, nn, kb + 1u, lane);
+            const unsigned int ka = fwd ? kr.x : kr.y, kb = fwd ? kr.y : kr.x;
+            // lanes 0 .. 2 * NCLS - 1: lower / upper end of the window of class lane >> 1 inside the resident part of that class (binary search)
+            int res = 0;
+            {
+                const int c = min(lane >> 1, L3D_ARC_NCLS - 1);
+                int lo = min(max(S.cls_off[c] - base, 0), cnt), hi = min(max(S.cls_off[c + 1] - base, 0), cnt);
+                const bool upper = lane & 1;
+                const unsigned int key = upper ? kb + 1u : ka - (1u << (L3D_ARC_CLS0 + c));
+                if (lane >= 2 * L3D_ARC_NCLS || rall) hi = lo;                       // no search
+                else if (upper && kb == 0xFFFFFFFFu) lo = hi;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (ent[mid].x < key) lo = mid + 1; else hi = mid;
+                }
+                res = lo;
             }
-            // up to three index ranges: the window (two pieces when it wraps around 2^32) and the always-candidates
-            const bool wrap = ws > kb && !rall;
-            for (int piece = 0; piece < 3; ++piece) {
-                int lo, hi;
-                if (piece == 0) { lo = wrap ? 0 : i0; hi = i1; }
-                else if (piece == 1) { lo = wrap ? i0 : 0; hi = wrap ? nn : 0; }
-                else { lo = nn; hi = cnt; }
+            // lane p < 2 * NCLS: piece p & 1 of the window of class p >> 1 (two pieces when the window wraps around 2^32); lane 2 * NCLS: the
+            // targets every row looks at.  A row outside the pencil model (rall) takes everything as one piece.
+            int plo = 0, phi = 0;
+            {
+                const int c = min(lane >> 1, L3D_ARC_NCLS - 1);
+                const int i0 = __shfl_sync(0xffffffffu, res, 2 * c), i1 = __shfl_sync(0xffffffffu, res, 2 * c + 1);
+                const int s_c = min(max(S.cls_off[c] - base, 0), cnt), e_c = min(max(S.cls_off[c + 1] - base, 0), cnt);
+                const bool wrap = ka - (1u << (L3D_ARC_CLS0 + c)) > kb;
+                if (lane < 2 * L3D_ARC_NCLS) {
+                    if (!(lane & 1)) { plo = wrap ? s_c : i0; phi = i1; }
+                    else if (wrap) { plo = i0; phi = e_c; }
+                } else if (lane == 2 * L3D_ARC_NCLS) { plo = min(max(S.cls_off[L3D_ARC_NCLS] - base, 0), cnt); phi = cnt; }
+                if (rall) { plo = 0; phi = lane == 0 ? cnt : 0; }
+            }
+            unsigned int pieces = __ballot_sync(0xffffffffu, phi > plo);
+            while (pieces) {
+                const int p = __ffs(pieces) - 1;
+                pieces &= pieces - 1u;
+                const int lo = __shfl_sync(0xffffffffu, plo, p), hi = __shfl_sync(0xffffffffu, phi, p);
                 for (int j0 = lo; j0 < hi; j0 += 32) {
                     const int idx = j0 + lane;
                     bool pass1 = false;

@@ -101,16 +101,13 @@ def arc_may_match(arc, k1, k2):
     return max(d1, d2) <= E3 and max(d1, d2) >= E1 and min(d1, d2) <= E2
 
 
-def window_bits(arcs):
-    """k_pair_arcs: the pair's window width = smallest 2^b (16 <= b <= 28) that at most 3 % of the targets exceed"""
-    hist = np.zeros(33, int)
-    for a in arcs:
-        if a is not None:
-            hist[16 if a[1] <= 65536 else (a[1] - 1).bit_length()] += 1
-    total, allowed, b, cum = hist[16:].sum(), max(8, 3 * len(arcs) // 100), 16, hist[16]
-    while b < 28 and total - cum > allowed:
-        b += 1; cum += hist[b]
-    return b
+NCLS, CLS0 = 8, 21
+
+
+def arc_class(w):
+    """class of a target by the length of its arc (l3d_device.cuh arc_class); NCLS = every row looks at it"""
+    b = 0 if w <= 1 else (w - 1).bit_length()
+    return 0 if b <= CLS0 else min(b - CLS0, NCLS)
 
 
 def in_window(A, k1, k2, wmax):

@@ -18,7 +18,6 @@ def test_arc_model_keeps_every_oracle_match(oracle, kind, epi):
         oc, oo, _, _ = oracle.match_lines(oracle.lib().orc_match_lines_f32, pi["ls"], pi["lt"], pi["F"], pi["Rs"], pi["Rt"], pi["Cs"], pi["Ct"], s, t, epi, 10)
         u, v, _ = m.basis(pi["F"])
         arcs = [m.target_arc(u, v, q, 1.0 / epi + 0.5) for q in pi["lt"]]
-        wmax = 1 << m.window_bits(arcs)
         for r in range(len(oc)):
             p = pi["ls"][r]
             k1, off1 = m.line_kappa(u, v, m.epipolar_line(pi["F"], p[0], p[1]))
@@ -29,8 +28,9 @@ def test_arc_model_keeps_every_oracle_match(oracle, kind, epi):
                 if a is None or off1 or off2:
                     continue                      # always a candidate
                 assert m.arc_may_match(a, k1, k2), (kind, s, t, r, int(oo[r, i]["tgt_seg"]))
-                if a[1] <= wmax:
-                    assert m.in_window(a[0], k1, k2, wmax), (kind, s, t, r, int(oo[r, i]["tgt_seg"]))
+                c = m.arc_class(a[1])
+                if c < m.NCLS:
+                    assert m.in_window(a[0], k1, k2, 1 << (m.CLS0 + c)), (kind, s, t, r, int(oo[r, i]["tgt_seg"]))
                     narrow_checked += 1
         if kind == "sideways" and epi == 0.25:    # ... and it is a filter: most cells of a row are rejected
             passed = total = 0
