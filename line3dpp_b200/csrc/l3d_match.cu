@@ -67,7 +67,7 @@ struct MatchSmem {
     float4 rowB[MK_ROWS];                            // (e2.y, e2.z, g, 0.95 * score-to-beat)
     float row_thr[MK_ROWS];                          // overlap of the current k-th best survivor (0 until k are known)
     int list_cnt[MK_ROWS];
-    unsigned int queue[MK_WARPS][96];                // level-1 survivors per warp: (row_local << 24) | tgt, filtered 64 at a time
+    unsigned int queue[MK_WARPS][128];               // level-1 survivors per warp: (row_local << 24) | tgt, filtered 64 at a time (up to 64 pushed per step)
     unsigned int queue2[MK_WARPS][96];               // level-2 survivors (filter_may_survive), evaluated exactly 32 at a time
     unsigned long long bars[MK_STAGES];
     // per-CTA constants of the (rarely executed, deliberately out-of-line) exact path
@@ -99,7 +99,20 @@ __device__ __noinline__ void prune_row(MatchSmem& S, int row, int lane)
     __syncwarp();
     const int n = min(S.list_cnt[row], S.cap);
     const unsigned long long k = lane < n ? S.lists[row][lane] : 0ull;
-    const int r = rank_in_row(S.lists[row], n, k);
+    int r;
+    if (knn <= 16) {          // k rounds of warp maximum (keys are unique and > 0) instead of ranking all n keys against each other
+        bool active = lane < n;
+        const unsigned int hi = (unsigned int)(k >> 32), lo = (unsigned int)k;
+        r = 64;
+        const int rounds = min(knn, n);
+        for (int i = 0; i < rounds; ++i) {
+            const unsigned int m = __reduce_max_sync(0xffffffffu, active ? hi : 0u);
+            bool c = active && hi == m;
+            unsigned int bm = __ballot_sync(0xffffffffu, c);
+            if (__popc(bm) > 1) { const unsigned int l = __reduce_max_sync(0xffffffffu, c ? lo : 0u); c = c && lo == l; }
+            if (c) { r = i; active = false; }
+        }
+    } else r = rank_in_row(S.lists[row], n, k);
     __syncwarp();
     if (lane < n && r < knn) S.lists[row][r] = k;
     __syncwarp();
@@ -497,15 +510,18 @@ __device__ __forceinline__ void match_topk_body(const float4* __restrict__ segs,
                 const int p = __ffs(pieces) - 1;
                 pieces &= pieces - 1u;
                 const int lo = __shfl_sync(0xffffffffu, plo, p), hi = __shfl_sync(0xffffffffu, phi, p);
-                for (int j0 = lo; j0 < hi; j0 += 32) {
-                    const int idx = j0 + lane;
-                    bool pass1 = false;
-                    unsigned int tj = 0u;
-                    if (idx < hi) { const uint4 e = ent[idx]; pass1 = arc_may_match(e, kr.x, kr.y) || rall; tj = e.w; }
-                    const unsigned int b = __ballot_sync(0xffffffffu, pass1);
-                    if (b) {
-                        if (pass1) S.queue[warp][qn + __popc(b & lt_mask)] = ((unsigned int)rl << 24) | tj;
-                        qn += __popc(b);
+                for (int j0 = lo; j0 < hi; j0 += 64) {          // two entries per lane: half the loop / vote / push overhead per entry
+                    const int ia = j0 + lane, ib = ia + 32;
+                    bool pa = false, pb = false;
+                    unsigned int ta = 0u, tb = 0u;
+                    if (ia < hi) { const uint4 e = ent[ia]; pa = arc_may_match(e, kr.x, kr.y) || rall; ta = e.w; }
+                    if (ib < hi) { const uint4 e = ent[ib]; pb = arc_may_match(e, kr.x, kr.y) || rall; tb = e.w; }
+                    const unsigned int ba = __ballot_sync(0xffffffffu, pa), bb = __ballot_sync(0xffffffffu, pb);
+                    if (ba | bb) {
+                        if (pa) S.queue[warp][qn + __popc(ba & lt_mask)] = ((unsigned int)rl << 24) | ta;
+                        qn += __popc(ba);
+                        if (pb) S.queue[warp][qn + __popc(bb & lt_mask)] = ((unsigned int)rl << 24) | tb;
+                        qn += __popc(bb);
                         __syncwarp();
                         if (qn >= 64) {
                             qn -= 64;
