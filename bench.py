@@ -229,7 +229,10 @@ def run_ours(args):
             print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"}))
             return 2
     torch.cuda.set_device(local_rank)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # rank 0 prints ONE JSON line: the "NCCL version ..." banner goes to stdout unless NCCL's log is pointed elsewhere (measured on the
+    # 2-GPU box: banner with NCCL_DEBUG unset, none with NCCL_DEBUG=WARN + NCCL_DEBUG_FILE=/dev/stderr)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = capi.Context(local_rank)
