@@ -3,14 +3,17 @@
 //   k_prep_segments : per-segment pre-pass; caches viewing rays and the interpretation-plane normal of every 2D
 //                     segment (the reference recomputes 4 mat-vecs + 5 normalisations per surviving PAIR,
 //                     cudawrapper.cu:148-154).
-//   k_match_topk    : production kernel.  One CTA = 64 source segments of one view pair; the target view's raw
-//                     float4 segment array is streamed through shared memory in 1024-segment stages by 1-D TMA
-//                     (cp.async.bulk + mbarrier, double buffered); lanes own target segments, rows are broadcast;
-//                     a conservative FMA pre-filter (27 flop + 2 rcp) discards ~98 % of the pairs, survivors are
-//                     compacted with ballots into a per-warp queue and evaluated 32 at a time by the exact,
-//                     reference-order arithmetic; per-row survivor keys live in shared memory and the k best are
-//                     selected and written once.  Replaces K_match_lines + the dense D2H + host priority-queue pass
-//                     (cudawrapper.cu:186-253, 570-650).  FP32-issue bound; compulsory HBM traffic ~0.1 B/pair-eval.
+//   k_pair_arcs,    : level-1 tables of the view pairs of one call (l3d_device.cuh "pencil parameter"): every target segment as an arc of
+//   k_arcs_gather     the epipolar pencil, grouped by arc length and sorted by arc start (one radix sort in between, l3d_capi.cu).
+//   k_match_topk    : production kernel.  One CTA = 64 source segments of one view pair; the pair's arc table is staged in shared
+//                     memory by 1-D TMA (cp.async.bulk + mbarrier, 3 x 16 KB in flight from the first instruction); a warp owns 8 rows
+//                     and, per row, binary-searches the window of every arc class, scans only those entries (13 integer instructions
+//                     each), compacts the survivors with ballots into a per-warp queue, runs the conservative float filter on 64 of
+//                     them at a time (27 flop + 2 rcp each, target segment gathered from L2), queues its survivors again and
+//                     evaluates those 32 at a time with the exact, reference-order arithmetic; per-row survivor keys live in shared
+//                     memory and the k best are selected and written once.  Replaces K_match_lines + the dense D2H + host
+//                     priority-queue pass (cudawrapper.cu:186-253, 570-650).  Instruction-issue / latency bound; compulsory HBM
+//                     traffic ~0.1 B/pair-eval.
 //   k_match_dense   : the reference's device contract (float4 depths + float overlap for EVERY cell,
 //                     cudawrapper.cu:186-253), same filter + exact path, coalesced 20 B/cell writes: HBM-write bound.
 #include "l3d_match.cuh"

@@ -18,9 +18,6 @@
 #ifndef MK_STAGES
 #define MK_STAGES 3                     /* TMA ring depth: 3072 target segments resident without reuse */
 #endif
-#ifndef MK_T
-#define MK_T 4                          /* target segments per lane per step */
-#endif
 #ifndef MK_CAP
 #define MK_CAP 32                       /* survivor keys kept per row before pruning to k (<= 32: one key per lane) */
 #endif

@@ -5,16 +5,13 @@
 """
 import json, os, subprocess, sys
 sys.path.insert(0, ".")
-VARIANTS = {
-    "base_T4_R8_B3": [],
-    "T2_R8_B4": ["MK_T=2", "MK_MINB=4"],
-    "T8_R8_B2": ["MK_T=8", "MK_MINB=2"],
-    "T4_R4_B3": ["MK_RPW=4"],
-    "T4_R4_B4": ["MK_RPW=4", "MK_MINB=4"],
-    "T4_R16_B2": ["MK_RPW=16", "MK_MINB=2"],
-    "T4_R8_B2": ["MK_MINB=2"],
-    "T4_R8_B3_TT512_S6": ["MK_TT=512", "MK_STAGES=6"],
-    "T4_R8_B3_W4": ["MK_WARPS=4", "MK_MINB=6"],
+VARIANTS = {     # round 2: the kernel scans arc windows (no MK_T any more); what is left to vary is rows per warp / CTAs per SM / ring depth
+    "base_R8_B3": [],
+    "R4_B3": ["MK_RPW=4"],
+    "R16_B2": ["MK_RPW=16", "MK_MINB=2"],
+    "R8_B2": ["MK_MINB=2"],
+    "R8_B4_S2_CAP24": ["MK_MINB=4", "MK_STAGES=2", "MK_CAP=24"],      # measured: 16 % slower (profiles/README.md)
+    "R8_B3_S2": ["MK_STAGES=2"],                                        # measured: 13 % slower
 }
 if sys.argv[1] == "build":
     from line3dpp_b200 import build
