@@ -369,6 +369,8 @@ def run_ours(args):
             "roofline": {"kernel": "k_match_topk", "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": (achieved_tf / fp32_peak) if fp32_peak else None,
                          "peak_source": "FFMA probe kernel run live in this process (MEASURED_PEAKS.json has no FP32 non-tensor figure)",
+                         "peak_nominal": nominal_fp32_tflops(clocks),
+                         "frac_of_nominal": (achieved_tf / nominal_fp32_tflops(clocks)) if nominal_fp32_tflops(clocks) else None,
                          "algorithmic_flop_per_pair_eval": FLOP_PER_PAIR_EVAL,
                          "hbm_frac": (pe_all / world * 0.1 / (ms_step * 1e-3) / 1e9) / peaks["hbm_gbs"],
                          "accounting": "achieved = pair evaluations x 100 flop (SURVEY 8d: what a kernel that evaluates every cell spends) / step time; "
@@ -398,6 +400,17 @@ def run_ours(args):
     ctx.close()
     sys.stdout.flush()
     return 0
+
+
+def nominal_fp32_tflops(clocks):
+    """148 SMs x 128 FP32 lanes x 2 flop x the SM clock sampled under load (74.5 TFLOP/s at 1965 MHz), next to the live probe"""
+    try:
+        import torch
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        mhz = float((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 0.0)
+        return sms * 128 * 2 * mhz * 1e6 / 1e12 if mhz > 0 else None
+    except Exception:   # noqa
+        return None
 
 
 def committed_capture(kernel: str):
