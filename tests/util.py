@@ -48,7 +48,8 @@ def rows_as_sets(counts, recs, fields=("tgt_seg", "overlap", "d_p1", "d_p2", "d_
 
 
 def two_view_scene(kind, n, seed):
-    """two views of the same random 3D lines with an epipolar geometry the ring scenes do not have"""
+    """two views of the same random 3D lines with an epipolar geometry the ring scenes do not have; kind = one of the named
+    geometries or an explicit [(R, C), (R, C)] camera pair"""
     import dataclasses
     base = synth.make_scene(2, n, seed, "dense")
     rng = np.random.default_rng(seed)
@@ -56,7 +57,8 @@ def two_view_scene(kind, n, seed):
     I = np.eye(3)
     rz = lambda a: np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
     ry = lambda a: np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
-    cams = {"sideways": [(I, (-0.3, 0.0, -4.0)), (I, (0.3, 0.0, -4.0))],            # epipole at infinity (E.z == 0), horizontal epipolar lines
+    cams = kind if not isinstance(kind, str) else {
+            "sideways": [(I, (-0.3, 0.0, -4.0)), (I, (0.3, 0.0, -4.0))],            # epipole at infinity (E.z == 0), horizontal epipolar lines
             "forward": [(I, (0.0, 0.0, -4.6)), (I, (0.04, -0.03, -3.7))],            # epipole inside the image
             "edge": [(I, (0.0, 0.0, -4.2)), (ry(0.05), (0.9, 0.1, -3.6))],           # epipole a little outside the image border
             "rolled": [(I, (-0.4, 0.1, -4.0)), (rz(1.45) @ ry(-0.08), (0.5, -0.2, -4.1))]}[kind]
