@@ -44,13 +44,14 @@ def test_arc_model_keeps_every_oracle_match(oracle, kind, epi):
     assert checked > 1000 and (narrow_checked > 500 or kind == "forward")
 
 
-def _check_pair(oracle, sc, epi, tag):
+def _check_pair(oracle, sc, epi, tag, knn=10):
+    """knn <= 0: every cell above epi_overlap is a match (the reference's keep-all mode) - the strongest form of the check"""
     checked = 0
     for s, t in ((0, 1), (1, 0)):
         pi = util.pair_inputs(sc, s, t)
         if len(pi["ls"]) == 0 or len(pi["lt"]) == 0:
             continue
-        oc, oo, _, _ = oracle.match_lines(oracle.lib().orc_match_lines_f32, pi["ls"], pi["lt"], pi["F"], pi["Rs"], pi["Rt"], pi["Cs"], pi["Ct"], s, t, epi, 10)
+        oc, oo, _, _ = oracle.match_lines(oracle.lib().orc_match_lines_f32, pi["ls"], pi["lt"], pi["F"], pi["Rs"], pi["Rt"], pi["Cs"], pi["Ct"], s, t, epi, knn)
         u, v, _ = m.basis(pi["F"])
         arcs = [m.target_arc(u, v, q, 1.0 / epi + 0.5) for q in pi["lt"]]
         for r in range(len(oc)):
@@ -90,5 +91,5 @@ def test_arc_model_random_camera_pairs(oracle):
         if trial % 5 == 1: d = np.array([1.0, 0.0, 0.0])          # pure sideways motion
         C1 = C0 + d * rng.uniform(0.05, 0.9)
         sc = util.two_view_scene([(np.eye(3), tuple(C0)), (rot(), tuple(C1))], 120, 100 + trial)
-        total += _check_pair(oracle, sc, 0.25, trial)
+        total += _check_pair(oracle, sc, 0.25, trial, knn=0 if trial % 2 else 10)
     assert total > 3000
