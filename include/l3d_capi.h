@@ -87,7 +87,10 @@ int l3d_update_view_params(l3d_ctx* ctx, int num_views, const l3d_view_desc* vie
  * overlap > epi_overlap and all four depths > 0 are kept (cudawrapper.cu:605-645); ties: smaller tgt_seg first.
  * 1 <= knn <= 32: the kNN best per src segment.  knn <= 0: keep ALL matches like the reference does (cudawrapper.cu:628-636),
  * in ascending tgt_seg order; the record array then uses the row stride l3d_match_stride() = the largest row of the job
- * (memory: total_rows * stride * 24 B).  Results stay on the device; fetch with the l3d_get_* calls. */
+ * (memory: total_rows * stride * 24 B).  knn > 32: the keep-all passes, then every row is cut to its knn best.
+ * Every call first builds the level-1 tables of its pairs (the target segments of a pair as arcs of the
+ * epipolar pencil, sorted): 16 B per (pair, target segment) kept until the next call + 28 B while they are built.
+ * Results stay on the device; fetch with the l3d_get_* calls. */
 int l3d_match_pairs(l3d_ctx* ctx, int num_pairs, const int32_t* pairs, const float* F, float epi_overlap, int knn);
 /* sharded form (view pairs are independent given all segment lists): the whole pair list is staged, so
  * row offsets and buffer sizes are those of the full job, but only pairs [first_pair, last_pair) are evaluated here;
