@@ -681,3 +681,19 @@ def test_nvm_cpu_reference_run_matches_fixture_statistically(oracle):
     m2, p2 = nu.chamfer(b, a)
     assert m1 < 0.005 * depth and m2 < 0.005 * depth, (m1, m2)
     assert p1 < 0.02 * depth and p2 < 0.02 * depth, (p1, p2)
+
+
+def test_bench_helpers_without_gpu():
+    """bench.py's bookkeeping helpers (committed ncu figures, nominal FP32 peak) never raise: a bad key or a CPU-only box yields None,
+    and the committed capture of the dominant kernel is there for `roofline.traffic` / `roofline.executed`"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    cap = b.committed_capture("k_match_topk")
+    assert cap and cap["warp_instructions"] > 1e10 and 0 < cap["issue_active_pct"] <= 100 and os.path.exists(os.path.join(ROOT, cap["capture"]))
+    assert b.committed_traffic("k_match_topk") > 3e9
+    assert b.committed_capture("no_such_kernel") is None and b.committed_traffic("no_such_kernel") is None
+    assert b.nominal_fp32_tflops(None) is None
+    v = b.nominal_fp32_tflops({"sm_mhz": 1965.0})        # None without a CUDA device, 148 x 128 x 2 x clock with one
+    assert v is None or 50.0 < v < 100.0
